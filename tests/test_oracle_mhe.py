@@ -1,0 +1,163 @@
+"""Oracle pinning, MHE part.  No reference fixtures exist, so the oracle is
+pinned by (1) the QP sizes and delayed-VO index table of a literal reading,
+(2) internal consistency: slack-elimination solve == dense KKT of the exported reference-ordered QP,
+reference-form marginalisation == information-form Schur complement, OSQP-style ADMM -> same point."""
+import numpy as np
+import pytest
+
+
+def _drive(oracle, st, i, steps, prm, on_step=None):
+    ekf = oracle.Ekf(oracle.ekf_params(rate=prm.rate))
+    m = oracle.Mhe(prm)
+    for s in range(steps):
+        vo = vq = None
+        if st["vo_flag"][s, i]:
+            vo = (st["vo_time_pre"][s, i], st["vo_time_now"][s, i], st["vo_rel_p"][s, :, i])
+            vq = st["vo_quat"][s, :, i]
+        ekf.tick(st["gyro"][s, :, i], st["accel"][s, :, i], st["imu_time"][s, i], vq, st["vo_time_now"][s, i])
+        q, _ = ekf.get()
+        m.step(s, imu_time=st["imu_time"][s, i], accel=st["accel"][s, :, i], gyro=st["gyro"][s, :, i], quat=q,
+               joint_pos=st["joint_pos"][s, :, i], joint_vel=st["joint_vel"][s, :, i],
+               foot_force=st["foot_force"][s, :, i], vo=vo)
+        if on_step:
+            on_step(s, m)
+    return m
+
+
+@pytest.fixture(scope="module")
+def lockstep_stream():
+    from decentralized_ekf_mhe_b200 import synth
+    return synth.to_numpy(synth.make_stream(2, 135))
+
+
+def test_qp_sizes(oracle, lockstep_stream):
+    sizes = {}
+    _drive(oracle, lockstep_stream, 0, 25, oracle.go1_params(), lambda s, m: sizes.__setitem__(s, m.dims()[3:]))
+    assert sizes[1] == (54, 36)
+    assert sizes[19] == (648, 468) and sizes[24] == (648, 468)
+
+
+def test_vo_index_table(oracle, lockstep_stream):
+    """SURVEY.md App. F, N=20, imu_time=T*0.005, frame j at j/30 s, 40 ms latency."""
+    rows = {}
+
+    def grab(s, m):
+        if lockstep_stream["vo_flag"][s, 0]:
+            rows[s] = m.vo_debug()
+
+    _drive(oracle, lockstep_stream, 0, 130, oracle.go1_params(), grab)
+    # T: (i_pre, i_now, w0)
+    for T, want in {15: (0, 6, 0), 22: (6, 13, 2), 28: (13, 20, 8)}.items():
+        assert tuple(rows[T][1:4]) == want and rows[T][8] == 0  # fewer than 4 way-points: no bounds
+    # T: (i_pre, i_now, w0, i0, ins, num, first discrete time)
+    assert rows[35][1:8] == [20, 26, 15, 20, 5, 7, 20]
+    assert rows[122][1:8] == [65, 72, 61, 65, 4, 8, 106] and rows[122][9] == 81  # ring saturated at 4N+1
+    assert rows[128][1:8] == [66, 73, 61, 66, 5, 8, 113]
+
+
+def test_vo_bound_rows(oracle, lockstep_stream):
+    """Rows written by Update_Image_bound (MheSrb.cpp:449-459) at T=35: 141,165,...,261."""
+    got = {}
+
+    def grab(s, m):
+        if s in (34, 35):
+            _, _, _, l, u = m.export_qp()
+            got[s] = np.where(l == u)[0], l.copy()
+
+    _drive(oracle, lockstep_stream, 0, 36, oracle.go1_params(), grab)
+    eq34 = set(got[34][0])
+    eq35 = set(got[35][0])
+    # at T=35 the window was 15..35 before marginalising stage 15 (24 rows) -> rows shift by -24
+    new_rows = sorted(r for r in eq35 if (r + 24) not in eq34 and (r % 24) in (21, 22, 23))
+    assert [r for r in new_rows if r % 24 == 21] == [141 - 24 + 24 * i for i in range(6)]
+
+
+def test_exact_solve_equals_dense_kkt(oracle, go1_stream_small):
+    st = go1_stream_small
+
+    def check(s, m):
+        if s in (1, 7, 19, 20, 33, 60, 90):
+            H, g, A, l, u = m.export_qp()
+            eq = l == u
+            assert np.all((l[~eq] <= -1e29) & (u[~eq] >= 1e29))  # reference: equality or free rows only
+            Ae, be = A[eq], l[eq]
+            nV, ne = H.shape[0], Ae.shape[0]
+            K = np.block([[H, Ae.T], [Ae, np.zeros((ne, ne))]])
+            z = np.linalg.solve(K, np.concatenate([-g, be]))[:nV]
+            np.testing.assert_allclose(m.solution(), z, rtol=0, atol=5e-9)
+            np.testing.assert_allclose(m.x()[3:6], z[nV - 21 + 3:nV - 21 + 6], rtol=0, atol=1e-9)
+
+    _drive(oracle, st, 3, 91, oracle.go1_params(), check)
+
+
+def test_marginalisation_equals_information_form(oracle, lockstep_stream):
+    """MheSrb.cpp:475-713 (dense (ds+dc+dm)^2 inverse) vs M+ = B'QB - B'QA (M_post + A'QA)^-1 A'QB.
+    Lock-step stream: VO bounds arrive 8 ticks late (<< N), so the stage being marginalised at step s
+    already carries its final bounds in the QP exported at step s-1."""
+    prev = {}
+    seen = {"eq": 0, "free": 0}
+
+    def check(s, m):
+        if s < 19:
+            return
+        H, g, A, l, u = m.export_qp()
+        if s >= 20:
+            Hp, gp, Ap, lp, up = prev["qp"]
+            M, n = Hp[:9, :9], gp[:9]
+            R, y, Hm = Hp[9:21, 9:21], lp[0:12], Ap[0:12, 0:9]
+            Ad, Qd, bd = Ap[12:21, 0:9], Hp[21:30, 21:30], lp[12:21]
+            eqvo = bool(np.all(lp[21:24] == up[21:24]))
+            seen["eq" if eqvo else "free"] += 1
+            At, Bt, Qt, lt = Ad, np.eye(9), Qd, bd
+            if eqvo:
+                S = np.hstack([np.eye(3), np.zeros((3, 6))])
+                At, Bt = np.vstack([Ad, S]), np.vstack([np.eye(9), S])
+                Qt = np.block([[Qd, np.zeros((9, 3))], [np.zeros((3, 9)), Hp[30:33, 30:33]]])
+                lt = np.concatenate([bd, lp[21:24]])
+            Mpost = M + Hm.T @ R @ Hm
+            npost = n - Hm.T @ R @ y
+            G = Mpost + At.T @ Qt @ At
+            Mn = Bt.T @ Qt @ Bt - Bt.T @ Qt @ At @ np.linalg.solve(G, At.T @ Qt @ Bt)
+            nn = Bt.T @ Qt @ lt + Bt.T @ Qt @ At @ np.linalg.solve(G, npost - At.T @ Qt @ lt)
+            Ma, na = m.arrival()
+            scale = np.abs(Mn).max()
+            np.testing.assert_allclose(Ma, Mn, rtol=0, atol=1e-10 * scale)
+            np.testing.assert_allclose(na, nn, rtol=0, atol=1e-10 * max(1.0, np.abs(nn).max()))
+            assert np.abs(Ma - Ma.T).max() <= 1e-12 * scale
+            # the arrival cost is what sits on the first state of the new window
+            np.testing.assert_array_equal(H[:9, :9], Ma)
+            np.testing.assert_array_equal(g[:9], na)
+        prev["qp"] = (H, g, A, l, u)
+
+    _drive(oracle, lockstep_stream, 0, 70, oracle.go1_params(), check)
+    assert seen["eq"] > 10 and seen["free"] > 10
+
+
+def test_admm_converges_to_exact(oracle, go1_stream_small):
+    st = go1_stream_small
+    r0, _, _ = oracle.run_batch(st, oracle.go1_params(solve_mode=0), oracle.ekf_params(rate=200), i1=4, nthreads=4,
+                                want=("x",))
+    r2, _, _ = oracle.run_batch(st, oracle.go1_params(solve_mode=2, abs_tol=1e-8, relative_tol=1e-8, time_limit=0.0),
+                                oracle.ekf_params(rate=200), i1=4, nthreads=4, want=("x", "admm_iters"))
+    err = np.abs(r2["x"][1:, 3:6, :4] - r0["x"][1:, 3:6, :4])
+    assert r2["admm_iters"][1:, :4].max() < 4000
+    # OSQP-style iterates at eps=1e-8 sit within a few 1e-6 m/s of the unique optimum (median ~1e-9)
+    assert err.max() < 5e-6 and np.median(err) < 1e-7
+
+
+def test_kf_alternative_matches_mhe_without_vo(oracle):
+    """with no delayed VO the MHE's x_T equals the Kalman filter estimate.
+    The reference's KF path runs InitializeKF() AND UpdateKF() on the first tick
+    (DecentralEst.cpp:140-141), i.e. it consumes sample 0 twice; feeding the MHE the same duplicated
+    sequence aligns the two: x_MHE(T+1 | s0,s0,s1,..) == x_KF(T | s0,s1,..)."""
+    from decentralized_ekf_mhe_b200 import synth
+    st = synth.to_numpy(synth.make_stream(2, 80, vo=False))
+    st_dup = {k: np.concatenate([v[:1], v], axis=0) for k, v in st.items()}
+    ep = oracle.ekf_params(rate=200)
+    quat = oracle.run_batch(st, oracle.go1_params(), ep, nthreads=2, run_mhe=False, want=("quat",))[0]["quat"]
+    quat_dup = np.concatenate([quat[:1], quat], axis=0)
+    r_m = oracle.run_batch(st_dup, oracle.go1_params(est_type=0), ep, nthreads=2, run_ekf=False, quat_in=quat_dup,
+                           want=("x",))[0]
+    r_k = oracle.run_batch(st, oracle.go1_params(est_type=1), ep, nthreads=2, run_ekf=False, quat_in=quat,
+                           want=("x",))[0]
+    np.testing.assert_allclose(r_m["x"][2:, 3:6], r_k["x"][1:, 3:6], rtol=0, atol=1e-9)
