@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the estimator hot path (BASELINE.json metric: EKF+MHE instance-steps/s at a 64K batch).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: CPU path on the host cores
+
+One "step" = one lock-step tick of every instance in the batch: EKF tick (+VO correct/replay when a VO
+message is due) + MHE update(T) (kinematics, stage assembly, VO bound insertion, marginalisation, full
+window solve, output).  Workload = BASELINE configs[1]: Go1, 65,536 instances per GPU, N=20, 200 Hz, fp64,
+synthetic trot stream with 30 Hz VO at 40 ms latency.  Instances shard over ranks with no
+collective on the data path (weak scaling: 65,536 instances per GPU).
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ekf_mhe_instance_steps_per_s"
+UNIT = "instance-steps/s"
+WORKLOAD = "go1_ekf_mhe_65536x_N20_fp64"
+FILL_STEPS = 24  # untimed: reach the steady state T >= N (window full, marginalisation active)
+
+# Exact operation tally of the committed algorithm (tests/hostsim/flopcount.cpp; mul and add counted
+# separately, FMA = 2; tests/test_flop_tally.py keeps these in sync with the kernels)
+FLOPS = dict(meas_update=657, propagate=656, propagate_vo=1496, ekf_predict=432, ekf_correct=641,
+             ekf_vo_correct=450, assemble_go1=1401, solve_epilogue=30)
+
+
+def algorithmic_work(N, n_vo_mean, elt=8):
+    """Per instance-step algorithmic bytes / flops of each kernel (tier A = full-window re-solve)."""
+    rec = 24 * elt + 1
+    solve_bytes = 2 * 54 * elt + (N + 1) * rec + 3 * 8 + 12 * 8 + 8
+    solve_flops = (N + 1) * FLOPS["meas_update"] + N * FLOPS["propagate"] + n_vo_mean * (
+        FLOPS["propagate_vo"] - FLOPS["propagate"]) + FLOPS["solve_epilogue"]
+    ekf_bytes = 7 * 8 + 2 * 20 * elt + 26 * elt + 8 + 4 * 8 + 4
+    ekf_flops = FLOPS["ekf_predict"] + FLOPS["ekf_correct"]
+    asm_bytes = 4 * elt + 7 * 8 + 24 * 8 + 4 * 8 + 1 + rec + 5 * 8 + 4 + 8
+    asm_flops = FLOPS["assemble_go1"]
+    return dict(solve=(solve_bytes, solve_flops), ekf=(ekf_bytes, ekf_flops), assemble=(asm_bytes, asm_flops))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.005):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                 getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        med = None
+        if self.samples:
+            s = sorted(self.samples)
+            med = s[len(s) // 2]
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_port_baseline(N, threads, steps_timed, instances_per_thread, mode="admm", seed=20240510):
+    """Times the oracle (CPU restatement) on a bounded sample of the same workload, one instance per thread."""
+    from decentralized_ekf_mhe_b200 import synth
+    from oracle import pyoracle as po
+    n = threads * instances_per_thread
+    S = N + 4 + steps_timed
+    st = synth.to_numpy(synth.make_stream(n, S, seed=seed))
+    if mode == "admm":
+        # reference-faithful: OSQP-style ADMM, cold setup every step, shipped tolerances, no wall-clock limit
+        prm = po.go1_params(N=N, solve_mode=2, time_limit=0.0)
+    else:
+        prm = po.go1_params(N=N, solve_mode=0)
+    res, wall, busy = po.run_batch(st, prm, po.ekf_params(rate=200), nthreads=threads, t_steady=N + 4, want=())
+    t = max(res["_busy_max"], 1e-9)
+    return n * steps_timed / t, t, n, S
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path on the host cores.  The reference
+    cannot be compiled in this image (needs rclcpp, Eigen3, osqp, OsqpEigen), so this
+    times the oracle port in its reference-faithful mode (OSQP-style ADMM with a cold setup every step,
+    the shipped eps 1e-6, no wall-clock limit) with every host thread, one instance per thread."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    K, W = args.steps, args.warmup
+    N = args.N
+    ipt = args.ref_instances_per_thread
+    from decentralized_ekf_mhe_b200 import synth
+    from oracle import pyoracle as po
+    n = cores * ipt
+    S = N + 4 + W + K
+    st = synth.to_numpy(synth.make_stream(n, S))
+    prm = po.go1_params(N=N, solve_mode=2, time_limit=0.0)
+    res, wall, busy = po.run_batch(st, prm, po.ekf_params(rate=200), nthreads=cores, t_steady=N + 4 + W, want=())
+    t = max(res["_busy_max"], 1e-9)
+    value = n * K / t
+    sample = (f"{n} instances ({ipt}/thread) x {K} steady-state ticks each per step-batch; oracle port, "
+              f"ADMM eps_abs=eps_rel=1e-6, cold setup every tick, time_limit=0")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 * t / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "N": N, "rate_hz": 200, "robot": "go1",
+                   "batch_per_step": n, "note": "CPU path; a step is one tick of a bounded sample batch"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=65536, help="instances per GPU")
+    ap.add_argument("--N", type=int, default=20)
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-instances-per-thread", type=int, default=4)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from decentralized_ekf_mhe_b200 import build as b
+    b.build()
+    from decentralized_ekf_mhe_b200 import estimator, synth
+    from decentralized_ekf_mhe_b200.sharding import env_rank, max_over_ranks, shard_range
+
+    rank, local_rank, world = env_rank()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, K = max(args.warmup, 3), args.steps
+    Ke = max(1, min(args.e2e_steps, K))
+    n = args.instances  # per GPU (weak scaling)
+    n_total = n * world
+    lo, hi = shard_range(n_total, rank, world)
+    assert hi - lo == n
+    N = args.N
+    S = FILL_STEPS + W + K + Ke
+    dev = torch.device("cuda", local_rank)
+
+    # ---- synthetic stream, resident in HBM before any timed region (each rank: its own instance range)
+    t_gen = time.time()
+    stream = synth.make_stream(n, S, seed=20240510 + 7919 * rank, device=dev, device_rng=True)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    vo_steps = [bool(stream["vo_flag"][s].any()) for s in range(S)]
+
+    prm = estimator.robot_params("go1", ekf_rate=200, N=N)
+    est = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
+    stores = [estimator.robot_store.from_stream(stream, s, with_vo=vo_steps[s]) for s in range(S)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    T = 0
+    for _ in range(FILL_STEPS + W):
+        est.step(T, stores[T])
+        T += 1
+    # ---- value: K steps, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    launches0 = est.launch_count()
+    sampler.start()
+    ev0.record()
+    for _ in range(K):
+        est.step(T, stores[T])
+        T += 1
+    ev1.record()
+    barrier()
+    ms_value = ev0.elapsed_time(ev1)
+    launches = est.launch_count() - launches0
+    ms_value = max_over_ranks(ms_value)
+    value = n_total * K / (ms_value * 1e-3)
+    n_vo_mean = float(est.window_vo_count().double().mean().item())
+
+    # ---- e2e: the same metric through dekf_step_host with pinned HOST buffers (H2D + D2H inside the timed region)
+    keys = ["gyro", "accel", "imu_time", "joint_pos", "joint_vel", "foot_force", "vo_quat", "vo_time_pre",
+            "vo_time_now", "vo_rel_p"]
+    rows = {k: (stream[k][0].numel() // n) for k in keys}
+    nrow = sum(rows.values())
+    pin_in = torch.empty(Ke, nrow, n, dtype=torch.float64).pin_memory()
+    pin_flag = torch.empty(Ke, n, dtype=torch.uint8).pin_memory()
+    r0 = 0
+    views = {}
+    for k in keys:
+        pin_in[:, r0:r0 + rows[k]] = stream[k][T:T + Ke].reshape(Ke, rows[k], n).cpu()
+        views[k] = (r0, r0 + rows[k])
+        r0 += rows[k]
+    pin_flag.copy_(stream["vo_flag"][T:T + Ke].cpu())
+    pin_out = torch.empty(16, n, dtype=torch.float64).pin_memory()
+    hout = {"quat": pin_out[0:4], "x": pin_out[4:13], "v_body": pin_out[13:16],
+            "contact": torch.empty(4, n, dtype=torch.uint8).pin_memory(),
+            "status": torch.empty(n, dtype=torch.int32).pin_memory()}
+    hins = []
+    h2d = 0
+    for j in range(Ke):
+        d = {k: pin_in[j, views[k][0]:views[k][1]] for k in keys}
+        has_vo = vo_steps[T + j]
+        d["vo_flag"] = pin_flag[j] if has_vo else None
+        hins.append(d)
+        h2d += (sum(rows[k] for k in keys[:6]) * 8 * n) + ((sum(rows[k] for k in keys[6:]) * 8 + 1) * n if has_vo else 0)
+    d2h = 16 * 8 * n + 4 * n + 4 * n
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    chk = 0.0
+    for j in range(Ke):
+        est.step_host(T, hins[j], hout)
+        chk += float(hout["x"][3, 0])  # read the result on the host
+        T += 1
+    ev1.record()
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+    ms_e2e = max_over_ranks(max(ev0.elapsed_time(ev1), wall_e2e * 1e3))  # device events vs host wall clock: the slower
+    e2e_value = n_total * Ke / (ms_e2e * 1e-3)
+    clocks = sampler.stop()
+
+    # ---- per-kernel device time (separate pass, CUDA events around every launch on the handle's stream)
+    # (a fresh handle re-plays the start of the stream: T must advance from 0 and the timed handle is past the end)
+    Kp = min(K, 50)
+    est2 = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
+    for s in range(FILL_STEPS + W):
+        est2.step(s, stores[s])
+    est2.profile(True)
+    for s in range(FILL_STEPS + W, FILL_STEPS + W + Kp):
+        est2.step(s, stores[s])
+    pms, pcnt = est2.profile_read()
+    est2.close()
+
+    line = None
+    if rank == 0:
+        hbm_peak, hbm_src = measured_peaks()
+        peaks = estimator.measure_peaks(local_rank)
+        elt = 8 if args.precision == "fp64" else 4
+        work = algorithmic_work(N, n_vo_mean, elt)
+        fma_peak = peaks["fp64_tflops"] if args.precision == "fp64" else peaks["fp32_tflops"]
+        kern = {}
+        for name in ("ekf", "assemble", "solve"):
+            if pcnt[name] == 0:
+                continue
+            dur = pms[name] / pcnt[name] * 1e-3
+            by, fl = work[name]
+            kern[name] = {"ms": dur * 1e3, "gbs": by * n / dur / 1e9, "tflops": fl * n / dur / 1e12,
+                          "bytes_per_instance": by, "flops_per_instance": fl}
+        share = {k: v["ms"] for k, v in kern.items()}
+        tot = sum(share.values()) or 1.0
+        dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else "solve"
+        kd = kern.get(dom, {"gbs": 0.0, "tflops": 0.0, "ms": 0.0})
+        t_hbm = work[dom][0] / (hbm_peak * 1e9)
+        t_fma = work[dom][1] / (fma_peak * 1e12) if fma_peak > 0 else 0.0
+        if t_fma >= t_hbm:
+            roof = {"bound": "fp64" if args.precision == "fp64" else "fp32", "achieved": kd["tflops"], "peak": fma_peak,
+                    "unit": "TFLOP/s", "frac": kd["tflops"] / fma_peak if fma_peak else None}
+        else:
+            roof = {"bound": "hbm", "achieved": kd["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": kd["gbs"] / hbm_peak}
+        roof.update({
+            "kernel": {"solve": "k_solve", "ekf": "k_ekf", "assemble": "k_assemble"}[dom],
+            "kernel_ms": kd["ms"], "kernel_share_of_step": kd["ms"] / tot,
+            "traffic": None,
+            "hbm": {"achieved": kd["gbs"], "peak": hbm_peak, "frac": kd["gbs"] / hbm_peak, "peak_source": hbm_src},
+            "fma": {"achieved": kd["tflops"], "peak": fma_peak, "frac": kd["tflops"] / fma_peak if fma_peak else None,
+                    "peak_source": "measured in this run (dekf_measure_fma_peak, non-tensor FMA)"},
+            "algorithmic": {"tier": "A (full-window re-solve every step)", "bytes_per_instance_step": work[dom][0],
+                            "flops_per_instance_step": work[dom][1], "vo_stages_in_window_mean": n_vo_mean},
+            "all_kernels": kern, "measured_copy_gbs": peaks["copy_gbs"],
+        })
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if (n == 65536 and N == 20 and args.precision == "fp64") else
+                       f"go1_ekf_mhe_{n}x_N{N}_{args.precision}",
+                       "robot": "go1", "instances_per_gpu": n, "instances_total": n_total, "N": N, "rate_hz": 200,
+                       "vo": "30 Hz, 40 ms latency, lock-step arrival", "parallelism": f"instance-shard x{world}",
+                       "cache": "per-step working set (window ring + inputs, >400 MB at 65,536 instances) exceeds the 126 MB L2; "
+                                "every step reads distinct input arrays",
+                       "fill_steps": FILL_STEPS, "stream_gen_s": round(t_gen, 2)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // Ke, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "ms_per_step": ms_e2e / Ke, "api": "dekf_step_host (pinned host buffers)",
+                    "host_checksum": chk},
+            "gpu_launches": launches,
+            "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
+            "roofline": roof,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            # bounded sample sized for ~cpu-seconds of work at ~250 instance-steps/s/core
+            steps_cpu = 60
+            ipt = max(1, int(args.cpu_seconds * 250 / steps_cpu))
+            v, t, nn, SS = cpu_port_baseline(N, cores, steps_cpu, ipt, mode="admm")
+            vd, td, _, _ = cpu_port_baseline(N, cores, 200, 4, mode="direct")
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{nn} instances x {steps_cpu} steady-state ticks, one instance per thread; oracle port in "
+                          f"reference-faithful mode (OSQP-style ADMM, cold setup every tick, eps 1e-6, no time limit); {t:.1f} s",
+                "direct_solve_value": vd,
+                "direct_solve_note": "same port with the exact banded solve instead of ADMM (algorithmic CPU baseline)"}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,895 @@
+// libdekf_b200.so: __global__ wrappers + the extern "C" boundary declared in include/dekf_b200.h.
+// sm_100a only.  No CPU fallback: every entry point needs a live CUDA context.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/dekf_b200.h"
+#include "estimator_core.cuh"
+#include "host_setup.hpp"
+
+namespace dekf {
+
+// ------------------------------------------------------------------------------------------------
+// kernels: one thread per estimator instance
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlock = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_ekf(const EkfConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
+                                                const Outputs out, int k, int32_t *status_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  const int st = ekf_tick<T>(c, dm, b, in, out, k, i);
+  b.status[i] = st;
+  if (status_out != nullptr) status_out[i] = st;
+}
+
+template <typename T, typename Model>
+__global__ void __launch_bounds__(kBlock) k_assemble(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
+                                                     const Outputs out, int Tk, int accumulate_status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  double q[4];
+#pragma unroll
+  for (int f = 0; f < 4; ++f)
+    q[f] = (in.quat != nullptr) ? in.quat[(size_t)f * dm.n + i] : (double)b.ekf_q[(size_t)f * dm.n + i];
+  const int st = mhe_assemble<T, Model>(c, dm, b, in, out, Tk, i, q);
+  b.status[i] = accumulate_status ? (b.status[i] | st) : st;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_solve(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
+                                                  const Outputs out, int Tk, int32_t *status_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  int st = b.status[i];
+  if (Tk >= 1) st |= mhe_solve<T>(c, dm, b, in, out, Tk, i);
+  b.status[i] = st;
+  if (status_out != nullptr) status_out[i] = st;
+}
+
+// whole tick in one launch (small batches: launch latency dominates)
+template <typename T, typename Model>
+__global__ void __launch_bounds__(kBlock) k_fused(const EkfConst<T> ec, const MheConst<T> mc, const Dims dm, const Buffers<T> b,
+                                                  const Inputs in, const Outputs out, int k, int Tk, int32_t *status_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  int st = ekf_tick<T>(ec, dm, b, in, out, k, i);
+  double q[4];
+#pragma unroll
+  for (int f = 0; f < 4; ++f) q[f] = (double)b.ekf_q[(size_t)f * dm.n + i];
+  st |= mhe_assemble<T, Model>(mc, dm, b, in, out, Tk, i, q);
+  if (Tk >= 1) st |= mhe_solve<T>(mc, dm, b, in, out, Tk, i);
+  b.status[i] = st;
+  if (status_out != nullptr) status_out[i] = st;
+}
+
+template <typename T>
+__global__ void k_init_state(const EkfConst<T> ec, const MheConst<T> mc, const Dims dm, const Buffers<T> b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  const int n = dm.n;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) b.ekf_q[(size_t)f * n + i] = ec.q0[f];
+#pragma unroll
+  for (int f = 0; f < 16; ++f) b.ekf_P[(size_t)f * n + i] = (f % 5 == 0) ? ec.P0[f / 5] : T(0);
+#pragma unroll
+  for (int f = 0; f < 45; ++f) b.arr_P[(size_t)f * n + i] = T(0);
+  const int diag[3] = {0, 3, 5};
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    b.arr_P[(size_t)(0 + diag[f]) * n + i] = mc.P0[f];
+    b.arr_P[(size_t)(6 + diag[f]) * n + i] = mc.P0[3 + f];
+    b.arr_P[(size_t)(12 + diag[f]) * n + i] = mc.P0[6 + f];
+  }
+#pragma unroll
+  for (int f = 0; f < 9; ++f) b.arr_x[(size_t)f * n + i] = T(0);
+#pragma unroll
+  for (int f = 0; f < 3; ++f) b.p_vo[(size_t)f * n + i] = 0.0;
+  b.wp_count[i] = 0;
+  b.pend_flag[i] = 0;
+  b.status[i] = 0;
+}
+
+// arrival cost getters: (P, x) -> dense 9x9 P, and (M_p, n_p) = (P^-1, -P^-1 x) (MheSrb.hpp:86-87)
+template <typename T>
+__global__ void k_get_arrival(const Dims dm, const Buffers<T> b, double *Pout, double *xout, int as_information) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  const int n = dm.n;
+  Cov9<T> P;
+  load_cov(b.arr_P, n, i, P);
+  double A[81], x[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      A[(0 + r) * 9 + 0 + c] = (double)P.pp(r, c);
+      A[(3 + r) * 9 + 3 + c] = (double)P.vv(r, c);
+      A[(6 + r) * 9 + 6 + c] = (double)P.bb(r, c);
+      A[(0 + r) * 9 + 3 + c] = (double)P.pv(r, c);
+      A[(3 + c) * 9 + 0 + r] = (double)P.pv(r, c);
+      A[(0 + r) * 9 + 6 + c] = (double)P.pb(r, c);
+      A[(6 + c) * 9 + 0 + r] = (double)P.pb(r, c);
+      A[(3 + r) * 9 + 6 + c] = (double)P.vb(r, c);
+      A[(6 + c) * 9 + 3 + r] = (double)P.vb(r, c);
+    }
+  for (int f = 0; f < 9; ++f) x[f] = (double)b.arr_x[(size_t)f * n + i];
+  if (as_information) {
+    // Cholesky A = L L', M = A^-1 column by column, n_p = -M x
+    double L[81];
+    for (int j = 0; j < 9; ++j) {
+      double d = A[j * 9 + j];
+      for (int k = 0; k < j; ++k) d -= L[j * 9 + k] * L[j * 9 + k];
+      d = sqrt(d);
+      L[j * 9 + j] = d;
+      for (int r = j + 1; r < 9; ++r) {
+        double v = A[r * 9 + j];
+        for (int k = 0; k < j; ++k) v -= L[r * 9 + k] * L[j * 9 + k];
+        L[r * 9 + j] = v / d;
+      }
+    }
+    double np[9];
+    for (int f = 0; f < 9; ++f) np[f] = 0.0;
+    for (int c = 0; c < 9; ++c) {
+      double y[9];
+      for (int r = 0; r < 9; ++r) {
+        double v = (r == c) ? 1.0 : 0.0;
+        for (int k = 0; k < r; ++k) v -= L[r * 9 + k] * y[k];
+        y[r] = v / L[r * 9 + r];
+      }
+      for (int r = 8; r >= 0; --r) {
+        double v = y[r];
+        for (int k = r + 1; k < 9; ++k) v -= L[k * 9 + r] * y[k];
+        y[r] = v / L[r * 9 + r];
+      }
+      for (int r = 0; r < 9; ++r) {
+        Pout[(size_t)(r * 9 + c) * n + i] = y[r];
+        np[r] -= y[r] * x[c];
+      }
+    }
+    for (int f = 0; f < 9; ++f) xout[(size_t)f * n + i] = np[f];
+  } else {
+    for (int f = 0; f < 81; ++f) Pout[(size_t)f * n + i] = A[f];
+    for (int f = 0; f < 9; ++f) xout[(size_t)f * n + i] = x[f];
+  }
+}
+
+template <typename T>
+__global__ void k_get_misc(const Dims dm, const Buffers<T> b, int Tk, double *p_vo, double *R_sb, double *ekfP) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  const int n = dm.n;
+  if (p_vo != nullptr)
+    for (int f = 0; f < 3; ++f) p_vo[(size_t)f * n + i] = b.p_vo[(size_t)f * n + i];
+  if (R_sb != nullptr) {
+    const T *rec = b.win + (size_t)(Tk % dm.NW) * REC_SIZE * n + i;
+    for (int f = 0; f < 9; ++f) R_sb[(size_t)f * n + i] = (double)rec[(size_t)(REC_R + f) * n];
+  }
+  if (ekfP != nullptr)
+    for (int f = 0; f < 16; ++f) ekfP[(size_t)f * n + i] = (double)b.ekf_P[(size_t)f * n + i];
+}
+
+template <typename T>
+__global__ void k_vo_count(const Dims dm, const Buffers<T> b, int Tk, int32_t *count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  int c = 0;
+  const int k0 = (Tk >= dm.N) ? Tk - dm.N + 1 : 0;
+  for (int k = k0; k < Tk; ++k) c += b.win_flag[(size_t)(k % dm.NW) * dm.n + i] != 0;
+  count[i] = c;
+}
+
+}  // namespace dekf
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+using namespace dekf;
+
+struct dekf_handle {
+  dekf_config cfg;
+  Dims dm;
+  int nl, nj, nq;
+  bool f32;
+  EkfConst<double> ec64;
+  MheConst<double> mc64;
+  EkfConst<float> ec32;
+  MheConst<float> mc32;
+  Buffers<double> b64;
+  Buffers<float> b32;
+  void *slab = nullptr;
+  size_t slab_bytes = 0;
+  // staging for the host-pointer path
+  double *stage_in = nullptr;   // packed doubles
+  uint8_t *stage_flag = nullptr;
+  double *stage_out = nullptr;  // quat4 x9 vbody3
+  uint8_t *stage_contact = nullptr;
+  int32_t *stage_status = nullptr;
+  // debug taps
+  double *tap_b_meas = nullptr, *tap_Q_meas = nullptr;
+  int32_t *tap_vo = nullptr, *tap_ekf = nullptr;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int ekf_k = 0;    // EKF ticks done
+  int next_T = 0;   // next MHE discrete time expected
+  int64_t launches = 0;
+  size_t extra_bytes = 0;
+  // optional per-kernel timing
+  bool prof = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double prof_ms[3] = {0, 0, 0};
+  int64_t prof_n[3] = {0, 0, 0};
+  std::string err;
+};
+
+namespace {
+
+int fail(dekf_handle *h, int code, const char *what, cudaError_t ce = cudaSuccess) {
+  if (h) {
+    h->err = what;
+    if (ce != cudaSuccess) {
+      h->err += ": ";
+      h->err += cudaGetErrorString(ce);
+    }
+  }
+  return code;
+}
+
+#define CK(call)                                                 \
+  do {                                                           \
+    cudaError_t e_ = (call);                                     \
+    if (e_ != cudaSuccess) return fail(h, DEKF_ECUDA, #call, e_); \
+  } while (0)
+
+inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <typename T>
+size_t carve(Buffers<T> &b, const Dims &dm, char *base) {
+  const StateSizes s = state_sizes(dm);
+  size_t off = 0;
+  auto take = [&](size_t count, size_t elt) {
+    char *p = base ? base + off : nullptr;
+    off += align_up(count * elt);
+    return p;
+  };
+  b.ekf_q = (T *)take(s.ekf_q, sizeof(T));
+  b.ekf_P = (T *)take(s.ekf_P, sizeof(T));
+  b.ekf_hist = (T *)take(s.ekf_hist, sizeof(T));
+  b.ekf_hist_time = (double *)take(s.ekf_hist_time, sizeof(double));
+  b.arr_P = (T *)take(s.arr_P, sizeof(T));
+  b.arr_x = (T *)take(s.arr_x, sizeof(T));
+  b.win = (T *)take(s.win, sizeof(T));
+  b.win_flag = (uint8_t *)take(s.win_flag, 1);
+  b.hist_time = (double *)take(s.hist_time, sizeof(double));
+  b.hist_quat = (double *)take(s.hist_quat, sizeof(double));
+  b.wp = (double *)take(s.wp, sizeof(double));
+  b.wp_time = (double *)take(s.wp_time, sizeof(double));
+  b.wp_count = (int32_t *)take(s.wp_count, sizeof(int32_t));
+  b.p_vo = (double *)take(s.p_vo, sizeof(double));
+  b.pend_flag = (uint8_t *)take(s.pend_flag, 1);
+  b.pend = (double *)take(s.pend, sizeof(double));
+  b.status = (int32_t *)take(s.status, sizeof(int32_t));
+  return off;
+}
+
+inline int grid_for(int n) { return (n + kBlock - 1) / kBlock; }
+
+// Event pair around one launch; the elapsed time is harvested lazily (next begin or read) so the stream is
+// only synchronised while profiling is enabled.
+struct ProfScope {
+  dekf_handle *h;
+  int slot;
+  ProfScope(dekf_handle *h_, int slot_) : h(h_), slot(slot_) {
+    if (h->prof) cudaEventRecord(h->ev0, h->stream);
+  }
+  ~ProfScope() {
+    if (h->prof) {
+      cudaEventRecord(h->ev1, h->stream);
+      cudaEventSynchronize(h->ev1);
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) {
+        h->prof_ms[slot] += ms;
+        h->prof_n[slot]++;
+      }
+    }
+  }
+};
+
+Inputs to_inputs(const dekf_inputs *in) {
+  Inputs r;
+  r.gyro = in->gyro;
+  r.accel = in->accel;
+  r.imu_time = in->imu_time;
+  r.joint_pos = in->joint_pos;
+  r.joint_vel = in->joint_vel;
+  r.foot_force = in->foot_force;
+  r.vo_flag = in->vo_flag;
+  r.vo_quat = in->vo_quat;
+  r.vo_time_pre = in->vo_time_pre;
+  r.vo_time_now = in->vo_time_now;
+  r.vo_rel_p = in->vo_rel_p;
+  r.quat = in->quat;
+  return r;
+}
+Outputs to_outputs(const dekf_handle *h, const dekf_outputs *out) {
+  Outputs r;
+  std::memset(&r, 0, sizeof(r));
+  if (out) {
+    r.quat = out->quat;
+    r.x = out->x;
+    r.v_body = out->v_body;
+    r.contact = out->contact;
+  }
+  r.dbg_b_meas = h->tap_b_meas;
+  r.dbg_Q_meas = h->tap_Q_meas;
+  r.dbg_vo = h->tap_vo;
+  r.dbg_ekf = h->tap_ekf;
+  return r;
+}
+
+template <typename T, typename Model>
+int launch_assemble(dekf_handle *h, const MheConst<T> &mc, const Buffers<T> &b, const Inputs &in, const Outputs &out,
+                    int T_, int acc) {
+  {
+    ProfScope ps(h, 1);
+    k_assemble<T, Model><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(mc, h->dm, b, in, out, T_, acc);
+  }
+  h->launches++;
+  return 0;
+}
+template <typename T, typename Model>
+int launch_fused(dekf_handle *h, const EkfConst<T> &ec, const MheConst<T> &mc, const Buffers<T> &b, const Inputs &in,
+                 const Outputs &out, int k, int T_, int32_t *status) {
+  {
+    ProfScope ps(h, 2);
+    k_fused<T, Model><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(ec, mc, h->dm, b, in, out, k, T_, status);
+  }
+  h->launches++;
+  return 0;
+}
+
+template <typename T>
+int do_assemble(dekf_handle *h, const MheConst<T> &mc, const Buffers<T> &b, const Inputs &in, const Outputs &out, int T_,
+                int acc) {
+  switch (h->cfg.robot) {
+    case DEKF_ROBOT_GO1: return launch_assemble<T, Go1Model<T>>(h, mc, b, in, out, T_, acc);
+    case DEKF_ROBOT_CASSIE: return launch_assemble<T, CassieModel<T>>(h, mc, b, in, out, T_, acc);
+    case DEKF_ROBOT_POGOX: return launch_assemble<T, PogoXModel<T>>(h, mc, b, in, out, T_, acc);
+  }
+  return DEKF_EINVAL;
+}
+template <typename T>
+int do_fused(dekf_handle *h, const EkfConst<T> &ec, const MheConst<T> &mc, const Buffers<T> &b, const Inputs &in,
+             const Outputs &out, int k, int T_, int32_t *status) {
+  switch (h->cfg.robot) {
+    case DEKF_ROBOT_GO1: return launch_fused<T, Go1Model<T>>(h, ec, mc, b, in, out, k, T_, status);
+    case DEKF_ROBOT_CASSIE: return launch_fused<T, CassieModel<T>>(h, ec, mc, b, in, out, k, T_, status);
+    case DEKF_ROBOT_POGOX: return launch_fused<T, PogoXModel<T>>(h, ec, mc, b, in, out, k, T_, status);
+  }
+  return DEKF_EINVAL;
+}
+
+int check_T(dekf_handle *h, int32_t T_) {
+  if (T_ != h->next_T) return fail(h, DEKF_ESTATE, "T must advance by one per call starting at 0 (initialize) -- call dekf_reset to restart");
+  return DEKF_OK;
+}
+
+int validate(const dekf_config *c, std::string &why) {
+  if (c->abi_version != DEKF_ABI_VERSION) { why = "abi_version mismatch"; return DEKF_EINVAL; }
+  if (c->n_instances < 1) { why = "n_instances < 1"; return DEKF_EINVAL; }
+  if (c->N < 2 || c->N > 4096) { why = "N out of range"; return DEKF_EINVAL; }
+  if (c->rate < 1 || c->ekf_rate < 1) { why = "rate < 1"; return DEKF_EINVAL; }
+  if (c->precision != DEKF_FP64 && c->precision != DEKF_FP32) { why = "precision"; return DEKF_EINVAL; }
+  if (c->robot < DEKF_ROBOT_GO1 || c->robot > DEKF_ROBOT_POGOX) { why = "robot"; return DEKF_EINVAL; }
+  if (c->num_legs != robot_num_legs(c->robot)) { why = "num_legs does not match the robot model"; return DEKF_EINVAL; }
+  if (c->leg_odom_type != 0) { why = "leg_odom_type 1 (foot-position states) is not built yet"; return DEKF_EINVAL; }
+  if (c->est_type != 0) { why = "est_type 1 (KF alternative) is not built yet"; return DEKF_EINVAL; }
+  if (c->ekf_hist_depth < 4) { why = "ekf_hist_depth < 4"; return DEKF_EINVAL; }
+  return DEKF_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// extern "C"
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int dekf_config_default_go1(dekf_config *cfg) {
+  if (!cfg) return DEKF_EINVAL;
+  fill_go1_defaults(cfg);
+  return DEKF_OK;
+}
+int dekf_config_default_cassie(dekf_config *cfg) {
+  if (!cfg) return DEKF_EINVAL;
+  fill_go1_defaults(cfg);
+  cfg->robot = DEKF_ROBOT_CASSIE;
+  cfg->num_legs = 2;
+  cfg->contact_effort_threshold = 150.0;
+  cfg->p_ib[0] = cfg->p_ib[1] = cfg->p_ib[2] = 0.0;
+  return DEKF_OK;
+}
+int dekf_config_default_pogox(dekf_config *cfg) {
+  if (!cfg) return DEKF_EINVAL;
+  fill_go1_defaults(cfg);
+  cfg->robot = DEKF_ROBOT_POGOX;
+  cfg->num_legs = 1;
+  cfg->contact_effort_threshold = 100.0;
+  cfg->p_ib[0] = cfg->p_ib[1] = cfg->p_ib[2] = 0.0;
+  return DEKF_OK;
+}
+
+int dekf_create(const dekf_config *cfg, dekf_handle **out) {
+  if (!cfg || !out) return DEKF_EINVAL;
+  *out = nullptr;
+  dekf_handle *h = new (std::nothrow) dekf_handle();
+  if (!h) return DEKF_ENOMEM;
+  std::string why;
+  int rc = validate(cfg, why);
+  if (rc != DEKF_OK) {
+    std::fprintf(stderr, "dekf_create: %s\n", why.c_str());
+    delete h;
+    return rc;
+  }
+  h->cfg = *cfg;
+  h->dm = make_dims(*cfg);
+  h->nl = robot_num_legs(cfg->robot);
+  h->nj = robot_nj(cfg->robot);
+  h->nq = h->nl * h->nj;
+  h->f32 = cfg->precision == DEKF_FP32;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+    std::fprintf(stderr, "dekf_create: no usable CUDA device (%s); there is no CPU fallback\n",
+                 ce == cudaSuccess ? "bad ordinal" : cudaGetErrorString(ce));
+    delete h;
+    return DEKF_ENODEV;
+  }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) {
+    delete h;
+    return DEKF_ENODEV;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major < 10) {
+    std::fprintf(stderr, "dekf_create: device is not sm_100-class (this library carries sm_100a code only)\n");
+    delete h;
+    return DEKF_ENODEV;
+  }
+  h->ec64 = make_ekf_const<double>(*cfg);
+  h->mc64 = make_mhe_const<double>(*cfg);
+  h->ec32 = make_ekf_const<float>(*cfg);
+  h->mc32 = make_mhe_const<float>(*cfg);
+  h->slab_bytes = h->f32 ? carve<float>(h->b32, h->dm, nullptr) : carve<double>(h->b64, h->dm, nullptr);
+  const size_t n = (size_t)cfg->n_instances;
+  const size_t in_doubles = (size_t)(3 + 3 + 1 + 2 * h->nq + h->nl + 4 + 1 + 1 + 3) * n;
+  const size_t out_doubles = (size_t)(4 + 9 + 3) * n;
+  auto bail = [&](int code, const char *what, cudaError_t e) {
+    std::fprintf(stderr, "dekf_create: %s: %s\n", what, cudaGetErrorString(e));
+    dekf_destroy(h);
+    return code;
+  };
+  if ((ce = cudaMalloc(&h->slab, h->slab_bytes)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc(state)", ce);
+  if ((ce = cudaMemsetAsync(h->slab, 0, h->slab_bytes, 0)) != cudaSuccess) return bail(DEKF_ECUDA, "memset", ce);
+  if (h->f32)
+    carve<float>(h->b32, h->dm, (char *)h->slab);
+  else
+    carve<double>(h->b64, h->dm, (char *)h->slab);
+  if ((ce = cudaMalloc((void **)&h->stage_in, in_doubles * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc(stage_in)", ce);
+  if ((ce = cudaMalloc((void **)&h->stage_flag, n)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+  if ((ce = cudaMalloc((void **)&h->stage_out, out_doubles * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+  if ((ce = cudaMalloc((void **)&h->stage_contact, (size_t)h->nl * n)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+  if ((ce = cudaMalloc((void **)&h->stage_status, n * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+  h->extra_bytes = (in_doubles + out_doubles) * sizeof(double) + n + (size_t)h->nl * n + n * sizeof(int32_t);
+  if (cfg->debug_taps) {
+    if ((ce = cudaMalloc((void **)&h->tap_b_meas, (size_t)3 * h->nl * n * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    if ((ce = cudaMalloc((void **)&h->tap_Q_meas, (size_t)6 * h->nl * n * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    if ((ce = cudaMalloc((void **)&h->tap_vo, (size_t)8 * n * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    if ((ce = cudaMalloc((void **)&h->tap_ekf, (size_t)3 * n * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    h->extra_bytes += (size_t)9 * h->nl * n * sizeof(double) + (size_t)11 * n * sizeof(int32_t);
+  }
+  if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(DEKF_ECUDA, "cudaStreamCreate", ce);
+  h->own_stream = true;
+  if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return bail(DEKF_ECUDA, "sync", ce);
+  rc = dekf_reset(h);
+  if (rc != DEKF_OK) {
+    std::fprintf(stderr, "dekf_create: reset failed: %s\n", h->err.c_str());
+    dekf_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return DEKF_OK;
+}
+
+int dekf_destroy(dekf_handle *h) {
+  if (!h) return DEKF_EINVAL;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaFree(h->slab);
+  cudaFree(h->stage_in);
+  cudaFree(h->stage_flag);
+  cudaFree(h->stage_out);
+  cudaFree(h->stage_contact);
+  cudaFree(h->stage_status);
+  cudaFree(h->tap_b_meas);
+  cudaFree(h->tap_Q_meas);
+  cudaFree(h->tap_vo);
+  cudaFree(h->tap_ekf);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+  return DEKF_OK;
+}
+
+int dekf_reset(dekf_handle *h) {
+  if (!h) return DEKF_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->slab, 0, h->slab_bytes, h->stream));
+  if (h->f32)
+    k_init_state<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->ec32, h->mc32, h->dm, h->b32);
+  else
+    k_init_state<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->ec64, h->mc64, h->dm, h->b64);
+  h->launches++;
+  CK(cudaGetLastError());
+  h->ekf_k = 0;
+  h->next_T = 0;
+  return DEKF_OK;
+}
+
+int dekf_set_stream(dekf_handle *h, void *cuda_stream) {
+  if (!h) return DEKF_EINVAL;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)cuda_stream;
+  h->own_stream = false;
+  return DEKF_OK;
+}
+void *dekf_get_stream(dekf_handle *h) { return h ? (void *)h->stream : nullptr; }
+const char *dekf_last_error(const dekf_handle *h) { return h ? h->err.c_str() : "null handle"; }
+int dekf_num_joints(const dekf_handle *h) { return h ? h->nq : DEKF_EINVAL; }
+int64_t dekf_launch_count(const dekf_handle *h) { return h ? h->launches : 0; }
+int64_t dekf_device_bytes(const dekf_handle *h) { return h ? (int64_t)(h->slab_bytes + h->extra_bytes) : 0; }
+
+int dekf_ekf_step(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out) {
+  if (!h || !in || !in->gyro || !in->accel || !in->imu_time) return fail(h, DEKF_EINVAL, "dekf_ekf_step: null input");
+  if (in->vo_flag && (!in->vo_quat || !in->vo_time_now)) return fail(h, DEKF_EINVAL, "dekf_ekf_step: vo_flag without vo_quat/vo_time_now");
+  CK(cudaSetDevice(h->cfg.device));
+  const Inputs di = to_inputs(in);
+  const Outputs dout = to_outputs(h, out);
+  int32_t *st = out ? out->status : nullptr;
+  {
+    ProfScope ps(h, 0);
+    if (h->f32)
+      k_ekf<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->ec32, h->dm, h->b32, di, dout, h->ekf_k, st);
+    else
+      k_ekf<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->ec64, h->dm, h->b64, di, dout, h->ekf_k, st);
+  }
+  h->launches++;
+  CK(cudaGetLastError());
+  h->ekf_k++;
+  return DEKF_OK;
+}
+
+static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out, int acc) {
+  if (!in->gyro || !in->accel || !in->imu_time || !in->joint_pos || !in->joint_vel || !in->foot_force)
+    return fail(h, DEKF_EINVAL, "dekf_mhe_step: null input");
+  if (in->vo_flag && (!in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
+    return fail(h, DEKF_EINVAL, "dekf_mhe_step: vo_flag without vo_time_pre/vo_time_now/vo_rel_p");
+  const Inputs di = to_inputs(in);
+  const Outputs dout = to_outputs(h, out);
+  int32_t *st = out ? out->status : nullptr;
+  int rc;
+  if (h->f32) {
+    rc = do_assemble<float>(h, h->mc32, h->b32, di, dout, T_, acc);
+    if (rc) return fail(h, rc, "assemble");
+    ProfScope ps(h, 2);
+    k_solve<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
+  } else {
+    rc = do_assemble<double>(h, h->mc64, h->b64, di, dout, T_, acc);
+    if (rc) return fail(h, rc, "assemble");
+    ProfScope ps(h, 2);
+    k_solve<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
+  }
+  h->launches++;
+  CK(cudaGetLastError());
+  h->next_T = T_ + 1;
+  return DEKF_OK;
+}
+
+int dekf_mhe_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out) {
+  if (!h || !in) return fail(h, DEKF_EINVAL, "dekf_mhe_step: null argument");
+  int rc = check_T(h, T_);
+  if (rc) return rc;
+  CK(cudaSetDevice(h->cfg.device));
+  return mhe_step_impl(h, T_, in, out, 0);
+}
+
+int dekf_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out) {
+  if (!h || !in) return fail(h, DEKF_EINVAL, "dekf_step: null argument");
+  int rc = check_T(h, T_);
+  if (rc) return rc;
+  if (!in->gyro || !in->accel || !in->imu_time || !in->joint_pos || !in->joint_vel || !in->foot_force)
+    return fail(h, DEKF_EINVAL, "dekf_step: null input");
+  if (in->vo_flag && (!in->vo_quat || !in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
+    return fail(h, DEKF_EINVAL, "dekf_step: vo_flag without the VO arrays");
+  CK(cudaSetDevice(h->cfg.device));
+  dekf_inputs in2 = *in;
+  in2.quat = nullptr;  // lock-step: the MHE consumes this tick's EKF quaternion
+  static const int fused_max = [] {
+    const char *e = std::getenv("DEKF_FUSED_MAX_N");
+    return e ? std::atoi(e) : 4096;
+  }();
+  if (h->dm.n <= fused_max) {
+    const Inputs di = to_inputs(&in2);
+    const Outputs dout = to_outputs(h, out);
+    int32_t *st = out ? out->status : nullptr;
+    if (h->f32)
+      rc = do_fused<float>(h, h->ec32, h->mc32, h->b32, di, dout, h->ekf_k, T_, st);
+    else
+      rc = do_fused<double>(h, h->ec64, h->mc64, h->b64, di, dout, h->ekf_k, T_, st);
+    if (rc) return fail(h, rc, "fused");
+    CK(cudaGetLastError());
+    h->ekf_k++;
+    h->next_T = T_ + 1;
+    return DEKF_OK;
+  }
+  dekf_outputs o_ekf;
+  std::memset(&o_ekf, 0, sizeof(o_ekf));
+  if (out) o_ekf.quat = out->quat;
+  rc = dekf_ekf_step(h, &in2, &o_ekf);
+  if (rc) return rc;
+  return mhe_step_impl(h, T_, &in2, out, 1);
+}
+
+int dekf_synchronize(dekf_handle *h) {
+  if (!h) return DEKF_EINVAL;
+  CK(cudaStreamSynchronize(h->stream));
+  return DEKF_OK;
+}
+
+int dekf_step_host(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out) {
+  if (!h || !in) return fail(h, DEKF_EINVAL, "dekf_step_host: null argument");
+  int rc = check_T(h, T_);
+  if (rc) return rc;
+  if (!in->gyro || !in->accel || !in->imu_time || !in->joint_pos || !in->joint_vel || !in->foot_force)
+    return fail(h, DEKF_EINVAL, "dekf_step_host: null input");
+  if (in->vo_flag && (!in->vo_quat || !in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
+    return fail(h, DEKF_EINVAL, "dekf_step_host: vo_flag without the VO arrays");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->dm.n;
+  // packed device staging: gyro3 accel3 time1 jpos jvel force | vo_quat4 tpre tnow relp3
+  const size_t cnt[10] = {3 * n, 3 * n, n, (size_t)h->nq * n, (size_t)h->nq * n, (size_t)h->nl * n, 4 * n, n, n, 3 * n};
+  const double *src[10] = {in->gyro, in->accel, in->imu_time, in->joint_pos, in->joint_vel, in->foot_force,
+                           in->vo_quat, in->vo_time_pre, in->vo_time_now, in->vo_rel_p};
+  double *dst[10];
+  {
+    size_t off = 0;
+    for (int a = 0; a < 10; ++a) {
+      dst[a] = h->stage_in + off;
+      off += cnt[a];
+    }
+  }
+  const int na = in->vo_flag ? 10 : 6;
+  // coalesce host ranges that are contiguous in the packed order into single copies
+  int a = 0;
+  while (a < na) {
+    int e = a;
+    size_t total = cnt[a];
+    while (e + 1 < na && src[e + 1] == src[e] + cnt[e]) {
+      ++e;
+      total += cnt[e];
+    }
+    CK(cudaMemcpyAsync(dst[a], src[a], total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    a = e + 1;
+  }
+  if (in->vo_flag) CK(cudaMemcpyAsync(h->stage_flag, in->vo_flag, n, cudaMemcpyHostToDevice, h->stream));
+  dekf_inputs din;
+  std::memset(&din, 0, sizeof(din));
+  din.gyro = dst[0];
+  din.accel = dst[1];
+  din.imu_time = dst[2];
+  din.joint_pos = dst[3];
+  din.joint_vel = dst[4];
+  din.foot_force = dst[5];
+  if (in->vo_flag) {
+    din.vo_flag = h->stage_flag;
+    din.vo_quat = dst[6];
+    din.vo_time_pre = dst[7];
+    din.vo_time_now = dst[8];
+    din.vo_rel_p = dst[9];
+  }
+  dekf_outputs dout;
+  std::memset(&dout, 0, sizeof(dout));
+  dout.quat = h->stage_out;
+  dout.x = h->stage_out + 4 * n;
+  dout.v_body = h->stage_out + 13 * n;
+  dout.contact = (out && out->contact) ? h->stage_contact : nullptr;
+  dout.status = (out && out->status) ? h->stage_status : nullptr;
+  rc = dekf_step(h, T_, &din, &dout);
+  if (rc) return rc;
+  if (out) {
+    const bool packed = out->quat && out->x && out->v_body && out->x == out->quat + 4 * n && out->v_body == out->x + 9 * n;
+    if (packed) {
+      CK(cudaMemcpyAsync(out->quat, h->stage_out, 16 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+      if (out->quat) CK(cudaMemcpyAsync(out->quat, dout.quat, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      if (out->x) CK(cudaMemcpyAsync(out->x, dout.x, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      if (out->v_body) CK(cudaMemcpyAsync(out->v_body, dout.v_body, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (out->contact) CK(cudaMemcpyAsync(out->contact, h->stage_contact, (size_t)h->nl * n, cudaMemcpyDeviceToHost, h->stream));
+    if (out->status) CK(cudaMemcpyAsync(out->status, h->stage_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  return DEKF_OK;
+}
+
+static int get_arrival(dekf_handle *h, double *P, double *x, int info) {
+  if (!h || !P || !x) return fail(h, DEKF_EINVAL, "null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->f32)
+    k_get_arrival<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->dm, h->b32, P, x, info);
+  else
+    k_get_arrival<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->dm, h->b64, P, x, info);
+  h->launches++;
+  CK(cudaGetLastError());
+  return DEKF_OK;
+}
+int dekf_get_arrival_cost(dekf_handle *h, double *M_p, double *n_p) { return get_arrival(h, M_p, n_p, 1); }
+int dekf_get_arrival_cov(dekf_handle *h, double *P, double *x) { return get_arrival(h, P, x, 0); }
+
+static int get_misc(dekf_handle *h, double *p_vo, double *R, double *ekfP) {
+  if (!h) return DEKF_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  const int Tk = h->next_T > 0 ? h->next_T - 1 : 0;
+  if (h->f32)
+    k_get_misc<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->dm, h->b32, Tk, p_vo, R, ekfP);
+  else
+    k_get_misc<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->dm, h->b64, Tk, p_vo, R, ekfP);
+  h->launches++;
+  CK(cudaGetLastError());
+  return DEKF_OK;
+}
+int dekf_get_p_vo(dekf_handle *h, double *p) { return p ? get_misc(h, p, nullptr, nullptr) : DEKF_EINVAL; }
+int dekf_get_R_sb(dekf_handle *h, double *R) { return R ? get_misc(h, nullptr, R, nullptr) : DEKF_EINVAL; }
+int dekf_get_ekf_cov(dekf_handle *h, double *P) { return P ? get_misc(h, nullptr, nullptr, P) : DEKF_EINVAL; }
+
+int dekf_get_window_vo_count(dekf_handle *h, int32_t *count) {
+  if (!h || !count) return DEKF_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  const int Tk = h->next_T > 0 ? h->next_T - 1 : 0;
+  if (h->f32)
+    k_vo_count<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->dm, h->b32, Tk, count);
+  else
+    k_vo_count<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->dm, h->b64, Tk, count);
+  h->launches++;
+  CK(cudaGetLastError());
+  return DEKF_OK;
+}
+
+int dekf_debug_taps(dekf_handle *h, double *b_meas, double *Q_meas, int32_t *vo_idx, int32_t *ekf_idx) {
+  if (!h) return DEKF_EINVAL;
+  if (!h->cfg.debug_taps) return fail(h, DEKF_EINVAL, "handle was created without debug_taps");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->dm.n;
+  if (b_meas) CK(cudaMemcpyAsync(b_meas, h->tap_b_meas, (size_t)3 * h->nl * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (Q_meas) CK(cudaMemcpyAsync(Q_meas, h->tap_Q_meas, (size_t)6 * h->nl * n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (vo_idx) CK(cudaMemcpyAsync(vo_idx, h->tap_vo, 8 * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+  if (ekf_idx) CK(cudaMemcpyAsync(ekf_idx, h->tap_ekf, 3 * n * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+  return DEKF_OK;
+}
+
+int dekf_profile_enable(dekf_handle *h, int32_t enable) {
+  if (!h) return DEKF_EINVAL;
+  CK(cudaSetDevice(h->cfg.device));
+  if (enable && !h->ev0) {
+    CK(cudaEventCreate(&h->ev0));
+    CK(cudaEventCreate(&h->ev1));
+  }
+  h->prof = enable != 0;
+  return DEKF_OK;
+}
+int dekf_profile_read(dekf_handle *h, double *ms, int64_t *count) {
+  if (!h || !ms || !count) return DEKF_EINVAL;
+  CK(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < 3; ++k) {
+    ms[k] = h->prof_ms[k];
+    count[k] = h->prof_n[k];
+    h->prof_ms[k] = 0;
+    h->prof_n[k] = 0;
+  }
+  return DEKF_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// roofline denominators
+// ------------------------------------------------------------------------------------------------
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T *out, int iters, T a, T b) {
+  // 16 independent FMA chains per thread keep the pipe full regardless of its latency
+  T x[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) x[j] = (T)(threadIdx.x + j);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) x[j] = x[j] * a + b;
+  }
+  T s = (T)0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) s += x[j];
+  if (s == (T)123456789) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <typename T>
+int measure_fma(double *tflops) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, threads = 256, iters = 4096;
+  T *out = nullptr;
+  if (cudaMalloc((void **)&out, (size_t)blocks * threads * sizeof(T)) != cudaSuccess) return DEKF_ENOMEM;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    k_fma_peak<T><<<blocks, threads>>>(out, iters, (T)1.0000001, (T)1e-7);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 16.0 * iters * (double)blocks * threads;
+    if (rep > 0 && ms > 0.f) best = fmax(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return cudaGetLastError() == cudaSuccess ? DEKF_OK : DEKF_ECUDA;
+}
+}  // namespace
+
+extern "C" int dekf_measure_fma_peak(int32_t device, int32_t precision, double *tflops) {
+  if (!tflops) return DEKF_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return DEKF_ENODEV;
+  return precision == DEKF_FP32 ? measure_fma<float>(tflops) : measure_fma<double>(tflops);
+}
+
+extern "C" int dekf_measure_copy_bw(int32_t device, double *gbs) {
+  if (!gbs) return DEKF_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return DEKF_ENODEV;
+  const size_t bytes = (size_t)1 << 31;  // 2 GiB each way, far above the 126 MB L2
+  void *a = nullptr, *b = nullptr;
+  if (cudaMalloc(&a, bytes) != cudaSuccess) return DEKF_ENOMEM;
+  if (cudaMalloc(&b, bytes) != cudaSuccess) {
+    cudaFree(a);
+    return DEKF_ENOMEM;
+  }
+  cudaMemset(a, 1, bytes);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    cudaEventRecord(e0);
+    cudaMemcpyAsync(b, a, bytes, cudaMemcpyDeviceToDevice, 0);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms > 0.f) best = fmax(best, 2.0 * (double)bytes / (ms * 1e-3) / 1e9);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(a);
+  cudaFree(b);
+  *gbs = best;
+  return cudaGetLastError() == cudaSuccess ? DEKF_OK : DEKF_ECUDA;
+}

@@ -1,0 +1,1011 @@
+// Per-instance estimator math: one estimator instance == one thread, all state in registers,
+// every HBM array laid out SoA [field][instance] so that a warp touches full 256-byte lines.
+//
+// Reference path replaced (file:line under /root/reference/src):
+//   orien_est/src/orien_ekf.cpp:77-89,108-228,270-357        -> ekf_tick()
+//   go1_example/src/go1Sub.cpp:64-125 + Expressions/*.cc     -> mhe_assemble() (kinematics, contact)
+//   decentral_legged_est/src/DecentralEst.cpp:353-583,864-985,987-1009, Spline/Bezier_simple.cpp
+//                                                            -> mhe_assemble() (stage record, VO sync)
+//   decentral_legged_est/src/MheSrb.cpp:272-349,475-723 (+OSQP) and DecentralEst.cpp:152-185
+//                                                            -> mhe_solve() (marginalise + window solve)
+//
+// Algorithm of mhe_solve: every row of the reference's QP is an equality with
+// its own quadratically-penalised slack (or a free VO placeholder), so the QP is a linear-Gaussian
+// smoothing problem and the only quantity read out is x_T (MheSrb.cpp:715-723).  x_T is therefore
+// the mean of a forward Kalman sweep over the window started from the arrival cost; the arrival
+// cost update (marginalizeQP) is exactly one stage of the same sweep.  The sweep is carried in
+// COVARIANCE form (P, x) -- no 9x9 factorisation, only 3x3 inverses, and it stays accurate in fp32
+// where the information form does not.
+#pragma once
+#include <stdint.h>
+
+#include "kinematics.cuh"
+#include "smallmat.cuh"
+
+namespace dekf {
+
+// ------------------------------------------------------------------------------------------------
+// layouts
+// ------------------------------------------------------------------------------------------------
+enum {
+  REC_R = 0,     // 9  R_sb of the sample (row-major)
+  REC_AS = 9,    // 3  a_s = R a_b + (0,0,-9.81)
+  REC_LAM = 12,  // 6  Lambda = sum_i Q_meas,i (symmetric)          } sufficient statistic of the
+  REC_ETA = 18,  // 3  eta    = sum_i Q_meas,i b_meas,i              } leg-odometry rows (H_i=[0 I 0])
+  REC_DLT = 21,  // 3  VO displacement node_{k+1}-node_k (valid iff flag)
+  REC_SIZE = 24
+};
+enum { EKF_HIST_FIELDS = 26 };  // gyro3 accel3 q4 P16 (time kept separately in double)
+
+enum StatusBits {
+  ST_EKF_VO_DROPPED = 1,     // "not storing enough imu info" (orien_ekf.cpp:178-183)
+  ST_EKF_VO_NO_REPLAY = 2,   // rel <= 1: rollback without VO (orien_ekf.cpp:191)
+  ST_EKF_HIST_OVERFLOW = 4,  // VO older than the device history ring (reference stacks are unbounded)
+  ST_MHE_VO_DROPPED = 8,     // DecentralEst.cpp:898-904
+  ST_MHE_VO_BOUNDED = 16,    // vo_to_be_processed_flag_ was set this step
+  ST_NONFINITE = 32
+};
+
+template <typename T>
+struct EkfConst {
+  T dt;
+  T Cg[3], Ca[3], Cvo[4];
+  T g[3];
+  T q0[4], P0[4];
+};
+
+template <typename T>
+struct MheConst {
+  T dt;
+  T d1[3];   // dt^2 C_p + dt^4/4 C_accel       (pp block of Q_dyn^-1 before rotation)
+  T d2[3];   // dt^3/2 C_accel                  (pv block)
+  T d3[3];   // dt^2 C_accel                    (vv block)
+  T cab[3];  // dt^2 C_accel_bias               (bb block)
+  T cvo[3];  // vo_p_std^2                       (Q_cam^-1 before rotation)
+  T cenc_v[8], cenc_p[8], cgy[3];
+  T q_swing[3];
+  T P0[9];   // prior covariance diag (p,v,b init std^2), prior mean 0
+  T p_ib[3];
+  double thr;  // contact threshold, compared in double on the raw input (bit-exact)
+  double dt_d;
+  int N;
+};
+
+struct Dims {
+  int n;   // instance stride of every array
+  int N;   // horizon
+  int NW;  // window ring slots  = N + 1
+  int HR;  // MHE history ring   = 4N + 1   (DecentralEst.cpp:963)
+  int D;   // EKF history ring depth
+};
+
+template <typename T>
+struct Buffers {
+  // EKF state
+  T *ekf_q;               // [4][n]
+  T *ekf_P;               // [16][n]
+  T *ekf_hist;            // [D][26][n]
+  double *ekf_hist_time;  // [D][n]
+  // MHE state
+  T *arr_P;               // [45][n] arrival covariance (pp6 vv6 bb6 pv9 pb9 vb9)
+  T *arr_x;               // [9][n]  arrival mean
+  T *win;                 // [NW][24][n]
+  uint8_t *win_flag;      // [NW][n]
+  double *hist_time;      // [HR][n]
+  double *hist_quat;      // [HR][4][n]
+  double *wp;             // [12][n] last 4 accumulated-VO way points
+  double *wp_time;        // [4][n]
+  int32_t *wp_count;      // [n]
+  double *p_vo;           // [3][n]
+  uint8_t *pend_flag;     // [n]   VO message latched at T==0 (robot_store.vo_new_ stays true)
+  double *pend;           // [5][n]
+  int32_t *status;        // [n]
+};
+
+struct Inputs {
+  const double *gyro, *accel, *imu_time, *joint_pos, *joint_vel, *foot_force;
+  const uint8_t *vo_flag;
+  const double *vo_quat, *vo_time_pre, *vo_time_now, *vo_rel_p;
+  const double *quat;  // external orientation for the MHE ([4][n]); nullptr -> EKF state
+};
+
+struct Outputs {
+  double *quat;      // [4][n]
+  double *x;         // [9][n]
+  double *v_body;    // [3][n]
+  uint8_t *contact;  // [nlegs][n]
+  // optional debug taps (may be nullptr)
+  double *dbg_b_meas;  // [3*nlegs][n]
+  double *dbg_Q_meas;  // [nlegs][6][n]  (symmetric 3x3 per leg)
+  int32_t *dbg_vo;     // [8][n]: processed,i_pre,i_now,w0,i0,ins,num,disc0
+  int32_t *dbg_ekf;    // [3][n]: cur, idx, nreplay
+};
+
+// ------------------------------------------------------------------------------------------------
+// orientation EKF
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct EkfState {
+  T q[4];
+  T P[16];
+};
+
+// orien_ekf.cpp:108-123 (+ :214-228 Ohm, :270-294 W with its indexing bug, :353-357)
+template <typename T>
+DEKF_HD void ekf_predict(const EkfConst<T> &c, EkfState<T> &s, const T w[3]) {
+  const T h = c.dt / T(2);
+  // F = I + dt/2 * Ohm
+  T F[16];
+  F[0] = T(1);  F[1] = -h * w[0]; F[2] = -h * w[1]; F[3] = -h * w[2];
+  F[4] = h * w[0];  F[5] = T(1);  F[6] = h * w[2];  F[7] = -h * w[1];
+  F[8] = h * w[1];  F[9] = -h * w[2]; F[10] = T(1); F[11] = h * w[0];
+  F[12] = h * w[2]; F[13] = h * w[1]; F[14] = -h * w[0]; F[15] = T(1);
+  // W from the UN-propagated quaternion; rows 2/3 as the reference computes them:
+  // row2 = (z, x, w), row3 = (-y, 0, 0)
+  const T k = T(0.5) * c.dt;
+  const T qw = s.q[0], qx = s.q[1], qy = s.q[2], qz = s.q[3];
+  T W[12];
+  W[0] = -k * qx; W[1] = -k * qy; W[2] = -k * qz;
+  W[3] = k * qw;  W[4] = -k * qz; W[5] = k * qy;
+  W[6] = k * qz;  W[7] = k * qx;  W[8] = k * qw;
+  W[9] = -k * qy; W[10] = T(0);   W[11] = T(0);
+  T qn[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) qn[r] = F[r * 4 + 0] * qw + F[r * 4 + 1] * qx + F[r * 4 + 2] * qy + F[r * 4 + 3] * qz;
+  T FP[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+      FP[r * 4 + cc] = F[r * 4 + 0] * s.P[0 * 4 + cc] + F[r * 4 + 1] * s.P[1 * 4 + cc] + F[r * 4 + 2] * s.P[2 * 4 + cc] +
+                       F[r * 4 + 3] * s.P[3 * 4 + cc];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      T v = FP[r * 4 + 0] * F[cc * 4 + 0] + FP[r * 4 + 1] * F[cc * 4 + 1] + FP[r * 4 + 2] * F[cc * 4 + 2] +
+            FP[r * 4 + 3] * F[cc * 4 + 3];
+      v += W[r * 3 + 0] * c.Cg[0] * W[cc * 3 + 0] + W[r * 3 + 1] * c.Cg[1] * W[cc * 3 + 1] +
+           W[r * 3 + 2] * c.Cg[2] * W[cc * 3 + 2];
+      s.P[r * 4 + cc] = v;
+    }
+  const T nrm = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) s.q[r] = qn[r] / nrm;
+}
+
+// orien_ekf.cpp:125-142 (+ :296-329)
+template <typename T>
+DEKF_HD void ekf_correct(const EkfConst<T> &c, EkfState<T> &s, const T a[3]) {
+  const T w = s.q[0], x = s.q[1], y = s.q[2], z = s.q[3];
+  const M3<T> R = quat_to_rot<T>(w, x, y, z);
+  const V3<T> g = v3<T>(c.g[0], c.g[1], c.g[2]);
+  const V3<T> a_hat = mul_t(R, g);
+  T H[12];
+  H[0] = g[0] * w + g[1] * z - g[2] * y;
+  H[1] = g[0] * x + g[1] * y + g[2] * z;
+  H[2] = -g[0] * y + g[1] * x - g[2] * w;
+  H[3] = -g[0] * z + g[1] * w + g[2] * x;
+  H[4] = -g[0] * z + g[1] * w + g[2] * x;
+  H[5] = g[0] * y - g[1] * x + g[2] * w;
+  H[6] = g[0] * x + g[1] * y + g[2] * z;
+  H[7] = -g[0] * w - g[1] * z + g[2] * y;
+  H[8] = g[0] * y - g[1] * x + g[2] * w;
+  H[9] = g[0] * z - g[1] * w - g[2] * x;
+  H[10] = g[0] * w + g[1] * z - g[2] * y;
+  H[11] = g[0] * x + g[1] * y + g[2] * z;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) H[i] = T(2) * H[i];
+  const T rel = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]) / sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+  T PHt[12];  // 4x3
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      PHt[r * 3 + cc] = s.P[r * 4 + 0] * H[cc * 4 + 0] + s.P[r * 4 + 1] * H[cc * 4 + 1] + s.P[r * 4 + 2] * H[cc * 4 + 2] +
+                        s.P[r * 4 + 3] * H[cc * 4 + 3];
+  M3<T> S;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      T v = H[r * 4 + 0] * PHt[0 * 3 + cc] + H[r * 4 + 1] * PHt[1 * 3 + cc] + H[r * 4 + 2] * PHt[2 * 3 + cc] +
+            H[r * 4 + 3] * PHt[3 * 3 + cc];
+      if (r == cc) v += rel * rel * c.Ca[r];
+      S(r, cc) = v;
+    }
+  const M3<T> Si = inverse(S);
+  T K[12];  // 4x3
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc)
+      K[r * 3 + cc] = PHt[r * 3 + 0] * Si(0, cc) + PHt[r * 3 + 1] * Si(1, cc) + PHt[r * 3 + 2] * Si(2, cc);
+  const T in0 = a[0] - a_hat[0], in1 = a[1] - a_hat[1], in2 = a[2] - a_hat[2];
+  T qn[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) qn[r] = s.q[r] + (K[r * 3 + 0] * in0 + K[r * 3 + 1] * in1 + K[r * 3 + 2] * in2);
+  T IKH[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+      IKH[r * 4 + cc] = ((r == cc) ? T(1) : T(0)) -
+                        (K[r * 3 + 0] * H[0 * 4 + cc] + K[r * 3 + 1] * H[1 * 4 + cc] + K[r * 3 + 2] * H[2 * 4 + cc]);
+  T Pn[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc)
+      Pn[r * 4 + cc] = IKH[r * 4 + 0] * s.P[0 * 4 + cc] + IKH[r * 4 + 1] * s.P[1 * 4 + cc] + IKH[r * 4 + 2] * s.P[2 * 4 + cc] +
+                       IKH[r * 4 + 3] * s.P[3 * 4 + cc];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s.P[i] = Pn[i];
+  const T nrm = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) s.q[r] = qn[r] / nrm;
+}
+
+// orien_ekf.cpp:144-154 (H = I4).  (P + C_vo) is SPD: K = P (P + C_vo)^-1 through an unrolled
+// Cholesky instead of the reference's pivoted LU.
+template <typename T>
+DEKF_HD void ekf_vo_correct(const EkfConst<T> &c, EkfState<T> &s, const T qv[4]) {
+  T L[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) L[r * 4 + cc] = T(0.5) * (s.P[r * 4 + cc] + s.P[cc * 4 + r]) + ((r == cc) ? c.Cvo[r] : T(0));
+  // in-place lower Cholesky
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    T d = L[j * 4 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d -= L[j * 4 + k] * L[j * 4 + k];
+    d = sqrt(d);
+    L[j * 4 + j] = d;
+    const T id = T(1) / d;
+#pragma unroll
+    for (int i = j + 1; i < 4; ++i) {
+      T v = L[i * 4 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v -= L[i * 4 + k] * L[j * 4 + k];
+      L[i * 4 + j] = v * id;
+    }
+  }
+  // K^T = S^-1 P^T : solve for each row r of P (as a column of P^T): K[r][:] = (S^-1 P[r][:]^T)^T
+  T K[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    T y[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      T v = s.P[r * 4 + i];
+#pragma unroll
+      for (int k = 0; k < i; ++k) v -= L[i * 4 + k] * y[k];
+      y[i] = v / L[i * 4 + i];
+    }
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+      T v = y[i];
+#pragma unroll
+      for (int k = i + 1; k < 4; ++k) v -= L[k * 4 + i] * y[k];
+      y[i] = v / L[i * 4 + i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) K[r * 4 + i] = y[i];
+  }
+  T in[4], qn[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) in[i] = qv[i] - s.q[i];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) qn[r] = s.q[r] + (K[r * 4 + 0] * in[0] + K[r * 4 + 1] * in[1] + K[r * 4 + 2] * in[2] + K[r * 4 + 3] * in[3]);
+  T Pn[16];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      T v = T(0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v += (((r == k) ? T(1) : T(0)) - K[r * 4 + k]) * s.P[k * 4 + cc];
+      Pn[r * 4 + cc] = v;
+    }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s.P[i] = Pn[i];
+  const T nrm = sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) s.q[r] = qn[r] / nrm;
+}
+
+// std::upper_bound over a ring of doubles: logical index j in [0,size) lives at slot
+// ((first + j) mod ring); returns the first j whose time is > v.
+DEKF_HD int ring_upper_bound(const double *times, int n, int i, int first, int size, int ring, double v) {
+  int lo = 0, len = size;
+  while (len > 0) {
+    const int half = len >> 1;
+    const int mid = lo + half;
+    const double t = times[(size_t)((first + mid) % ring) * n + i];
+    if (!(v < t)) {
+      lo = mid + 1;
+      len = len - half - 1;
+    } else {
+      len = half;
+    }
+  }
+  return lo;
+}
+
+// One EKF timer tick for instance i at discrete time k (orien_ekf.cpp:77-89 + get_measurement
+// :156-212).  Returns status bits.
+template <typename T>
+DEKF_HD int ekf_tick(const EkfConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
+                     int k, int i) {
+  const int n = dm.n, D = dm.D;
+  int status = 0;
+  EkfState<T> s;
+#pragma unroll
+  for (int f = 0; f < 4; ++f) s.q[f] = b.ekf_q[(size_t)f * n + i];
+#pragma unroll
+  for (int f = 0; f < 16; ++f) s.P[f] = b.ekf_P[(size_t)f * n + i];
+  T w[3], a[3];
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    w[f] = (T)in.gyro[(size_t)f * n + i];
+    a[f] = (T)in.accel[(size_t)f * n + i];
+  }
+  const double t_imu = in.imu_time[i];
+  // push (state BEFORE this tick's update), :158-163
+  {
+    T *h = b.ekf_hist + (size_t)(k % D) * EKF_HIST_FIELDS * n + i;
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      h[(size_t)f * n] = w[f];
+      h[(size_t)(3 + f) * n] = a[f];
+    }
+#pragma unroll
+    for (int f = 0; f < 4; ++f) h[(size_t)(6 + f) * n] = s.q[f];
+#pragma unroll
+    for (int f = 0; f < 16; ++f) h[(size_t)(10 + f) * n] = s.P[f];
+    b.ekf_hist_time[(size_t)(k % D) * n + i] = t_imu;
+  }
+  int dbg_cur = -2, dbg_idx = -2, dbg_nr = -2;
+  if (in.vo_flag != nullptr && in.vo_flag[i]) {
+    const double vt = in.vo_time_now[i];
+    T qv[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) qv[f] = (T)in.vo_quat[(size_t)f * n + i];
+    const int size = (k + 1 < D) ? (k + 1) : D;
+    const int first = k + 1 - size;  // discrete time of logical index 0
+    const int ub = ring_upper_bound(b.ekf_hist_time, n, i, first, size, D, vt);
+    dbg_cur = k;
+    dbg_nr = 0;
+    if (ub == 0) {
+      dbg_idx = -1;
+      status |= (first > 0) ? ST_EKF_HIST_OVERFLOW : ST_EKF_VO_DROPPED;
+    } else {
+      const int idx = first + ub - 1;  // :186
+      const int rel = k - idx;         // :187
+      dbg_idx = idx;
+      {
+        const T *h = b.ekf_hist + (size_t)(idx % D) * EKF_HIST_FIELDS * n + i;
+#pragma unroll
+        for (int f = 0; f < 4; ++f) s.q[f] = h[(size_t)(6 + f) * n];
+#pragma unroll
+        for (int f = 0; f < 16; ++f) s.P[f] = h[(size_t)(10 + f) * n];
+      }
+      if (rel <= 1) status |= ST_EKF_VO_NO_REPLAY;
+      for (int j = 0; j < rel - 1; ++j) {  // :191
+        const T *h = b.ekf_hist + (size_t)((idx + j) % D) * EKF_HIST_FIELDS * n + i;
+        T wj[3], aj[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+          wj[f] = h[(size_t)f * n];
+          aj[f] = h[(size_t)(3 + f) * n];
+        }
+        ekf_predict(c, s, wj);
+        ekf_correct(c, s, aj);
+        if (j == 0) ekf_vo_correct(c, s, qv);  // :197-202
+        dbg_nr++;
+      }
+    }
+  }
+  ekf_predict(c, s, w);  // :82
+  ekf_correct(c, s, a);  // :83
+#pragma unroll
+  for (int f = 0; f < 4; ++f) b.ekf_q[(size_t)f * n + i] = s.q[f];
+#pragma unroll
+  for (int f = 0; f < 16; ++f) b.ekf_P[(size_t)f * n + i] = s.P[f];
+  if (out.quat != nullptr) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) out.quat[(size_t)f * n + i] = (double)s.q[f];
+  }
+  if (out.dbg_ekf != nullptr) {
+    out.dbg_ekf[(size_t)0 * n + i] = dbg_cur;
+    out.dbg_ekf[(size_t)1 * n + i] = dbg_idx;
+    out.dbg_ekf[(size_t)2 * n + i] = dbg_nr;
+  }
+  return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MHE: stage assembly (kinematics, contact, measurement statistic, VO synchronisation)
+// ------------------------------------------------------------------------------------------------
+// Bezier_simple.cpp:73-82, evaluation order kept
+DEKF_HD void bezier_point(double out[3], double u, const double *P0, const double *P1, const double *P2, const double *P3) {
+#pragma unroll
+  for (int cdx = 0; cdx < 3; ++cdx) {
+    double point = u * u * u * ((-1) * P0[cdx] + 3 * P1[cdx] - 3 * P2[cdx] + P3[cdx]);
+    point += u * u * (3 * P0[cdx] - 6 * P1[cdx] + 3 * P2[cdx]);
+    point += u * ((-3) * P0[cdx] + 3 * P1[cdx]);
+    point += P0[cdx];
+    out[cdx] = point;
+  }
+}
+
+// GetMeasurement(T) + the Measurement_T / Dynamic_T / VO_T data of UpdateMHE (DecentralEst.cpp:
+// 374-424, 474-478, 496-572, 864-985) + UpdateVOConstraints (:987-1009) for instance i.
+// q_ext: orientation to use ([w,x,y,z]); written to the history ring un-normalised like the reference
+// stores R of the normalised quaternion.
+template <typename T, typename Model>
+DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in,
+                         const Outputs &out, int Tk, int i, const double qd[4]) {
+  constexpr int NL = Model::NLEG, NJ = Model::NJ;
+  const int n = dm.n, N = dm.N, NW = dm.NW, HR = dm.HR;
+  int status = 0;
+
+  // ---- VO synchronisation against the history BEFORE this sample is pushed (:883-945)
+  int vo_new = (in.vo_flag != nullptr) ? (int)in.vo_flag[i] : 0;
+  double t_pre = 0.0, t_now = 0.0, relp[3] = {0.0, 0.0, 0.0};
+  if (vo_new) {
+    t_pre = in.vo_time_pre[i];
+    t_now = in.vo_time_now[i];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) relp[f] = in.vo_rel_p[(size_t)f * n + i];
+  }
+  if (Tk == 0) {
+    // stack is empty: the message stays latched in robot_store (vo_new_ remains true)
+    b.pend_flag[i] = (uint8_t)vo_new;
+    if (vo_new) {
+      b.pend[(size_t)0 * n + i] = t_pre;
+      b.pend[(size_t)1 * n + i] = t_now;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) b.pend[(size_t)(2 + f) * n + i] = relp[f];
+    }
+    vo_new = 0;
+  } else if (Tk == 1 && !vo_new && b.pend_flag[i]) {
+    vo_new = 1;
+    t_pre = b.pend[(size_t)0 * n + i];
+    t_now = b.pend[(size_t)1 * n + i];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) relp[f] = b.pend[(size_t)(2 + f) * n + i];
+  }
+  int dbg[8] = {-2, -2, -2, -2, -2, -2, -2, -2};
+  if (vo_new) {
+    const int size = (Tk < HR) ? Tk : HR;  // samples held: discrete times Tk-size .. Tk-1
+    const int first = Tk - size;
+    dbg[0] = 0;
+    const int ub = ring_upper_bound(b.hist_time, n, i, first, size, HR, t_pre);  // :895
+    if (ub == 0) {
+      status |= ST_MHE_VO_DROPPED;  // :898-904
+      dbg[1] = -1;
+    } else {
+      const int i_pre = ub - 1;  // :907
+      const int i_now = ring_upper_bound(b.hist_time, n, i, first, size, HR, t_now) - 1;  // :911-913
+      // R_vo_sb_pre_ = R_input_rotation_stack_[i_pre]  (:909)
+      const double *hq = b.hist_quat + (size_t)((first + i_pre) % HR) * 4 * n + i;
+      const M3<double> Rp = quat_to_rot<double>(hq[0], hq[(size_t)n], hq[(size_t)2 * n], hq[(size_t)3 * n]);
+      double pv[3];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        pv[f] = b.p_vo[(size_t)f * n + i] + (Rp(f, 0) * relp[0] + Rp(f, 1) * relp[1] + Rp(f, 2) * relp[2]);  // :915
+        b.p_vo[(size_t)f * n + i] = pv[f];
+      }
+      const int w0 = size - ((N < Tk) ? N : Tk);  // :917
+      const int i0 = (w0 > i_pre) ? w0 : i_pre;   // :918
+      const double t_start = b.hist_time[(size_t)((first + i0) % HR) * n + i];  // :919
+      const int disc0 = first + i0;                                             // :920
+      // add_way_point (Bezier_simple.cpp:12-27): keep the last four
+      int cnt = b.wp_count[i];
+      double wp[4][3], wt[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        wt[p] = b.wp_time[(size_t)p * n + i];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) wp[p][f] = b.wp[(size_t)(p * 3 + f) * n + i];
+      }
+      if (cnt < 4) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          if (p == cnt) {
+            wt[p] = t_now;
+#pragma unroll
+            for (int f = 0; f < 3; ++f) wp[p][f] = pv[f];
+          }
+        cnt++;
+      } else {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          wt[p] = wt[p + 1];
+#pragma unroll
+          for (int f = 0; f < 3; ++f) wp[p][f] = wp[p + 1][f];
+        }
+        wt[3] = t_now;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) wp[3][f] = pv[f];
+      }
+      b.wp_count[i] = cnt;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        b.wp_time[(size_t)p * n + i] = wt[p];
+#pragma unroll
+        for (int f = 0; f < 3; ++f) b.wp[(size_t)(p * 3 + f) * n + i] = wp[p][f];
+      }
+      dbg[0] = 1;
+      dbg[1] = i_pre;
+      dbg[2] = i_now;
+      dbg[3] = w0;
+      dbg[4] = i0;
+      if (i_now > w0 && cnt >= 4) {  // :925
+        const int ins = i0 - w0;         // :927
+        const int num = i_now - i0 + 1;  // :928
+        dbg[5] = ins;
+        dbg[6] = num;
+        dbg[7] = disc0;
+        status |= ST_MHE_VO_BOUNDED;
+        // set_interval + interpolate_waypoint (Bezier_simple.cpp:29-71) + UpdateVOConstraints
+        const double t_interval = wt[3] - wt[0];
+        const double u_inc = c.dt_d / t_interval;
+        const double u0 = (t_start - wt[0]) / t_interval;
+        double node_pre[3];
+        bezier_point(node_pre, u0 + u_inc * 0.0, wp[0], wp[1], wp[2], wp[3]);
+        for (int j = 1; j < num; ++j) {
+          double node[3];
+          bezier_point(node, u0 + u_inc * (double)j, wp[0], wp[1], wp[2], wp[3]);
+          const int d = disc0 + j - 1;  // VO_measurement_{disc0 + (j-1)}  (:1004)
+          T *rec = b.win + (size_t)(d % NW) * REC_SIZE * n + i;
+#pragma unroll
+          for (int f = 0; f < 3; ++f) {
+            rec[(size_t)(REC_DLT + f) * n] = (T)(node[f] - node_pre[f]);
+            node_pre[f] = node[f];
+          }
+          b.win_flag[(size_t)(d % NW) * n + i] = 1;
+        }
+      }
+    }
+  }
+  if (out.dbg_vo != nullptr) {
+#pragma unroll
+    for (int f = 0; f < 8; ++f) out.dbg_vo[(size_t)f * n + i] = dbg[f];
+  }
+
+  // ---- current sample (:867-879)
+  const M3<T> R = quat_to_rot<T>((T)qd[0], (T)qd[1], (T)qd[2], (T)qd[3]);
+  V3<T> ab, om;
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    ab[f] = (T)in.accel[(size_t)f * n + i];
+    om[f] = (T)in.gyro[(size_t)f * n + i];
+  }
+  V3<T> as = mul(R, ab);
+  as[2] += T(-9.81);
+
+  // ---- legs: contact, kinematics, leg-odometry statistic (go1Sub.cpp:64-125, DecentralEst.cpp:509-546)
+  S3<T> Qb_sum;  // sum over stance legs of (G C G')^-1, body frame
+#pragma unroll
+  for (int f = 0; f < 6; ++f) Qb_sum.a[f] = T(0);
+  V3<T> Qbeta_sum = v3<T>(T(0), T(0), T(0));  // sum over stance legs of (G C G')^-1 beta_i
+  V3<T> beta_swing = v3<T>(T(0), T(0), T(0));  // sum over swing legs of beta_i
+  int n_swing = 0;
+#pragma unroll
+  for (int leg = 0; leg < NL; ++leg) {
+    const double force = in.foot_force[(size_t)leg * n + i];
+    const bool contact = (force >= c.thr);  // go1Sub.cpp:74, exact
+    if (out.contact != nullptr) out.contact[(size_t)leg * n + i] = contact ? 1 : 0;
+    T q[NJ], dq[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      q[j] = (T)in.joint_pos[(size_t)(leg * NJ + j) * n + i];
+      dq[j] = (T)in.joint_vel[(size_t)(leg * NJ + j) * n + i];
+    }
+    V3<T> p;
+    T J[3 * NJ];
+    Model::leg_fk(leg, q, p, J);
+    p[0] += c.p_ib[0];
+    p[1] += c.p_ib[1];
+    p[2] += c.p_ib[2];
+    // beta = -(J dq + omega x p)   (b_meas = R beta, :515-516)
+    V3<T> Jdq = v3<T>(T(0), T(0), T(0));
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      Jdq[0] += J[0 * NJ + j] * dq[j];
+      Jdq[1] += J[1 * NJ + j] * dq[j];
+      Jdq[2] += J[2 * NJ + j] * dq[j];
+    }
+    const V3<T> wxp = cross(om, p);
+    const V3<T> beta = v3<T>(-(Jdq[0] + wxp[0]), -(Jdq[1] + wxp[1]), -(Jdq[2] + wxp[2]));
+    // C_b = G C G', G = [-J, -omega^x J, p^x], C = blkdiag(C_enc_vel, C_enc_pos, C_gyro) (:523-543)
+    S3<T> Cb;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) Cb.a[f] = T(0);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const V3<T> col = v3<T>(J[0 * NJ + j], J[1 * NJ + j], J[2 * NJ + j]);
+      const V3<T> wc = cross(om, col);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = r; cc < 3; ++cc)
+          Cb.a[S3<T>::idx(r, cc)] += c.cenc_v[j] * col[r] * col[cc] + c.cenc_p[j] * wc[r] * wc[cc];
+    }
+    {
+      const M3<T> ps = skew(p);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = r; cc < 3; ++cc)
+          Cb.a[S3<T>::idx(r, cc)] += c.cgy[0] * ps(r, 0) * ps(cc, 0) + c.cgy[1] * ps(r, 1) * ps(cc, 1) + c.cgy[2] * ps(r, 2) * ps(cc, 2);
+    }
+    const S3<T> Qb = inverse(Cb);
+    const V3<T> Qbeta = mul(Qb, beta);
+    if (contact) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) Qb_sum.a[f] += Qb.a[f];
+      Qbeta_sum = add(Qbeta_sum, Qbeta);
+    } else {
+      beta_swing = add(beta_swing, beta);
+      n_swing++;
+    }
+    if (out.dbg_b_meas != nullptr) {
+      const V3<T> bm = mul(R, beta);
+#pragma unroll
+      for (int f = 0; f < 3; ++f) out.dbg_b_meas[(size_t)(leg * 3 + f) * n + i] = (double)bm[f];
+    }
+    if (out.dbg_Q_meas != nullptr) {
+      S3<T> Qw = rsrt(R, Qb);
+      if (!contact) {
+        Qw.a[0] = c.q_swing[0];
+        Qw.a[1] = T(0);
+        Qw.a[2] = T(0);
+        Qw.a[3] = c.q_swing[1];
+        Qw.a[4] = T(0);
+        Qw.a[5] = c.q_swing[2];
+      }
+#pragma unroll
+      for (int f = 0; f < 6; ++f) out.dbg_Q_meas[(size_t)(leg * 6 + f) * n + i] = (double)Qw.a[f];
+    }
+  }
+  // Lambda = R Qb_sum R' + n_swing diag(q_swing);  eta = R Qbeta_sum + diag(q_swing) R beta_swing
+  S3<T> Lam = rsrt(R, Qb_sum);
+  Lam.a[0] += (T)n_swing * c.q_swing[0];
+  Lam.a[3] += (T)n_swing * c.q_swing[1];
+  Lam.a[5] += (T)n_swing * c.q_swing[2];
+  V3<T> eta = mul(R, Qbeta_sum);
+  {
+    const V3<T> Rb = mul(R, beta_swing);
+    eta[0] += c.q_swing[0] * Rb[0];
+    eta[1] += c.q_swing[1] * Rb[1];
+    eta[2] += c.q_swing[2] * Rb[2];
+  }
+
+  // ---- push (:949-975): history ring + stage record of discrete time Tk
+  b.hist_time[(size_t)(Tk % HR) * n + i] = in.imu_time[i];
+#pragma unroll
+  for (int f = 0; f < 4; ++f) b.hist_quat[((size_t)(Tk % HR) * 4 + f) * n + i] = qd[f];
+  {
+    T *rec = b.win + (size_t)(Tk % NW) * REC_SIZE * n + i;
+#pragma unroll
+    for (int f = 0; f < 9; ++f) rec[(size_t)(REC_R + f) * n] = R.a[f];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) rec[(size_t)(REC_AS + f) * n] = as[f];
+#pragma unroll
+    for (int f = 0; f < 6; ++f) rec[(size_t)(REC_LAM + f) * n] = Lam.a[f];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) rec[(size_t)(REC_ETA + f) * n] = eta[f];
+#pragma unroll
+    for (int f = 0; f < 3; ++f) rec[(size_t)(REC_DLT + f) * n] = T(0);
+    b.win_flag[(size_t)(Tk % NW) * n + i] = 0;  // VO row of stage Tk starts as a free placeholder (:474-481)
+  }
+  return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MHE: covariance-form window sweep
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Cov9 {
+  S3<T> pp, vv, bb;
+  M3<T> pv, pb, vb;
+};
+template <typename T>
+struct Vec9 {
+  V3<T> p, v, b;
+};
+
+template <typename T>
+DEKF_HD void load_cov(const T *base, int n, int i, Cov9<T> &P) {
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    P.pp.a[f] = base[(size_t)f * n + i];
+    P.vv.a[f] = base[(size_t)(6 + f) * n + i];
+    P.bb.a[f] = base[(size_t)(12 + f) * n + i];
+  }
+#pragma unroll
+  for (int f = 0; f < 9; ++f) {
+    P.pv.a[f] = base[(size_t)(18 + f) * n + i];
+    P.pb.a[f] = base[(size_t)(27 + f) * n + i];
+    P.vb.a[f] = base[(size_t)(36 + f) * n + i];
+  }
+}
+template <typename T>
+DEKF_HD void store_cov(T *base, int n, int i, const Cov9<T> &P) {
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    base[(size_t)f * n + i] = P.pp.a[f];
+    base[(size_t)(6 + f) * n + i] = P.vv.a[f];
+    base[(size_t)(12 + f) * n + i] = P.bb.a[f];
+  }
+#pragma unroll
+  for (int f = 0; f < 9; ++f) {
+    base[(size_t)(18 + f) * n + i] = P.pv.a[f];
+    base[(size_t)(27 + f) * n + i] = P.pb.a[f];
+    base[(size_t)(36 + f) * n + i] = P.vb.a[f];
+  }
+}
+
+// Leg-odometry update of stage k: rows A_meas x_k - v_k = b_meas, cost 1/2 v' Q_meas v with
+// A_meas = [0 I 0] per leg (DecentralEst.cpp:95-98, :575-581) == one 3-dim measurement of v_s with
+// information Lambda and information vector eta.  P <- P - P_v W P_v', W = (Lambda^-1 + P_vv)^-1
+// = (I + Lambda P_vv)^-1 Lambda  (never inverts Lambda: swing legs carry 1e-14).
+template <typename T>
+DEKF_HD void meas_update(Cov9<T> &P, Vec9<T> &x, const S3<T> &Lam, const V3<T> &eta) {
+  const M3<T> Pvv = to_m3(P.vv);
+  const M3<T> LamM = to_m3(Lam);
+  M3<T> Z = mul(LamM, Pvv);
+  Z(0, 0) += T(1);
+  Z(1, 1) += T(1);
+  Z(2, 2) += T(1);
+  const M3<T> Zi = inverse(Z);
+  const M3<T> W = mul(Zi, LamM);  // symmetric
+  const V3<T> r = sub(eta, mul(Lam, x.v));
+  const V3<T> t = mul(Zi, r);
+  const M3<T> Kp = mul(P.pv, W);
+  const M3<T> Kv = mul(Pvv, W);
+  const M3<T> Kb = mul_tn(P.vb, W);
+  x.p = add(x.p, mul(P.pv, t));
+  x.v = add(x.v, mul(Pvv, t));
+  x.b = add(x.b, mul_t(P.vb, t));
+  // P -= K P_v'
+  const S3<T> dpp = mul_nt_sym(Kp, P.pv);
+  const M3<T> dpv = mul(Kp, Pvv);
+  const M3<T> dpb = mul(Kp, P.vb);
+  const M3<T> dvv = mul(Kv, Pvv);
+  const M3<T> dvb = mul(Kv, P.vb);
+  const M3<T> dbb = mul(Kb, P.vb);
+#pragma unroll
+  for (int f = 0; f < 6; ++f) P.pp.a[f] -= dpp.a[f];
+#pragma unroll
+  for (int f = 0; f < 9; ++f) {
+    P.pv.a[f] -= dpv.a[f];
+    P.pb.a[f] -= dpb.a[f];
+    P.vb.a[f] -= dvb.a[f];
+  }
+  const S3<T> dvvs = upper(dvv), dbbs = upper(dbb);
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    P.vv.a[f] -= dvvs.a[f];
+    P.bb.a[f] -= dbbs.a[f];
+  }
+}
+
+// Dynamics k -> k+1: rows A_k x_k - x_{k+1} - w_k = b_k with cost 1/2 w' Q_dyn w
+// (DecentralEst.cpp:387-424, Q_dyn^-1 = blkdiag(G C G', dt^2 C_ab) in closed form, no 6x6 inverse)
+// and, when the VO row of the stage has been made an equality (:1004-1005), the relative-position
+// measurement  p_{k+1} - p_k = Delta_k + vcam,  cov(vcam) = R diag(vo_p_std^2) R' (:477).
+template <typename T>
+DEKF_HD void propagate(const MheConst<T> &c, Cov9<T> &P, Vec9<T> &x, const M3<T> &R, const V3<T> &as, bool vo,
+                       const V3<T> &dlt) {
+  const T dt = c.dt, h = T(0.5) * c.dt * c.dt;
+  const S3<T> C1 = rdrt(R, v3<T>(c.d1[0], c.d1[1], c.d1[2]));
+  const S3<T> C2 = rdrt(R, v3<T>(c.d2[0], c.d2[1], c.d2[2]));
+  const S3<T> C3 = rdrt(R, v3<T>(c.d3[0], c.d3[1], c.d3[2]));
+  const M3<T> RPbp = mul_nt(R, P.pb);  // R * P_bp
+  const M3<T> RPbv = mul_nt(R, P.vb);  // R * P_bv
+  const M3<T> RPbb = mul(R, P.bb);
+  const V3<T> Rxb = mul(R, x.b);
+  // mean shift of the position difference h(x) = p+ - p = dt v - h R b + h a_s
+  const V3<T> hmean = v3<T>(dt * x.v[0] - h * Rxb[0] + h * as[0], dt * x.v[1] - h * Rxb[1] + h * as[1],
+                            dt * x.v[2] - h * Rxb[2] + h * as[2]);
+  M3<T> Up, Uv, Ub;
+  S3<T> Sinn;
+  if (vo) {
+    // P L' with L = [0, dt I, -h R]
+    const M3<T> Ep = mul_nt(P.pb, R);
+    const M3<T> Ev = mul_nt(P.vb, R);
+    const M3<T> Pvv = to_m3(P.vv);
+    M3<T> PLp, PLv, PLb;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        PLp(r, cc) = dt * P.pv(r, cc) - h * Ep(r, cc);
+        PLv(r, cc) = dt * Pvv(r, cc) - h * Ev(r, cc);
+        PLb(r, cc) = dt * P.vb(cc, r) - h * RPbb(cc, r);
+      }
+    const M3<T> RPLb = mul(R, PLb);
+    const M3<T> C1m = to_m3(C1), C2m = to_m3(C2);
+    M3<T> Vh;
+#pragma unroll
+    for (int f = 0; f < 9; ++f) {
+      Vh.a[f] = dt * PLv.a[f] - h * RPLb.a[f];
+      Up.a[f] = PLp.a[f] + Vh.a[f] + C1m.a[f];
+      Uv.a[f] = PLv.a[f] - dt * RPLb.a[f] + C2m.a[f];
+      Ub.a[f] = PLb.a[f];
+    }
+    Sinn = add(add(upper(Vh), C1), rdrt(R, v3<T>(c.cvo[0], c.cvo[1], c.cvo[2])));
+  }
+  // time update P+ = A P A' + Q_dyn^-1, A = [[I, dt I, -h R],[0, I, -dt R],[0,0,I]]
+  {
+    const M3<T> Ppp = to_m3(P.pp), Pvv = to_m3(P.vv);
+    M3<T> APpp, APpv, APpb, APvv, APvb;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        APpp(r, cc) = Ppp(r, cc) + dt * P.pv(cc, r) - h * RPbp(r, cc);
+        APpv(r, cc) = P.pv(r, cc) + dt * Pvv(r, cc) - h * RPbv(r, cc);
+        APpb(r, cc) = P.pb(r, cc) + dt * P.vb(r, cc) - h * RPbb(r, cc);
+        APvv(r, cc) = Pvv(r, cc) - dt * RPbv(r, cc);
+        APvb(r, cc) = P.vb(r, cc) - dt * RPbb(r, cc);
+      }
+    const M3<T> X = mul_nt(APpb, R);
+    const M3<T> Y = mul_nt(APvb, R);
+    M3<T> npp, nvv;
+#pragma unroll
+    for (int f = 0; f < 9; ++f) {
+      npp.a[f] = APpp.a[f] + dt * APpv.a[f] - h * X.a[f];
+      nvv.a[f] = APvv.a[f] - dt * Y.a[f];
+    }
+    const M3<T> C2m = to_m3(C2);
+    P.pp = add(upper(npp), C1);
+    P.vv = add(upper(nvv), C3);
+#pragma unroll
+    for (int f = 0; f < 9; ++f) {
+      P.pv.a[f] = APpv.a[f] - dt * X.a[f] + C2m.a[f];
+      P.pb.a[f] = APpb.a[f];
+      P.vb.a[f] = APvb.a[f];
+    }
+    P.bb.a[0] += c.cab[0];
+    P.bb.a[3] += c.cab[1];
+    P.bb.a[5] += c.cab[2];
+  }
+  x.p = add(x.p, hmean);
+  x.v = v3<T>(x.v[0] - dt * Rxb[0] + dt * as[0], x.v[1] - dt * Rxb[1] + dt * as[1], x.v[2] - dt * Rxb[2] + dt * as[2]);
+  if (vo) {
+    const S3<T> Si = inverse(Sinn);
+    const M3<T> Kp = mul(Up, Si), Kv = mul(Uv, Si), Kb = mul(Ub, Si);
+    const V3<T> nu = sub(dlt, hmean);
+    x.p = add(x.p, mul(Kp, nu));
+    x.v = add(x.v, mul(Kv, nu));
+    x.b = add(x.b, mul(Kb, nu));
+    const S3<T> dpp = mul_nt_sym(Kp, Up), dvv = mul_nt_sym(Kv, Uv), dbb = mul_nt_sym(Kb, Ub);
+    const M3<T> dpv = mul_nt(Kp, Uv), dpb = mul_nt(Kp, Ub), dvb = mul_nt(Kv, Ub);
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+      P.pp.a[f] -= dpp.a[f];
+      P.vv.a[f] -= dvv.a[f];
+      P.bb.a[f] -= dbb.a[f];
+    }
+#pragma unroll
+    for (int f = 0; f < 9; ++f) {
+      P.pv.a[f] -= dpv.a[f];
+      P.pb.a[f] -= dpb.a[f];
+      P.vb.a[f] -= dvb.a[f];
+    }
+  }
+}
+
+template <typename T>
+struct StageRec {
+  M3<T> R;
+  V3<T> as;
+  S3<T> Lam;
+  V3<T> eta, dlt;
+  bool vo;
+};
+
+template <typename T>
+DEKF_HD void load_stage(const Dims &dm, const Buffers<T> &b, int k, int i, StageRec<T> &s) {
+  const int n = dm.n;
+  const T *rec = b.win + (size_t)(k % dm.NW) * REC_SIZE * n + i;
+#pragma unroll
+  for (int f = 0; f < 9; ++f) s.R.a[f] = rec[(size_t)(REC_R + f) * n];
+#pragma unroll
+  for (int f = 0; f < 3; ++f) s.as[f] = rec[(size_t)(REC_AS + f) * n];
+#pragma unroll
+  for (int f = 0; f < 6; ++f) s.Lam.a[f] = rec[(size_t)(REC_LAM + f) * n];
+#pragma unroll
+  for (int f = 0; f < 3; ++f) s.eta[f] = rec[(size_t)(REC_ETA + f) * n];
+#pragma unroll
+  for (int f = 0; f < 3; ++f) s.dlt[f] = rec[(size_t)(REC_DLT + f) * n];
+  s.vo = b.win_flag[(size_t)(k % dm.NW) * n + i] != 0;
+}
+
+// update(T) after UpdateMHE/UpdateVOConstraints: marginalizeQP(T-N) if T >= N, solve, read x_T,
+// v_MHE_b (DecentralEst.cpp:167-185).  Tier A: the whole window is re-swept every step, like the
+// reference re-solves the whole QP every step.
+template <typename T>
+DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
+                      int Tk, int i) {
+  const int n = dm.n, N = dm.N;
+  Cov9<T> P;
+  Vec9<T> x;
+  int k0;
+  if (Tk < N) {
+    // Prior_0: Q_prior = blkdiag(Q_p0, Q_v0, Q_b0), x_prior = 0 (DecentralEst.cpp:232-253)
+#pragma unroll
+    for (int f = 0; f < 6; ++f) P.pp.a[f] = P.vv.a[f] = P.bb.a[f] = T(0);
+#pragma unroll
+    for (int f = 0; f < 9; ++f) P.pv.a[f] = P.pb.a[f] = P.vb.a[f] = T(0);
+    P.pp.a[0] = c.P0[0];
+    P.pp.a[3] = c.P0[1];
+    P.pp.a[5] = c.P0[2];
+    P.vv.a[0] = c.P0[3];
+    P.vv.a[3] = c.P0[4];
+    P.vv.a[5] = c.P0[5];
+    P.bb.a[0] = c.P0[6];
+    P.bb.a[3] = c.P0[7];
+    P.bb.a[5] = c.P0[8];
+    x.p = x.v = x.b = v3<T>(T(0), T(0), T(0));
+    k0 = 0;
+  } else {
+    load_cov(b.arr_P, n, i, P);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      x.p[f] = b.arr_x[(size_t)f * n + i];
+      x.v[f] = b.arr_x[(size_t)(3 + f) * n + i];
+      x.b[f] = b.arr_x[(size_t)(6 + f) * n + i];
+    }
+    k0 = Tk - N;
+  }
+  StageRec<T> s;
+  for (int k = k0; k < Tk; ++k) {
+    load_stage(dm, b, k, i, s);
+    meas_update(P, x, s.Lam, s.eta);
+    propagate(c, P, x, s.R, s.as, s.vo, s.dlt);
+    if (k == Tk - N) {
+      // marginalizeQP(T-N): the arrival cost moves to x_{T-N+1} (MheSrb.cpp:475-713)
+      store_cov(b.arr_P, n, i, P);
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        b.arr_x[(size_t)f * n + i] = x.p[f];
+        b.arr_x[(size_t)(3 + f) * n + i] = x.v[f];
+        b.arr_x[(size_t)(6 + f) * n + i] = x.b[f];
+      }
+    }
+  }
+  load_stage(dm, b, Tk, i, s);
+  meas_update(P, x, s.Lam, s.eta);
+  // getsolution(T) + v_MHE_b = R_sb (v + omega x p_imu_2_opti) (DecentralEst.cpp:181-185)
+  V3<T> om;
+#pragma unroll
+  for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
+  const V3<T> lever = v3<T>(T(0.016041), T(0.089061), T(0.0579875));
+  const V3<T> vb = mul(s.R, add(x.v, cross(om, lever)));
+  int status = 0;
+  const T chk = x.p[0] + x.p[1] + x.p[2] + x.v[0] + x.v[1] + x.v[2] + x.b[0] + x.b[1] + x.b[2];
+  if (!(chk == chk) || !(chk - chk == T(0))) status |= ST_NONFINITE;
+  if (out.x != nullptr) {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      out.x[(size_t)f * n + i] = (double)x.p[f];
+      out.x[(size_t)(3 + f) * n + i] = (double)x.v[f];
+      out.x[(size_t)(6 + f) * n + i] = (double)x.b[f];
+    }
+  }
+  if (out.v_body != nullptr) {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) out.v_body[(size_t)f * n + i] = (double)vb[f];
+  }
+  return status;
+}
+
+}  // namespace dekf

@@ -1,0 +1,166 @@
+// Host-side parameter derivation: dekf_config (== robot_params + orien_ekf parameters) -> the
+// constant blocks the kernels take by value.  Plain C++ (no CUDA) so the CPU math-debug harness in
+// tests/hostsim can share it.
+#pragma once
+#include <cmath>
+#include <cstring>
+
+#include "../../include/dekf_b200.h"
+#include "estimator_core.cuh"
+
+namespace dekf {
+
+inline void fill_go1_defaults(dekf_config *c) {
+  // go1_example/config/parameters_go1.yaml:5-50 (est_sub) and :68-75 (orien_sub)
+  std::memset(c, 0, sizeof(*c));
+  c->abi_version = DEKF_ABI_VERSION;
+  c->n_instances = 1;
+  c->precision = DEKF_FP64;
+  c->robot = DEKF_ROBOT_GO1;
+  c->ekf_hist_depth = 64;
+  for (int i = 0; i < 3; ++i) {
+    c->p_init_std[i] = 0.001;
+    c->v_init_std[i] = 0.001;
+    c->foot_init_std[i] = 0.001;
+    c->accel_bias_init_std[i] = 0.0001;
+    c->p_process_std[i] = 0.001;
+    c->gyro_input_std[i] = 0.03;
+    c->foot_slide_std[i] = 0.003;
+    c->foot_swing_std[i] = 10000000.0;
+    c->vo_p_std[i] = 0.000015;
+    c->ekf_process_std[i] = 0.1;
+    c->ekf_gravity_meas_std[i] = 4.0;
+  }
+  for (int i = 0; i < 8; ++i) {
+    c->joint_position_std[i] = 0.04;
+    c->joint_velocity_std[i] = 0.22;
+  }
+  c->accel_input_std[0] = 0.025;
+  c->accel_input_std[1] = 0.025;
+  c->accel_input_std[2] = 0.02;
+  c->accel_bias_std[0] = 0.07;
+  c->accel_bias_std[1] = 0.02;
+  c->accel_bias_std[2] = 0.03;
+  c->quaternion_ib[0] = 1.0;
+  c->p_ib[0] = 0.01592;
+  c->p_ib[1] = 0.06659;
+  c->p_ib[2] = 0.00617;
+  c->num_legs = 4;
+  c->leg_odom_type = 0;
+  c->contact_effort_threshold = 150.0;
+  c->rate = 200;
+  c->N = 20;
+  c->est_type = 0;
+  c->rho = 0.1;
+  c->alpha = 1.6;
+  c->delta = 0.00001;
+  c->sigma = 0.00001;
+  c->verbose = 0;
+  c->adaptRho = 1;
+  c->polish = 0;
+  c->maxQPIter = 4000;
+  c->primTol = 1e-6;
+  c->dualTol = 1e-6;
+  c->realtiveTol = 1e-6;
+  c->absTol = 1e-6;
+  c->timeLimit = 0.0028;
+  for (int i = 0; i < 4; ++i) {
+    c->ekf_init_std[i] = 0.001;
+    c->ekf_vo_meas_std[i] = 0.0001;
+  }
+  c->ekf_quaternion_init[0] = 1.0;
+  c->ekf_rate = 500;
+}
+
+inline int robot_num_legs(int robot) { return robot == DEKF_ROBOT_CASSIE ? 2 : (robot == DEKF_ROBOT_POGOX ? 1 : 4); }
+inline int robot_nj(int robot) { return robot == DEKF_ROBOT_CASSIE ? 5 : 3; }
+
+inline Dims make_dims(const dekf_config &c) {
+  Dims d;
+  d.n = c.n_instances;
+  d.N = c.N;
+  d.NW = c.N + 1;
+  d.HR = 4 * c.N + 1;
+  d.D = c.ekf_hist_depth;
+  return d;
+}
+
+template <typename T>
+inline EkfConst<T> make_ekf_const(const dekf_config &c) {
+  EkfConst<T> e;
+  e.dt = (T)(1 / static_cast<double>(c.ekf_rate));  // orien_ekf.cpp:25
+  for (int i = 0; i < 3; ++i) {
+    e.Cg[i] = (T)std::pow(c.ekf_process_std[i], 2);       // :28
+    e.Ca[i] = (T)std::pow(c.ekf_gravity_meas_std[i], 2);  // :29
+  }
+  for (int i = 0; i < 4; ++i) {
+    e.Cvo[i] = (T)std::pow(c.ekf_vo_meas_std[i], 2);  // :30
+    e.P0[i] = (T)std::pow(c.ekf_init_std[i], 2);      // :27
+    e.q0[i] = (T)c.ekf_quaternion_init[i];            // :31-33
+  }
+  e.g[0] = (T)0;
+  e.g[1] = (T)0;
+  e.g[2] = (T)9.81;  // :11
+  return e;
+}
+
+template <typename T>
+inline MheConst<T> make_mhe_const(const dekf_config &c) {
+  MheConst<T> m;
+  const double dt = 1.0 / c.rate;  // DecentralEst.cpp:15
+  m.dt = (T)dt;
+  m.dt_d = dt;
+  m.N = c.N;
+  m.thr = c.contact_effort_threshold;
+  for (int i = 0; i < 3; ++i) {
+    const double Cp = std::pow(c.p_process_std[i], 2), Ca = std::pow(c.accel_input_std[i], 2);
+    // Q_dyn^-1 = G C G' with G = [[R dt, R dt^2/2],[0, R dt]], C = blkdiag(C_p, C_accel)
+    // (DecentralEst.cpp:409-418) = blk(R,R) [[dt^2 Cp + dt^4/4 Ca, dt^3/2 Ca],[., dt^2 Ca]] blk(R,R)'
+    m.d1[i] = (T)(dt * dt * Cp + 0.25 * dt * dt * dt * dt * Ca);
+    m.d2[i] = (T)(0.5 * dt * dt * dt * Ca);
+    m.d3[i] = (T)(dt * dt * Ca);
+    m.cab[i] = (T)(dt * dt * std::pow(c.accel_bias_std[i], 2));  // (Q_accel_bias/dt^2)^-1, :422-424
+    m.cvo[i] = (T)std::pow(c.vo_p_std[i], 2);                    // Q_cam^-1 = R diag R', :477
+    m.cgy[i] = (T)std::pow(c.gyro_input_std[i], 2);
+    m.q_swing[i] = (T)(1 / std::pow(c.foot_swing_std[i], 2));
+    m.P0[0 + i] = (T)std::pow(c.p_init_std[i], 2);  // Q_prior^-1, :239-253
+    m.P0[3 + i] = (T)std::pow(c.v_init_std[i], 2);
+    m.P0[6 + i] = (T)std::pow(c.accel_bias_init_std[i], 2);
+    m.p_ib[i] = (T)c.p_ib[i];
+  }
+  for (int i = 0; i < 8; ++i) {
+    m.cenc_v[i] = (T)std::pow(c.joint_velocity_std[i], 2);
+    m.cenc_p[i] = (T)std::pow(c.joint_position_std[i], 2);
+  }
+  return m;
+}
+
+// fields per instance of every state array, in units of elements
+struct StateSizes {
+  size_t ekf_q, ekf_P, ekf_hist, ekf_hist_time, arr_P, arr_x, win, win_flag, hist_time, hist_quat, wp, wp_time,
+      wp_count, p_vo, pend_flag, pend, status;
+};
+inline StateSizes state_sizes(const Dims &d) {
+  StateSizes s;
+  const size_t n = (size_t)d.n;
+  s.ekf_q = 4 * n;
+  s.ekf_P = 16 * n;
+  s.ekf_hist = (size_t)d.D * EKF_HIST_FIELDS * n;
+  s.ekf_hist_time = (size_t)d.D * n;
+  s.arr_P = 45 * n;
+  s.arr_x = 9 * n;
+  s.win = (size_t)d.NW * REC_SIZE * n;
+  s.win_flag = (size_t)d.NW * n;
+  s.hist_time = (size_t)d.HR * n;
+  s.hist_quat = (size_t)d.HR * 4 * n;
+  s.wp = 12 * n;
+  s.wp_time = 4 * n;
+  s.wp_count = n;
+  s.p_vo = 3 * n;
+  s.pend_flag = n;
+  s.pend = 5 * n;
+  s.status = n;
+  return s;
+}
+
+}  // namespace dekf

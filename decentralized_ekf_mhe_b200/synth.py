@@ -160,7 +160,8 @@ class Trajectory:
 
 
 def make_stream(n, S, *, robot="go1", seed=20240510, dt=0.005, device="cpu", s0=0, vo=True,
-                vo_rate=30.0, vo_latency=0.040, vo_jitter=False, amp_jitter=False, truth=False):
+                vo_rate=30.0, vo_latency=0.040, vo_jitter=False, amp_jitter=False, truth=False,
+                device_rng=False):
     """Generate steps ``s0 .. s0+S-1`` of the synthetic stream for ``n`` instances.
 
     vo_jitter=False: every instance sees VO frames at t_j = j / vo_rate (lock-step arrival, the
@@ -196,8 +197,12 @@ def make_stream(n, S, *, robot="go1", seed=20240510, dt=0.005, device="cpu", s0=
     for si in range(S):
         k = s0 + si
         t = k * dt
-        g = torch.Generator(device="cpu").manual_seed(int(seed) * 1000003 + k)
-        noise = torch.randn(16 + 2 * nl * nj + nl, n, generator=g, dtype=f64).to(device)
+        if device_rng:  # large benchmark streams: draw on the device (not reproducible across devices)
+            g = torch.Generator(device=device).manual_seed(int(seed) * 1000003 + k)
+            noise = torch.randn(16 + 2 * nl * nj + nl, n, generator=g, dtype=f64, device=device)
+        else:
+            g = torch.Generator(device="cpu").manual_seed(int(seed) * 1000003 + k)
+            noise = torch.randn(16 + 2 * nl * nj + nl, n, generator=g, dtype=f64).to(device)
         r, p, y = tr.rpy(t)
         dr, dp_, dy = tr.rpy_rate(t)
         R = euler_to_rot(r, p, y)  # [n,3,3]

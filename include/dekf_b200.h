@@ -1,0 +1,188 @@
+/* dekf_b200.h -- C ABI of the B200-native batched legged-robot estimator (libdekf_b200.so).
+ *
+ * Drop-in boundary for the estimator hot path of well-robotics/Decentralized_EKF_MHE.  The
+ * reference has no FFI layer: its boundary is the C++ class API.  Each entry point below names the
+ * reference interface it replaces (paths relative to /root/reference/src):
+ *
+ *   dekf_config / dekf_create   struct robot_params                decentral_legged_est/include/decentral_legged_est/DecentralEst.hpp:18-63
+ *                               + orien_ekf ctor parameters        orien_est/src/orien_ekf.cpp:13-33
+ *                               + DecentralizedEstimation::initialize(sub, params)   DecentralEst.hpp:101, DecentralEst.cpp:9-150
+ *   dekf_inputs                 struct robot_store                 DecentralEst.hpp:65-94 (the per-tick sensor snapshot;
+ *                               filled by go1Sub::imu_callback / lo_callback, go1_example/src/go1Sub.cpp:30-126,
+ *                               robotSub::vo_callback / orien_filter_callback, EstSub.cpp:34-55, orien_ekf callbacks :47-75)
+ *   dekf_ekf_step               orien_ekf::timerCallback           orien_est/src/orien_ekf.cpp:77-89
+ *                               (= get_measurement :156, gyro_nonlinear_predict :108, gyro_nonlinear_correct :125,
+ *                                vo_nonlinear_correct :144)        orien_est/include/orien_ekf.hpp:79-83
+ *   dekf_mhe_step               DecentralizedEstimation::initialize (T==0) / ::update(int T) (T>=1)
+ *                               DecentralEst.hpp:101-102, DecentralEst.cpp:9,152; inside it MHEproblem::updateQP /
+ *                               marginalizeQP / initQP / solveQP / getsolution, MheSrb.hpp:99-103
+ *   dekf_step                   both timers in lock-step (EKF tick, then MHE update on its quaternion)
+ *   dekf_outputs                public result members R_sb_, x_MHE_, v_MHE_b_ (DecentralEst.hpp:279-285) and the
+ *                               imu/filter quaternion (orien_ekf.cpp:92-95)
+ *   dekf_get_arrival_cost       MHEproblem::M_p, n_p               MheSrb.hpp:86-87
+ *   dekf_get_p_vo               DecentralizedEstimation::p_vo_accmulate_   DecentralEst.hpp:280
+ *   dekf_reset                  DecentralizedEstimation::reset()   DecentralEst.hpp:103
+ *
+ * Conventions
+ *   - One handle steps `n_instances` independent estimator instances; instance i never reads
+ *     instance j.  One caller thread per handle (like the reference's single-threaded executor).
+ *   - Every array is SoA `[field][instance]`, instance fastest, `instance stride == n_instances`.
+ *   - `dekf_*_step` take DEVICE pointers and are stream-ordered on the handle's stream (no host
+ *     synchronisation); `dekf_step_host` takes HOST pointers (pinned for full speed), copies in,
+ *     steps, copies the results out and synchronises -- the end-to-end path.
+ *   - Quaternions are [w,x,y,z].  Times are seconds in double; they are compared in double even in
+ *     the fp32 arithmetic path so that index logic stays bit-exact.
+ *   - Return value: 0 on success, a negative DEKF_E* code otherwise; never throws, never aborts.
+ *     Per-instance conditions (dropped VO, non-finite state) are reported through `status` bits.
+ *   - There is NO CPU fallback: without a CUDA device dekf_create fails with DEKF_ENODEV.
+ */
+#ifndef DEKF_B200_H
+#define DEKF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEKF_ABI_VERSION 1
+
+enum {
+  DEKF_OK = 0,
+  DEKF_EINVAL = -1,   /* bad argument / unsupported configuration */
+  DEKF_ENODEV = -2,   /* no CUDA device / wrong architecture */
+  DEKF_ENOMEM = -3,   /* device allocation failed */
+  DEKF_ECUDA = -4,    /* CUDA runtime error (see dekf_last_error) */
+  DEKF_ESTATE = -5    /* call order violated (e.g. T does not follow the previous T) */
+};
+
+enum { DEKF_ROBOT_GO1 = 0, DEKF_ROBOT_CASSIE = 1, DEKF_ROBOT_POGOX = 2 };
+enum { DEKF_FP64 = 0, DEKF_FP32 = 1 };
+
+/* per-instance status bits (OR-ed over the calls of one step) */
+enum {
+  DEKF_ST_EKF_VO_DROPPED = 1,    /* VO stamp older than all stored IMU samples (orien_ekf.cpp:178-183) */
+  DEKF_ST_EKF_VO_NO_REPLAY = 2,  /* rel <= 1: state rolled back, VO not applied (orien_ekf.cpp:191) */
+  DEKF_ST_EKF_HIST_OVERFLOW = 4, /* VO older than the device-side history ring (reference keeps everything) */
+  DEKF_ST_MHE_VO_DROPPED = 8,    /* DecentralEst.cpp:898-904 */
+  DEKF_ST_MHE_VO_BOUNDED = 16,   /* VO bounds were inserted this step (vo_to_be_processed_flag_) */
+  DEKF_ST_NONFINITE = 32
+};
+
+typedef struct dekf_config {
+  int32_t abi_version;   /* DEKF_ABI_VERSION */
+  int32_t n_instances;
+  int32_t device;        /* CUDA device ordinal */
+  int32_t precision;     /* DEKF_FP64 | DEKF_FP32 (arithmetic + state type; inputs/outputs stay double) */
+  int32_t robot;         /* DEKF_ROBOT_* (kinematics compiled as __device__ functions) */
+  int32_t ekf_hist_depth;/* EKF replay ring depth in ticks (>= max VO latency in ticks + 2) */
+  int32_t debug_taps;    /* allocate b_meas / Q_meas / index-logic taps (parity tests) */
+  int32_t reserved0;
+
+  /* ---- robot_params (DecentralEst.hpp:18-63; YAML names in EstSub.cpp:125-207) */
+  double p_process_std[3], accel_input_std[3], accel_bias_std[3], gyro_input_std[3];
+  double quaternion_ib[4], p_ib[3];
+  int32_t num_legs, leg_odom_type;
+  double joint_position_std[8], joint_velocity_std[8]; /* per joint of a leg (reference: 3) */
+  double foot_slide_std[3], foot_swing_std[3];
+  double contact_effort_threshold;
+  double p_init_std[3], v_init_std[3], foot_init_std[3], accel_bias_init_std[3];
+  double vo_p_std[3];
+  int32_t rate, N, est_type, reserved1;
+  /* OSQP settings are accepted for source compatibility and ignored: the window is solved
+   * directly (exactly), see DESIGN.md section 4. */
+  double rho, alpha, delta, sigma;
+  int32_t verbose, adaptRho, polish, maxQPIter;
+  double realtiveTol, absTol, primTol, dualTol, timeLimit;
+
+  /* ---- orien_ekf parameters (orien_ekf.cpp:13-18) */
+  double ekf_init_std[4], ekf_process_std[3], ekf_gravity_meas_std[3], ekf_vo_meas_std[4];
+  double ekf_quaternion_init[4];
+  int32_t ekf_rate, reserved2;
+} dekf_config;
+
+/* Per-tick sensor snapshot of all instances.  NULL vo_flag == no VO message for anybody. */
+typedef struct dekf_inputs {
+  const double *gyro;        /* [3][n]  robot_store.angular_b_  (rad/s, body) */
+  const double *accel;       /* [3][n]  robot_store.accel_b_    (m/s^2, body, incl. gravity) */
+  const double *imu_time;    /* [n]     robot_store.imu_time_ */
+  const double *joint_pos;   /* [num_legs*nj][n] joint_states_position_[0..] */
+  const double *joint_vel;   /* [num_legs*nj][n] joint_states_velocity_ */
+  const double *foot_force;  /* [num_legs][n]    joint_states_position_[12+i] (go1Sub.cpp:74) */
+  const uint8_t *vo_flag;    /* [n]     robot_store.vo_new_ / orien_ekf vo_new_ */
+  const double *vo_quat;     /* [4][n]  orb/pos orientation (orien_ekf.cpp:47-58) */
+  const double *vo_time_pre; /* [n]     robot_store.vo_time_pre_ */
+  const double *vo_time_now; /* [n]     robot_store.vo_time_now_ (also the orb/pos stamp) */
+  const double *vo_rel_p;    /* [3][n]  robot_store.vo_p_body_pre_2_body_ */
+  const double *quat;        /* [4][n]  robot_store.quaternion_ for dekf_mhe_step; NULL = use the EKF state */
+} dekf_inputs;
+
+typedef struct dekf_outputs {
+  double *quat;     /* [4][n] EKF quaternion after the tick (may be NULL) */
+  double *x;        /* [9][n] x_MHE_ = [p_s, v_s, accel bias] (valid for T>=1; may be NULL) */
+  double *v_body;   /* [3][n] v_MHE_b_ (may be NULL) */
+  uint8_t *contact; /* [num_legs][n] contact flags (may be NULL) */
+  int32_t *status;  /* [n] status bits of this call (may be NULL) */
+} dekf_outputs;
+
+typedef struct dekf_handle dekf_handle;
+
+/* parameters_go1.yaml (go1_example/config) with the EKF block of the same file */
+int dekf_config_default_go1(dekf_config *cfg);
+/* builder-defined model parameter sets (the reference ships Go1 only) */
+int dekf_config_default_cassie(dekf_config *cfg);
+int dekf_config_default_pogox(dekf_config *cfg);
+
+int dekf_create(const dekf_config *cfg, dekf_handle **out);
+int dekf_destroy(dekf_handle *h);
+int dekf_reset(dekf_handle *h);
+/* cudaStream_t to order the step calls on (default: a private non-blocking stream) */
+int dekf_set_stream(dekf_handle *h, void *cuda_stream);
+void *dekf_get_stream(dekf_handle *h);
+const char *dekf_last_error(const dekf_handle *h);
+int dekf_num_joints(const dekf_handle *h); /* num_legs * joints per leg */
+
+/* Device-pointer, stream-ordered entry points. */
+int dekf_ekf_step(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out);
+int dekf_mhe_step(dekf_handle *h, int32_t T, const dekf_inputs *in, const dekf_outputs *out);
+int dekf_step(dekf_handle *h, int32_t T, const dekf_inputs *in, const dekf_outputs *out);
+
+/* Host-pointer entry point: H2D copies of `in`, dekf_step, D2H copies of `out`, stream sync. */
+int dekf_step_host(dekf_handle *h, int32_t T, const dekf_inputs *in, const dekf_outputs *out);
+int dekf_synchronize(dekf_handle *h);
+
+/* Getters (device pointers, stream-ordered). */
+int dekf_get_arrival_cost(dekf_handle *h, double *M_p /*[81][n]*/, double *n_p /*[9][n]*/);
+int dekf_get_arrival_cov(dekf_handle *h, double *P /*[81][n]*/, double *x /*[9][n]*/);
+int dekf_get_p_vo(dekf_handle *h, double *p /*[3][n]*/);
+int dekf_get_R_sb(dekf_handle *h, double *R /*[9][n]*/);
+int dekf_get_ekf_cov(dekf_handle *h, double *P /*[16][n]*/);
+/* number of window stages whose VO row is currently an equality (LinearConstraint.equality, MheSrb.hpp:38) */
+int dekf_get_window_vo_count(dekf_handle *h, int32_t *count /*[n]*/);
+/* debug taps of the last step (only when cfg.debug_taps != 0): copied into caller DEVICE buffers, any may be NULL.
+ * b_meas/Q_meas: DecentralEst.cpp:515-546 per leg (Q as symmetric 3x3: 00,01,02,11,12,22);
+ * vo_idx: processed,i_pre,i_now,w0,i0,ins,num,disc0 of DecentralEst.cpp:883-945 (-2 = not set);
+ * ekf_idx: cur,idx,nreplay of orien_ekf.cpp:186-205. */
+int dekf_debug_taps(dekf_handle *h, double *b_meas /*[3*legs][n]*/, double *Q_meas /*[legs][6][n]*/,
+                    int32_t *vo_idx /*[8][n]*/, int32_t *ekf_idx /*[3][n]*/);
+
+/* Per-kernel device time of the step kernels (CUDA events on the handle's stream around every launch while
+ * enabled).  ms[3] / count[3]: 0 = EKF tick, 1 = stage assembly, 2 = window solve (or the fused kernel).
+ * Reading synchronises the stream and clears the accumulators. */
+int dekf_profile_enable(dekf_handle *h, int32_t enable);
+int dekf_profile_read(dekf_handle *h, double *ms /*[3]*/, int64_t *count /*[3]*/);
+
+/* Roofline denominators measured on the device (the driver's MEASURED_PEAKS.json has no FP64/FP32 FMA figure):
+ * dense non-tensor FMA throughput in TFLOP/s (FMA = 2 flop) and a device-to-device copy in GB/s (read+write). */
+int dekf_measure_fma_peak(int32_t device, int32_t precision, double *tflops);
+int dekf_measure_copy_bw(int32_t device, double *gbs);
+
+/* Number of kernel launches issued by this handle so far (bench.py "gpu_launches"). */
+int64_t dekf_launch_count(const dekf_handle *h);
+/* Bytes of device memory held by the handle. */
+int64_t dekf_device_bytes(const dekf_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEKF_B200_H */

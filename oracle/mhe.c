@@ -381,7 +381,9 @@ static void get_measurement(orc_mhe *m, int T) {
     double vo_p[3] = {m->store.vo_p[0], m->store.vo_p[1], m->store.vo_p[2]};
     double t_pre = m->store.vo_time_pre, t_now = m->store.vo_time_now;
     m->store.vo_new = 0; /* :891 */
-    memset(m->vo_dbg, 0, sizeof(m->vo_dbg));
+    for (int q = 0; q < 10; ++q) m->vo_dbg[q] = -2;
+    m->vo_dbg[0] = 0;
+    m->vo_dbg[8] = 0;
     m->vo_dbg[9] = m->nstack;
     int ub = upper_bound_hist(m->stack, m->nstack, t_pre); /* :895 */
     if (ub == 0) {

@@ -127,7 +127,7 @@ def lib():
         L.orc_run_batch.restype = C.c_double
         L.orc_run_batch.argtypes = [C.POINTER(Params), C.POINTER(EkfParams), C.POINTER(Stream),
                                     C.POINTER(Outputs), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                    C.c_int, dp]
+                                    C.c_int, dp, dp]
         _LIB = L
     return _LIB
 
@@ -387,8 +387,10 @@ def run_batch(stream, prm=None, ep=None, *, i0=0, i1=None, nthreads=1, run_ekf=T
         res["admm_iters"] = np.zeros((S, n), dtype=np.int32)
         out.admm_iters = res["admm_iters"].ctypes.data_as(ip)
     busy = C.c_double()
+    bmax = C.c_double()
     wall = lib().orc_run_batch(C.byref(prm), C.byref(ep), C.byref(st), C.byref(out), i0, i1, nthreads,
-                               int(run_ekf), int(run_mhe), t_steady, C.byref(busy))
+                               int(run_ekf), int(run_mhe), t_steady, C.byref(busy), C.byref(bmax))
+    res["_busy_max"] = bmax.value
     return res, wall, busy.value
 
 

@@ -171,7 +171,7 @@ static void *worker(void *arg) {
  * threads (so steps/s/core = (i1-i0)*(S-t_steady)/busy_seconds). */
 double orc_run_batch(const orc_params *prm, const orc_ekf_params *eprm, const orc_stream *st,
                      orc_outputs *out, int i0, int i1, int nthreads, int run_ekf, int run_mhe,
-                     int t_steady, double *busy_seconds) {
+                     int t_steady, double *busy_seconds, double *busy_max) {
   if (nthreads < 1) nthreads = 1;
   int cnt = i1 - i0;
   if (nthreads > cnt) nthreads = cnt > 0 ? cnt : 1;
@@ -190,11 +190,13 @@ double orc_run_batch(const orc_params *prm, const orc_ekf_params *eprm, const or
     jobs[t].t_steady = t_steady;
     pthread_create(&th[t], NULL, worker, &jobs[t]);
   }
-  double busy = 0.0;
+  double busy = 0.0, bmax = 0.0;
   for (int t = 0; t < nthreads; ++t) {
     pthread_join(th[t], NULL);
     busy += jobs[t].seconds;
+    if (jobs[t].seconds > bmax) bmax = jobs[t].seconds;
   }
+  if (busy_max) *busy_max = bmax;
   double wall = now_s() - t0;
   if (busy_seconds) *busy_seconds = busy;
   free(jobs);

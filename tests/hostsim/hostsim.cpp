@@ -1,0 +1,141 @@
+// MATH-DEBUG HARNESS, NOT A PRODUCT PATH.
+// Compiles the per-instance kernel bodies (csrc/estimator_core.cuh, __host__ __device__) with g++
+// and loops them over instances on the CPU so that the algebra of the kernels can be checked against
+// the oracle in the GPU-less build container.  It is built only by tests/test_hostsim.py into
+// tests/hostsim/_build/, is not part of libdekf_b200.so, is not importable from the package and is
+// never timed.  The product path has no CPU fallback (dekf_create fails without a CUDA device).
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../decentralized_ekf_mhe_b200/csrc/host_setup.hpp"
+
+using namespace dekf;
+
+namespace {
+template <typename T>
+struct Sim {
+  dekf_config cfg;
+  Dims dm;
+  EkfConst<T> ec;
+  MheConst<T> mc;
+  Buffers<T> b;
+  std::vector<std::vector<char>> store;
+
+  template <typename U>
+  U *alloc(size_t count) {
+    store.emplace_back(count * sizeof(U) + 64, 0);
+    return reinterpret_cast<U *>(store.back().data());
+  }
+  explicit Sim(const dekf_config &c) : cfg(c) {
+    dm = make_dims(c);
+    ec = make_ekf_const<T>(c);
+    mc = make_mhe_const<T>(c);
+    StateSizes s = state_sizes(dm);
+    b.ekf_q = alloc<T>(s.ekf_q);
+    b.ekf_P = alloc<T>(s.ekf_P);
+    b.ekf_hist = alloc<T>(s.ekf_hist);
+    b.ekf_hist_time = alloc<double>(s.ekf_hist_time);
+    b.arr_P = alloc<T>(s.arr_P);
+    b.arr_x = alloc<T>(s.arr_x);
+    b.win = alloc<T>(s.win);
+    b.win_flag = alloc<uint8_t>(s.win_flag);
+    b.hist_time = alloc<double>(s.hist_time);
+    b.hist_quat = alloc<double>(s.hist_quat);
+    b.wp = alloc<double>(s.wp);
+    b.wp_time = alloc<double>(s.wp_time);
+    b.wp_count = alloc<int32_t>(s.wp_count);
+    b.p_vo = alloc<double>(s.p_vo);
+    b.pend_flag = alloc<uint8_t>(s.pend_flag);
+    b.pend = alloc<double>(s.pend);
+    b.status = alloc<int32_t>(s.status);
+    const int n = dm.n;
+    for (int i = 0; i < n; ++i) {
+      for (int f = 0; f < 4; ++f) {
+        b.ekf_q[(size_t)f * n + i] = ec.q0[f];
+        b.ekf_P[(size_t)(f * 5) * n + i] = ec.P0[f];
+      }
+      const int diag[3] = {0, 3, 5};
+      for (int f = 0; f < 3; ++f) {
+        b.arr_P[(size_t)(0 + diag[f]) * n + i] = mc.P0[f];
+        b.arr_P[(size_t)(6 + diag[f]) * n + i] = mc.P0[3 + f];
+        b.arr_P[(size_t)(12 + diag[f]) * n + i] = mc.P0[6 + f];
+      }
+    }
+  }
+};
+
+template <typename T, typename Model>
+void run(const dekf_config &cfg, int S, const double *gyro, const double *accel, const double *imu_time,
+         const double *joint_pos, const double *joint_vel, const double *foot_force, const uint8_t *vo_flag,
+         const double *vo_quat, const double *vo_time_pre, const double *vo_time_now, const double *vo_rel_p,
+         const double *quat_in, double *quat_out, double *x_out, double *vb_out, uint8_t *contact_out,
+         int32_t *vo_dbg, int32_t *ekf_dbg, double *pvo_out, int32_t *status_out, double *arrP_out, double *arrx_out) {
+  Sim<T> sim(cfg);
+  const int n = cfg.n_instances;
+  const int nq = Model::NLEG * Model::NJ, nl = Model::NLEG;
+  for (int s = 0; s < S; ++s) {
+    Inputs in;
+    in.gyro = gyro + (size_t)s * 3 * n;
+    in.accel = accel + (size_t)s * 3 * n;
+    in.imu_time = imu_time + (size_t)s * n;
+    in.joint_pos = joint_pos + (size_t)s * nq * n;
+    in.joint_vel = joint_vel + (size_t)s * nq * n;
+    in.foot_force = foot_force + (size_t)s * nl * n;
+    in.vo_flag = vo_flag ? vo_flag + (size_t)s * n : nullptr;
+    in.vo_quat = vo_quat + (size_t)s * 4 * n;
+    in.vo_time_pre = vo_time_pre + (size_t)s * n;
+    in.vo_time_now = vo_time_now + (size_t)s * n;
+    in.vo_rel_p = vo_rel_p + (size_t)s * 3 * n;
+    in.quat = quat_in ? quat_in + (size_t)s * 4 * n : nullptr;
+    Outputs out;
+    std::memset(&out, 0, sizeof(out));
+    out.quat = quat_out + (size_t)s * 4 * n;
+    out.x = x_out + (size_t)s * 9 * n;
+    out.v_body = vb_out + (size_t)s * 3 * n;
+    out.contact = contact_out + (size_t)s * nl * n;
+    out.dbg_vo = vo_dbg + (size_t)s * 8 * n;
+    out.dbg_ekf = ekf_dbg + (size_t)s * 3 * n;
+    for (int i = 0; i < n; ++i) {
+      int st = ekf_tick<T>(sim.ec, sim.dm, sim.b, in, out, s, i);
+      double q[4];
+      for (int f = 0; f < 4; ++f)
+        q[f] = in.quat ? in.quat[(size_t)f * n + i] : (double)sim.b.ekf_q[(size_t)f * n + i];
+      st |= mhe_assemble<T, Model>(sim.mc, sim.dm, sim.b, in, out, s, i, q);
+      if (s >= 1) st |= mhe_solve<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
+      status_out[(size_t)s * n + i] = st;
+      for (int f = 0; f < 3; ++f) pvo_out[((size_t)s * 3 + f) * n + i] = sim.b.p_vo[(size_t)f * n + i];
+    }
+  }
+  for (size_t k = 0; k < (size_t)45 * n; ++k) arrP_out[k] = (double)sim.b.arr_P[k];
+  for (size_t k = 0; k < (size_t)9 * n; ++k) arrx_out[k] = (double)sim.b.arr_x[k];
+}
+}  // namespace
+
+extern "C" {
+void hostsim_default_go1(dekf_config *c) { fill_go1_defaults(c); }
+int hostsim_run(const dekf_config *cfg, int S, const double *gyro, const double *accel, const double *imu_time,
+                const double *joint_pos, const double *joint_vel, const double *foot_force, const uint8_t *vo_flag,
+                const double *vo_quat, const double *vo_time_pre, const double *vo_time_now, const double *vo_rel_p,
+                const double *quat_in, double *quat_out, double *x_out, double *vb_out, uint8_t *contact_out,
+                int32_t *vo_dbg, int32_t *ekf_dbg, double *pvo_out, int32_t *status_out, double *arrP_out,
+                double *arrx_out) {
+#define ARGS *cfg, S, gyro, accel, imu_time, joint_pos, joint_vel, foot_force, vo_flag, vo_quat, vo_time_pre, \
+             vo_time_now, vo_rel_p, quat_in, quat_out, x_out, vb_out, contact_out, vo_dbg, ekf_dbg, pvo_out,  \
+             status_out, arrP_out, arrx_out
+  const bool f32 = cfg->precision == DEKF_FP32;
+  switch (cfg->robot) {
+    case DEKF_ROBOT_GO1:
+      if (f32) run<float, Go1Model<float>>(ARGS); else run<double, Go1Model<double>>(ARGS);
+      return 0;
+    case DEKF_ROBOT_CASSIE:
+      if (f32) run<float, CassieModel<float>>(ARGS); else run<double, CassieModel<double>>(ARGS);
+      return 0;
+    case DEKF_ROBOT_POGOX:
+      if (f32) run<float, PogoXModel<float>>(ARGS); else run<double, PogoXModel<double>>(ARGS);
+      return 0;
+  }
+  return -1;
+}
+}

@@ -1,0 +1,81 @@
+"""Kernel-math check without a GPU: the per-instance kernel bodies (csrc/estimator_core.cuh, written
+__host__ __device__) are compiled for the host by tests/hostsim (a debug harness, not shipped) and
+compared with the oracle.  The real parity tests run the CUDA path through the C ABI (-m gpu)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+
+
+def _cfg(**over):
+    import pyhostsim as hs
+    from decentralized_ekf_mhe_b200.params import DekfConfig
+    lib = C.CDLL(hs.build())
+    cfg = DekfConfig()
+    lib.hostsim_default_go1(C.byref(cfg))
+    cfg.ekf_rate = 200
+    cfg.update(**over)
+    return cfg
+
+
+def test_kernel_math_matches_oracle_fp64(oracle, go1_stream_small):
+    import pyhostsim as hs
+    st = go1_stream_small
+    r = hs.run(st, _cfg())
+    ro, _, _ = oracle.run_batch(st, oracle.go1_params(), oracle.ekf_params(rate=200), nthreads=4)
+    assert np.abs(r["quat"] - ro["quat"]).max() < 1e-9           # north-star: quaternions 1e-9
+    assert np.abs(r["x"][1:, 3:6] - ro["x"][1:, 3:6]).max() < 1e-6  # north-star: velocity 1e-6 m/s
+    assert np.abs(r["x"][1:] - ro["x"][1:]).max() < 1e-8
+    assert np.array_equal(r["contact"], ro["contact"])            # contact sets bit-exact
+    assert np.array_equal(r["vo_dbg"], ro["vo_dbg"][:, :8])        # VO index logic bit-exact
+    assert np.array_equal(r["ekf_dbg"], ro["ekf_dbg"])             # EKF replay index logic bit-exact
+    assert np.abs(r["p_vo"] - ro["p_vo"]).max() < 1e-12
+
+
+def test_kernel_math_matches_oracle_fp32(oracle, go1_stream_small):
+    import pyhostsim as hs
+    st = go1_stream_small
+    r = hs.run(st, _cfg(precision=1))
+    ro, _, _ = oracle.run_batch(st, oracle.go1_params(), oracle.ekf_params(rate=200), nthreads=4)
+    assert np.abs(r["x"][1:, 3:6] - ro["x"][1:, 3:6]).max() < 1e-4  # north-star: fp32 1e-4 m/s
+    assert np.array_equal(r["contact"], ro["contact"])
+    assert np.array_equal(r["vo_dbg"], ro["vo_dbg"][:, :8])
+    assert np.array_equal(r["ekf_dbg"], ro["ekf_dbg"])
+
+
+def test_arrival_cost_matches_reference_form(oracle, go1_stream_small):
+    import pyhostsim as hs
+    st = go1_stream_small
+    r = hs.run(st, _cfg())
+    ro, _, _ = oracle.run_batch(st, oracle.go1_params(), oracle.ekf_params(rate=200), nthreads=4, want=("arrival",))
+    n = st["gyro"].shape[2]
+    for i in range(n):
+        P = np.zeros((9, 9))
+        a = r["arr_P"][:, i]
+        sym = lambda v: np.array([[v[0], v[1], v[2]], [v[1], v[3], v[4]], [v[2], v[4], v[5]]])
+        P[0:3, 0:3], P[3:6, 3:6], P[6:9, 6:9] = sym(a[0:6]), sym(a[6:12]), sym(a[12:18])
+        P[0:3, 3:6], P[0:3, 6:9], P[3:6, 6:9] = a[18:27].reshape(3, 3), a[27:36].reshape(3, 3), a[36:45].reshape(3, 3)
+        P = np.triu(P) + np.triu(P, 1).T
+        M = np.linalg.inv(P)
+        Mo = ro["M_p"][:, i].reshape(9, 9)
+        np.testing.assert_allclose(M, Mo, rtol=0, atol=1e-7 * np.abs(Mo).max())
+        np.testing.assert_allclose(-M @ r["arr_x"][:, i], ro["n_p"][:, i], rtol=0, atol=1e-7 * max(1, np.abs(ro["n_p"][:, i]).max()))
+
+
+@pytest.mark.parametrize("robot,rid,nl", [("cassie", 1, 2), ("pogox", 2, 1)])
+def test_builder_models_match_generalised_oracle(oracle, robot, rid, nl):
+    import pyhostsim as hs
+    from decentralized_ekf_mhe_b200 import synth
+    st = synth.to_numpy(synth.make_stream(4, 140, robot=robot, vo_jitter=True))
+    thr = 150.0 if robot == "cassie" else 100.0
+    r = hs.run(st, _cfg(robot=rid, num_legs=nl, contact_effort_threshold=thr, p_ib=(0.0, 0.0, 0.0)))
+    prm = oracle.go1_params(robot=rid, num_legs=nl, contact_effort_threshold=thr, p_ib=(0.0, 0.0, 0.0))
+    ro, _, _ = oracle.run_batch(st, prm, oracle.ekf_params(rate=200), nthreads=4)
+    assert np.abs(r["x"][1:, 3:6] - ro["x"][1:, 3:6]).max() < 1e-6
+    assert np.array_equal(r["contact"], ro["contact"])
+    assert np.array_equal(r["vo_dbg"], ro["vo_dbg"][:, :8])
+    assert r["contact"].any() and not r["contact"].all()
