@@ -36,7 +36,7 @@ FLOPS = dict(meas_update=657, propagate=656, propagate_vo=1496, ekf_predict=432,
 
 def algorithmic_work(N, n_vo_mean, elt=8):
     """Per instance-step algorithmic bytes / flops of each kernel (tier A = full-window re-solve)."""
-    rec = 24 * elt + 1
+    rec = 25 * elt
     solve_bytes = 2 * 54 * elt + (N + 1) * rec + 3 * 8 + 12 * 8 + 8
     solve_flops = (N + 1) * FLOPS["meas_update"] + N * FLOPS["propagate"] + n_vo_mean * (
         FLOPS["propagate_vo"] - FLOPS["propagate"]) + FLOPS["solve_epilogue"]

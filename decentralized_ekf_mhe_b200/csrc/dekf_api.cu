@@ -1,5 +1,6 @@
 // libdekf_b200.so: __global__ wrappers + the extern "C" boundary declared in include/dekf_b200.h.
 // sm_100a only.  No CPU fallback: every entry point needs a live CUDA context.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(kBlock) k_assemble(const MheConst<T> c, const 
   double q[4];
 #pragma unroll
   for (int f = 0; f < 4; ++f)
-    q[f] = (in.quat != nullptr) ? in.quat[(size_t)f * dm.n + i] : (double)b.ekf_q[(size_t)f * dm.n + i];
+    q[f] = (in.quat != nullptr) ? in.quat[(size_t)f * dm.n + i] : (double)b.ekf_q[(size_t)f * dm.ns + i];
   const int st = mhe_assemble<T, Model>(c, dm, b, in, out, Tk, i, q);
   b.status[i] = accumulate_status ? (b.status[i] | st) : st;
 }
@@ -53,6 +54,139 @@ __global__ void __launch_bounds__(kBlock) k_solve(const MheConst<T> c, const Dim
   if (status_out != nullptr) status_out[i] = st;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// window solve with TMA-staged stage tiles
+// ------------------------------------------------------------------------------------------------
+// One CTA = 128 consecutive instances.  The window ring is a 2-D tensor [NW*25 rows][ns instances]; the record of
+// stage k for the CTA's instances is the box {128 instances, 25 rows} at (i0, slot*25).  One elected thread fetches
+// each stage with ONE cp.async.bulk.tensor.2d (SASS: UTMALDG) into a kStages-deep shared-memory ring; completion
+// is signalled on a "full" mbarrier (expect_tx), consumers hand the buffer back through an "empty" mbarrier.
+// The stage record is read from shared memory at the point of use instead of being parked in registers.
+constexpr int kTile = 128;
+constexpr int kStages = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <typename T>
+struct SmemStageSource {
+  T *tiles;         // [kStages][REC_SIZE][kTile]
+  uint64_t *full;   // [kStages]
+  uint64_t *empty;  // [kStages]
+  const CUtensorMap *map;
+  int NW, i0, tid, k0, nst;
+
+  __device__ __forceinline__ void issue(int j) const {  // elected thread only
+    const int buf = j % kStages;
+    const int slot = (k0 + j) % NW;
+    mbar_expect_tx(&full[buf], (uint32_t)(REC_SIZE * kTile * sizeof(T)));
+    tma_load_2d(tiles + (size_t)buf * REC_SIZE * kTile, map, i0, slot * REC_SIZE, &full[buf]);
+  }
+  __device__ __forceinline__ void acquire(int j) const { mbar_wait(&full[j % kStages], (uint32_t)((j / kStages) & 1)); }
+  __device__ __forceinline__ void release(int j) const {
+    mbar_arrive(&empty[j % kStages]);
+    // the elected thread refills the buffer of the PREVIOUS stage (everybody has long released it) with the
+    // stage kStages-1 ahead of the current one
+    if (tid == 0 && j >= 1 && (j - 1 + kStages) < nst) {
+      mbar_wait(&empty[(j - 1) % kStages], (uint32_t)(((j - 1) / kStages) & 1));
+      issue(j - 1 + kStages);
+    }
+  }
+  __device__ __forceinline__ const T *row(int j, int f) const {
+    return tiles + ((size_t)(j % kStages) * REC_SIZE + f) * kTile + tid;
+  }
+  __device__ __forceinline__ void meas(int j, int, S3<T> &Lam, V3<T> &eta) const {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) Lam.a[f] = *row(j, REC_LAM + f);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) eta[f] = *row(j, REC_ETA + f);
+  }
+  __device__ __forceinline__ void rot(int j, int, M3<T> &R) const {
+#pragma unroll
+    for (int f = 0; f < 9; ++f) R.a[f] = *row(j, REC_R + f);
+  }
+  __device__ __forceinline__ void dyn(int j, int, V3<T> &as, V3<T> &dlt, bool &vo) const {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      as[f] = *row(j, REC_AS + f);
+      dlt[f] = *row(j, REC_DLT + f);
+    }
+    vo = *row(j, REC_FLAG) != T(0);
+  }
+};
+
+template <typename T>
+constexpr size_t solve_tma_smem_bytes() {
+  return (size_t)kStages * REC_SIZE * kTile * sizeof(T) + 2 * kStages * sizeof(uint64_t);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTile) k_solve_tma(const __grid_constant__ CUtensorMap tmap, const MheConst<T> c, const Dims dm,
+                                                     const Buffers<T> b, const Inputs in, const Outputs out, int Tk,
+                                                     int32_t *status_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemStageSource<T> src;
+  src.tiles = reinterpret_cast<T *>(smem_raw);
+  src.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * REC_SIZE * kTile * sizeof(T));
+  src.empty = src.full + kStages;
+  src.map = &tmap;
+  src.NW = dm.NW;
+  src.i0 = blockIdx.x * kTile;
+  src.tid = threadIdx.x;
+  src.k0 = (Tk < dm.N) ? 0 : Tk - dm.N;
+  src.nst = Tk - src.k0 + 1;
+  const int active = min(kTile, dm.n - src.i0);  // consumers in this CTA (thread 0 is always one of them)
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&src.full[s], 1);
+      mbar_init(&src.empty[s], (uint32_t)active);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int pre = src.nst < kStages ? src.nst : kStages;
+    for (int j = 0; j < pre; ++j) src.issue(j);
+  }
+  const int i = src.i0 + threadIdx.x;
+  if (i >= dm.n) return;
+  int st = b.status[i];
+  st |= mhe_solve<T>(c, dm, b, in, out, Tk, i, src);
+  b.status[i] = st;
+  if (status_out != nullptr) status_out[i] = st;
+}
+
 // whole tick in one launch (small batches: launch latency dominates)
 template <typename T, typename Model>
 __global__ void __launch_bounds__(kBlock) k_fused(const EkfConst<T> ec, const MheConst<T> mc, const Dims dm, const Buffers<T> b,
@@ -62,7 +196,7 @@ __global__ void __launch_bounds__(kBlock) k_fused(const EkfConst<T> ec, const Mh
   int st = ekf_tick<T>(ec, dm, b, in, out, k, i);
   double q[4];
 #pragma unroll
-  for (int f = 0; f < 4; ++f) q[f] = (double)b.ekf_q[(size_t)f * dm.n + i];
+  for (int f = 0; f < 4; ++f) q[f] = (double)b.ekf_q[(size_t)f * dm.ns + i];
   st |= mhe_assemble<T, Model>(mc, dm, b, in, out, Tk, i, q);
   if (Tk >= 1) st |= mhe_solve<T>(mc, dm, b, in, out, Tk, i);
   b.status[i] = st;
@@ -73,7 +207,7 @@ template <typename T>
 __global__ void k_init_state(const EkfConst<T> ec, const MheConst<T> mc, const Dims dm, const Buffers<T> b) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
-  const int n = dm.n;
+  const int n = dm.ns;
 #pragma unroll
   for (int f = 0; f < 4; ++f) b.ekf_q[(size_t)f * n + i] = ec.q0[f];
 #pragma unroll
@@ -101,9 +235,9 @@ template <typename T>
 __global__ void k_get_arrival(const Dims dm, const Buffers<T> b, double *Pout, double *xout, int as_information) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
-  const int n = dm.n;
+  const int n = dm.n, ns = dm.ns;
   Cov9<T> P;
-  load_cov(b.arr_P, n, i, P);
+  load_cov(b.arr_P, ns, i, P);
   double A[81], x[9];
   for (int r = 0; r < 3; ++r)
     for (int c = 0; c < 3; ++c) {
@@ -117,7 +251,7 @@ __global__ void k_get_arrival(const Dims dm, const Buffers<T> b, double *Pout, d
       A[(3 + r) * 9 + 6 + c] = (double)P.vb(r, c);
       A[(6 + c) * 9 + 3 + r] = (double)P.vb(r, c);
     }
-  for (int f = 0; f < 9; ++f) x[f] = (double)b.arr_x[(size_t)f * n + i];
+  for (int f = 0; f < 9; ++f) x[f] = (double)b.arr_x[(size_t)f * ns + i];
   if (as_information) {
     // Cholesky A = L L', M = A^-1 column by column, n_p = -M x
     double L[81];
@@ -162,15 +296,15 @@ template <typename T>
 __global__ void k_get_misc(const Dims dm, const Buffers<T> b, int Tk, double *p_vo, double *R_sb, double *ekfP) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
-  const int n = dm.n;
+  const int n = dm.n, ns = dm.ns;
   if (p_vo != nullptr)
-    for (int f = 0; f < 3; ++f) p_vo[(size_t)f * n + i] = b.p_vo[(size_t)f * n + i];
+    for (int f = 0; f < 3; ++f) p_vo[(size_t)f * n + i] = b.p_vo[(size_t)f * ns + i];
   if (R_sb != nullptr) {
-    const T *rec = b.win + (size_t)(Tk % dm.NW) * REC_SIZE * n + i;
-    for (int f = 0; f < 9; ++f) R_sb[(size_t)f * n + i] = (double)rec[(size_t)(REC_R + f) * n];
+    const T *rec = b.win + (size_t)(Tk % dm.NW) * REC_SIZE * ns + i;
+    for (int f = 0; f < 9; ++f) R_sb[(size_t)f * n + i] = (double)rec[(size_t)(REC_R + f) * ns];
   }
   if (ekfP != nullptr)
-    for (int f = 0; f < 16; ++f) ekfP[(size_t)f * n + i] = (double)b.ekf_P[(size_t)f * n + i];
+    for (int f = 0; f < 16; ++f) ekfP[(size_t)f * n + i] = (double)b.ekf_P[(size_t)f * ns + i];
 }
 
 template <typename T>
@@ -179,7 +313,7 @@ __global__ void k_vo_count(const Dims dm, const Buffers<T> b, int Tk, int32_t *c
   if (i >= dm.n) return;
   int c = 0;
   const int k0 = (Tk >= dm.N) ? Tk - dm.N + 1 : 0;
-  for (int k = k0; k < Tk; ++k) c += b.win_flag[(size_t)(k % dm.NW) * dm.n + i] != 0;
+  for (int k = k0; k < Tk; ++k) c += b.win[((size_t)(k % dm.NW) * REC_SIZE + REC_FLAG) * dm.ns + i] != T(0);
   count[i] = c;
 }
 
@@ -218,6 +352,9 @@ struct dekf_handle {
   int next_T = 0;   // next MHE discrete time expected
   int64_t launches = 0;
   size_t extra_bytes = 0;
+  CUtensorMap tmap;      // window ring as a 2-D tensor [NW*25][ns] (TMA box = one stage record of one tile)
+  int fused_max = 4096;  // batches up to this size take the single fused launch (DEKF_FUSED_MAX_N at create)
+  bool use_tma = true;   // window solve with TMA-staged stage tiles (DEKF_NO_TMA=1 at create: plain global loads)
   // optional per-kernel timing
   bool prof = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -263,7 +400,6 @@ size_t carve(Buffers<T> &b, const Dims &dm, char *base) {
   b.arr_P = (T *)take(s.arr_P, sizeof(T));
   b.arr_x = (T *)take(s.arr_x, sizeof(T));
   b.win = (T *)take(s.win, sizeof(T));
-  b.win_flag = (uint8_t *)take(s.win_flag, 1);
   b.hist_time = (double *)take(s.hist_time, sizeof(double));
   b.hist_quat = (double *)take(s.hist_quat, sizeof(double));
   b.wp = (double *)take(s.wp, sizeof(double));
@@ -459,6 +595,16 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     delete h;
     return DEKF_ENODEV;
   }
+  if (const char *e = std::getenv("DEKF_FUSED_MAX_N")) h->fused_max = std::atoi(e);
+  if (const char *e = std::getenv("DEKF_NO_TMA")) h->use_tma = std::atoi(e) == 0;
+  ce = cudaFuncSetAttribute(k_solve_tma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_tma_smem_bytes<double>());
+  if (ce == cudaSuccess)
+    ce = cudaFuncSetAttribute(k_solve_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_tma_smem_bytes<float>());
+  if (ce != cudaSuccess) {
+    std::fprintf(stderr, "dekf_create: cudaFuncSetAttribute(k_solve_tma): %s\n", cudaGetErrorString(ce));
+    delete h;
+    return DEKF_ECUDA;
+  }
   h->ec64 = make_ekf_const<double>(*cfg);
   h->mc64 = make_mhe_const<double>(*cfg);
   h->ec32 = make_ekf_const<float>(*cfg);
@@ -478,6 +624,34 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     carve<float>(h->b32, h->dm, (char *)h->slab);
   else
     carve<double>(h->b64, h->dm, (char *)h->slab);
+  if (h->use_tma) {
+    // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (ce != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+      std::fprintf(stderr, "dekf_create: cuTensorMapEncodeTiled is not available from this driver\n");
+      dekf_destroy(h);
+      return DEKF_ECUDA;
+    }
+    const size_t elt = h->f32 ? sizeof(float) : sizeof(double);
+    void *base = h->f32 ? (void *)h->b32.win : (void *)h->b64.win;
+    const cuuint64_t gdim[2] = {(cuuint64_t)h->dm.ns, (cuuint64_t)h->dm.NW * REC_SIZE};
+    const cuuint64_t gstride[1] = {(cuuint64_t)h->dm.ns * elt};
+    const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)REC_SIZE};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = ((encode_fn)fn)(&h->tmap, h->f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim,
+                                  gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      std::fprintf(stderr, "dekf_create: cuTensorMapEncodeTiled failed (%d)\n", (int)cr);
+      dekf_destroy(h);
+      return DEKF_ECUDA;
+    }
+  }
   if ((ce = cudaMalloc((void **)&h->stage_in, in_doubles * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc(stage_in)", ce);
   if ((ce = cudaMalloc((void **)&h->stage_flag, n)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
   if ((ce = cudaMalloc((void **)&h->stage_out, out_doubles * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
@@ -583,16 +757,24 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
   const Outputs dout = to_outputs(h, out);
   int32_t *st = out ? out->status : nullptr;
   int rc;
+  const bool tma = h->use_tma && T_ >= 1;
+  const int tiles = h->dm.ns / kTile;
   if (h->f32) {
     rc = do_assemble<float>(h, h->mc32, h->b32, di, dout, T_, acc);
     if (rc) return fail(h, rc, "assemble");
     ProfScope ps(h, 2);
-    k_solve<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
+    if (tma)
+      k_solve_tma<float><<<tiles, kTile, solve_tma_smem_bytes<float>(), h->stream>>>(h->tmap, h->mc32, h->dm, h->b32, di, dout, T_, st);
+    else
+      k_solve<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
   } else {
     rc = do_assemble<double>(h, h->mc64, h->b64, di, dout, T_, acc);
     if (rc) return fail(h, rc, "assemble");
     ProfScope ps(h, 2);
-    k_solve<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
+    if (tma)
+      k_solve_tma<double><<<tiles, kTile, solve_tma_smem_bytes<double>(), h->stream>>>(h->tmap, h->mc64, h->dm, h->b64, di, dout, T_, st);
+    else
+      k_solve<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
   }
   h->launches++;
   CK(cudaGetLastError());
@@ -619,11 +801,7 @@ int dekf_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outp
   CK(cudaSetDevice(h->cfg.device));
   dekf_inputs in2 = *in;
   in2.quat = nullptr;  // lock-step: the MHE consumes this tick's EKF quaternion
-  static const int fused_max = [] {
-    const char *e = std::getenv("DEKF_FUSED_MAX_N");
-    return e ? std::atoi(e) : 4096;
-  }();
-  if (h->dm.n <= fused_max) {
+  if (h->dm.n <= h->fused_max) {
     const Inputs di = to_inputs(&in2);
     const Outputs dout = to_outputs(h, out);
     int32_t *st = out ? out->status : nullptr;

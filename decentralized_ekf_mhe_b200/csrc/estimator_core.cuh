@@ -33,7 +33,8 @@ enum {
   REC_LAM = 12,  // 6  Lambda = sum_i Q_meas,i (symmetric)          } sufficient statistic of the
   REC_ETA = 18,  // 3  eta    = sum_i Q_meas,i b_meas,i              } leg-odometry rows (H_i=[0 I 0])
   REC_DLT = 21,  // 3  VO displacement node_{k+1}-node_k (valid iff flag)
-  REC_SIZE = 24
+  REC_FLAG = 24, // 1  VO row of the stage is an equality (1) or still the free placeholder (0)
+  REC_SIZE = 25  //    one record = one [25][128] TMA box per 128-instance tile
 };
 enum { EKF_HIST_FIELDS = 26 };  // gyro3 accel3 q4 P16 (time kept separately in double)
 
@@ -72,7 +73,8 @@ struct MheConst {
 };
 
 struct Dims {
-  int n;   // instance stride of every array
+  int n;   // number of instances == stride of every caller-owned (input / output) array
+  int ns;  // stride of the handle-owned state arrays: n rounded up to the 128-instance tile of the TMA path
   int N;   // horizon
   int NW;  // window ring slots  = N + 1
   int HR;  // MHE history ring   = 4N + 1   (DecentralEst.cpp:963)
@@ -89,8 +91,7 @@ struct Buffers {
   // MHE state
   T *arr_P;               // [45][n] arrival covariance (pp6 vv6 bb6 pv9 pb9 vb9)
   T *arr_x;               // [9][n]  arrival mean
-  T *win;                 // [NW][24][n]
-  uint8_t *win_flag;      // [NW][n]
+  T *win;                 // [NW][25][ns]
   double *hist_time;      // [HR][n]
   double *hist_quat;      // [HR][4][n]
   double *wp;             // [12][n] last 4 accumulated-VO way points
@@ -339,13 +340,13 @@ DEKF_HD int ring_upper_bound(const double *times, int n, int i, int first, int s
 template <typename T>
 DEKF_HD int ekf_tick(const EkfConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
                      int k, int i) {
-  const int n = dm.n, D = dm.D;
+  const int n = dm.n, ns = dm.ns, D = dm.D;
   int status = 0;
   EkfState<T> s;
 #pragma unroll
-  for (int f = 0; f < 4; ++f) s.q[f] = b.ekf_q[(size_t)f * n + i];
+  for (int f = 0; f < 4; ++f) s.q[f] = b.ekf_q[(size_t)f * ns + i];
 #pragma unroll
-  for (int f = 0; f < 16; ++f) s.P[f] = b.ekf_P[(size_t)f * n + i];
+  for (int f = 0; f < 16; ++f) s.P[f] = b.ekf_P[(size_t)f * ns + i];
   T w[3], a[3];
 #pragma unroll
   for (int f = 0; f < 3; ++f) {
@@ -355,17 +356,17 @@ DEKF_HD int ekf_tick(const EkfConst<T> &c, const Dims &dm, const Buffers<T> &b, 
   const double t_imu = in.imu_time[i];
   // push (state BEFORE this tick's update), :158-163
   {
-    T *h = b.ekf_hist + (size_t)(k % D) * EKF_HIST_FIELDS * n + i;
+    T *h = b.ekf_hist + (size_t)(k % D) * EKF_HIST_FIELDS * ns + i;
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
-      h[(size_t)f * n] = w[f];
-      h[(size_t)(3 + f) * n] = a[f];
+      h[(size_t)f * ns] = w[f];
+      h[(size_t)(3 + f) * ns] = a[f];
     }
 #pragma unroll
-    for (int f = 0; f < 4; ++f) h[(size_t)(6 + f) * n] = s.q[f];
+    for (int f = 0; f < 4; ++f) h[(size_t)(6 + f) * ns] = s.q[f];
 #pragma unroll
-    for (int f = 0; f < 16; ++f) h[(size_t)(10 + f) * n] = s.P[f];
-    b.ekf_hist_time[(size_t)(k % D) * n + i] = t_imu;
+    for (int f = 0; f < 16; ++f) h[(size_t)(10 + f) * ns] = s.P[f];
+    b.ekf_hist_time[(size_t)(k % D) * ns + i] = t_imu;
   }
   int dbg_cur = -2, dbg_idx = -2, dbg_nr = -2;
   if (in.vo_flag != nullptr && in.vo_flag[i]) {
@@ -375,7 +376,7 @@ DEKF_HD int ekf_tick(const EkfConst<T> &c, const Dims &dm, const Buffers<T> &b, 
     for (int f = 0; f < 4; ++f) qv[f] = (T)in.vo_quat[(size_t)f * n + i];
     const int size = (k + 1 < D) ? (k + 1) : D;
     const int first = k + 1 - size;  // discrete time of logical index 0
-    const int ub = ring_upper_bound(b.ekf_hist_time, n, i, first, size, D, vt);
+    const int ub = ring_upper_bound(b.ekf_hist_time, ns, i, first, size, D, vt);
     dbg_cur = k;
     dbg_nr = 0;
     if (ub == 0) {
@@ -386,20 +387,20 @@ DEKF_HD int ekf_tick(const EkfConst<T> &c, const Dims &dm, const Buffers<T> &b, 
       const int rel = k - idx;         // :187
       dbg_idx = idx;
       {
-        const T *h = b.ekf_hist + (size_t)(idx % D) * EKF_HIST_FIELDS * n + i;
+        const T *h = b.ekf_hist + (size_t)(idx % D) * EKF_HIST_FIELDS * ns + i;
 #pragma unroll
-        for (int f = 0; f < 4; ++f) s.q[f] = h[(size_t)(6 + f) * n];
+        for (int f = 0; f < 4; ++f) s.q[f] = h[(size_t)(6 + f) * ns];
 #pragma unroll
-        for (int f = 0; f < 16; ++f) s.P[f] = h[(size_t)(10 + f) * n];
+        for (int f = 0; f < 16; ++f) s.P[f] = h[(size_t)(10 + f) * ns];
       }
       if (rel <= 1) status |= ST_EKF_VO_NO_REPLAY;
       for (int j = 0; j < rel - 1; ++j) {  // :191
-        const T *h = b.ekf_hist + (size_t)((idx + j) % D) * EKF_HIST_FIELDS * n + i;
+        const T *h = b.ekf_hist + (size_t)((idx + j) % D) * EKF_HIST_FIELDS * ns + i;
         T wj[3], aj[3];
 #pragma unroll
         for (int f = 0; f < 3; ++f) {
-          wj[f] = h[(size_t)f * n];
-          aj[f] = h[(size_t)(3 + f) * n];
+          wj[f] = h[(size_t)f * ns];
+          aj[f] = h[(size_t)(3 + f) * ns];
         }
         ekf_predict(c, s, wj);
         ekf_correct(c, s, aj);
@@ -411,9 +412,9 @@ DEKF_HD int ekf_tick(const EkfConst<T> &c, const Dims &dm, const Buffers<T> &b, 
   ekf_predict(c, s, w);  // :82
   ekf_correct(c, s, a);  // :83
 #pragma unroll
-  for (int f = 0; f < 4; ++f) b.ekf_q[(size_t)f * n + i] = s.q[f];
+  for (int f = 0; f < 4; ++f) b.ekf_q[(size_t)f * ns + i] = s.q[f];
 #pragma unroll
-  for (int f = 0; f < 16; ++f) b.ekf_P[(size_t)f * n + i] = s.P[f];
+  for (int f = 0; f < 16; ++f) b.ekf_P[(size_t)f * ns + i] = s.P[f];
   if (out.quat != nullptr) {
 #pragma unroll
     for (int f = 0; f < 4; ++f) out.quat[(size_t)f * n + i] = (double)s.q[f];
@@ -449,7 +450,7 @@ template <typename T, typename Model>
 DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in,
                          const Outputs &out, int Tk, int i, const double qd[4]) {
   constexpr int NL = Model::NLEG, NJ = Model::NJ;
-  const int n = dm.n, N = dm.N, NW = dm.NW, HR = dm.HR;
+  const int n = dm.n, ns = dm.ns, N = dm.N, NW = dm.NW, HR = dm.HR;
   int status = 0;
 
   // ---- VO synchronisation against the history BEFORE this sample is pushed (:883-945)
@@ -465,52 +466,52 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
     // stack is empty: the message stays latched in robot_store (vo_new_ remains true)
     b.pend_flag[i] = (uint8_t)vo_new;
     if (vo_new) {
-      b.pend[(size_t)0 * n + i] = t_pre;
-      b.pend[(size_t)1 * n + i] = t_now;
+      b.pend[(size_t)0 * ns + i] = t_pre;
+      b.pend[(size_t)1 * ns + i] = t_now;
 #pragma unroll
-      for (int f = 0; f < 3; ++f) b.pend[(size_t)(2 + f) * n + i] = relp[f];
+      for (int f = 0; f < 3; ++f) b.pend[(size_t)(2 + f) * ns + i] = relp[f];
     }
     vo_new = 0;
   } else if (Tk == 1 && !vo_new && b.pend_flag[i]) {
     vo_new = 1;
-    t_pre = b.pend[(size_t)0 * n + i];
-    t_now = b.pend[(size_t)1 * n + i];
+    t_pre = b.pend[(size_t)0 * ns + i];
+    t_now = b.pend[(size_t)1 * ns + i];
 #pragma unroll
-    for (int f = 0; f < 3; ++f) relp[f] = b.pend[(size_t)(2 + f) * n + i];
+    for (int f = 0; f < 3; ++f) relp[f] = b.pend[(size_t)(2 + f) * ns + i];
   }
   int dbg[8] = {-2, -2, -2, -2, -2, -2, -2, -2};
   if (vo_new) {
     const int size = (Tk < HR) ? Tk : HR;  // samples held: discrete times Tk-size .. Tk-1
     const int first = Tk - size;
     dbg[0] = 0;
-    const int ub = ring_upper_bound(b.hist_time, n, i, first, size, HR, t_pre);  // :895
+    const int ub = ring_upper_bound(b.hist_time, ns, i, first, size, HR, t_pre);  // :895
     if (ub == 0) {
       status |= ST_MHE_VO_DROPPED;  // :898-904
       dbg[1] = -1;
     } else {
       const int i_pre = ub - 1;  // :907
-      const int i_now = ring_upper_bound(b.hist_time, n, i, first, size, HR, t_now) - 1;  // :911-913
+      const int i_now = ring_upper_bound(b.hist_time, ns, i, first, size, HR, t_now) - 1;  // :911-913
       // R_vo_sb_pre_ = R_input_rotation_stack_[i_pre]  (:909)
-      const double *hq = b.hist_quat + (size_t)((first + i_pre) % HR) * 4 * n + i;
-      const M3<double> Rp = quat_to_rot<double>(hq[0], hq[(size_t)n], hq[(size_t)2 * n], hq[(size_t)3 * n]);
+      const double *hq = b.hist_quat + (size_t)((first + i_pre) % HR) * 4 * ns + i;
+      const M3<double> Rp = quat_to_rot<double>(hq[0], hq[(size_t)ns], hq[(size_t)2 * ns], hq[(size_t)3 * ns]);
       double pv[3];
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
-        pv[f] = b.p_vo[(size_t)f * n + i] + (Rp(f, 0) * relp[0] + Rp(f, 1) * relp[1] + Rp(f, 2) * relp[2]);  // :915
-        b.p_vo[(size_t)f * n + i] = pv[f];
+        pv[f] = b.p_vo[(size_t)f * ns + i] + (Rp(f, 0) * relp[0] + Rp(f, 1) * relp[1] + Rp(f, 2) * relp[2]);  // :915
+        b.p_vo[(size_t)f * ns + i] = pv[f];
       }
       const int w0 = size - ((N < Tk) ? N : Tk);  // :917
       const int i0 = (w0 > i_pre) ? w0 : i_pre;   // :918
-      const double t_start = b.hist_time[(size_t)((first + i0) % HR) * n + i];  // :919
+      const double t_start = b.hist_time[(size_t)((first + i0) % HR) * ns + i];  // :919
       const int disc0 = first + i0;                                             // :920
       // add_way_point (Bezier_simple.cpp:12-27): keep the last four
       int cnt = b.wp_count[i];
       double wp[4][3], wt[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        wt[p] = b.wp_time[(size_t)p * n + i];
+        wt[p] = b.wp_time[(size_t)p * ns + i];
 #pragma unroll
-        for (int f = 0; f < 3; ++f) wp[p][f] = b.wp[(size_t)(p * 3 + f) * n + i];
+        for (int f = 0; f < 3; ++f) wp[p][f] = b.wp[(size_t)(p * 3 + f) * ns + i];
       }
       if (cnt < 4) {
 #pragma unroll
@@ -535,9 +536,9 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
       b.wp_count[i] = cnt;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        b.wp_time[(size_t)p * n + i] = wt[p];
+        b.wp_time[(size_t)p * ns + i] = wt[p];
 #pragma unroll
-        for (int f = 0; f < 3; ++f) b.wp[(size_t)(p * 3 + f) * n + i] = wp[p][f];
+        for (int f = 0; f < 3; ++f) b.wp[(size_t)(p * 3 + f) * ns + i] = wp[p][f];
       }
       dbg[0] = 1;
       dbg[1] = i_pre;
@@ -561,13 +562,13 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
           double node[3];
           bezier_point(node, u0 + u_inc * (double)j, wp[0], wp[1], wp[2], wp[3]);
           const int d = disc0 + j - 1;  // VO_measurement_{disc0 + (j-1)}  (:1004)
-          T *rec = b.win + (size_t)(d % NW) * REC_SIZE * n + i;
+          T *rec = b.win + (size_t)(d % NW) * REC_SIZE * ns + i;
 #pragma unroll
           for (int f = 0; f < 3; ++f) {
-            rec[(size_t)(REC_DLT + f) * n] = (T)(node[f] - node_pre[f]);
+            rec[(size_t)(REC_DLT + f) * ns] = (T)(node[f] - node_pre[f]);
             node_pre[f] = node[f];
           }
-          b.win_flag[(size_t)(d % NW) * n + i] = 1;
+          rec[(size_t)REC_FLAG * ns] = T(1);
         }
       }
     }
@@ -687,22 +688,22 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
   }
 
   // ---- push (:949-975): history ring + stage record of discrete time Tk
-  b.hist_time[(size_t)(Tk % HR) * n + i] = in.imu_time[i];
+  b.hist_time[(size_t)(Tk % HR) * ns + i] = in.imu_time[i];
 #pragma unroll
-  for (int f = 0; f < 4; ++f) b.hist_quat[((size_t)(Tk % HR) * 4 + f) * n + i] = qd[f];
+  for (int f = 0; f < 4; ++f) b.hist_quat[((size_t)(Tk % HR) * 4 + f) * ns + i] = qd[f];
   {
-    T *rec = b.win + (size_t)(Tk % NW) * REC_SIZE * n + i;
+    T *rec = b.win + (size_t)(Tk % NW) * REC_SIZE * ns + i;
 #pragma unroll
-    for (int f = 0; f < 9; ++f) rec[(size_t)(REC_R + f) * n] = R.a[f];
+    for (int f = 0; f < 9; ++f) rec[(size_t)(REC_R + f) * ns] = R.a[f];
 #pragma unroll
-    for (int f = 0; f < 3; ++f) rec[(size_t)(REC_AS + f) * n] = as[f];
+    for (int f = 0; f < 3; ++f) rec[(size_t)(REC_AS + f) * ns] = as[f];
 #pragma unroll
-    for (int f = 0; f < 6; ++f) rec[(size_t)(REC_LAM + f) * n] = Lam.a[f];
+    for (int f = 0; f < 6; ++f) rec[(size_t)(REC_LAM + f) * ns] = Lam.a[f];
 #pragma unroll
-    for (int f = 0; f < 3; ++f) rec[(size_t)(REC_ETA + f) * n] = eta[f];
+    for (int f = 0; f < 3; ++f) rec[(size_t)(REC_ETA + f) * ns] = eta[f];
 #pragma unroll
-    for (int f = 0; f < 3; ++f) rec[(size_t)(REC_DLT + f) * n] = T(0);
-    b.win_flag[(size_t)(Tk % NW) * n + i] = 0;  // VO row of stage Tk starts as a free placeholder (:474-481)
+    for (int f = 0; f < 3; ++f) rec[(size_t)(REC_DLT + f) * ns] = T(0);
+    rec[(size_t)REC_FLAG * ns] = T(0);  // VO row of stage Tk starts as a free placeholder (:474-481)
   }
   return status;
 }
@@ -912,30 +913,51 @@ struct StageRec {
   bool vo;
 };
 
+// Stage records straight from the HBM window ring (fused small-batch kernel, host debug harness).
 template <typename T>
-DEKF_HD void load_stage(const Dims &dm, const Buffers<T> &b, int k, int i, StageRec<T> &s) {
-  const int n = dm.n;
-  const T *rec = b.win + (size_t)(k % dm.NW) * REC_SIZE * n + i;
+struct GlobalStageSource {
+  const Dims &dm;
+  const Buffers<T> &b;
+  int i;
+  DEKF_HD GlobalStageSource(const Dims &dm_, const Buffers<T> &b_, int i_) : dm(dm_), b(b_), i(i_) {}
+  DEKF_HD void acquire(int /*ordinal*/) const {}
+  DEKF_HD void release(int /*ordinal*/) const {}
+  DEKF_HD const T *rec(int k) const { return b.win + (size_t)(k % dm.NW) * REC_SIZE * dm.ns + i; }
+  DEKF_HD void meas(int, int k, S3<T> &Lam, V3<T> &eta) const {
+    const T *r = rec(k);
+    const size_t ns = (size_t)dm.ns;
 #pragma unroll
-  for (int f = 0; f < 9; ++f) s.R.a[f] = rec[(size_t)(REC_R + f) * n];
+    for (int f = 0; f < 6; ++f) Lam.a[f] = r[(REC_LAM + f) * ns];
 #pragma unroll
-  for (int f = 0; f < 3; ++f) s.as[f] = rec[(size_t)(REC_AS + f) * n];
+    for (int f = 0; f < 3; ++f) eta[f] = r[(REC_ETA + f) * ns];
+  }
+  DEKF_HD void rot(int, int k, M3<T> &R) const {
+    const T *r = rec(k);
+    const size_t ns = (size_t)dm.ns;
 #pragma unroll
-  for (int f = 0; f < 6; ++f) s.Lam.a[f] = rec[(size_t)(REC_LAM + f) * n];
+    for (int f = 0; f < 9; ++f) R.a[f] = r[(REC_R + f) * ns];
+  }
+  DEKF_HD void dyn(int, int k, V3<T> &as, V3<T> &dlt, bool &vo) const {
+    const T *r = rec(k);
+    const size_t ns = (size_t)dm.ns;
 #pragma unroll
-  for (int f = 0; f < 3; ++f) s.eta[f] = rec[(size_t)(REC_ETA + f) * n];
-#pragma unroll
-  for (int f = 0; f < 3; ++f) s.dlt[f] = rec[(size_t)(REC_DLT + f) * n];
-  s.vo = b.win_flag[(size_t)(k % dm.NW) * n + i] != 0;
-}
+    for (int f = 0; f < 3; ++f) {
+      as[f] = r[(REC_AS + f) * ns];
+      dlt[f] = r[(REC_DLT + f) * ns];
+    }
+    vo = r[REC_FLAG * ns] != T(0);
+  }
+};
 
 // update(T) after UpdateMHE/UpdateVOConstraints: marginalizeQP(T-N) if T >= N, solve, read x_T,
 // v_MHE_b (DecentralEst.cpp:167-185).  Tier A: the whole window is re-swept every step, like the
-// reference re-solves the whole QP every step.
-template <typename T>
+// reference re-solves the whole QP every step.  `src` hands out the stage records: ordinal j = 0.. is
+// the position in the sweep (stage k0 + j), acquire/release bracket the use of one record (the TMA
+// path maps them onto the full/empty mbarriers of its shared-memory ring).
+template <typename T, typename Source>
 DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
-                      int Tk, int i) {
-  const int n = dm.n, N = dm.N;
+                      int Tk, int i, Source &src) {
+  const int n = dm.n, ns = dm.ns, N = dm.N;
   Cov9<T> P;
   Vec9<T> x;
   int k0;
@@ -957,39 +979,61 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
     x.p = x.v = x.b = v3<T>(T(0), T(0), T(0));
     k0 = 0;
   } else {
-    load_cov(b.arr_P, n, i, P);
+    load_cov(b.arr_P, ns, i, P);
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
-      x.p[f] = b.arr_x[(size_t)f * n + i];
-      x.v[f] = b.arr_x[(size_t)(3 + f) * n + i];
-      x.b[f] = b.arr_x[(size_t)(6 + f) * n + i];
+      x.p[f] = b.arr_x[(size_t)f * ns + i];
+      x.v[f] = b.arr_x[(size_t)(3 + f) * ns + i];
+      x.b[f] = b.arr_x[(size_t)(6 + f) * ns + i];
     }
     k0 = Tk - N;
   }
-  StageRec<T> s;
   for (int k = k0; k < Tk; ++k) {
-    load_stage(dm, b, k, i, s);
-    meas_update(P, x, s.Lam, s.eta);
-    propagate(c, P, x, s.R, s.as, s.vo, s.dlt);
+    const int j = k - k0;
+    src.acquire(j);
+    {
+      S3<T> Lam;
+      V3<T> eta;
+      src.meas(j, k, Lam, eta);
+      meas_update(P, x, Lam, eta);
+    }
+    {
+      M3<T> R;
+      V3<T> as, dlt;
+      bool vo;
+      src.rot(j, k, R);
+      src.dyn(j, k, as, dlt, vo);
+      src.release(j);
+      propagate(c, P, x, R, as, vo, dlt);
+    }
     if (k == Tk - N) {
       // marginalizeQP(T-N): the arrival cost moves to x_{T-N+1} (MheSrb.cpp:475-713)
-      store_cov(b.arr_P, n, i, P);
+      store_cov(b.arr_P, ns, i, P);
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
-        b.arr_x[(size_t)f * n + i] = x.p[f];
-        b.arr_x[(size_t)(3 + f) * n + i] = x.v[f];
-        b.arr_x[(size_t)(6 + f) * n + i] = x.b[f];
+        b.arr_x[(size_t)f * ns + i] = x.p[f];
+        b.arr_x[(size_t)(3 + f) * ns + i] = x.v[f];
+        b.arr_x[(size_t)(6 + f) * ns + i] = x.b[f];
       }
     }
   }
-  load_stage(dm, b, Tk, i, s);
-  meas_update(P, x, s.Lam, s.eta);
+  M3<T> RT;
+  {
+    const int j = Tk - k0;
+    src.acquire(j);
+    S3<T> Lam;
+    V3<T> eta;
+    src.meas(j, Tk, Lam, eta);
+    src.rot(j, Tk, RT);
+    src.release(j);
+    meas_update(P, x, Lam, eta);
+  }
   // getsolution(T) + v_MHE_b = R_sb (v + omega x p_imu_2_opti) (DecentralEst.cpp:181-185)
   V3<T> om;
 #pragma unroll
   for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
   const V3<T> lever = v3<T>(T(0.016041), T(0.089061), T(0.0579875));
-  const V3<T> vb = mul(s.R, add(x.v, cross(om, lever)));
+  const V3<T> vb = mul(RT, add(x.v, cross(om, lever)));
   int status = 0;
   const T chk = x.p[0] + x.p[1] + x.p[2] + x.v[0] + x.v[1] + x.v[2] + x.b[0] + x.b[1] + x.b[2];
   if (!(chk == chk) || !(chk - chk == T(0))) status |= ST_NONFINITE;
@@ -1006,6 +1050,13 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
     for (int f = 0; f < 3; ++f) out.v_body[(size_t)f * n + i] = (double)vb[f];
   }
   return status;
+}
+
+template <typename T>
+DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
+                      int Tk, int i) {
+  GlobalStageSource<T> src(dm, b, i);
+  return mhe_solve<T>(c, dm, b, in, out, Tk, i, src);
 }
 
 }  // namespace dekf

@@ -78,6 +78,7 @@ inline int robot_nj(int robot) { return robot == DEKF_ROBOT_CASSIE ? 5 : 3; }
 inline Dims make_dims(const dekf_config &c) {
   Dims d;
   d.n = c.n_instances;
+  d.ns = (c.n_instances + 127) / 128 * 128;
   d.N = c.N;
   d.NW = c.N + 1;
   d.HR = 4 * c.N + 1;
@@ -137,12 +138,12 @@ inline MheConst<T> make_mhe_const(const dekf_config &c) {
 
 // fields per instance of every state array, in units of elements
 struct StateSizes {
-  size_t ekf_q, ekf_P, ekf_hist, ekf_hist_time, arr_P, arr_x, win, win_flag, hist_time, hist_quat, wp, wp_time,
+  size_t ekf_q, ekf_P, ekf_hist, ekf_hist_time, arr_P, arr_x, win, hist_time, hist_quat, wp, wp_time,
       wp_count, p_vo, pend_flag, pend, status;
 };
 inline StateSizes state_sizes(const Dims &d) {
   StateSizes s;
-  const size_t n = (size_t)d.n;
+  const size_t n = (size_t)d.ns;
   s.ekf_q = 4 * n;
   s.ekf_P = 16 * n;
   s.ekf_hist = (size_t)d.D * EKF_HIST_FIELDS * n;
@@ -150,7 +151,6 @@ inline StateSizes state_sizes(const Dims &d) {
   s.arr_P = 45 * n;
   s.arr_x = 9 * n;
   s.win = (size_t)d.NW * REC_SIZE * n;
-  s.win_flag = (size_t)d.NW * n;
   s.hist_time = (size_t)d.HR * n;
   s.hist_quat = (size_t)d.HR * 4 * n;
   s.wp = 12 * n;

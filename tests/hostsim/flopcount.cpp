@@ -93,7 +93,6 @@ int main() {
   Buffers<CT> b;
   std::memset(&b, 0, sizeof(b));
   b.win = win.data();
-  b.win_flag = fl.data();
   b.hist_time = d.data();
   b.hist_quat = d.data() + 128;
   b.wp = d.data() + 1024;

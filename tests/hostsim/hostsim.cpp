@@ -40,7 +40,6 @@ struct Sim {
     b.arr_P = alloc<T>(s.arr_P);
     b.arr_x = alloc<T>(s.arr_x);
     b.win = alloc<T>(s.win);
-    b.win_flag = alloc<uint8_t>(s.win_flag);
     b.hist_time = alloc<double>(s.hist_time);
     b.hist_quat = alloc<double>(s.hist_quat);
     b.wp = alloc<double>(s.wp);
@@ -50,8 +49,8 @@ struct Sim {
     b.pend_flag = alloc<uint8_t>(s.pend_flag);
     b.pend = alloc<double>(s.pend);
     b.status = alloc<int32_t>(s.status);
-    const int n = dm.n;
-    for (int i = 0; i < n; ++i) {
+    const int n = dm.ns;
+    for (int i = 0; i < dm.n; ++i) {
       for (int f = 0; f < 4; ++f) {
         b.ekf_q[(size_t)f * n + i] = ec.q0[f];
         b.ekf_P[(size_t)(f * 5) * n + i] = ec.P0[f];
@@ -101,15 +100,17 @@ void run(const dekf_config &cfg, int S, const double *gyro, const double *accel,
       int st = ekf_tick<T>(sim.ec, sim.dm, sim.b, in, out, s, i);
       double q[4];
       for (int f = 0; f < 4; ++f)
-        q[f] = in.quat ? in.quat[(size_t)f * n + i] : (double)sim.b.ekf_q[(size_t)f * n + i];
+        q[f] = in.quat ? in.quat[(size_t)f * n + i] : (double)sim.b.ekf_q[(size_t)f * sim.dm.ns + i];
       st |= mhe_assemble<T, Model>(sim.mc, sim.dm, sim.b, in, out, s, i, q);
       if (s >= 1) st |= mhe_solve<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
       status_out[(size_t)s * n + i] = st;
-      for (int f = 0; f < 3; ++f) pvo_out[((size_t)s * 3 + f) * n + i] = sim.b.p_vo[(size_t)f * n + i];
+      for (int f = 0; f < 3; ++f) pvo_out[((size_t)s * 3 + f) * n + i] = sim.b.p_vo[(size_t)f * sim.dm.ns + i];
     }
   }
-  for (size_t k = 0; k < (size_t)45 * n; ++k) arrP_out[k] = (double)sim.b.arr_P[k];
-  for (size_t k = 0; k < (size_t)9 * n; ++k) arrx_out[k] = (double)sim.b.arr_x[k];
+  for (int f = 0; f < 45; ++f)
+    for (int i = 0; i < n; ++i) arrP_out[(size_t)f * n + i] = (double)sim.b.arr_P[(size_t)f * sim.dm.ns + i];
+  for (int f = 0; f < 9; ++f)
+    for (int i = 0; i < n; ++i) arrx_out[(size_t)f * n + i] = (double)sim.b.arr_x[(size_t)f * sim.dm.ns + i];
 }
 }  // namespace
 

@@ -18,4 +18,4 @@ def test_flop_tally_matches_bench_constants():
         assert bench.FLOPS[k] == tally[k], (k, bench.FLOPS[k], tally[k])
     assert tally["assemble_go1_sincos"] == 12  # 3 sincos per leg instead of the generated code's 14 trig calls
     by, fl = bench.algorithmic_work(20, 10.0)["solve"]
-    assert by == 2 * 54 * 8 + 21 * 193 + 24 + 96 + 8 and 30000 < fl < 45000
+    assert by == 2 * 54 * 8 + 21 * 200 + 24 + 96 + 8 and 30000 < fl < 45000

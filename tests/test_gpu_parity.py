@@ -92,6 +92,28 @@ def test_go1_fp64_lockstep_vs_oracle(est_mod, oracle):
     est.close()
 
 
+@pytest.mark.parametrize("env", [{"DEKF_FUSED_MAX_N": "0"}, {"DEKF_FUSED_MAX_N": "0", "DEKF_NO_TMA": "1"}],
+                         ids=["split+tma", "split+global-loads"])
+@pytest.mark.parametrize("precision,n", [("fp64", 300), ("fp32", 129)])
+def test_go1_split_kernel_paths_vs_oracle(est_mod, oracle, monkeypatch, env, precision, n):
+    """The large-batch path (k_ekf, k_assemble, k_solve_tma: TMA-staged stage tiles) on parity-sized batches,
+    including a ragged last tile, and the plain-global-load solve kernel it replaced."""
+    from decentralized_ekf_mhe_b200 import synth
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    st = synth.to_numpy(synth.make_stream(n, 150, vo_jitter=True))
+    est, r = _run_lockstep(est_mod, st, precision=precision)
+    ro, _, _ = oracle.run_batch(st, oracle.go1_params(), oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1)
+    tol = TOL_V if precision == "fp64" else TOL_V32
+    assert np.abs(r["x"][1:, 3:6] - ro["x"][1:, 3:6]).max() < tol
+    if precision == "fp64":
+        assert np.abs(r["quat"] - ro["quat"]).max() < TOL_Q
+    assert np.array_equal(r["contact"], ro["contact"])
+    vo, ek = _mask_vo(r, st)
+    assert np.array_equal(vo, ro["vo_dbg"][:, :8]) and np.array_equal(ek, ro["ekf_dbg"])
+    est.close()
+
+
 def test_go1_matches_committed_golden(est_mod):
     g = np.load(os.path.join(HERE, "golden", "go1_stream_golden.npz"))
     st = {k[3:]: g[k] for k in g.files if k.startswith("in_")}
