@@ -128,6 +128,45 @@ def cpu_port_baseline(N, threads, steps_timed, instances_per_thread, mode="admm"
     return n * steps_timed / t, t, n, S
 
 
+def batch1_latency(estimator, synth, device, precision, N, steps=300):
+    """Batch-1 lock-step tick latency: device time per tick (dekf_run over a resident stream, CUDA events) and host
+    wall clock of one dekf_step_host call (pinned host buffers in and out, synchronised)."""
+    import torch
+    dev = torch.device("cuda", device)
+    S = N + 8 + steps
+    st = synth.make_stream(1, S, seed=777, device=dev, device_rng=True)
+    vo = [bool(st["vo_flag"][s].any()) for s in range(S)]
+    prm = estimator.robot_params("go1", ekf_rate=200, N=N)
+    est = estimator.BatchedEstimator(prm, 1, device=device, precision=precision)
+    cut = {k: v for k, v in st.items() if torch.is_tensor(v) and v.shape[0] == S}
+    est.run(0, N + 8, cut, vo[:N + 8])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    est.run(N + 8, steps // 2, {k: v[N + 8:] for k, v in cut.items()}, vo[N + 8:N + 8 + steps // 2])
+    e1.record()
+    torch.cuda.synchronize()
+    dev_us = e0.elapsed_time(e1) * 1e3 / (steps // 2)
+    keys = ["gyro", "accel", "imu_time", "joint_pos", "joint_vel", "foot_force", "vo_quat", "vo_time_pre", "vo_time_now",
+            "vo_rel_p", "vo_flag"]
+    T = N + 8 + steps // 2
+    host = {k: st[k][T:].cpu().pin_memory() for k in keys}
+    out = {"quat": torch.empty(4, 1, dtype=torch.float64).pin_memory(), "x": torch.empty(9, 1, dtype=torch.float64).pin_memory(),
+           "v_body": torch.empty(3, 1, dtype=torch.float64).pin_memory()}
+    ts = []
+    for j in range(S - T):
+        d = {k: host[k][j] for k in keys}
+        if not vo[T + j]:
+            d["vo_flag"] = None
+        t0 = time.perf_counter()
+        est.step_host(T + j, d, out)
+        ts.append(time.perf_counter() - t0)
+    est.close()
+    ts.sort()
+    return {"device_us_per_tick": dev_us, "host_call_us_median": 1e6 * ts[len(ts) // 2], "host_call_us_p99": 1e6 * ts[int(len(ts) * 0.99)],
+            "ticks": len(ts), "api": "dekf_step_host, n_instances=1 (k_fused: one launch per tick)"}
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU implementation of the path on the host cores.  The reference
     cannot be compiled in this image (needs rclcpp, Eigen3, osqp, OsqpEigen), so this
@@ -202,7 +241,7 @@ def main():
     lo, hi = shard_range(n_total, rank, world)
     assert hi - lo == n
     N = args.N
-    S = FILL_STEPS + W + K + Ke
+    S = FILL_STEPS + W + K + Ke + 20
     dev = torch.device("cuda", local_rank)
 
     # ---- synthetic stream, resident in HBM before any timed region (each rank: its own instance range)
@@ -214,27 +253,29 @@ def main():
 
     prm = estimator.robot_params("go1", ekf_rate=200, N=N)
     est = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
-    stores = [estimator.robot_store.from_stream(stream, s, with_vo=vo_steps[s]) for s in range(S)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def sub(a, b):
+        d = {k: v[a:b] for k, v in stream.items() if torch.is_tensor(v) and v.shape[0] == S}
+        return d
+
     T = 0
-    for _ in range(FILL_STEPS + W):
-        est.step(T, stores[T])
-        T += 1
-    # ---- value: K steps, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+    est.run(T, FILL_STEPS + W, sub(0, FILL_STEPS + W), vo_steps[:FILL_STEPS + W])
+    T += FILL_STEPS + W
+    # ---- value: K ticks in one dekf_run call, inputs resident in HBM, CUDA events on the launching stream, max over ranks
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    timed = sub(T, T + K)
     barrier()
     launches0 = est.launch_count()
     sampler.start()
     ev0.record()
-    for _ in range(K):
-        est.step(T, stores[T])
-        T += 1
+    est.run(T, K, timed, vo_steps[T:T + K])
+    T += K
     ev1.record()
     barrier()
     ms_value = ev0.elapsed_time(ev1)
@@ -243,59 +284,61 @@ def main():
     value = n_total * K / (ms_value * 1e-3)
     n_vo_mean = float(est.window_vo_count().double().mean().item())
 
-    # ---- e2e: the same metric through dekf_step_host with pinned HOST buffers (H2D + D2H inside the timed region)
+    # ---- e2e: the same metric through dekf_run_host with pinned HOST streams: every tick's inputs are copied H2D and
+    # every tick's results (quat, x_MHE, v_body, contact, status) are copied D2H inside the timed region
     keys = ["gyro", "accel", "imu_time", "joint_pos", "joint_vel", "foot_force", "vo_quat", "vo_time_pre",
             "vo_time_now", "vo_rel_p"]
     rows = {k: (stream[k][0].numel() // n) for k in keys}
-    nrow = sum(rows.values())
-    pin_in = torch.empty(Ke, nrow, n, dtype=torch.float64).pin_memory()
-    pin_flag = torch.empty(Ke, n, dtype=torch.uint8).pin_memory()
-    r0 = 0
-    views = {}
-    for k in keys:
-        pin_in[:, r0:r0 + rows[k]] = stream[k][T:T + Ke].reshape(Ke, rows[k], n).cpu()
-        views[k] = (r0, r0 + rows[k])
-        r0 += rows[k]
-    pin_flag.copy_(stream["vo_flag"][T:T + Ke].cpu())
-    pin_out = torch.empty(16, n, dtype=torch.float64).pin_memory()
-    hout = {"quat": pin_out[0:4], "x": pin_out[4:13], "v_body": pin_out[13:16],
-            "contact": torch.empty(4, n, dtype=torch.uint8).pin_memory(),
-            "status": torch.empty(n, dtype=torch.int32).pin_memory()}
-    hins = []
+    hst = {k: stream[k][T:T + Ke].reshape(Ke, rows[k], n).cpu().pin_memory() for k in keys}
+    hst["vo_flag"] = stream["vo_flag"][T:T + Ke].cpu().pin_memory()
+    hout = {"quat": torch.empty(Ke, 4, n, dtype=torch.float64).pin_memory(),
+            "x": torch.empty(Ke, 9, n, dtype=torch.float64).pin_memory(),
+            "v_body": torch.empty(Ke, 3, n, dtype=torch.float64).pin_memory(),
+            "contact": torch.empty(Ke, 4, n, dtype=torch.uint8).pin_memory(),
+            "status": torch.empty(Ke, n, dtype=torch.int32).pin_memory()}
     h2d = 0
     for j in range(Ke):
-        d = {k: pin_in[j, views[k][0]:views[k][1]] for k in keys}
         has_vo = vo_steps[T + j]
-        d["vo_flag"] = pin_flag[j] if has_vo else None
-        hins.append(d)
         h2d += (sum(rows[k] for k in keys[:6]) * 8 * n) + ((sum(rows[k] for k in keys[6:]) * 8 + 1) * n if has_vo else 0)
     d2h = 16 * 8 * n + 4 * n + 4 * n
     barrier()
     t0 = time.perf_counter()
     ev0.record()
-    chk = 0.0
-    for j in range(Ke):
-        est.step_host(T, hins[j], hout)
-        chk += float(hout["x"][3, 0])  # read the result on the host
-        T += 1
+    est.run_host(T, Ke, hst, vo_steps[T:T + Ke], out=hout, out_per_step=True)
+    chk = float(hout["x"][:, 3, 0].sum())  # read the results on the host
+    T += Ke
     ev1.record()
     barrier()
     wall_e2e = time.perf_counter() - t0
     ms_e2e = max_over_ranks(max(ev0.elapsed_time(ev1), wall_e2e * 1e3))  # device events vs host wall clock: the slower
     e2e_value = n_total * Ke / (ms_e2e * 1e-3)
+    # single-tick host path (dekf_step_host: copy in, step, copy out, sync) for comparison
+    Ks = min(20, S - T)
+    one_out = {"quat": hout["quat"][0], "x": hout["x"][0], "v_body": hout["v_body"][0]}
+    hs1 = {k: stream[k][T:T + Ks].reshape(Ks, rows[k], n).cpu().pin_memory() for k in keys}
+    hs1["vo_flag"] = stream["vo_flag"][T:T + Ks].cpu().pin_memory()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for j in range(Ks):
+        d = {k: hs1[k][j] for k in keys}
+        d["vo_flag"] = hs1["vo_flag"][j] if vo_steps[T] else None
+        est.step_host(T, d, one_out)
+        T += 1
+    ms_step_host = (time.perf_counter() - t0) * 1e3 / max(Ks, 1)
     clocks = sampler.stop()
 
-    # ---- per-kernel device time (separate pass, CUDA events around every launch on the handle's stream)
-    # (a fresh handle re-plays the start of the stream: T must advance from 0 and the timed handle is past the end)
+    # ---- per-kernel device time: event pairs around every launch of a second handle (no host sync between launches),
+    # over Kp ticks of the same stream (a fresh handle re-plays the stream from T=0)
     Kp = min(K, 50)
     est2 = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
-    for s in range(FILL_STEPS + W):
-        est2.step(s, stores[s])
+    est2.run(0, FILL_STEPS + W, sub(0, FILL_STEPS + W), vo_steps[:FILL_STEPS + W])
     est2.profile(True)
-    for s in range(FILL_STEPS + W, FILL_STEPS + W + Kp):
-        est2.step(s, stores[s])
+    est2.run(FILL_STEPS + W, Kp, sub(FILL_STEPS + W, FILL_STEPS + W + Kp), vo_steps[FILL_STEPS + W:FILL_STEPS + W + Kp])
     pms, pcnt = est2.profile_read()
     est2.close()
+
+    # ---- batch-1 step latency (BASELINE metric, second half): one instance, lock-step tick
+    lat = batch1_latency(estimator, synth, local_rank, args.precision, N) if rank == 0 else None
 
     line = None
     if rank == 0:
@@ -324,8 +367,11 @@ def main():
         else:
             roof = {"bound": "hbm", "achieved": kd["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": kd["gbs"] / hbm_peak}
         roof.update({
-            "kernel": {"solve": "k_solve", "ekf": "k_ekf", "assemble": "k_assemble"}[dom],
+            "kernel": {"solve": "k_solve_tma", "ekf": "k_ekf", "assemble": "k_assemble"}[dom],
             "kernel_ms": kd["ms"], "kernel_share_of_step": kd["ms"] / tot,
+            "kernel_ms_source": "CUDA event pair around every launch on the launching stream, mean over the ticks of a "
+                                "separate pass of the same workload (no host sync between launches)",
+            "step_ms_sum_of_kernels": tot,
             "traffic": None,
             "hbm": {"achieved": kd["gbs"], "peak": hbm_peak, "frac": kd["gbs"] / hbm_peak, "peak_source": hbm_src},
             "fma": {"achieved": kd["tflops"], "peak": fma_peak, "frac": kd["tflops"] / fma_peak if fma_peak else None,
@@ -346,8 +392,11 @@ def main():
                                 "every step reads distinct input arrays",
                        "fill_steps": FILL_STEPS, "stream_gen_s": round(t_gen, 2)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // Ke, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "ms_per_step": ms_e2e / Ke, "api": "dekf_step_host (pinned host buffers)",
-                    "host_checksum": chk},
+                    "steps": Ke, "ms_per_step": ms_e2e / Ke,
+                    "api": "dekf_run_host (pinned host streams; H2D | kernels | D2H pipelined over ticks, every tick's "
+                           "inputs copied in and results copied out)",
+                    "single_tick_host_call_ms": ms_step_host, "host_checksum": chk},
+            "latency_batch1": lat,
             "gpu_launches": launches,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "roofline": roof,

@@ -15,8 +15,9 @@ ip = C.POINTER(C.c_int32)
 SYMBOLS = [
     "dekf_config_default_go1", "dekf_config_default_cassie", "dekf_config_default_pogox", "dekf_create",
     "dekf_destroy", "dekf_reset", "dekf_set_stream", "dekf_get_stream", "dekf_last_error", "dekf_num_joints",
-    "dekf_ekf_step", "dekf_mhe_step", "dekf_step", "dekf_step_host", "dekf_synchronize", "dekf_get_arrival_cost",
-    "dekf_get_arrival_cov", "dekf_get_p_vo", "dekf_get_R_sb", "dekf_get_ekf_cov", "dekf_get_window_vo_count", "dekf_debug_taps",
+    "dekf_ekf_step", "dekf_mhe_step", "dekf_step", "dekf_step_host", "dekf_mhe_step_host", "dekf_ekf_step_host",
+    "dekf_run", "dekf_run_host", "dekf_synchronize", "dekf_get_arrival_cost",
+    "dekf_get_arrival_cov", "dekf_get_p_vo", "dekf_get_R_sb", "dekf_get_ekf_cov", "dekf_get_window_vo_count", "dekf_get_host", "dekf_debug_taps",
     "dekf_launch_count", "dekf_device_bytes", "dekf_profile_enable", "dekf_profile_read", "dekf_measure_fma_peak",
     "dekf_measure_copy_bw",
 ]
@@ -61,12 +62,17 @@ def load():
     L.dekf_last_error.restype = C.c_char_p
     L.dekf_num_joints.argtypes = [hp]
     L.dekf_ekf_step.argtypes = [hp, C.POINTER(DekfInputs), C.POINTER(DekfOutputs)]
-    for name in ("dekf_mhe_step", "dekf_step", "dekf_step_host"):
+    L.dekf_ekf_step_host.argtypes = [hp, C.POINTER(DekfInputs), C.POINTER(DekfOutputs)]
+    for name in ("dekf_run", "dekf_run_host"):
+        getattr(L, name).argtypes = [hp, C.c_int32, C.c_int32, C.POINTER(DekfInputs), C.c_void_p, C.POINTER(DekfOutputs),
+                                     C.c_int32]
+    for name in ("dekf_mhe_step", "dekf_step", "dekf_step_host", "dekf_mhe_step_host"):
         getattr(L, name).argtypes = [hp, C.c_int32, C.POINTER(DekfInputs), C.POINTER(DekfOutputs)]
     L.dekf_get_arrival_cost.argtypes = [hp, C.c_void_p, C.c_void_p]
     L.dekf_get_arrival_cov.argtypes = [hp, C.c_void_p, C.c_void_p]
     for name in ("dekf_get_p_vo", "dekf_get_R_sb", "dekf_get_ekf_cov", "dekf_get_window_vo_count"):
         getattr(L, name).argtypes = [hp, C.c_void_p]
+    L.dekf_get_host.argtypes = [hp, C.c_int32, C.c_void_p]
     L.dekf_debug_taps.argtypes = [hp, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dekf_profile_enable.argtypes = [hp, C.c_int32]
     L.dekf_profile_read.argtypes = [hp, dp, C.POINTER(C.c_int64)]

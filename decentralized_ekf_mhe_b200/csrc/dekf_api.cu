@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/dekf_b200.h"
 #include "estimator_core.cuh"
@@ -22,17 +23,17 @@ constexpr int kBlock = 128;
 
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_ekf(const EkfConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
-                                                const Outputs out, int k, int32_t *status_out) {
+                                                const Outputs out, int k, int32_t *status_state, int32_t *status_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
   const int st = ekf_tick<T>(c, dm, b, in, out, k, i);
-  b.status[i] = st;
+  status_state[i] = st;  // b.status, or a ring slot when the EKF runs ahead of the MHE (dekf_run)
   if (status_out != nullptr) status_out[i] = st;
 }
 
 template <typename T, typename Model>
 __global__ void __launch_bounds__(kBlock) k_assemble(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
-                                                     const Outputs out, int Tk, int accumulate_status) {
+                                                     const Outputs out, int Tk, const int32_t *prev_status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
   double q[4];
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(kBlock) k_assemble(const MheConst<T> c, const 
   for (int f = 0; f < 4; ++f)
     q[f] = (in.quat != nullptr) ? in.quat[(size_t)f * dm.n + i] : (double)b.ekf_q[(size_t)f * dm.ns + i];
   const int st = mhe_assemble<T, Model>(c, dm, b, in, out, Tk, i, q);
-  b.status[i] = accumulate_status ? (b.status[i] | st) : st;
+  b.status[i] = (prev_status != nullptr) ? (prev_status[i] | st) : st;  // prev_status: this tick's EKF status bits
 }
 
 template <typename T>
@@ -55,137 +56,9 @@ __global__ void __launch_bounds__(kBlock) k_solve(const MheConst<T> c, const Dim
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// window solve with TMA-staged stage tiles
-// ------------------------------------------------------------------------------------------------
-// One CTA = 128 consecutive instances.  The window ring is a 2-D tensor [NW*25 rows][ns instances]; the record of
-// stage k for the CTA's instances is the box {128 instances, 25 rows} at (i0, slot*25).  One elected thread fetches
-// each stage with ONE cp.async.bulk.tensor.2d (SASS: UTMALDG) into a kStages-deep shared-memory ring; completion
-// is signalled on a "full" mbarrier (expect_tx), consumers hand the buffer back through an "empty" mbarrier.
-// The stage record is read from shared memory at the point of use instead of being parked in registers.
-constexpr int kTile = 128;
-constexpr int kStages = 3;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
-      : "memory");
-}
-
-template <typename T>
-struct SmemStageSource {
-  T *tiles;         // [kStages][REC_SIZE][kTile]
-  uint64_t *full;   // [kStages]
-  uint64_t *empty;  // [kStages]
-  const CUtensorMap *map;
-  int NW, i0, tid, k0, nst;
-
-  __device__ __forceinline__ void issue(int j) const {  // elected thread only
-    const int buf = j % kStages;
-    const int slot = (k0 + j) % NW;
-    mbar_expect_tx(&full[buf], (uint32_t)(REC_SIZE * kTile * sizeof(T)));
-    tma_load_2d(tiles + (size_t)buf * REC_SIZE * kTile, map, i0, slot * REC_SIZE, &full[buf]);
-  }
-  __device__ __forceinline__ void acquire(int j) const { mbar_wait(&full[j % kStages], (uint32_t)((j / kStages) & 1)); }
-  __device__ __forceinline__ void release(int j) const {
-    mbar_arrive(&empty[j % kStages]);
-    // the elected thread refills the buffer of the PREVIOUS stage (everybody has long released it) with the
-    // stage kStages-1 ahead of the current one
-    if (tid == 0 && j >= 1 && (j - 1 + kStages) < nst) {
-      mbar_wait(&empty[(j - 1) % kStages], (uint32_t)(((j - 1) / kStages) & 1));
-      issue(j - 1 + kStages);
-    }
-  }
-  __device__ __forceinline__ const T *row(int j, int f) const {
-    return tiles + ((size_t)(j % kStages) * REC_SIZE + f) * kTile + tid;
-  }
-  __device__ __forceinline__ void meas(int j, int, S3<T> &Lam, V3<T> &eta) const {
-#pragma unroll
-    for (int f = 0; f < 6; ++f) Lam.a[f] = *row(j, REC_LAM + f);
-#pragma unroll
-    for (int f = 0; f < 3; ++f) eta[f] = *row(j, REC_ETA + f);
-  }
-  __device__ __forceinline__ void rot(int j, int, M3<T> &R) const {
-#pragma unroll
-    for (int f = 0; f < 9; ++f) R.a[f] = *row(j, REC_R + f);
-  }
-  __device__ __forceinline__ void dyn(int j, int, V3<T> &as, V3<T> &dlt, bool &vo) const {
-#pragma unroll
-    for (int f = 0; f < 3; ++f) {
-      as[f] = *row(j, REC_AS + f);
-      dlt[f] = *row(j, REC_DLT + f);
-    }
-    vo = *row(j, REC_FLAG) != T(0);
-  }
-};
-
-template <typename T>
-constexpr size_t solve_tma_smem_bytes() {
-  return (size_t)kStages * REC_SIZE * kTile * sizeof(T) + 2 * kStages * sizeof(uint64_t);
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kTile) k_solve_tma(const __grid_constant__ CUtensorMap tmap, const MheConst<T> c, const Dims dm,
-                                                     const Buffers<T> b, const Inputs in, const Outputs out, int Tk,
-                                                     int32_t *status_out) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemStageSource<T> src;
-  src.tiles = reinterpret_cast<T *>(smem_raw);
-  src.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * REC_SIZE * kTile * sizeof(T));
-  src.empty = src.full + kStages;
-  src.map = &tmap;
-  src.NW = dm.NW;
-  src.i0 = blockIdx.x * kTile;
-  src.tid = threadIdx.x;
-  src.k0 = (Tk < dm.N) ? 0 : Tk - dm.N;
-  src.nst = Tk - src.k0 + 1;
-  const int active = min(kTile, dm.n - src.i0);  // consumers in this CTA (thread 0 is always one of them)
-  if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&src.full[s], 1);
-      mbar_init(&src.empty[s], (uint32_t)active);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int pre = src.nst < kStages ? src.nst : kStages;
-    for (int j = 0; j < pre; ++j) src.issue(j);
-  }
-  const int i = src.i0 + threadIdx.x;
-  if (i >= dm.n) return;
-  int st = b.status[i];
-  st |= mhe_solve<T>(c, dm, b, in, out, Tk, i, src);
-  b.status[i] = st;
-  if (status_out != nullptr) status_out[i] = st;
-}
+}  // namespace dekf
+#include "solve_tma.cuh"
+namespace dekf {
 
 // whole tick in one launch (small batches: launch latency dominates)
 template <typename T, typename Model>
@@ -324,6 +197,14 @@ __global__ void k_vo_count(const Dims dm, const Buffers<T> b, int Tk, int32_t *c
 // ------------------------------------------------------------------------------------------------
 using namespace dekf;
 
+struct StageSet {
+  double *in = nullptr;      // packed doubles (in_counts order)
+  uint8_t *flag = nullptr;
+  double *out = nullptr;     // quat4 x9 v_body3
+  uint8_t *contact = nullptr;
+  int32_t *status = nullptr;
+};
+
 struct dekf_handle {
   dekf_config cfg;
   Dims dm;
@@ -337,12 +218,18 @@ struct dekf_handle {
   Buffers<float> b32;
   void *slab = nullptr;
   size_t slab_bytes = 0;
-  // staging for the host-pointer path
-  double *stage_in = nullptr;   // packed doubles
-  uint8_t *stage_flag = nullptr;
-  double *stage_out = nullptr;  // quat4 x9 vbody3
-  uint8_t *stage_contact = nullptr;
-  int32_t *stage_status = nullptr;
+  // device staging of the host-pointer entry points (set 1 and the copy streams only exist after dekf_run_host)
+  StageSet stage[2];
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  // dekf_run: the EKF ticks run ahead of the MHE on their own stream through a small ring of quaternions / status words
+  static constexpr int kAhead = 4;
+  cudaStream_t s_ekf = nullptr, s_mhe = nullptr;  // lowest / highest stream priority
+  cudaEvent_t ev_join = nullptr;
+  double *quat_ring = nullptr;      // [kAhead][4][n]
+  int32_t *status_ring = nullptr;   // [kAhead][n]
+  cudaEvent_t ev_ekf[kAhead] = {nullptr, nullptr, nullptr, nullptr}, ev_mhe[kAhead] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   // debug taps
   double *tap_b_meas = nullptr, *tap_Q_meas = nullptr;
   int32_t *tap_vo = nullptr, *tap_ekf = nullptr;
@@ -355,15 +242,23 @@ struct dekf_handle {
   CUtensorMap tmap;      // window ring as a 2-D tensor [NW*25][ns] (TMA box = one stage record of one tile)
   int fused_max = 4096;  // batches up to this size take the single fused launch (DEKF_FUSED_MAX_N at create)
   bool use_tma = true;   // window solve with TMA-staged stage tiles (DEKF_NO_TMA=1 at create: plain global loads)
-  // optional per-kernel timing
+  // optional per-kernel timing: an event pair around every launch, no host synchronisation until the read
   bool prof = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  struct ProfRec {
+    cudaEvent_t e0, e1;
+    int slot;
+  };
+  std::vector<ProfRec> prof_recs;   // pairs recorded since the last read
+  std::vector<ProfRec> prof_free;   // recycled pairs
   double prof_ms[3] = {0, 0, 0};
   int64_t prof_n[3] = {0, 0, 0};
   std::string err;
 };
 
 namespace {
+
+int alloc_stage_set(dekf_handle *h, StageSet &ss);
+void free_stage_set(StageSet &ss);
 
 int fail(dekf_handle *h, int code, const char *what, cudaError_t ce = cudaSuccess) {
   if (h) {
@@ -414,24 +309,28 @@ size_t carve(Buffers<T> &b, const Dims &dm, char *base) {
 
 inline int grid_for(int n) { return (n + kBlock - 1) / kBlock; }
 
-// Event pair around one launch; the elapsed time is harvested lazily (next begin or read) so the stream is
-// only synchronised while profiling is enabled.
+// Event pair around one launch on the handle's stream; elapsed times are harvested by dekf_profile_read.
 struct ProfScope {
   dekf_handle *h;
-  int slot;
-  ProfScope(dekf_handle *h_, int slot_) : h(h_), slot(slot_) {
-    if (h->prof) cudaEventRecord(h->ev0, h->stream);
+  dekf_handle::ProfRec rec;
+  bool on;
+  cudaStream_t st;
+  ProfScope(dekf_handle *h_, int slot, cudaStream_t st_ = nullptr) : h(h_), on(h_->prof), st(st_ ? st_ : h_->stream) {
+    if (!on) return;
+    if (!h->prof_free.empty()) {
+      rec = h->prof_free.back();
+      h->prof_free.pop_back();
+    } else if (cudaEventCreate(&rec.e0) != cudaSuccess || cudaEventCreate(&rec.e1) != cudaSuccess) {
+      on = false;
+      return;
+    }
+    rec.slot = slot;
+    cudaEventRecord(rec.e0, st);
   }
   ~ProfScope() {
-    if (h->prof) {
-      cudaEventRecord(h->ev1, h->stream);
-      cudaEventSynchronize(h->ev1);
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) {
-        h->prof_ms[slot] += ms;
-        h->prof_n[slot]++;
-      }
-    }
+    if (!on) return;
+    cudaEventRecord(rec.e1, st);
+    h->prof_recs.push_back(rec);
   }
 };
 
@@ -469,7 +368,7 @@ Outputs to_outputs(const dekf_handle *h, const dekf_outputs *out) {
 
 template <typename T, typename Model>
 int launch_assemble(dekf_handle *h, const MheConst<T> &mc, const Buffers<T> &b, const Inputs &in, const Outputs &out,
-                    int T_, int acc) {
+                    int T_, const int32_t *acc) {
   {
     ProfScope ps(h, 1);
     k_assemble<T, Model><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(mc, h->dm, b, in, out, T_, acc);
@@ -490,7 +389,7 @@ int launch_fused(dekf_handle *h, const EkfConst<T> &ec, const MheConst<T> &mc, c
 
 template <typename T>
 int do_assemble(dekf_handle *h, const MheConst<T> &mc, const Buffers<T> &b, const Inputs &in, const Outputs &out, int T_,
-                int acc) {
+                const int32_t *acc) {
   switch (h->cfg.robot) {
     case DEKF_ROBOT_GO1: return launch_assemble<T, Go1Model<T>>(h, mc, b, in, out, T_, acc);
     case DEKF_ROBOT_CASSIE: return launch_assemble<T, CassieModel<T>>(h, mc, b, in, out, T_, acc);
@@ -611,8 +510,6 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
   h->mc32 = make_mhe_const<float>(*cfg);
   h->slab_bytes = h->f32 ? carve<float>(h->b32, h->dm, nullptr) : carve<double>(h->b64, h->dm, nullptr);
   const size_t n = (size_t)cfg->n_instances;
-  const size_t in_doubles = (size_t)(3 + 3 + 1 + 2 * h->nq + h->nl + 4 + 1 + 1 + 3) * n;
-  const size_t out_doubles = (size_t)(4 + 9 + 3) * n;
   auto bail = [&](int code, const char *what, cudaError_t e) {
     std::fprintf(stderr, "dekf_create: %s: %s\n", what, cudaGetErrorString(e));
     dekf_destroy(h);
@@ -652,12 +549,7 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
       return DEKF_ECUDA;
     }
   }
-  if ((ce = cudaMalloc((void **)&h->stage_in, in_doubles * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc(stage_in)", ce);
-  if ((ce = cudaMalloc((void **)&h->stage_flag, n)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
-  if ((ce = cudaMalloc((void **)&h->stage_out, out_doubles * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
-  if ((ce = cudaMalloc((void **)&h->stage_contact, (size_t)h->nl * n)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
-  if ((ce = cudaMalloc((void **)&h->stage_status, n * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
-  h->extra_bytes = (in_doubles + out_doubles) * sizeof(double) + n + (size_t)h->nl * n + n * sizeof(int32_t);
+  h->extra_bytes = 0;
   if (cfg->debug_taps) {
     if ((ce = cudaMalloc((void **)&h->tap_b_meas, (size_t)3 * h->nl * n * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
     if ((ce = cudaMalloc((void **)&h->tap_Q_meas, (size_t)6 * h->nl * n * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
@@ -683,18 +575,38 @@ int dekf_destroy(dekf_handle *h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->slab);
-  cudaFree(h->stage_in);
-  cudaFree(h->stage_flag);
-  cudaFree(h->stage_out);
-  cudaFree(h->stage_contact);
-  cudaFree(h->stage_status);
+  free_stage_set(h->stage[0]);
+  free_stage_set(h->stage[1]);
+  if (h->s_ekf) cudaStreamDestroy(h->s_ekf);
+  if (h->s_mhe) cudaStreamDestroy(h->s_mhe);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  cudaFree(h->quat_ring);
+  cudaFree(h->status_ring);
+  for (int k = 0; k < dekf_handle::kAhead; ++k) {
+    if (h->ev_ekf[k]) cudaEventDestroy(h->ev_ekf[k]);
+    if (h->ev_mhe[k]) cudaEventDestroy(h->ev_mhe[k]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+  if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+  for (int k = 0; k < 2; ++k) {
+    if (h->ev_h2d[k]) cudaEventDestroy(h->ev_h2d[k]);
+    if (h->ev_comp[k]) cudaEventDestroy(h->ev_comp[k]);
+    if (h->ev_d2h[k]) cudaEventDestroy(h->ev_d2h[k]);
+  }
   cudaFree(h->tap_b_meas);
   cudaFree(h->tap_Q_meas);
   cudaFree(h->tap_vo);
   cudaFree(h->tap_ekf);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto &r : h->prof_recs) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto &r : h->prof_free) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
   delete h;
   return DEKF_OK;
 }
@@ -728,19 +640,20 @@ int dekf_num_joints(const dekf_handle *h) { return h ? h->nq : DEKF_EINVAL; }
 int64_t dekf_launch_count(const dekf_handle *h) { return h ? h->launches : 0; }
 int64_t dekf_device_bytes(const dekf_handle *h) { return h ? (int64_t)(h->slab_bytes + h->extra_bytes) : 0; }
 
-int dekf_ekf_step(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out) {
-  if (!h || !in || !in->gyro || !in->accel || !in->imu_time) return fail(h, DEKF_EINVAL, "dekf_ekf_step: null input");
-  if (in->vo_flag && (!in->vo_quat || !in->vo_time_now)) return fail(h, DEKF_EINVAL, "dekf_ekf_step: vo_flag without vo_quat/vo_time_now");
-  CK(cudaSetDevice(h->cfg.device));
+// one EKF tick of all instances on `stream`; status_state: where the tick's status bits are kept for the MHE to OR in
+static int ekf_launch(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out, int32_t *status_state,
+                      cudaStream_t stream) {
   const Inputs di = to_inputs(in);
   const Outputs dout = to_outputs(h, out);
   int32_t *st = out ? out->status : nullptr;
   {
-    ProfScope ps(h, 0);
+    ProfScope ps(h, 0, stream);
     if (h->f32)
-      k_ekf<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->ec32, h->dm, h->b32, di, dout, h->ekf_k, st);
+      k_ekf<float><<<grid_for(h->dm.n), kBlock, 0, stream>>>(h->ec32, h->dm, h->b32, di, dout, h->ekf_k,
+                                                             status_state ? status_state : h->b32.status, st);
     else
-      k_ekf<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->ec64, h->dm, h->b64, di, dout, h->ekf_k, st);
+      k_ekf<double><<<grid_for(h->dm.n), kBlock, 0, stream>>>(h->ec64, h->dm, h->b64, di, dout, h->ekf_k,
+                                                              status_state ? status_state : h->b64.status, st);
   }
   h->launches++;
   CK(cudaGetLastError());
@@ -748,7 +661,15 @@ int dekf_ekf_step(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out
   return DEKF_OK;
 }
 
-static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out, int acc) {
+int dekf_ekf_step(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out) {
+  if (!h || !in || !in->gyro || !in->accel || !in->imu_time) return fail(h, DEKF_EINVAL, "dekf_ekf_step: null input");
+  if (in->vo_flag && (!in->vo_quat || !in->vo_time_now)) return fail(h, DEKF_EINVAL, "dekf_ekf_step: vo_flag without vo_quat/vo_time_now");
+  CK(cudaSetDevice(h->cfg.device));
+  return ekf_launch(h, in, out, nullptr, h->stream);
+}
+
+static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out, const int32_t *acc,
+                         cudaEvent_t after_assemble = nullptr) {
   if (!in->gyro || !in->accel || !in->imu_time || !in->joint_pos || !in->joint_vel || !in->foot_force)
     return fail(h, DEKF_EINVAL, "dekf_mhe_step: null input");
   if (in->vo_flag && (!in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
@@ -762,6 +683,7 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
   if (h->f32) {
     rc = do_assemble<float>(h, h->mc32, h->b32, di, dout, T_, acc);
     if (rc) return fail(h, rc, "assemble");
+    if (after_assemble) cudaEventRecord(after_assemble, h->stream);
     ProfScope ps(h, 2);
     if (tma)
       k_solve_tma<float><<<tiles, kTile, solve_tma_smem_bytes<float>(), h->stream>>>(h->tmap, h->mc32, h->dm, h->b32, di, dout, T_, st);
@@ -770,6 +692,7 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
   } else {
     rc = do_assemble<double>(h, h->mc64, h->b64, di, dout, T_, acc);
     if (rc) return fail(h, rc, "assemble");
+    if (after_assemble) cudaEventRecord(after_assemble, h->stream);
     ProfScope ps(h, 2);
     if (tma)
       k_solve_tma<double><<<tiles, kTile, solve_tma_smem_bytes<double>(), h->stream>>>(h->tmap, h->mc64, h->dm, h->b64, di, dout, T_, st);
@@ -787,7 +710,7 @@ int dekf_mhe_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_
   int rc = check_T(h, T_);
   if (rc) return rc;
   CK(cudaSetDevice(h->cfg.device));
-  return mhe_step_impl(h, T_, in, out, 0);
+  return mhe_step_impl(h, T_, in, out, nullptr);
 }
 
 int dekf_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out) {
@@ -820,7 +743,7 @@ int dekf_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outp
   if (out) o_ekf.quat = out->quat;
   rc = dekf_ekf_step(h, &in2, &o_ekf);
   if (rc) return rc;
-  return mhe_step_impl(h, T_, &in2, out, 1);
+  return mhe_step_impl(h, T_, &in2, out, h->f32 ? h->b32.status : h->b64.status);
 }
 
 int dekf_synchronize(dekf_handle *h) {
@@ -829,79 +752,314 @@ int dekf_synchronize(dekf_handle *h) {
   return DEKF_OK;
 }
 
-int dekf_step_host(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out) {
-  if (!h || !in) return fail(h, DEKF_EINVAL, "dekf_step_host: null argument");
-  int rc = check_T(h, T_);
-  if (rc) return rc;
-  if (!in->gyro || !in->accel || !in->imu_time || !in->joint_pos || !in->joint_vel || !in->foot_force)
-    return fail(h, DEKF_EINVAL, "dekf_step_host: null input");
-  if (in->vo_flag && (!in->vo_quat || !in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
-    return fail(h, DEKF_EINVAL, "dekf_step_host: vo_flag without the VO arrays");
-  CK(cudaSetDevice(h->cfg.device));
+}  // extern "C"
+
+// ---- host-pointer entry points --------------------------------------------------------------------------------
+namespace {
+enum HostKind { HK_STEP = 0, HK_MHE = 1, HK_EKF = 2 };
+constexpr int kNumIn = 11;  // gyro accel imu_time joint_pos joint_vel foot_force | vo_quat vo_time_pre vo_time_now vo_rel_p | quat
+
+void in_counts(const dekf_handle *h, size_t cnt[kNumIn]) {
   const size_t n = (size_t)h->dm.n;
-  // packed device staging: gyro3 accel3 time1 jpos jvel force | vo_quat4 tpre tnow relp3
-  const size_t cnt[10] = {3 * n, 3 * n, n, (size_t)h->nq * n, (size_t)h->nq * n, (size_t)h->nl * n, 4 * n, n, n, 3 * n};
-  const double *src[10] = {in->gyro, in->accel, in->imu_time, in->joint_pos, in->joint_vel, in->foot_force,
-                           in->vo_quat, in->vo_time_pre, in->vo_time_now, in->vo_rel_p};
-  double *dst[10];
-  {
-    size_t off = 0;
-    for (int a = 0; a < 10; ++a) {
-      dst[a] = h->stage_in + off;
-      off += cnt[a];
-    }
+  const size_t c[kNumIn] = {3 * n, 3 * n, n, (size_t)h->nq * n, (size_t)h->nq * n, (size_t)h->nl * n, 4 * n, n, n, 3 * n, 4 * n};
+  for (int a = 0; a < kNumIn; ++a) cnt[a] = c[a];
+}
+
+int alloc_stage_set(dekf_handle *h, StageSet &ss) {
+  if (ss.in) return DEKF_OK;
+  const size_t n = (size_t)h->dm.n;
+  size_t cnt[kNumIn], tot = 0;
+  in_counts(h, cnt);
+  for (int a = 0; a < kNumIn; ++a) tot += cnt[a];
+  CK(cudaMalloc((void **)&ss.in, tot * sizeof(double)));
+  CK(cudaMalloc((void **)&ss.flag, n));
+  CK(cudaMalloc((void **)&ss.out, 16 * n * sizeof(double)));
+  CK(cudaMalloc((void **)&ss.contact, (size_t)h->nl * n));
+  CK(cudaMalloc((void **)&ss.status, n * sizeof(int32_t)));
+  h->extra_bytes += (tot + 16 * n) * sizeof(double) + n + (size_t)h->nl * n + n * sizeof(int32_t);
+  return DEKF_OK;
+}
+void free_stage_set(StageSet &ss) {
+  cudaFree(ss.in);
+  cudaFree(ss.flag);
+  cudaFree(ss.out);
+  cudaFree(ss.contact);
+  cudaFree(ss.status);
+  ss = StageSet();
+}
+
+// H2D copies of one tick's inputs on stream `st`; `din` receives the device pointers (NULL where the host gave NULL)
+int stage_inputs(dekf_handle *h, const StageSet &ss, const dekf_inputs *in, cudaStream_t st, dekf_inputs *din) {
+  const size_t n = (size_t)h->dm.n;
+  size_t cnt[kNumIn];
+  in_counts(h, cnt);
+  const bool vo = in->vo_flag != nullptr;
+  const double *src[kNumIn] = {in->gyro, in->accel, in->imu_time, in->joint_pos, in->joint_vel, in->foot_force,
+                               vo ? in->vo_quat : nullptr, vo ? in->vo_time_pre : nullptr, vo ? in->vo_time_now : nullptr,
+                               vo ? in->vo_rel_p : nullptr, in->quat};
+  double *dst[kNumIn];
+  size_t off = 0;
+  for (int a = 0; a < kNumIn; ++a) {
+    dst[a] = ss.in + off;
+    off += cnt[a];
   }
-  const int na = in->vo_flag ? 10 : 6;
-  // coalesce host ranges that are contiguous in the packed order into single copies
+  // host ranges that are contiguous in the packed order go as single copies
   int a = 0;
-  while (a < na) {
+  while (a < kNumIn) {
+    if (!src[a]) {
+      ++a;
+      continue;
+    }
     int e = a;
     size_t total = cnt[a];
-    while (e + 1 < na && src[e + 1] == src[e] + cnt[e]) {
+    while (e + 1 < kNumIn && src[e + 1] && src[e + 1] == src[e] + cnt[e]) {
       ++e;
       total += cnt[e];
     }
-    CK(cudaMemcpyAsync(dst[a], src[a], total * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dst[a], src[a], total * sizeof(double), cudaMemcpyHostToDevice, st));
     a = e + 1;
   }
-  if (in->vo_flag) CK(cudaMemcpyAsync(h->stage_flag, in->vo_flag, n, cudaMemcpyHostToDevice, h->stream));
+  if (vo) CK(cudaMemcpyAsync(ss.flag, in->vo_flag, n, cudaMemcpyHostToDevice, st));
+  std::memset(din, 0, sizeof(*din));
+  const double **dp[kNumIn] = {&din->gyro, &din->accel, &din->imu_time, &din->joint_pos, &din->joint_vel, &din->foot_force,
+                               &din->vo_quat, &din->vo_time_pre, &din->vo_time_now, &din->vo_rel_p, &din->quat};
+  for (int k = 0; k < kNumIn; ++k) *dp[k] = src[k] ? dst[k] : nullptr;
+  din->vo_flag = vo ? ss.flag : nullptr;
+  return DEKF_OK;
+}
+
+void stage_outputs(const dekf_handle *h, const StageSet &ss, const dekf_outputs *out, dekf_outputs *dout) {
+  const size_t n = (size_t)h->dm.n;
+  std::memset(dout, 0, sizeof(*dout));
+  dout->quat = ss.out;
+  dout->x = ss.out + 4 * n;
+  dout->v_body = ss.out + 13 * n;
+  dout->contact = (out && out->contact) ? ss.contact : nullptr;
+  dout->status = (out && out->status) ? ss.status : nullptr;
+}
+
+// D2H copies of one tick's results on stream `st` into the host arrays of `out` (+ step offset in elements of n)
+int unstage_outputs(dekf_handle *h, const StageSet &ss, const dekf_outputs *out, size_t step, cudaStream_t st, int kind) {
+  if (!out) return DEKF_OK;
+  const size_t n = (size_t)h->dm.n;
+  double *q = out->quat ? out->quat + step * 4 * n : nullptr;
+  double *x = (out->x && kind != HK_EKF) ? out->x + step * 9 * n : nullptr;
+  double *v = (out->v_body && kind != HK_EKF) ? out->v_body + step * 3 * n : nullptr;
+  if (kind == HK_MHE) q = nullptr;
+  if (q && x && v && x == q + 4 * n && v == x + 9 * n) {
+    CK(cudaMemcpyAsync(q, ss.out, 16 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  } else {
+    if (q) CK(cudaMemcpyAsync(q, ss.out, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (x) CK(cudaMemcpyAsync(x, ss.out + 4 * n, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (v) CK(cudaMemcpyAsync(v, ss.out + 13 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  if (out->contact && kind != HK_EKF)
+    CK(cudaMemcpyAsync(out->contact + step * h->nl * n, ss.contact, (size_t)h->nl * n, cudaMemcpyDeviceToHost, st));
+  if (out->status) CK(cudaMemcpyAsync(out->status + step * n, ss.status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  return DEKF_OK;
+}
+
+int device_call(dekf_handle *h, int kind, int32_t T_, const dekf_inputs *din, const dekf_outputs *dout) {
+  switch (kind) {
+    case HK_STEP: return dekf_step(h, T_, din, dout);
+    case HK_MHE: return dekf_mhe_step(h, T_, din, dout);
+    default: return dekf_ekf_step(h, din, dout);
+  }
+}
+
+int host_call(dekf_handle *h, int kind, int32_t T_, const dekf_inputs *in, const dekf_outputs *out) {
+  if (!h || !in) return fail(h, DEKF_EINVAL, "host entry point: null argument");
+  CK(cudaSetDevice(h->cfg.device));
   dekf_inputs din;
-  std::memset(&din, 0, sizeof(din));
-  din.gyro = dst[0];
-  din.accel = dst[1];
-  din.imu_time = dst[2];
-  din.joint_pos = dst[3];
-  din.joint_vel = dst[4];
-  din.foot_force = dst[5];
-  if (in->vo_flag) {
-    din.vo_flag = h->stage_flag;
-    din.vo_quat = dst[6];
-    din.vo_time_pre = dst[7];
-    din.vo_time_now = dst[8];
-    din.vo_rel_p = dst[9];
-  }
   dekf_outputs dout;
-  std::memset(&dout, 0, sizeof(dout));
-  dout.quat = h->stage_out;
-  dout.x = h->stage_out + 4 * n;
-  dout.v_body = h->stage_out + 13 * n;
-  dout.contact = (out && out->contact) ? h->stage_contact : nullptr;
-  dout.status = (out && out->status) ? h->stage_status : nullptr;
-  rc = dekf_step(h, T_, &din, &dout);
+  int rc = alloc_stage_set(h, h->stage[0]);
   if (rc) return rc;
-  if (out) {
-    const bool packed = out->quat && out->x && out->v_body && out->x == out->quat + 4 * n && out->v_body == out->x + 9 * n;
-    if (packed) {
-      CK(cudaMemcpyAsync(out->quat, h->stage_out, 16 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    } else {
-      if (out->quat) CK(cudaMemcpyAsync(out->quat, dout.quat, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      if (out->x) CK(cudaMemcpyAsync(out->x, dout.x, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      if (out->v_body) CK(cudaMemcpyAsync(out->v_body, dout.v_body, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    }
-    if (out->contact) CK(cudaMemcpyAsync(out->contact, h->stage_contact, (size_t)h->nl * n, cudaMemcpyDeviceToHost, h->stream));
-    if (out->status) CK(cudaMemcpyAsync(out->status, h->stage_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  }
+  rc = stage_inputs(h, h->stage[0], in, h->stream, &din);
+  if (rc) return rc;
+  stage_outputs(h, h->stage[0], out, &dout);
+  rc = device_call(h, kind, T_, &din, &dout);
+  if (rc) return rc;
+  rc = unstage_outputs(h, h->stage[0], out, 0, h->stream, kind);
+  if (rc) return rc;
   CK(cudaStreamSynchronize(h->stream));
+  return DEKF_OK;
+}
+
+// rows of every input stream (elements per tick = rows * n)
+void offset_inputs(const dekf_handle *h, const dekf_inputs *in, size_t s, bool vo, dekf_inputs *o) {
+  const size_t n = (size_t)h->dm.n;
+  auto at = [&](const double *p, size_t rows) { return p ? p + s * rows * n : nullptr; };
+  std::memset(o, 0, sizeof(*o));
+  o->gyro = at(in->gyro, 3);
+  o->accel = at(in->accel, 3);
+  o->imu_time = at(in->imu_time, 1);
+  o->joint_pos = at(in->joint_pos, h->nq);
+  o->joint_vel = at(in->joint_vel, h->nq);
+  o->foot_force = at(in->foot_force, h->nl);
+  o->quat = at(in->quat, 4);
+  if (vo && in->vo_flag) {
+    o->vo_flag = in->vo_flag + s * n;
+    o->vo_quat = at(in->vo_quat, 4);
+    o->vo_time_pre = at(in->vo_time_pre, 1);
+    o->vo_time_now = at(in->vo_time_now, 1);
+    o->vo_rel_p = at(in->vo_rel_p, 3);
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int dekf_step_host(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out) {
+  return host_call(h, HK_STEP, T_, in, out);
+}
+int dekf_mhe_step_host(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out) {
+  return host_call(h, HK_MHE, T_, in, out);
+}
+int dekf_ekf_step_host(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out) {
+  return host_call(h, HK_EKF, 0, in, out);
+}
+
+int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const uint8_t *vo_steps, const dekf_outputs *out,
+             int32_t out_per_step) {
+  if (!h || !in || S < 0) return fail(h, DEKF_EINVAL, "dekf_run: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->dm.n;
+  auto outputs_of = [&](int32_t s, dekf_outputs *os) {
+    std::memset(os, 0, sizeof(*os));
+    if (out && (out_per_step || s == S - 1)) {
+      const size_t o = out_per_step ? (size_t)s : 0;
+      os->quat = out->quat ? out->quat + o * 4 * n : nullptr;
+      os->x = out->x ? out->x + o * 9 * n : nullptr;
+      os->v_body = out->v_body ? out->v_body + o * 3 * n : nullptr;
+      os->contact = out->contact ? out->contact + o * h->nl * n : nullptr;
+      os->status = out->status ? out->status + o * n : nullptr;
+    }
+  };
+  // small batches (one fused launch per tick) and tapped handles: plain tick loop
+  if (h->dm.n <= h->fused_max || h->cfg.debug_taps || S < 2) {
+    for (int32_t s = 0; s < S; ++s) {
+      dekf_inputs is;
+      offset_inputs(h, in, (size_t)s, !vo_steps || vo_steps[s], &is);
+      dekf_outputs os;
+      outputs_of(s, &os);
+      const int rc = dekf_step(h, T0 + s, &is, &os);
+      if (rc) return rc;
+    }
+    return DEKF_OK;
+  }
+  // Large batches.  The orientation EKF does not depend on the MHE, so its ticks run ahead (up to kAhead ticks) on a
+  // LOW-priority stream and hand each tick's quaternion / status word over through a ring, while k_assemble / k_solve
+  // run on a HIGH-priority stream: the block scheduler only dispatches EKF CTAs when no window-solve CTA is pending,
+  // i.e. into the SMs the solve kernel leaves idle in its last wave (1.73 waves at 65,536 instances).
+  constexpr int QA = dekf_handle::kAhead;
+  int rc = check_T(h, T0);
+  if (rc) return rc;
+  if (!in->gyro || !in->accel || !in->imu_time || !in->joint_pos || !in->joint_vel || !in->foot_force)
+    return fail(h, DEKF_EINVAL, "dekf_run: null input");
+  if (in->vo_flag && (!in->vo_quat || !in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
+    return fail(h, DEKF_EINVAL, "dekf_run: vo_flag without the VO arrays");
+  if (!h->s_ekf) {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = numerically largest = lowest priority
+    CK(cudaStreamCreateWithPriority(&h->s_ekf, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&h->s_mhe, cudaStreamNonBlocking, hi));
+    CK(cudaMalloc((void **)&h->quat_ring, (size_t)QA * 4 * n * sizeof(double)));
+    CK(cudaMalloc((void **)&h->status_ring, (size_t)QA * n * sizeof(int32_t)));
+    h->extra_bytes += (size_t)QA * n * (4 * sizeof(double) + sizeof(int32_t));
+    for (int k = 0; k < QA; ++k) {
+      CK(cudaEventCreateWithFlags(&h->ev_ekf[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_mhe[k], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
+  // fork both internal streams off the caller-visible stream, join back at the end
+  cudaStream_t user = h->stream;
+  CK(cudaEventRecord(h->ev_fork, user));
+  CK(cudaStreamWaitEvent(h->s_ekf, h->ev_fork, 0));
+  CK(cudaStreamWaitEvent(h->s_mhe, h->ev_fork, 0));
+  h->stream = h->s_mhe;  // mhe_step_impl launches on h->stream
+  for (int32_t s = 0; s < S && rc == DEKF_OK; ++s) {
+    const int slot = s % QA;
+    dekf_inputs is;
+    offset_inputs(h, in, (size_t)s, !vo_steps || vo_steps[s], &is);
+    is.quat = nullptr;
+    dekf_outputs os;
+    outputs_of(s, &os);
+    double *qslot = h->quat_ring + (size_t)slot * 4 * n;
+    int32_t *sslot = h->status_ring + (size_t)slot * n;
+    cudaError_t ce = cudaSuccess;
+    if (s >= QA) ce = cudaStreamWaitEvent(h->s_ekf, h->ev_mhe[slot], 0);  // k_assemble of tick s-QA has consumed the slot
+    dekf_outputs oe;
+    std::memset(&oe, 0, sizeof(oe));
+    oe.quat = qslot;
+    if (ce == cudaSuccess) rc = ekf_launch(h, &is, &oe, sslot, h->s_ekf);
+    if (rc) break;
+    if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_ekf[slot], h->s_ekf);
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(h->s_mhe, h->ev_ekf[slot], 0);
+    if (ce == cudaSuccess && os.quat) ce = cudaMemcpyAsync(os.quat, qslot, 4 * n * sizeof(double), cudaMemcpyDeviceToDevice, h->s_mhe);
+    if (ce != cudaSuccess) {
+      rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
+      break;
+    }
+    is.quat = qslot;
+    rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, h->ev_mhe[slot]);
+  }
+  h->stream = user;
+  cudaEventRecord(h->ev_join, h->s_mhe);
+  cudaStreamWaitEvent(user, h->ev_join, 0);
+  cudaEventRecord(h->ev_join, h->s_ekf);
+  cudaStreamWaitEvent(user, h->ev_join, 0);
+  return rc;
+}
+
+int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const uint8_t *vo_steps, const dekf_outputs *out,
+                  int32_t out_per_step) {
+  if (!h || !in || S < 0) return fail(h, DEKF_EINVAL, "dekf_run_host: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = alloc_stage_set(h, h->stage[0]);
+  if (rc) return rc;
+  rc = alloc_stage_set(h, h->stage[1]);
+  if (rc) return rc;
+  if (!h->s_h2d) {
+    CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CK(cudaEventCreateWithFlags(&h->ev_h2d[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_comp[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_d2h[k], cudaEventDisableTiming));
+    }
+  }
+  // software pipeline over ticks: H2D of tick s+1 | kernels of tick s | D2H of tick s-1 on three streams, two staging sets
+  CK(cudaEventRecord(h->ev_comp[0], h->stream));  // order after whatever the caller queued on the handle's stream
+  CK(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[0], 0));
+  CK(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[0], 0));
+  for (int32_t s = 0; s < S; ++s) {
+    const int b = s & 1;
+    const bool want_out = out && (out_per_step || s == S - 1);
+    dekf_inputs is, din;
+    offset_inputs(h, in, (size_t)s, !vo_steps || vo_steps[s], &is);
+    if (s >= 2) CK(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));  // kernels of tick s-2 are done with staging set b
+    rc = stage_inputs(h, h->stage[b], &is, h->s_h2d, &din);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[b], 0));
+    if (s >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_d2h[b], 0));  // results of tick s-2 have left staging set b
+    dekf_outputs dout;
+    stage_outputs(h, h->stage[b], want_out ? out : nullptr, &dout);
+    rc = dekf_step(h, T0 + s, &din, &dout);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->ev_comp[b], h->stream));
+    CK(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
+    if (want_out) {
+      rc = unstage_outputs(h, h->stage[b], out, out_per_step ? (size_t)s : 0, h->s_d2h, HK_STEP);
+      if (rc) return rc;
+    }
+    CK(cudaEventRecord(h->ev_d2h[b], h->s_d2h));
+  }
+  CK(cudaStreamSynchronize(h->s_h2d));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaStreamSynchronize(h->s_d2h));
   return DEKF_OK;
 }
 
@@ -948,6 +1106,39 @@ int dekf_get_window_vo_count(dekf_handle *h, int32_t *count) {
   return DEKF_OK;
 }
 
+int dekf_get_host(dekf_handle *h, int32_t what, void *host_out) {
+  if (!h || !host_out) return fail(h, DEKF_EINVAL, "dekf_get_host: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t n = (size_t)h->dm.n;
+  const size_t rows[6] = {9, 3, 81, 9, 16, 1};
+  if (what < 0 || what > DEKF_GET_VO_COUNT) return fail(h, DEKF_EINVAL, "dekf_get_host: unknown selector");
+  double *d = nullptr;
+  CK(cudaMalloc((void **)&d, (size_t)90 * n * sizeof(double)));
+  int rc = DEKF_OK;
+  const void *src = d;
+  size_t bytes = rows[what] * n * sizeof(double);
+  switch (what) {
+    case DEKF_GET_R_SB: rc = dekf_get_R_sb(h, d); break;
+    case DEKF_GET_P_VO: rc = dekf_get_p_vo(h, d); break;
+    case DEKF_GET_ARRIVAL_M: rc = dekf_get_arrival_cost(h, d, d + 81 * n); break;
+    case DEKF_GET_ARRIVAL_N:
+      rc = dekf_get_arrival_cost(h, d, d + 81 * n);
+      src = d + 81 * n;
+      break;
+    case DEKF_GET_EKF_COV: rc = dekf_get_ekf_cov(h, d); break;
+    default:
+      rc = dekf_get_window_vo_count(h, (int32_t *)d);
+      bytes = n * sizeof(int32_t);
+  }
+  cudaError_t ce = cudaSuccess;
+  if (rc == DEKF_OK) ce = cudaMemcpyAsync(host_out, src, bytes, cudaMemcpyDeviceToHost, h->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (rc) return rc;
+  if (ce != cudaSuccess) return fail(h, DEKF_ECUDA, "dekf_get_host", ce);
+  return DEKF_OK;
+}
+
 int dekf_debug_taps(dekf_handle *h, double *b_meas, double *Q_meas, int32_t *vo_idx, int32_t *ekf_idx) {
   if (!h) return DEKF_EINVAL;
   if (!h->cfg.debug_taps) return fail(h, DEKF_EINVAL, "handle was created without debug_taps");
@@ -963,16 +1154,21 @@ int dekf_debug_taps(dekf_handle *h, double *b_meas, double *Q_meas, int32_t *vo_
 int dekf_profile_enable(dekf_handle *h, int32_t enable) {
   if (!h) return DEKF_EINVAL;
   CK(cudaSetDevice(h->cfg.device));
-  if (enable && !h->ev0) {
-    CK(cudaEventCreate(&h->ev0));
-    CK(cudaEventCreate(&h->ev1));
-  }
   h->prof = enable != 0;
   return DEKF_OK;
 }
 int dekf_profile_read(dekf_handle *h, double *ms, int64_t *count) {
   if (!h || !ms || !count) return DEKF_EINVAL;
   CK(cudaStreamSynchronize(h->stream));
+  for (auto &r : h->prof_recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+      h->prof_ms[r.slot] += t;
+      h->prof_n[r.slot]++;
+    }
+    h->prof_free.push_back(r);
+  }
+  h->prof_recs.clear();
   for (int k = 0; k < 3; ++k) {
     ms[k] = h->prof_ms[k];
     count[k] = h->prof_n[k];

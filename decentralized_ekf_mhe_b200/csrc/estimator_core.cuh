@@ -63,6 +63,8 @@ struct MheConst {
   T d3[3];   // dt^2 C_accel                    (vv block)
   T cab[3];  // dt^2 C_accel_bias               (bb block)
   T cvo[3];  // vo_p_std^2                       (Q_cam^-1 before rotation)
+  // the same four diagonals as (d[0], d[1]-d[0], d[2]-d[0]) for the two-term form R diag(d) R' = d0 I + e1 r1r1' + e2 r2r2'
+  T n1[3], n2[3], n3[3], nvo[3];
   T cenc_v[8], cenc_p[8], cgy[3];
   T q_swing[3];
   T P0[9];   // prior covariance diag (p,v,b init std^2), prior mean 0
@@ -904,6 +906,244 @@ DEKF_HD void propagate(const MheConst<T> &c, Cov9<T> &P, Vec9<T> &x, const M3<T>
   }
 }
 
+// ---- version 2 of the two sweep stages: same algebra as meas_update / propagate above, organised as in-place
+// accumulations (every product term is one FMA on its destination block, short-lived temporaries only) --------------
+template <typename T>
+DEKF_HD void meas_update2(Cov9<T> &P, Vec9<T> &x, const S3<T> &Lam, const V3<T> &eta) {
+  const M3<T> Pvv = to_m3(P.vv);
+  M3<T> Z;  // I + Lam P_vv
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T v = (r == c) ? T(1) : T(0);
+      v += Lam(r, 0) * Pvv(0, c);
+      v += Lam(r, 1) * Pvv(1, c);
+      v += Lam(r, 2) * Pvv(2, c);
+      Z(r, c) = v;
+    }
+  const M3<T> Zi = inverse(Z);
+  M3<T> W;  // (Lam^-1 + P_vv)^-1 = Zi Lam, symmetric: upper triangle computed, mirrored
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = r; c < 3; ++c) {
+      const T v = Zi(r, 0) * Lam(0, c) + Zi(r, 1) * Lam(1, c) + Zi(r, 2) * Lam(2, c);
+      W(r, c) = v;
+      W(c, r) = v;
+    }
+  V3<T> rr = eta;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    T v = rr[r];
+    v -= Lam(r, 0) * x.v[0];
+    v -= Lam(r, 1) * x.v[1];
+    v -= Lam(r, 2) * x.v[2];
+    rr[r] = v;
+  }
+  const V3<T> t = mul(Zi, rr);
+  add_mul(x.p, P.pv, t);
+  add_mul(x.v, Pvv, t);
+  add_mul_t(x.b, P.vb, t);
+  // P -= P_v W P_v',  P_v = [P_pv; P_vv; P_vb']  -- block rows in an order that lets every block be updated in place
+  {
+    const M3<T> Kp = mul(P.pv, W);
+    sub_mul_nt_sym(P.pp, Kp, P.pv);
+    sub_mul(P.pb, Kp, P.vb);
+    sub_mul(P.pv, Kp, Pvv);
+  }
+  {
+    const M3<T> G = mul(W, P.vb);
+    sub_mul_tn_sym(P.bb, P.vb, G);
+    sub_mul(P.vb, Pvv, G);
+  }
+  {
+    const M3<T> Kv = mul(Pvv, W);
+    sub_mul_sym(P.vv, Kv, Pvv);
+  }
+}
+
+template <typename T>
+DEKF_HD void propagate2(const MheConst<T> &c, Cov9<T> &P, Vec9<T> &x, const M3<T> &R, const V3<T> &as, bool vo,
+                        const V3<T> &dlt) {
+  const T dt = c.dt, h = T(0.5) * c.dt * c.dt;
+  // mean: p+ = p + dt v + h (a_s - R b),  v+ = v + dt (a_s - R b)
+  const V3<T> Rxb = mul(R, x.b);
+  const V3<T> acc = sub(as, Rxb);
+  const V3<T> hmean = v3<T>(dt * x.v[0] + h * acc[0], dt * x.v[1] + h * acc[1], dt * x.v[2] + h * acc[2]);
+  // products with the bias blocks shared by the time update and the VO row
+  const M3<T> Cv = mul_nt(P.vb, R);      // P_vb R'
+  const M3<T> B = mul(R, to_m3(P.bb));   // R P_bb
+  const S3<T> BR = mul_nt_sym(B, R);     // R P_bb R'
+  M3<T> Cp = mul_nt(P.pb, R);            // P_pb R'  (old P_pb)
+  const RotOuter<T> ro = rot_outer(R);
+  const S3<T> C1 = rdrt2(ro, c.n1), C2 = rdrt2(ro, c.n2);
+  M3<T> Up, Uv, Ub;
+  S3<T> Sinn;
+  if (vo) {
+    // d = p+ - p = L x + (noise),  L = [0, dt I, -h R];  U = Cov(x+, d),  Sinn = Cov(d) + R diag(vo_p_std^2) R'
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        const T plp = dt * P.pv(r, cc) - h * Cp(r, cc);
+        const T plv = dt * P.vv(r, cc) - h * Cv(r, cc);
+        const T plb = dt * P.vb(cc, r) - h * B(cc, r);
+        const T rplb = dt * Cv(cc, r) - h * BR(r, cc);  // (R PL_b)(r,cc)
+        const T vh = dt * plv - h * rplb;
+        Up(r, cc) = plp + vh + C1(r, cc);
+        Uv(r, cc) = plv - dt * rplb + C2(r, cc);
+        Ub(r, cc) = plb;
+        if (r <= cc) Sinn.a[S3<T>::idx(r, cc)] = vh + C1(r, cc);
+      }
+    const S3<T> Cvo = rdrt2(ro, c.nvo);
+#pragma unroll
+    for (int f = 0; f < 6; ++f) Sinn.a[f] += Cvo.a[f];
+  }
+  // time update in place: A = A1 A2, A2: p += dt v, A1: p -= h R b, v -= dt R b
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = r; cc < 3; ++cc) {
+      // P_pp += dt (P_pv' + P_pv_new),  P_pv_new = P_pv + dt P_vv
+      const T s = P.pv(cc, r) + (P.pv(r, cc) + dt * P.vv(r, cc));
+      P.pp.a[S3<T>::idx(r, cc)] += dt * s;
+    }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      P.pv(r, cc) += dt * P.vv(r, cc);
+      P.pb(r, cc) += dt * P.vb(r, cc);
+      Cp(r, cc) += dt * Cv(r, cc);  // (P_pb + dt P_vb) R'
+    }
+  const T hh = h * h, hdt = h * dt, dt2 = dt * dt;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = r; cc < 3; ++cc) {
+      const int k = S3<T>::idx(r, cc);
+      P.pp.a[k] += hh * BR.a[k] - h * (Cp(r, cc) + Cp(cc, r)) + C1.a[k];
+      P.vv.a[k] += dt2 * BR.a[k] - dt * (Cv(r, cc) + Cv(cc, r));
+    }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      P.pv(r, cc) += hdt * BR(r, cc) - dt * Cp(r, cc) - h * Cv(cc, r) + C2(r, cc);
+      P.pb(r, cc) -= h * B(r, cc);
+      P.vb(r, cc) -= dt * B(r, cc);
+    }
+  {
+    const S3<T> C3 = rdrt2(ro, c.n3);
+#pragma unroll
+    for (int f = 0; f < 6; ++f) P.vv.a[f] += C3.a[f];
+  }
+  P.bb.a[0] += c.cab[0];
+  P.bb.a[3] += c.cab[1];
+  P.bb.a[5] += c.cab[2];
+  x.p = add(x.p, hmean);
+  x.v = v3<T>(x.v[0] + dt * acc[0], x.v[1] + dt * acc[1], x.v[2] + dt * acc[2]);
+  if (vo) {
+    const S3<T> Si = inverse(Sinn);
+    const M3<T> Sim = to_m3(Si);
+    const V3<T> nu = sub(dlt, hmean);
+    const V3<T> t = mul(Si, nu);
+    add_mul(x.p, Up, t);
+    add_mul(x.v, Uv, t);
+    add_mul(x.b, Ub, t);
+    {
+      const M3<T> Kp = mul(Up, Sim);
+      sub_mul_nt_sym(P.pp, Kp, Up);
+      sub_mul_nt(P.pv, Kp, Uv);
+      sub_mul_nt(P.pb, Kp, Ub);
+    }
+    {
+      const M3<T> Kv = mul(Uv, Sim);
+      sub_mul_nt_sym(P.vv, Kv, Uv);
+      sub_mul_nt(P.vb, Kv, Ub);
+    }
+    {
+      const M3<T> Kb = mul(Ub, Sim);
+      sub_mul_nt_sym(P.bb, Kb, Ub);
+    }
+  }
+}
+
+// ---- version 3: version 1 with the determinant reciprocal taken off the critical path (products on the adjugate) ----
+template <typename T>
+DEKF_HD void meas_update3(Cov9<T> &P, Vec9<T> &x, const S3<T> &Lam, const V3<T> &eta) {
+  const M3<T> Pvv = to_m3(P.vv);
+  const M3<T> LamM = to_m3(Lam);
+  M3<T> Z = mul(LamM, Pvv);
+  Z(0, 0) += T(1);
+  Z(1, 1) += T(1);
+  Z(2, 2) += T(1);
+  T det;
+  const M3<T> Za = adjugate(Z, det);
+  const T id = T(1) / det;
+  const M3<T> Wu = mul(Za, LamM);
+  const V3<T> r = sub(eta, mul(Lam, x.v));
+  const V3<T> tu = mul(Za, r);
+  const M3<T> W = scale(id, Wu);
+  const V3<T> t = scale(id, tu);
+  const M3<T> Kp = mul(P.pv, W);
+  const M3<T> Kv = mul(Pvv, W);
+  const M3<T> Kb = mul_tn(P.vb, W);
+  x.p = add(x.p, mul(P.pv, t));
+  x.v = add(x.v, mul(Pvv, t));
+  x.b = add(x.b, mul_t(P.vb, t));
+  const S3<T> dpp = mul_nt_sym(Kp, P.pv);
+  const M3<T> dpv = mul(Kp, Pvv);
+  const M3<T> dpb = mul(Kp, P.vb);
+  const M3<T> dvv = mul(Kv, Pvv);
+  const M3<T> dvb = mul(Kv, P.vb);
+  const M3<T> dbb = mul(Kb, P.vb);
+#pragma unroll
+  for (int f = 0; f < 6; ++f) P.pp.a[f] -= dpp.a[f];
+#pragma unroll
+  for (int f = 0; f < 9; ++f) {
+    P.pv.a[f] -= dpv.a[f];
+    P.pb.a[f] -= dpb.a[f];
+    P.vb.a[f] -= dvb.a[f];
+  }
+  const S3<T> dvvs = upper(dvv), dbbs = upper(dbb);
+#pragma unroll
+  for (int f = 0; f < 6; ++f) {
+    P.vv.a[f] -= dvvs.a[f];
+    P.bb.a[f] -= dbbs.a[f];
+  }
+}
+
+// Math policy of the sweep: MV / PV select the version of the measurement / propagation stage.
+template <int MV, int PV>
+struct MathSel {
+  template <typename T>
+  DEKF_HD static void meas(Cov9<T> &P, Vec9<T> &x, const S3<T> &Lam, const V3<T> &eta) {
+    if constexpr (MV == 1)
+      meas_update(P, x, Lam, eta);
+    else if constexpr (MV == 2)
+      meas_update2(P, x, Lam, eta);
+    else
+      meas_update3(P, x, Lam, eta);
+  }
+  template <typename T>
+  DEKF_HD static void prop(const MheConst<T> &c, Cov9<T> &P, Vec9<T> &x, const M3<T> &R, const V3<T> &as, bool vo,
+                           const V3<T> &dlt) {
+    if constexpr (PV == 1)
+      propagate(c, P, x, R, as, vo, dlt);
+    else
+      propagate2(c, P, x, R, as, vo, dlt);
+  }
+};
+// Measured on B200 (tools/tune_solve.cu, profiles/r01_tune_solve.md): fp64 is register-bound at 255 registers, the
+// in-place propagation of version 2 spills more there (139 vs 121 us/launch); fp32 has registers to spare and takes
+// the version with the fewest instructions (67.7 vs 77.4 us/launch).
+template <typename T>
+struct DefaultMath : MathSel<2, 1> {};
+template <>
+struct DefaultMath<float> : MathSel<2, 2> {};
+
 template <typename T>
 struct StageRec {
   M3<T> R;
@@ -954,7 +1194,7 @@ struct GlobalStageSource {
 // reference re-solves the whole QP every step.  `src` hands out the stage records: ordinal j = 0.. is
 // the position in the sweep (stage k0 + j), acquire/release bracket the use of one record (the TMA
 // path maps them onto the full/empty mbarriers of its shared-memory ring).
-template <typename T, typename Source>
+template <typename T, typename Source, typename Math = DefaultMath<T>>
 DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
                       int Tk, int i, Source &src) {
   const int n = dm.n, ns = dm.ns, N = dm.N;
@@ -988,23 +1228,28 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
     }
     k0 = Tk - N;
   }
-  for (int k = k0; k < Tk; ++k) {
+  // one copy of each stage body in the instruction stream (the loop is ~2.4k instructions; the I-cache matters)
+  M3<T> RT;
+  for (int k = k0;; ++k) {
     const int j = k - k0;
     src.acquire(j);
     {
       S3<T> Lam;
       V3<T> eta;
       src.meas(j, k, Lam, eta);
-      meas_update(P, x, Lam, eta);
+      Math::meas(P, x, Lam, eta);
+    }
+    src.rot(j, k, RT);
+    if (k == Tk) {
+      src.release(j);
+      break;
     }
     {
-      M3<T> R;
       V3<T> as, dlt;
       bool vo;
-      src.rot(j, k, R);
       src.dyn(j, k, as, dlt, vo);
       src.release(j);
-      propagate(c, P, x, R, as, vo, dlt);
+      Math::prop(c, P, x, RT, as, vo, dlt);
     }
     if (k == Tk - N) {
       // marginalizeQP(T-N): the arrival cost moves to x_{T-N+1} (MheSrb.cpp:475-713)
@@ -1016,17 +1261,6 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
         b.arr_x[(size_t)(6 + f) * ns + i] = x.b[f];
       }
     }
-  }
-  M3<T> RT;
-  {
-    const int j = Tk - k0;
-    src.acquire(j);
-    S3<T> Lam;
-    V3<T> eta;
-    src.meas(j, Tk, Lam, eta);
-    src.rot(j, Tk, RT);
-    src.release(j);
-    meas_update(P, x, Lam, eta);
   }
   // getsolution(T) + v_MHE_b = R_sb (v + omega x p_imu_2_opti) (DecentralEst.cpp:181-185)
   V3<T> om;

@@ -129,6 +129,12 @@ inline MheConst<T> make_mhe_const(const dekf_config &c) {
     m.P0[6 + i] = (T)std::pow(c.accel_bias_init_std[i], 2);
     m.p_ib[i] = (T)c.p_ib[i];
   }
+  for (int i = 0; i < 3; ++i) {
+    m.n1[i] = (i == 0) ? m.d1[0] : m.d1[i] - m.d1[0];
+    m.n2[i] = (i == 0) ? m.d2[0] : m.d2[i] - m.d2[0];
+    m.n3[i] = (i == 0) ? m.d3[0] : m.d3[i] - m.d3[0];
+    m.nvo[i] = (i == 0) ? m.cvo[0] : m.cvo[i] - m.cvo[0];
+  }
   for (int i = 0; i < 8; ++i) {
     m.cenc_v[i] = (T)std::pow(c.joint_velocity_std[i], 2);
     m.cenc_p[i] = (T)std::pow(c.joint_position_std[i], 2);

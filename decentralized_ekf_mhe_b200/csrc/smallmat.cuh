@@ -223,6 +223,169 @@ DEKF_HD M3<T> inverse(const M3<T> &m) {
   return r;
 }
 
+
+// ---- accumulate-in-place products: every term is one fused multiply-add on the destination ----------------
+// P -= A * B
+template <typename T>
+DEKF_HD void sub_mul(M3<T> &P, const M3<T> &A, const M3<T> &B) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T v = P(r, c);
+      v -= A(r, 0) * B(0, c);
+      v -= A(r, 1) * B(1, c);
+      v -= A(r, 2) * B(2, c);
+      P(r, c) = v;
+    }
+}
+// upper(P) -= upper(A * B)      (A * B symmetric)
+template <typename T>
+DEKF_HD void sub_mul_sym(S3<T> &P, const M3<T> &A, const M3<T> &B) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = r; c < 3; ++c) {
+      T v = P.a[S3<T>::idx(r, c)];
+      v -= A(r, 0) * B(0, c);
+      v -= A(r, 1) * B(1, c);
+      v -= A(r, 2) * B(2, c);
+      P.a[S3<T>::idx(r, c)] = v;
+    }
+}
+// upper(P) -= upper(A * B^T)
+template <typename T>
+DEKF_HD void sub_mul_nt_sym(S3<T> &P, const M3<T> &A, const M3<T> &B) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = r; c < 3; ++c) {
+      T v = P.a[S3<T>::idx(r, c)];
+      v -= A(r, 0) * B(c, 0);
+      v -= A(r, 1) * B(c, 1);
+      v -= A(r, 2) * B(c, 2);
+      P.a[S3<T>::idx(r, c)] = v;
+    }
+}
+// P -= A * B^T
+template <typename T>
+DEKF_HD void sub_mul_nt(M3<T> &P, const M3<T> &A, const M3<T> &B) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T v = P(r, c);
+      v -= A(r, 0) * B(c, 0);
+      v -= A(r, 1) * B(c, 1);
+      v -= A(r, 2) * B(c, 2);
+      P(r, c) = v;
+    }
+}
+// upper(P) -= upper(A^T * B)
+template <typename T>
+DEKF_HD void sub_mul_tn_sym(S3<T> &P, const M3<T> &A, const M3<T> &B) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = r; c < 3; ++c) {
+      T v = P.a[S3<T>::idx(r, c)];
+      v -= A(0, r) * B(0, c);
+      v -= A(1, r) * B(1, c);
+      v -= A(2, r) * B(2, c);
+      P.a[S3<T>::idx(r, c)] = v;
+    }
+}
+// x += A * t,  x += A^T * t
+template <typename T>
+DEKF_HD void add_mul(V3<T> &x, const M3<T> &A, const V3<T> &t) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    T v = x[r];
+    v += A(r, 0) * t[0];
+    v += A(r, 1) * t[1];
+    v += A(r, 2) * t[2];
+    x[r] = v;
+  }
+}
+template <typename T>
+DEKF_HD void add_mul_t(V3<T> &x, const M3<T> &A, const V3<T> &t) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    T v = x[r];
+    v += A(0, r) * t[0];
+    v += A(1, r) * t[1];
+    v += A(2, r) * t[2];
+    x[r] = v;
+  }
+}
+// R diag(d) R^T = d0 I + (d1-d0) r1 r1^T + (d2-d0) r2 r2^T with r1, r2 the 2nd/3rd columns of the rotation R (the
+// columns are orthonormal): o1 = r1 r1^T, o2 = r2 r2^T are shared between all the noise blocks of a stage.
+template <typename T>
+struct RotOuter {
+  S3<T> o1, o2;
+};
+template <typename T>
+DEKF_HD RotOuter<T> rot_outer(const M3<T> &R) {
+  RotOuter<T> o;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = r; c < 3; ++c) {
+      o.o1.a[S3<T>::idx(r, c)] = R(r, 1) * R(c, 1);
+      o.o2.a[S3<T>::idx(r, c)] = R(r, 2) * R(c, 2);
+    }
+  return o;
+}
+// e = (d0, d1-d0, d2-d0)
+template <typename T>
+DEKF_HD S3<T> rdrt2(const RotOuter<T> &o, const T e[3]) {
+  S3<T> s;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) s.a[i] = e[1] * o.o1.a[i] + e[2] * o.o2.a[i];
+  s.a[0] += e[0];
+  s.a[3] += e[0];
+  s.a[5] += e[0];
+  return s;
+}
+
+// unscaled inverses: adj(m) and det(m), inverse = adj / det.  Lets the caller run independent products on the adjugate
+// while the reciprocal of the determinant (a long dependent chain in fp64) is in flight.
+template <typename T>
+DEKF_HD M3<T> adjugate(const M3<T> &m, T &det) {
+  M3<T> r;
+  r(0, 0) = m(1, 1) * m(2, 2) - m(1, 2) * m(2, 1);
+  r(1, 0) = m(1, 2) * m(2, 0) - m(1, 0) * m(2, 2);
+  r(2, 0) = m(1, 0) * m(2, 1) - m(1, 1) * m(2, 0);
+  det = m(0, 0) * r(0, 0) + m(0, 1) * r(1, 0) + m(0, 2) * r(2, 0);
+  r(0, 1) = m(0, 2) * m(2, 1) - m(0, 1) * m(2, 2);
+  r(1, 1) = m(0, 0) * m(2, 2) - m(0, 2) * m(2, 0);
+  r(2, 1) = m(0, 1) * m(2, 0) - m(0, 0) * m(2, 1);
+  r(0, 2) = m(0, 1) * m(1, 2) - m(0, 2) * m(1, 1);
+  r(1, 2) = m(0, 2) * m(1, 0) - m(0, 0) * m(1, 2);
+  r(2, 2) = m(0, 0) * m(1, 1) - m(0, 1) * m(1, 0);
+  return r;
+}
+template <typename T>
+DEKF_HD S3<T> adjugate(const S3<T> &s, T &det) {
+  const T a = s.a[0], b = s.a[1], c = s.a[2], d = s.a[3], e = s.a[4], f = s.a[5];
+  S3<T> r;
+  r.a[0] = d * f - e * e;
+  r.a[1] = c * e - b * f;
+  r.a[2] = b * e - c * d;
+  det = a * r.a[0] + b * r.a[1] + c * r.a[2];
+  r.a[3] = a * f - c * c;
+  r.a[4] = b * c - a * e;
+  r.a[5] = a * d - b * b;
+  return r;
+}
+template <typename T>
+DEKF_HD M3<T> scale(T s, const M3<T> &m) {
+  M3<T> r;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) r.a[i] = s * m.a[i];
+  return r;
+}
+
 // Eigen Quaterniond(q).normalized().toRotationMatrix(), q = [w,x,y,z]
 // (orien_ekf.cpp:296-305, DecentralEst.cpp:867)
 template <typename T>

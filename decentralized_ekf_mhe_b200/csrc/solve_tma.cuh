@@ -1,0 +1,143 @@
+// Window solve with TMA-staged stage tiles (sm_100a).  Included by dekf_api.cu (product) and tools/tune_solve.cu
+// (kernel tuning harness).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "estimator_core.cuh"
+
+namespace dekf {
+
+// ------------------------------------------------------------------------------------------------
+// window solve with TMA-staged stage tiles
+// ------------------------------------------------------------------------------------------------
+// One CTA = 128 consecutive instances.  The window ring is a 2-D tensor [NW*25 rows][ns instances]; the record of
+// stage k for the CTA's instances is the box {128 instances, 25 rows} at (i0, slot*25).  One elected thread fetches
+// each stage with ONE cp.async.bulk.tensor.2d (SASS: UTMALDG) into a kStages-deep shared-memory ring; completion
+// is signalled on a "full" mbarrier (expect_tx), consumers hand the buffer back through an "empty" mbarrier.
+// The stage record is read from shared memory at the point of use instead of being parked in registers.
+constexpr int kTile = 128;
+constexpr int kStages = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <typename T, int TILE = kTile, int STAGES = kStages>
+struct SmemStageSource {
+  T *tiles;         // [STAGES][REC_SIZE][TILE]
+  uint64_t *full;   // [STAGES]
+  uint64_t *empty;  // [STAGES]
+  const CUtensorMap *map;
+  int NW, i0, tid, k0, nst;
+
+  __device__ __forceinline__ void issue(int j) const {  // elected thread only
+    const int buf = j % STAGES;
+    const int slot = (k0 + j) % NW;
+    mbar_expect_tx(&full[buf], (uint32_t)(REC_SIZE * TILE * sizeof(T)));
+    tma_load_2d(tiles + (size_t)buf * REC_SIZE * TILE, map, i0, slot * REC_SIZE, &full[buf]);
+  }
+  __device__ __forceinline__ void acquire(int j) const { mbar_wait(&full[j % STAGES], (uint32_t)((j / STAGES) & 1)); }
+  __device__ __forceinline__ void release(int j) const {
+    mbar_arrive(&empty[j % STAGES]);
+    // the elected thread refills the buffer of the PREVIOUS stage (everybody has long released it) with the
+    // stage STAGES-1 ahead of the current one
+    if (tid == 0 && j >= 1 && (j - 1 + STAGES) < nst) {
+      mbar_wait(&empty[(j - 1) % STAGES], (uint32_t)(((j - 1) / STAGES) & 1));
+      issue(j - 1 + STAGES);
+    }
+  }
+  __device__ __forceinline__ const T *row(int j, int f) const {
+    return tiles + ((size_t)(j % STAGES) * REC_SIZE + f) * TILE + tid;
+  }
+  __device__ __forceinline__ void meas(int j, int, S3<T> &Lam, V3<T> &eta) const {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) Lam.a[f] = *row(j, REC_LAM + f);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) eta[f] = *row(j, REC_ETA + f);
+  }
+  __device__ __forceinline__ void rot(int j, int, M3<T> &R) const {
+#pragma unroll
+    for (int f = 0; f < 9; ++f) R.a[f] = *row(j, REC_R + f);
+  }
+  __device__ __forceinline__ void dyn(int j, int, V3<T> &as, V3<T> &dlt, bool &vo) const {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      as[f] = *row(j, REC_AS + f);
+      dlt[f] = *row(j, REC_DLT + f);
+    }
+    vo = *row(j, REC_FLAG) != T(0);
+  }
+};
+
+template <typename T, int TILE = kTile, int STAGES = kStages>
+constexpr size_t solve_tma_smem_bytes() {
+  return (size_t)STAGES * REC_SIZE * TILE * sizeof(T) + 2 * STAGES * sizeof(uint64_t);
+}
+
+template <typename T, int TILE = kTile, int STAGES = kStages, int MINB = 1, typename Math = DefaultMath<T>>
+__global__ void __launch_bounds__(TILE, MINB) k_solve_tma(const __grid_constant__ CUtensorMap tmap, const MheConst<T> c, const Dims dm,
+                                                     const Buffers<T> b, const Inputs in, const Outputs out, int Tk,
+                                                     int32_t *status_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemStageSource<T, TILE, STAGES> src;
+  src.tiles = reinterpret_cast<T *>(smem_raw);
+  src.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * REC_SIZE * TILE * sizeof(T));
+  src.empty = src.full + STAGES;
+  src.map = &tmap;
+  src.NW = dm.NW;
+  src.i0 = blockIdx.x * TILE;
+  src.tid = threadIdx.x;
+  src.k0 = (Tk < dm.N) ? 0 : Tk - dm.N;
+  src.nst = Tk - src.k0 + 1;
+  const int active = min(TILE, dm.n - src.i0);  // consumers in this CTA (thread 0 is always one of them)
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&src.full[s], 1);
+      mbar_init(&src.empty[s], (uint32_t)active);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int pre = src.nst < STAGES ? src.nst : STAGES;
+    for (int j = 0; j < pre; ++j) src.issue(j);
+  }
+  const int i = src.i0 + threadIdx.x;
+  if (i >= dm.n) return;
+  int st = b.status[i];
+  st |= mhe_solve<T, SmemStageSource<T, TILE, STAGES>, Math>(c, dm, b, in, out, Tk, i, src);
+  b.status[i] = st;
+  if (status_out != nullptr) status_out[i] = st;
+}
+
+}  // namespace dekf

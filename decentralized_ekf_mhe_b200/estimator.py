@@ -373,6 +373,46 @@ class BatchedEstimator:
                                _ptr(host_out.get("contact")), _ptr(host_out.get("status")))
         h.check(h.L.dekf_step_host(h.h, int(T), C.byref(inp), C.byref(out)), "dekf_step_host")
 
+    _IN_KEYS = ("gyro", "accel", "imu_time", "joint_pos", "joint_vel", "foot_force", "vo_flag", "vo_quat", "vo_time_pre",
+                "vo_time_now", "vo_rel_p")
+    _OUT_KEYS = ("quat", "x", "v_body", "contact", "status")
+
+    def _run(self, fn, name, T0, S, stream, vo_steps, out, out_per_step):
+        h = self._hd
+        s0 = int(stream.get("_offset", 0))
+        ptrs = []
+        for k in self._IN_KEYS:
+            t = stream.get(k)
+            if t is None:
+                ptrs.append(None)
+                continue
+            if t.shape[0] < s0 + S or not t.is_contiguous():
+                raise DekfError(f"stream[{k!r}] must be contiguous with at least {s0 + S} ticks")
+            ptrs.append(_ptr(t[s0]))
+        inp = _lib.DekfInputs(*ptrs, None)
+        o = out or {}
+        if out is not None:
+            outs = _lib.DekfOutputs(*[_ptr(o.get(k)) for k in self._OUT_KEYS])
+        elif name == "dekf_run":
+            outs = self._hd._out
+        else:
+            outs = _lib.DekfOutputs(None, None, None, None, None)
+        mask = None
+        if vo_steps is not None:
+            mask = (C.c_uint8 * S)(*[1 if v else 0 for v in vo_steps[:S]])
+        h.check(fn(h.h, int(T0), int(S), C.byref(inp), mask, C.byref(outs), int(bool(out_per_step))), name)
+
+    def run(self, T0, S, stream, vo_steps=None, out=None, out_per_step=False):
+        """``S`` lock-step ticks ``T0..T0+S-1`` in one library call (dekf_run).  ``stream``: dict of DEVICE tensors
+        ``[ticks, rows, n]`` with the synth.make_stream keys (tick 0 of the tensors is tick ``T0`` unless
+        ``stream['_offset']`` says otherwise); ``vo_steps``: per-tick bools (any instance has VO); ``out``: dict of
+        device tensors (``[S, rows, n]`` when ``out_per_step``), default: the handle's own result tensors (last tick)."""
+        self._run(self._hd.L.dekf_run, "dekf_run", T0, S, stream, vo_steps, out, out_per_step)
+
+    def run_host(self, T0, S, stream, vo_steps=None, out=None, out_per_step=False):
+        """Same with pinned HOST tensors: pipelined H2D | kernels | D2H, returns when the results are in host memory."""
+        self._run(self._hd.L.dekf_run_host, "dekf_run_host", T0, S, stream, vo_steps, out, out_per_step)
+
     def reset(self):
         self._hd.check(self._hd.L.dekf_reset(self._hd.h), "dekf_reset")
 

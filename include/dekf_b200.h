@@ -17,6 +17,8 @@
  *                               DecentralEst.hpp:101-102, DecentralEst.cpp:9,152; inside it MHEproblem::updateQP /
  *                               marginalizeQP / initQP / solveQP / getsolution, MheSrb.hpp:99-103
  *   dekf_step                   both timers in lock-step (EKF tick, then MHE update on its quaternion)
+ *   dekf_run                    S such ticks over a [step][field][instance] stream (robotSub::timerCallback driven S
+ *                               times, EstSub.cpp:58-91)
  *   dekf_outputs                public result members R_sb_, x_MHE_, v_MHE_b_ (DecentralEst.hpp:279-285) and the
  *                               imu/filter quaternion (orien_ekf.cpp:92-95)
  *   dekf_get_arrival_cost       MHEproblem::M_p, n_p               MheSrb.hpp:86-87
@@ -147,8 +149,23 @@ int dekf_ekf_step(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out
 int dekf_mhe_step(dekf_handle *h, int32_t T, const dekf_inputs *in, const dekf_outputs *out);
 int dekf_step(dekf_handle *h, int32_t T, const dekf_inputs *in, const dekf_outputs *out);
 
-/* Host-pointer entry point: H2D copies of `in`, dekf_step, D2H copies of `out`, stream sync. */
+/* S consecutive lock-step ticks T0 .. T0+S-1 in one call (trajectory sweeps, Monte-Carlo runs): every non-NULL array of
+ * `in` is a stream [S][rows][n] (tick stride = rows*n elements; vo_flag is [S][n]).  `vo_steps` (HOST array [S], may be
+ * NULL) marks the ticks at which any instance carries a VO message; the other ticks skip the VO arrays.  With
+ * out_per_step != 0 the arrays of `out` are streams [S][rows][n] too, otherwise they receive the last tick only.
+ * Device pointers, stream-ordered, no host synchronisation. */
+int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const uint8_t *vo_steps, const dekf_outputs *out,
+             int32_t out_per_step);
+
+/* Host-pointer entry points (pinned memory for full speed): H2D copies of `in`, the device call, D2H copies of `out`,
+ * stream sync.  dekf_mhe_step_host / dekf_ekf_step_host are what a single-robot ROS node binds. */
 int dekf_step_host(dekf_handle *h, int32_t T, const dekf_inputs *in, const dekf_outputs *out);
+int dekf_mhe_step_host(dekf_handle *h, int32_t T, const dekf_inputs *in, const dekf_outputs *out);
+int dekf_ekf_step_host(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out);
+/* dekf_run with HOST streams: a three-stream software pipeline (H2D of tick s+1 | kernels of tick s | D2H of tick s-1)
+ * over two device staging sets; returns after the last result has landed in host memory. */
+int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const uint8_t *vo_steps,
+                  const dekf_outputs *out, int32_t out_per_step);
 int dekf_synchronize(dekf_handle *h);
 
 /* Getters (device pointers, stream-ordered). */
@@ -159,6 +176,18 @@ int dekf_get_R_sb(dekf_handle *h, double *R /*[9][n]*/);
 int dekf_get_ekf_cov(dekf_handle *h, double *P /*[16][n]*/);
 /* number of window stages whose VO row is currently an equality (LinearConstraint.equality, MheSrb.hpp:38) */
 int dekf_get_window_vo_count(dekf_handle *h, int32_t *count /*[n]*/);
+/* Host-pointer getter for callers without a CUDA runtime of their own (the C++ facade, a ROS node): `what` selects one
+ * of the arrays above, `host_out` receives it (same [rows][n] layout, double; int32 for DEKF_GET_VO_COUNT).
+ * Synchronises the handle's stream. */
+enum {
+  DEKF_GET_R_SB = 0,       /* [9][n]  */
+  DEKF_GET_P_VO = 1,       /* [3][n]  */
+  DEKF_GET_ARRIVAL_M = 2,  /* [81][n] M_p */
+  DEKF_GET_ARRIVAL_N = 3,  /* [9][n]  n_p */
+  DEKF_GET_EKF_COV = 4,    /* [16][n] */
+  DEKF_GET_VO_COUNT = 5    /* [n] int32 */
+};
+int dekf_get_host(dekf_handle *h, int32_t what, void *host_out);
 /* debug taps of the last step (only when cfg.debug_taps != 0): copied into caller DEVICE buffers, any may be NULL.
  * b_meas/Q_meas: DecentralEst.cpp:515-546 per leg (Q as symmetric 3x3: 00,01,02,11,12,22);
  * vo_idx: processed,i_pre,i_now,w0,i0,ins,num,disc0 of DecentralEst.cpp:883-945 (-2 = not set);

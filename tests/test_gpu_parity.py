@@ -172,6 +172,78 @@ def test_separate_class_api_with_external_quaternion(est_mod, oracle):
         np.testing.assert_allclose(R[:, :, i], oracle.quat_to_rot(qs[-1, :, i]), atol=1e-12)
 
 
+def test_run_and_run_host_equal_step_loop(est_mod, monkeypatch):
+    """dekf_run (S ticks per call, device streams) and dekf_run_host (pinned host streams, pipelined copies) return
+    bit-identical per-tick results to the tick-by-tick loop, on the large-batch kernel path."""
+    from decentralized_ekf_mhe_b200 import synth
+    monkeypatch.setenv("DEKF_FUSED_MAX_N", "0")
+    n, S = 200, 70
+    st_t = synth.make_stream(n, S, vo_jitter=True)
+    st = synth.to_numpy(st_t)
+    _, r = _run_lockstep(est_mod, st)
+    vo_steps = [bool(st["vo_flag"][s].any()) for s in range(S)]
+    prm = est_mod.robot_params("go1", ekf_rate=200)
+    for host in (False, True):
+        est = est_mod.BatchedEstimator(prm, n)
+        if host:
+            stream = {k: v.contiguous().pin_memory() for k, v in st_t.items() if torch.is_tensor(v) and v.shape[0] == S}
+            mk = lambda *shape, dt=torch.float64: torch.zeros(*shape, dtype=dt).pin_memory()
+        else:
+            stream = {k: v.cuda().contiguous() for k, v in st_t.items() if torch.is_tensor(v) and v.shape[0] == S}
+            mk = lambda *shape, dt=torch.float64: torch.zeros(*shape, dtype=dt, device="cuda")
+        out = {"quat": mk(S, 4, n), "x": mk(S, 9, n), "v_body": mk(S, 3, n), "contact": mk(S, 4, n, dt=torch.uint8),
+               "status": mk(S, n, dt=torch.int32)}
+        # two calls (30 + 40 ticks) to cover the T0 / stream-offset bookkeeping
+        first = {k: v[:30] for k, v in stream.items()}
+        o1 = {k: v[:30] for k, v in out.items()}
+        rest = {k: v[30:] for k, v in stream.items()}
+        o2 = {k: v[30:] for k, v in out.items()}
+        fn = est.run_host if host else est.run
+        fn(0, 30, first, vo_steps[:30], out=o1, out_per_step=True)
+        fn(30, 40, rest, vo_steps[30:], out=o2, out_per_step=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(out["quat"].cpu().numpy(), r["quat"])
+        assert np.array_equal(out["x"].cpu().numpy()[1:], r["x"][1:])
+        assert np.array_equal(out["v_body"].cpu().numpy()[1:], r["v_body"][1:])
+        assert np.array_equal(out["contact"].cpu().numpy(), r["contact"])
+        assert np.array_equal(out["status"].cpu().numpy(), r["status"])
+        est.close()
+
+
+def test_single_robot_host_entry_points(est_mod, oracle):
+    """dekf_ekf_step_host / dekf_mhe_step_host with n_instances=1 and plain host arrays: the binding a ROS node
+    uses, EKF at 500 Hz feeding the MHE at 200 Hz is not needed here -- both at 200 Hz."""
+    import ctypes as C
+    from decentralized_ekf_mhe_b200 import _lib, synth
+    st = synth.to_numpy(synth.make_stream(1, 90, vo_jitter=True))
+    L = _lib.load()
+    prm = est_mod.robot_params("go1", ekf_rate=200)
+    hd = est_mod._Handle(prm, 1)
+    q = np.zeros((4, 1))
+    x = np.zeros((9, 1))
+    vb = np.zeros((3, 1))
+    qs, xs = [], []
+    P = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+    for s in range(90):
+        a = {k: np.ascontiguousarray(st[k][s]) for k in st if isinstance(st[k], np.ndarray) and st[k].shape[0] == 90}
+        vo = bool(a["vo_flag"].any())
+        ein = _lib.DekfInputs(P(a["gyro"]), P(a["accel"]), P(a["imu_time"]), None, None, None, P(a["vo_flag"]) if vo else None,
+                              P(a["vo_quat"]) if vo else None, None, P(a["vo_time_now"]) if vo else None, None, None)
+        eout = _lib.DekfOutputs(P(q), None, None, None, None)
+        assert L.dekf_ekf_step_host(hd.h, C.byref(ein), C.byref(eout)) == 0
+        qs.append(q.copy())
+        min_ = _lib.DekfInputs(P(a["gyro"]), P(a["accel"]), P(a["imu_time"]), P(a["joint_pos"]), P(a["joint_vel"]),
+                               P(a["foot_force"]), P(a["vo_flag"]) if vo else None, None, P(a["vo_time_pre"]) if vo else None,
+                               P(a["vo_time_now"]) if vo else None, P(a["vo_rel_p"]) if vo else None, P(q))
+        mout = _lib.DekfOutputs(None, P(x), P(vb), None, None)
+        assert L.dekf_mhe_step_host(hd.h, s, C.byref(min_), C.byref(mout)) == 0
+        xs.append(x.copy())
+    ro, _, _ = oracle.run_batch(st, oracle.go1_params(), oracle.ekf_params(rate=200), nthreads=1)
+    assert np.abs(np.array(qs) - ro["quat"]).max() < TOL_Q
+    assert np.abs(np.array(xs)[1:, 3:6] - ro["x"][1:, 3:6]).max() < TOL_V
+    hd.close()
+
+
 def test_host_pointer_path_equals_device_path(est_mod):
     """dekf_step_host (H2D + step + D2H + sync) returns exactly what the device-pointer path returns."""
     from decentralized_ekf_mhe_b200 import synth
