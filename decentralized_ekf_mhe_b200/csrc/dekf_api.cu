@@ -55,6 +55,17 @@ __global__ void __launch_bounds__(kBlock) k_solve(const MheConst<T> c, const Dim
   if (status_out != nullptr) status_out[i] = st;
 }
 
+// KF alternative (est_type 1): one predict + correct per tick instead of the window solve
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_kf(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
+                                               const Outputs out, int Tk, int32_t *status_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  int st = b.status[i];
+  st |= kf_update<T>(c, dm, b, in, out, Tk, i);
+  b.status[i] = st;
+  if (status_out != nullptr) status_out[i] = st;
+}
 
 }  // namespace dekf
 #include "solve_tma.cuh"
@@ -71,7 +82,10 @@ __global__ void __launch_bounds__(kBlock) k_fused(const EkfConst<T> ec, const Mh
 #pragma unroll
   for (int f = 0; f < 4; ++f) q[f] = (double)b.ekf_q[(size_t)f * dm.ns + i];
   st |= mhe_assemble<T, Model>(mc, dm, b, in, out, Tk, i, q);
-  if (Tk >= 1) st |= mhe_solve<T>(mc, dm, b, in, out, Tk, i);
+  if (mc.est_type == 1)
+    st |= kf_update<T>(mc, dm, b, in, out, Tk, i);
+  else if (Tk >= 1)
+    st |= mhe_solve<T>(mc, dm, b, in, out, Tk, i);
   b.status[i] = st;
   if (status_out != nullptr) status_out[i] = st;
 }
@@ -422,7 +436,7 @@ int validate(const dekf_config *c, std::string &why) {
   if (c->robot < DEKF_ROBOT_GO1 || c->robot > DEKF_ROBOT_POGOX) { why = "robot"; return DEKF_EINVAL; }
   if (c->num_legs != robot_num_legs(c->robot)) { why = "num_legs does not match the robot model"; return DEKF_EINVAL; }
   if (c->leg_odom_type != 0) { why = "leg_odom_type 1 (foot-position states) is not built yet"; return DEKF_EINVAL; }
-  if (c->est_type != 0) { why = "est_type 1 (KF alternative) is not built yet"; return DEKF_EINVAL; }
+  if (c->est_type != 0 && c->est_type != 1) { why = "est_type must be 0 (MHE) or 1 (KF alternative)"; return DEKF_EINVAL; }
   if (c->ekf_hist_depth < 4) { why = "ekf_hist_depth < 4"; return DEKF_EINVAL; }
   return DEKF_OK;
 }
@@ -679,13 +693,16 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
   int32_t *st = out ? out->status : nullptr;
   int rc;
   const bool tma = h->use_tma && T_ >= 1;
+  const bool kf = h->cfg.est_type == 1;
   const int tiles = h->dm.ns / kTile;
   if (h->f32) {
     rc = do_assemble<float>(h, h->mc32, h->b32, di, dout, T_, acc);
     if (rc) return fail(h, rc, "assemble");
     if (after_assemble) cudaEventRecord(after_assemble, h->stream);
     ProfScope ps(h, 2);
-    if (tma)
+    if (kf)
+      k_kf<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
+    else if (tma)
       k_solve_tma<float><<<tiles, kTile, solve_tma_smem_bytes<float>(), h->stream>>>(h->tmap, h->mc32, h->dm, h->b32, di, dout, T_, st);
     else
       k_solve<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
@@ -694,7 +711,9 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
     if (rc) return fail(h, rc, "assemble");
     if (after_assemble) cudaEventRecord(after_assemble, h->stream);
     ProfScope ps(h, 2);
-    if (tma)
+    if (kf)
+      k_kf<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
+    else if (tma)
       k_solve_tma<double><<<tiles, kTile, solve_tma_smem_bytes<double>(), h->stream>>>(h->tmap, h->mc64, h->dm, h->b64, di, dout, T_, st);
     else
       k_solve<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
@@ -1110,8 +1129,8 @@ int dekf_get_host(dekf_handle *h, int32_t what, void *host_out) {
   if (!h || !host_out) return fail(h, DEKF_EINVAL, "dekf_get_host: null argument");
   CK(cudaSetDevice(h->cfg.device));
   const size_t n = (size_t)h->dm.n;
-  const size_t rows[6] = {9, 3, 81, 9, 16, 1};
-  if (what < 0 || what > DEKF_GET_VO_COUNT) return fail(h, DEKF_EINVAL, "dekf_get_host: unknown selector");
+  const size_t rows[8] = {9, 3, 81, 9, 16, 1, 81, 9};
+  if (what < 0 || what > DEKF_GET_ARRIVAL_MEAN) return fail(h, DEKF_EINVAL, "dekf_get_host: unknown selector");
   double *d = nullptr;
   CK(cudaMalloc((void **)&d, (size_t)90 * n * sizeof(double)));
   int rc = DEKF_OK;
@@ -1126,6 +1145,11 @@ int dekf_get_host(dekf_handle *h, int32_t what, void *host_out) {
       src = d + 81 * n;
       break;
     case DEKF_GET_EKF_COV: rc = dekf_get_ekf_cov(h, d); break;
+    case DEKF_GET_ARRIVAL_COV: rc = dekf_get_arrival_cov(h, d, d + 81 * n); break;
+    case DEKF_GET_ARRIVAL_MEAN:
+      rc = dekf_get_arrival_cov(h, d, d + 81 * n);
+      src = d + 81 * n;
+      break;
     default:
       rc = dekf_get_window_vo_count(h, (int32_t *)d);
       bytes = n * sizeof(int32_t);

@@ -72,6 +72,7 @@ struct MheConst {
   double thr;  // contact threshold, compared in double on the raw input (bit-exact)
   double dt_d;
   int N;
+  int est_type;  // 0: MHE (DecentralEst.cpp:156-187), 1: KF alternative (:189-196, :592-861)
 };
 
 struct Dims {
@@ -464,7 +465,18 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
 #pragma unroll
     for (int f = 0; f < 3; ++f) relp[f] = in.vo_rel_p[(size_t)f * n + i];
   }
-  if (Tk == 0) {
+  const bool kf = c.est_type == 1;
+  if (kf) {
+    // KF alternative: initialize() runs InitializeKF + UpdateKF (DecentralEst.cpp:139-141), i.e. GetMeasurement(0)
+    // twice at T==0: the first call sees an empty stack (message stays latched, :884), the second one sees
+    // [sample 0] and consumes it.  Every later call is GetMeasurement(0) too (:787), so w0 == stack size and no
+    // VO bound is ever inserted; only p_vo_accmulate_ and the way points advance.
+    if (Tk == 0) {
+      b.hist_time[i] = in.imu_time[i];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) b.hist_quat[(size_t)f * ns + i] = qd[f];
+    }
+  } else if (Tk == 0) {
     // stack is empty: the message stays latched in robot_store (vo_new_ remains true)
     b.pend_flag[i] = (uint8_t)vo_new;
     if (vo_new) {
@@ -483,8 +495,9 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
   }
   int dbg[8] = {-2, -2, -2, -2, -2, -2, -2, -2};
   if (vo_new) {
-    const int size = (Tk < HR) ? Tk : HR;  // samples held: discrete times Tk-size .. Tk-1
-    const int first = Tk - size;
+    // samples held: discrete times Tk-size .. Tk-1 (KF alternative at T==0: sample 0 itself, see above)
+    const int size = (kf && Tk == 0) ? 1 : ((Tk < HR) ? Tk : HR);
+    const int first = (kf && Tk == 0) ? 0 : Tk - size;
     dbg[0] = 0;
     const int ub = ring_upper_bound(b.hist_time, ns, i, first, size, HR, t_pre);  // :895
     if (ub == 0) {
@@ -502,9 +515,10 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
         pv[f] = b.p_vo[(size_t)f * ns + i] + (Rp(f, 0) * relp[0] + Rp(f, 1) * relp[1] + Rp(f, 2) * relp[2]);  // :915
         b.p_vo[(size_t)f * ns + i] = pv[f];
       }
-      const int w0 = size - ((N < Tk) ? N : Tk);  // :917
-      const int i0 = (w0 > i_pre) ? w0 : i_pre;   // :918
-      const double t_start = b.hist_time[(size_t)((first + i0) % HR) * ns + i];  // :919
+      const int w0 = kf ? size : size - ((N < Tk) ? N : Tk);  // :917 (KF alternative: GetMeasurement(0) -> min(N,0))
+      const int i0 = (w0 > i_pre) ? w0 : i_pre;               // :918
+      // :919 (the reference reads one past the end here in the KF alternative; the value is unused then)
+      const double t_start = (i0 < size) ? b.hist_time[(size_t)((first + i0) % HR) * ns + i] : 0.0;
       const int disc0 = first + i0;                                             // :920
       // add_way_point (Bezier_simple.cpp:12-27): keep the last four
       int cnt = b.wp_count[i];
@@ -1291,6 +1305,87 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
                       int Tk, int i) {
   GlobalStageSource<T> src(dm, b, i);
   return mhe_solve<T>(c, dm, b, in, out, Tk, i, src);
+}
+
+// KF alternative, est_type_ == 1 (DecentralEst.cpp:592-861 InitializeKF / UpdateKF, :189-196 output): the same
+// linear-Gaussian model filtered one sample at a time, (x_KF_, C_KF_) kept in arr_x / arr_P.  T == 0 is
+// InitializeKF + UpdateKF on the same sample (DecentralEst.cpp:139-141): prior -> correct(0) -> predict with
+// (R_0, a_s,0) -> correct(0) again.  T >= 1: predict with the previous sample's (R, a_s) (:706-707 read the
+// stack back BEFORE GetMeasurement), correct with the new sample (:787-860).  The correction uses the
+// sufficient statistic (Lambda, eta) of the leg-odometry rows like the MHE sweep; C_KF_ stays symmetric.
+template <typename T, typename Math = DefaultMath<T>>
+DEKF_HD int kf_update(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
+                      int Tk, int i) {
+  const int n = dm.n, ns = dm.ns;
+  GlobalStageSource<T> src(dm, b, i);
+  Cov9<T> P;
+  Vec9<T> x;
+  S3<T> Lam;
+  V3<T> eta, as, dlt;
+  M3<T> R;
+  bool vo;
+  if (Tk == 0) {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) P.pp.a[f] = P.vv.a[f] = P.bb.a[f] = T(0);
+#pragma unroll
+    for (int f = 0; f < 9; ++f) P.pv.a[f] = P.pb.a[f] = P.vb.a[f] = T(0);
+    P.pp.a[0] = c.P0[0];
+    P.pp.a[3] = c.P0[1];
+    P.pp.a[5] = c.P0[2];
+    P.vv.a[0] = c.P0[3];
+    P.vv.a[3] = c.P0[4];
+    P.vv.a[5] = c.P0[5];
+    P.bb.a[0] = c.P0[6];
+    P.bb.a[3] = c.P0[7];
+    P.bb.a[5] = c.P0[8];
+    x.p = x.v = x.b = v3<T>(T(0), T(0), T(0));
+    src.meas(0, 0, Lam, eta);
+    Math::meas(P, x, Lam, eta);  // :697-699
+  } else {
+    load_cov(b.arr_P, ns, i, P);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      x.p[f] = b.arr_x[(size_t)f * ns + i];
+      x.v[f] = b.arr_x[(size_t)(3 + f) * ns + i];
+      x.b[f] = b.arr_x[(size_t)(6 + f) * ns + i];
+    }
+  }
+  const int kp = (Tk == 0) ? 0 : Tk - 1;
+  src.rot(0, kp, R);
+  src.dyn(0, kp, as, dlt, vo);
+  Math::prop(c, P, x, R, as, false, dlt);  // :783-785 (the KF alternative has no VO rows)
+  src.meas(0, Tk, Lam, eta);
+  Math::meas(P, x, Lam, eta);  // :858-860
+  src.rot(0, Tk, R);
+  store_cov(b.arr_P, ns, i, P);
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    b.arr_x[(size_t)f * ns + i] = x.p[f];
+    b.arr_x[(size_t)(3 + f) * ns + i] = x.v[f];
+    b.arr_x[(size_t)(6 + f) * ns + i] = x.b[f];
+  }
+  // v_KF_b_ = R_sb (v + omega x p_imu_2_opti) (:192-194)
+  V3<T> om;
+#pragma unroll
+  for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
+  const V3<T> lever = v3<T>(T(0.016041), T(0.089061), T(0.0579875));
+  const V3<T> vb = mul(R, add(x.v, cross(om, lever)));
+  int status = 0;
+  const T chk = x.p[0] + x.p[1] + x.p[2] + x.v[0] + x.v[1] + x.v[2] + x.b[0] + x.b[1] + x.b[2];
+  if (!(chk == chk) || !(chk - chk == T(0))) status |= ST_NONFINITE;
+  if (out.x != nullptr) {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      out.x[(size_t)f * n + i] = (double)x.p[f];
+      out.x[(size_t)(3 + f) * n + i] = (double)x.v[f];
+      out.x[(size_t)(6 + f) * n + i] = (double)x.b[f];
+    }
+  }
+  if (out.v_body != nullptr) {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) out.v_body[(size_t)f * n + i] = (double)vb[f];
+  }
+  return status;
 }
 
 }  // namespace dekf

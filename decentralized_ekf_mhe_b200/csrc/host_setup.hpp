@@ -112,6 +112,7 @@ inline MheConst<T> make_mhe_const(const dekf_config &c) {
   m.dt = (T)dt;
   m.dt_d = dt;
   m.N = c.N;
+  m.est_type = c.est_type;
   m.thr = c.contact_effort_threshold;
   for (int i = 0; i < 3; ++i) {
     const double Cp = std::pow(c.p_process_std[i], 2), Ca = std::pow(c.accel_input_std[i], 2);

@@ -207,8 +207,6 @@ class DecentralizedEstimation:
     # -- reference API ---------------------------------------------------------------------------
     def initialize(self, sub, params):
         self.robot_sub_ptr_, self.params_ptr_ = sub, params
-        if params.est_type_ != 0:
-            raise DekfError("est_type 1 (KF alternative) is not built yet")
         self._hd = _Handle(params, self._n, self._device, self._precision, self._taps)
         self._step_mhe(0)
 
@@ -229,6 +227,19 @@ class DecentralizedEstimation:
     @property
     def v_MHE_b_(self):
         return self._hd.v_body
+
+    # KF alternative, est_type_ == 1 (DecentralEst.hpp:286-291): the step outputs are x_KF_ / v_KF_b_ then
+    @property
+    def x_KF_(self):
+        return self._hd.x
+
+    @property
+    def v_KF_b_(self):
+        return self._hd.v_body
+
+    @property
+    def C_KF_(self):
+        return self.mhe_qp_.arrival_cov()[0]
 
     @property
     def contact_(self):

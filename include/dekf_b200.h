@@ -15,7 +15,10 @@
  *                                vo_nonlinear_correct :144)        orien_est/include/orien_ekf.hpp:79-83
  *   dekf_mhe_step               DecentralizedEstimation::initialize (T==0) / ::update(int T) (T>=1)
  *                               DecentralEst.hpp:101-102, DecentralEst.cpp:9,152; inside it MHEproblem::updateQP /
- *                               marginalizeQP / initQP / solveQP / getsolution, MheSrb.hpp:99-103
+ *                               marginalizeQP / initQP / solveQP / getsolution, MheSrb.hpp:99-103.
+ *                               cfg.est_type == 1 selects the KF alternative instead (InitializeKF / UpdateKF,
+ *                               DecentralEst.cpp:592-861): outputs x / v_body are then x_KF_ / v_KF_b_ (valid from
+ *                               T == 0) and dekf_get_arrival_cov returns (C_KF_, x_KF_)
  *   dekf_step                   both timers in lock-step (EKF tick, then MHE update on its quaternion)
  *   dekf_run                    S such ticks over a [step][field][instance] stream (robotSub::timerCallback driven S
  *                               times, EstSub.cpp:58-91)
@@ -185,7 +188,9 @@ enum {
   DEKF_GET_ARRIVAL_M = 2,  /* [81][n] M_p */
   DEKF_GET_ARRIVAL_N = 3,  /* [9][n]  n_p */
   DEKF_GET_EKF_COV = 4,    /* [16][n] */
-  DEKF_GET_VO_COUNT = 5    /* [n] int32 */
+  DEKF_GET_VO_COUNT = 5,   /* [n] int32 */
+  DEKF_GET_ARRIVAL_COV = 6,  /* [81][n] arrival covariance; est_type 1: C_KF_ (DecentralEst.hpp:288) */
+  DEKF_GET_ARRIVAL_MEAN = 7  /* [9][n]  arrival mean;       est_type 1: x_KF_ */
 };
 int dekf_get_host(dekf_handle *h, int32_t what, void *host_out);
 /* debug taps of the last step (only when cfg.debug_taps != 0): copied into caller DEVICE buffers, any may be NULL.

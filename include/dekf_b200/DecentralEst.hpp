@@ -235,8 +235,11 @@ class DecentralizedEstimation {
     n_ = cfg.n_instances;
     nl_ = cfg.num_legs;
     nq_ = dekf_num_joints(h_);
-    x_MHE_.assign(9 * (size_t)n_, 0.0);
-    v_MHE_b_.assign(3 * (size_t)n_, 0.0);
+    kf_ = cfg.est_type == 1;
+    x_MHE_.assign(kf_ ? 0 : 9 * (size_t)n_, 0.0);
+    v_MHE_b_.assign(kf_ ? 0 : 3 * (size_t)n_, 0.0);
+    x_KF_.assign(kf_ ? 9 * (size_t)n_ : 0, 0.0);
+    v_KF_b_.assign(kf_ ? 3 * (size_t)n_ : 0, 0.0);
     R_sb_.assign(9 * (size_t)n_, 0.0);
     p_vo_accmulate_.assign(3 * (size_t)n_, 0.0);
     status_.assign(n_, 0);
@@ -257,6 +260,14 @@ class DecentralizedEstimation {
   std::vector<double> p_vo_accmulate_;  // [3][n]
   std::vector<double> x_MHE_;           // [9][n]  p_s, v_s, accel bias
   std::vector<double> v_MHE_b_;         // [3][n]
+  // KF alternative, est_type_ == 1 (DecentralEst.hpp:286-291): filled instead of x_MHE_ / v_MHE_b_
+  std::vector<double> x_KF_;            // [9][n]
+  std::vector<double> v_KF_b_;          // [3][n]
+  std::vector<double> C_KF_() const {   // [81][n] row-major 9x9 per instance
+    std::vector<double> c(81 * (size_t)n_);
+    detail::check(dekf_get_host(h_, DEKF_GET_ARRIVAL_COV, c.data()), h_, "dekf_get_host");
+    return c;
+  }
   std::vector<int32_t> status_;         // [n] DEKF_ST_* bits of the last update
 
   // MHEproblem::M_p / n_p (MheSrb.hpp:86-87) of every instance
@@ -297,8 +308,8 @@ class DecentralizedEstimation {
     }
     dekf_outputs out;
     std::memset(&out, 0, sizeof(out));
-    out.x = x_MHE_.data();
-    out.v_body = v_MHE_b_.data();
+    out.x = kf_ ? x_KF_.data() : x_MHE_.data();
+    out.v_body = kf_ ? v_KF_b_.data() : v_MHE_b_.data();
     st.contact_.resize((size_t)nl_ * n_);
     out.contact = st.contact_.data();
     out.status = status_.data();
@@ -312,6 +323,7 @@ class DecentralizedEstimation {
   std::shared_ptr<robot_params> params_ptr_;
   dekf_handle *h_ = nullptr;
   int n_ = 0, nl_ = 0, nq_ = 0;
+  bool kf_ = false;
 };
 
 }  // namespace dekf

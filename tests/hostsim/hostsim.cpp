@@ -102,7 +102,10 @@ void run(const dekf_config &cfg, int S, const double *gyro, const double *accel,
       for (int f = 0; f < 4; ++f)
         q[f] = in.quat ? in.quat[(size_t)f * n + i] : (double)sim.b.ekf_q[(size_t)f * sim.dm.ns + i];
       st |= mhe_assemble<T, Model>(sim.mc, sim.dm, sim.b, in, out, s, i, q);
-      if (s >= 1) st |= mhe_solve<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
+      if (cfg.est_type == 1)
+        st |= kf_update<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
+      else if (s >= 1)
+        st |= mhe_solve<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
       status_out[(size_t)s * n + i] = st;
       for (int f = 0; f < 3; ++f) pvo_out[((size_t)s * 3 + f) * n + i] = sim.b.p_vo[(size_t)f * sim.dm.ns + i];
     }

@@ -79,3 +79,15 @@ def test_builder_models_match_generalised_oracle(oracle, robot, rid, nl):
     assert np.array_equal(r["contact"], ro["contact"])
     assert np.array_equal(r["vo_dbg"], ro["vo_dbg"][:, :8])
     assert r["contact"].any() and not r["contact"].all()
+
+
+def test_kf_alternative_matches_oracle(oracle, go1_stream_small):
+    """est_type 1 (DecentralEst.cpp:592-861): x_KF_, v_KF_b_ and p_vo_accmulate_ against the oracle's KF path."""
+    import pyhostsim as hs
+    st = go1_stream_small
+    r = hs.run(st, _cfg(est_type=1))
+    ro, _, _ = oracle.run_batch(st, oracle.go1_params(est_type=1), oracle.ekf_params(rate=200), nthreads=4)
+    assert np.abs(r["x"][1:] - ro["x"][1:]).max() < 1e-10
+    assert np.abs(r["v_body"][1:] - ro["v_body"][1:]).max() < 1e-10
+    assert np.abs(r["p_vo"] - ro["p_vo"]).max() < 1e-12
+    assert np.abs(ro["p_vo"]).max() > 0.1  # VO messages were consumed
