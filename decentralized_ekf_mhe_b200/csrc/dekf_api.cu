@@ -55,6 +55,19 @@ __global__ void __launch_bounds__(kBlock) k_solve(const MheConst<T> c, const Dim
   if (status_out != nullptr) status_out[i] = st;
 }
 
+// state-constrained window solve (cfg.v_box_enable): marginalise + primal-dual active set on the block-tridiagonal QP
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_solve_box(const MheConst<T> c, const BoxConst bc, const Dims dm, const Buffers<T> b,
+                                                      const BoxBuffers bb, const Inputs in, const Outputs out, int Tk,
+                                                      int32_t *status_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  int st = b.status[i];
+  if (Tk >= 1) st |= mhe_solve_box<T>(c, bc, dm, b, bb, in, out, Tk, i);
+  b.status[i] = st;
+  if (status_out != nullptr) status_out[i] = st;
+}
+
 // KF alternative (est_type 1): one predict + correct per tick instead of the window solve
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_kf(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
@@ -230,6 +243,8 @@ struct dekf_handle {
   MheConst<float> mc32;
   Buffers<double> b64;
   Buffers<float> b32;
+  BoxConst bc;
+  BoxBuffers bb = {nullptr, nullptr, nullptr, nullptr};
   void *slab = nullptr;
   size_t slab_bytes = 0;
   // device staging of the host-pointer entry points (set 1 and the copy streams only exist after dekf_run_host)
@@ -438,6 +453,11 @@ int validate(const dekf_config *c, std::string &why) {
   if (c->leg_odom_type != 0) { why = "leg_odom_type 1 (foot-position states) is not built yet"; return DEKF_EINVAL; }
   if (c->est_type != 0 && c->est_type != 1) { why = "est_type must be 0 (MHE) or 1 (KF alternative)"; return DEKF_EINVAL; }
   if (c->ekf_hist_depth < 4) { why = "ekf_hist_depth < 4"; return DEKF_EINVAL; }
+  if (c->v_box_enable) {
+    if (c->est_type != 0) { why = "v_box_enable needs est_type 0 (the KF alternative has no constraints)"; return DEKF_EINVAL; }
+    for (int i = 0; i < 3; ++i)
+      if (!(c->v_box_lo[i] < c->v_box_hi[i])) { why = "v_box_lo must be < v_box_hi"; return DEKF_EINVAL; }
+  }
   return DEKF_OK;
 }
 
@@ -564,6 +584,16 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     }
   }
   h->extra_bytes = 0;
+  h->bc = make_box_const(*cfg);
+  if (cfg->v_box_enable) {
+    const size_t ns = (size_t)h->dm.ns;
+    const size_t fac = (size_t)h->dm.N * BOX_FAC * ns * sizeof(double), act = (size_t)h->dm.NW * ns;
+    if ((ce = cudaMalloc((void **)&h->bb.fac, fac)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc(box factor scratch)", ce);
+    if ((ce = cudaMalloc((void **)&h->bb.act, act)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    if ((ce = cudaMalloc((void **)&h->bb.iters, ns * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    if ((ce = cudaMalloc((void **)&h->bb.nactive, ns * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    h->extra_bytes += fac + act + 2 * ns * sizeof(int32_t);
+  }
   if (cfg->debug_taps) {
     if ((ce = cudaMalloc((void **)&h->tap_b_meas, (size_t)3 * h->nl * n * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
     if ((ce = cudaMalloc((void **)&h->tap_Q_meas, (size_t)6 * h->nl * n * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
@@ -589,6 +619,10 @@ int dekf_destroy(dekf_handle *h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->slab);
+  cudaFree(h->bb.fac);
+  cudaFree(h->bb.act);
+  cudaFree(h->bb.iters);
+  cudaFree(h->bb.nactive);
   free_stage_set(h->stage[0]);
   free_stage_set(h->stage[1]);
   if (h->s_ekf) cudaStreamDestroy(h->s_ekf);
@@ -629,6 +663,11 @@ int dekf_reset(dekf_handle *h) {
   if (!h) return DEKF_EINVAL;
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemsetAsync(h->slab, 0, h->slab_bytes, h->stream));
+  if (h->bb.act) {
+    CK(cudaMemsetAsync(h->bb.act, 0, (size_t)h->dm.NW * h->dm.ns, h->stream));
+    CK(cudaMemsetAsync(h->bb.iters, 0, (size_t)h->dm.ns * sizeof(int32_t), h->stream));
+    CK(cudaMemsetAsync(h->bb.nactive, 0, (size_t)h->dm.ns * sizeof(int32_t), h->stream));
+  }
   if (h->f32)
     k_init_state<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->ec32, h->mc32, h->dm, h->b32);
   else
@@ -702,6 +741,8 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
     ProfScope ps(h, 2);
     if (kf)
       k_kf<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
+    else if (h->bc.enable)
+      k_solve_box<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->bc, h->dm, h->b32, h->bb, di, dout, T_, st);
     else if (tma)
       k_solve_tma<float><<<tiles, kTile, solve_tma_smem_bytes<float>(), h->stream>>>(h->tmap, h->mc32, h->dm, h->b32, di, dout, T_, st);
     else
@@ -713,6 +754,8 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
     ProfScope ps(h, 2);
     if (kf)
       k_kf<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
+    else if (h->bc.enable)
+      k_solve_box<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->bc, h->dm, h->b64, h->bb, di, dout, T_, st);
     else if (tma)
       k_solve_tma<double><<<tiles, kTile, solve_tma_smem_bytes<double>(), h->stream>>>(h->tmap, h->mc64, h->dm, h->b64, di, dout, T_, st);
     else
@@ -743,7 +786,7 @@ int dekf_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outp
   CK(cudaSetDevice(h->cfg.device));
   dekf_inputs in2 = *in;
   in2.quat = nullptr;  // lock-step: the MHE consumes this tick's EKF quaternion
-  if (h->dm.n <= h->fused_max) {
+  if (h->dm.n <= h->fused_max && !h->bc.enable) {
     const Inputs di = to_inputs(&in2);
     const Outputs dout = to_outputs(h, out);
     int32_t *st = out ? out->status : nullptr;
@@ -955,7 +998,7 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     }
   };
   // small batches (one fused launch per tick) and tapped handles: plain tick loop
-  if (h->dm.n <= h->fused_max || h->cfg.debug_taps || S < 2) {
+  if ((h->dm.n <= h->fused_max && !h->bc.enable) || h->cfg.debug_taps || S < 2) {
     for (int32_t s = 0; s < S; ++s) {
       dekf_inputs is;
       offset_inputs(h, in, (size_t)s, !vo_steps || vo_steps[s], &is);
@@ -1160,6 +1203,16 @@ int dekf_get_host(dekf_handle *h, int32_t what, void *host_out) {
   cudaFree(d);
   if (rc) return rc;
   if (ce != cudaSuccess) return fail(h, DEKF_ECUDA, "dekf_get_host", ce);
+  return DEKF_OK;
+}
+
+int dekf_get_qp_info(dekf_handle *h, int32_t *iters, int32_t *n_active) {
+  if (!h) return DEKF_EINVAL;
+  if (!h->bc.enable) return fail(h, DEKF_EINVAL, "handle was created without v_box_enable");
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t bytes = (size_t)h->dm.n * sizeof(int32_t);
+  if (iters) CK(cudaMemcpyAsync(iters, h->bb.iters, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  if (n_active) CK(cudaMemcpyAsync(n_active, h->bb.nactive, bytes, cudaMemcpyDeviceToDevice, h->stream));
   return DEKF_OK;
 }
 

@@ -44,7 +44,8 @@ enum StatusBits {
   ST_EKF_HIST_OVERFLOW = 4,  // VO older than the device history ring (reference stacks are unbounded)
   ST_MHE_VO_DROPPED = 8,     // DecentralEst.cpp:898-904
   ST_MHE_VO_BOUNDED = 16,    // vo_to_be_processed_flag_ was set this step
-  ST_NONFINITE = 32
+  ST_NONFINITE = 32,
+  ST_QP_MAXITER = 64         // constrained window solve: active set still changing at max_iter
 };
 
 template <typename T>

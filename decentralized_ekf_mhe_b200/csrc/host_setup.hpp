@@ -7,6 +7,7 @@
 
 #include "../../include/dekf_b200.h"
 #include "estimator_core.cuh"
+#include "box_solve.cuh"
 
 namespace dekf {
 
@@ -141,6 +142,29 @@ inline MheConst<T> make_mhe_const(const dekf_config &c) {
     m.cenc_p[i] = (T)std::pow(c.joint_position_std[i], 2);
   }
   return m;
+}
+
+// constants of the state-constrained solve (always double)
+inline BoxConst make_box_const(const dekf_config &c) {
+  BoxConst b;
+  std::memset(&b, 0, sizeof(b));
+  b.enable = c.v_box_enable != 0;
+  b.max_iter = c.v_box_max_iter > 0 ? c.v_box_max_iter : 50;
+  const double dt = 1.0 / c.rate;
+  b.dt = dt;
+  for (int i = 0; i < 3; ++i) {
+    b.lo[i] = c.v_box_lo[i];
+    b.hi[i] = c.v_box_hi[i];
+    const double Cp = std::pow(c.p_process_std[i], 2), Ca = std::pow(c.accel_input_std[i], 2);
+    const double d1 = dt * dt * Cp + 0.25 * dt * dt * dt * dt * Ca, d2 = 0.5 * dt * dt * dt * Ca, d3 = dt * dt * Ca;
+    const double det = d1 * d3 - d2 * d2;  // (G C G')^-1 per axis, DecentralEst.cpp:409-418
+    b.qa[i] = d3 / det;
+    b.qb[i] = -d2 / det;
+    b.qc[i] = d1 / det;
+    b.qab[i] = 1.0 / (dt * dt * std::pow(c.accel_bias_std[i], 2));  // Q_accel_bias / dt^2, :422-424
+    b.qvo[i] = 1.0 / std::pow(c.vo_p_std[i], 2);                    // Q_vo, :477
+  }
+  return b;
 }
 
 // fields per instance of every state array, in units of elements

@@ -437,6 +437,14 @@ class BatchedEstimator:
         h.check(h.L.dekf_get_window_vo_count(h.h, _ptr(c)), "dekf_get_window_vo_count")
         return c
 
+    def qp_info(self):
+        """(factorisations, active bounds) [n] int32 of the last state-constrained solve (params.v_box_enable)."""
+        h = self._hd
+        it = torch.empty(h.n, dtype=torch.int32, device=h.device)
+        na = torch.empty(h.n, dtype=torch.int32, device=h.device)
+        h.check(h.L.dekf_get_qp_info(h.h, _ptr(it), _ptr(na)), "dekf_get_qp_info")
+        return it, na
+
     def profile(self, enable):
         self._hd.check(self._hd.L.dekf_profile_enable(self._hd.h, int(bool(enable))), "dekf_profile_enable")
 

@@ -10,7 +10,7 @@ ROBOT_IDS = {"go1": ROBOT_GO1, "cassie": ROBOT_CASSIE, "pogox": ROBOT_POGOX}
 
 # per-instance status bits (include/dekf_b200.h)
 ST_EKF_VO_DROPPED, ST_EKF_VO_NO_REPLAY, ST_EKF_HIST_OVERFLOW = 1, 2, 4
-ST_MHE_VO_DROPPED, ST_MHE_VO_BOUNDED, ST_NONFINITE = 8, 16, 32
+ST_MHE_VO_DROPPED, ST_MHE_VO_BOUNDED, ST_NONFINITE, ST_QP_MAXITER = 8, 16, 32, 64
 
 
 class DekfConfig(C.Structure):
@@ -33,6 +33,8 @@ class DekfConfig(C.Structure):
         ("ekf_init_std", C.c_double * 4), ("ekf_process_std", C.c_double * 3),
         ("ekf_gravity_meas_std", C.c_double * 3), ("ekf_vo_meas_std", C.c_double * 4),
         ("ekf_quaternion_init", C.c_double * 4), ("ekf_rate", C.c_int32), ("reserved2", C.c_int32),
+        ("v_box_enable", C.c_int32), ("v_box_max_iter", C.c_int32),
+        ("v_box_lo", C.c_double * 3), ("v_box_hi", C.c_double * 3),
     ]
 
     def update(self, **over):

@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define DEKF_ABI_VERSION 1
+#define DEKF_ABI_VERSION 2
 
 enum {
   DEKF_OK = 0,
@@ -71,7 +71,8 @@ enum {
   DEKF_ST_EKF_HIST_OVERFLOW = 4, /* VO older than the device-side history ring (reference keeps everything) */
   DEKF_ST_MHE_VO_DROPPED = 8,    /* DecentralEst.cpp:898-904 */
   DEKF_ST_MHE_VO_BOUNDED = 16,   /* VO bounds were inserted this step (vo_to_be_processed_flag_) */
-  DEKF_ST_NONFINITE = 32
+  DEKF_ST_NONFINITE = 32,
+  DEKF_ST_QP_MAXITER = 64        /* state-constrained solve (v_box_enable): active set still changing at the iteration cap */
 };
 
 typedef struct dekf_config {
@@ -104,6 +105,12 @@ typedef struct dekf_config {
   double ekf_init_std[4], ekf_process_std[3], ekf_gravity_meas_std[3], ekf_vo_meas_std[4];
   double ekf_quaternion_init[4];
   int32_t ekf_rate, reserved2;
+
+  /* ---- state constraints (builder extension; the reference's MHEproblem::addConstraints(name, lb, ub) with
+   * lb < ub, MheSrb.cpp:58-68, is never exercised by DecentralEst.cpp).  v_box_enable != 0 adds the rows
+   * v_box_lo <= v_s of x_k <= v_box_hi for every state of the window at solve time (est_type 0 only). */
+  int32_t v_box_enable, v_box_max_iter; /* max_iter 0 = default (50 factorisations) */
+  double v_box_lo[3], v_box_hi[3];
 } dekf_config;
 
 /* Per-tick sensor snapshot of all instances.  NULL vo_flag == no VO message for anybody. */
@@ -210,6 +217,10 @@ int dekf_profile_read(dekf_handle *h, double *ms /*[3]*/, int64_t *count /*[3]*/
  * dense non-tensor FMA throughput in TFLOP/s (FMA = 2 flop) and a device-to-device copy in GB/s (read+write). */
 int dekf_measure_fma_peak(int32_t device, int32_t precision, double *tflops);
 int dekf_measure_copy_bw(int32_t device, double *gbs);
+
+/* State-constrained solve bookkeeping of the last step (device pointers, any may be NULL): factorisations used and
+ * number of active bounds in the window, per instance.  DEKF_EINVAL unless the handle has v_box_enable. */
+int dekf_get_qp_info(dekf_handle *h, int32_t *iters /*[n]*/, int32_t *n_active /*[n]*/);
 
 /* Number of kernel launches issued by this handle so far (bench.py "gpu_launches"). */
 int64_t dekf_launch_count(const dekf_handle *h);

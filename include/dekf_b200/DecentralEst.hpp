@@ -55,6 +55,10 @@ struct robot_params {
   // batch / device (not in the reference)
   int robot_ = DEKF_ROBOT_GO1;
   int n_instances_ = 1, device_ = 0, precision_ = DEKF_FP64, ekf_hist_depth_ = 64;
+  // state constraints lo <= v_s <= hi on every window state (what MHEproblem::addConstraints(name, lb, ub),
+  // MheSrb.cpp:58-68, would add; never exercised by the reference)
+  bool v_box_enable_ = false;
+  std::vector<double> v_box_lo_{-1e30, -1e30, -1e30}, v_box_hi_{1e30, 1e30, 1e30};
 
   // go1_example/config/parameters_go1.yaml
   static robot_params go1() {
@@ -107,6 +111,11 @@ struct robot_params {
     p.ekf_rate_ = c.ekf_rate;
     p.robot_ = c.robot;
     p.ekf_hist_depth_ = c.ekf_hist_depth;
+    p.v_box_enable_ = c.v_box_enable != 0;
+    if (p.v_box_enable_) {
+      p.v_box_lo_ = v(c.v_box_lo, 3);
+      p.v_box_hi_ = v(c.v_box_hi, 3);
+    }
     return p;
   }
   dekf_config to_config() const {
@@ -143,6 +152,9 @@ struct robot_params {
     c.rate = rate_;
     c.N = N_;
     c.est_type = est_type_;
+    c.v_box_enable = v_box_enable_;
+    put(c.v_box_lo, v_box_lo_, 3, "v_box_lo_");
+    put(c.v_box_hi, v_box_hi_, 3, "v_box_hi_");
     c.rho = rho_;
     c.alpha = alpha_;
     c.delta = delta_;

@@ -912,7 +912,65 @@ static int solve_exact(orc_mhe *m) {
       }
     }
   }
-  int rc = la_chol_solve_banded(Nm, rhs, n, 2 * ds - 1);
+  int rc;
+  if (m->P.v_box_enable) {
+    /* Builder extension (never exercised by the reference): rows lo <= v_s of x_j <= hi for every state of
+     * the window at solve time -- what MHEproblem::addConstraints(name, lb, ub) + a dependency on x_j with the
+     * selector [0 I 0] would add (MheSrb.cpp:58-68).  Exact optimum by a primal-dual active-set iteration on the
+     * normal equations in x: fix the active components at their bound, solve, read the multipliers off the
+     * residual of the free system, update the set; stops when the set repeats itself. */
+    double *N0 = dalloc(n * n), *r0 = dalloc(n), *xs = dalloc(n);
+    int *act = (int *)calloc((size_t)n, sizeof(int)), *nact = (int *)calloc((size_t)n, sizeof(int));
+    la_copy(N0, Nm, n * n);
+    la_copy(r0, rhs, n);
+    rc = 0;
+    int it = 0;
+    for (it = 0; it < 200; ++it) {
+      la_copy(Nm, N0, n * n);
+      la_copy(rhs, r0, n);
+      for (int a = 0; a < n; ++a) {
+        if (!act[a]) continue;
+        double beta = act[a] > 0 ? m->P.v_box_hi[(a % ds) - 3] : m->P.v_box_lo[(a % ds) - 3];
+        for (int i = 0; i < n; ++i) rhs[i] -= Nm[i * n + a] * beta;
+      }
+      for (int a = 0; a < n; ++a) {
+        if (!act[a]) continue;
+        double beta = act[a] > 0 ? m->P.v_box_hi[(a % ds) - 3] : m->P.v_box_lo[(a % ds) - 3];
+        for (int i = 0; i < n; ++i) Nm[i * n + a] = Nm[a * n + i] = 0.0;
+        Nm[a * n + a] = 1.0;
+        rhs[a] = beta;
+      }
+      rc = la_chol_solve_banded(Nm, rhs, n, 2 * ds - 1);
+      la_copy(xs, rhs, n);
+      int changed = 0;
+      for (int j = 0; j < K; ++j)
+        for (int c = 0; c < 3; ++c) {
+          int a = j * ds + 3 + c;
+          double grad = -r0[a];
+          for (int i = 0; i < n; ++i) grad += N0[a * n + i] * xs[i];
+          int na;
+          if (act[a] > 0)
+            na = (-grad > 0.0) ? 1 : 0; /* multiplier of the upper bound */
+          else if (act[a] < 0)
+            na = (grad > 0.0) ? -1 : 0; /* multiplier of the lower bound */
+          else
+            na = (xs[a] > m->P.v_box_hi[c]) ? 1 : ((xs[a] < m->P.v_box_lo[c]) ? -1 : 0);
+          nact[a] = na;
+          if (na != act[a]) changed = 1;
+        }
+      if (!changed) break;
+      memcpy(act, nact, sizeof(int) * (size_t)n);
+    }
+    m->admm_iters = it + 1;
+    la_copy(rhs, xs, n);
+    free(N0);
+    free(r0);
+    free(xs);
+    free(act);
+    free(nact);
+  } else {
+    rc = la_chol_solve_banded(Nm, rhs, n, 2 * ds - 1);
+  }
   /* full primal in reference ordering */
   la_zero(m->solution, m->nVar);
   for (int j = 0; j < K; ++j) {
@@ -1017,8 +1075,25 @@ static void solve_qp(orc_mhe *m) {
         }
       }
     }
-    orc_admm_solve_triplets(nV, nC, P.n, P.i, P.j, P.x, A.n, A.i, A.j, A.x, g, m->lb_all, m->ub_all, &m->P,
-                            m->solution, &m->admm_iters);
+    if (m->P.v_box_enable) {
+      /* builder extension: inequality rows lo <= v_s of x_j <= hi appended after the reference's rows */
+      int nC2 = nC + 3 * m->nwin;
+      double *l2 = dalloc(nC2), *u2 = dalloc(nC2);
+      la_copy(l2, m->lb_all, nC);
+      la_copy(u2, m->ub_all, nC);
+      for (int j = 0; j < m->nwin; ++j)
+        for (int c = 0; c < 3; ++c) {
+          trip_put(&A, nC + 3 * j + c, var_x(m, j) + 3 + c, 1.0);
+          l2[nC + 3 * j + c] = m->P.v_box_lo[c];
+          u2[nC + 3 * j + c] = m->P.v_box_hi[c];
+        }
+      orc_admm_solve_triplets(nV, nC2, P.n, P.i, P.j, P.x, A.n, A.i, A.j, A.x, g, l2, u2, &m->P, m->solution,
+                              &m->admm_iters);
+      free(l2);
+      free(u2);
+    } else
+      orc_admm_solve_triplets(nV, nC, P.n, P.i, P.j, P.x, A.n, A.i, A.j, A.x, g, m->lb_all, m->ub_all, &m->P,
+                              m->solution, &m->admm_iters);
     free(g);
     free(P.i);
     free(P.j);

@@ -20,6 +20,8 @@ struct Sim {
   Dims dm;
   EkfConst<T> ec;
   MheConst<T> mc;
+  BoxConst bc;
+  BoxBuffers bb;
   Buffers<T> b;
   std::vector<std::vector<char>> store;
 
@@ -32,6 +34,11 @@ struct Sim {
     dm = make_dims(c);
     ec = make_ekf_const<T>(c);
     mc = make_mhe_const<T>(c);
+    bc = make_box_const(c);
+    bb.fac = alloc<double>((size_t)dm.N * BOX_FAC * dm.ns);
+    bb.act = alloc<uint8_t>((size_t)dm.NW * dm.ns);
+    bb.iters = alloc<int32_t>(dm.ns);
+    bb.nactive = alloc<int32_t>(dm.ns);
     StateSizes s = state_sizes(dm);
     b.ekf_q = alloc<T>(s.ekf_q);
     b.ekf_P = alloc<T>(s.ekf_P);
@@ -70,7 +77,8 @@ void run(const dekf_config &cfg, int S, const double *gyro, const double *accel,
          const double *joint_pos, const double *joint_vel, const double *foot_force, const uint8_t *vo_flag,
          const double *vo_quat, const double *vo_time_pre, const double *vo_time_now, const double *vo_rel_p,
          const double *quat_in, double *quat_out, double *x_out, double *vb_out, uint8_t *contact_out,
-         int32_t *vo_dbg, int32_t *ekf_dbg, double *pvo_out, int32_t *status_out, double *arrP_out, double *arrx_out) {
+         int32_t *vo_dbg, int32_t *ekf_dbg, double *pvo_out, int32_t *status_out, double *arrP_out, double *arrx_out,
+         int32_t *qp_out) {
   Sim<T> sim(cfg);
   const int n = cfg.n_instances;
   const int nq = Model::NLEG * Model::NJ, nl = Model::NLEG;
@@ -104,8 +112,14 @@ void run(const dekf_config &cfg, int S, const double *gyro, const double *accel,
       st |= mhe_assemble<T, Model>(sim.mc, sim.dm, sim.b, in, out, s, i, q);
       if (cfg.est_type == 1)
         st |= kf_update<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
+      else if (s >= 1 && cfg.v_box_enable)
+        st |= mhe_solve_box<T>(sim.mc, sim.bc, sim.dm, sim.b, sim.bb, in, out, s, i);
       else if (s >= 1)
         st |= mhe_solve<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
+      if (qp_out) {
+        qp_out[((size_t)s * 2 + 0) * n + i] = cfg.v_box_enable && s >= 1 ? sim.bb.iters[i] : 0;
+        qp_out[((size_t)s * 2 + 1) * n + i] = cfg.v_box_enable && s >= 1 ? sim.bb.nactive[i] : 0;
+      }
       status_out[(size_t)s * n + i] = st;
       for (int f = 0; f < 3; ++f) pvo_out[((size_t)s * 3 + f) * n + i] = sim.b.p_vo[(size_t)f * sim.dm.ns + i];
     }
@@ -124,10 +138,10 @@ int hostsim_run(const dekf_config *cfg, int S, const double *gyro, const double 
                 const double *vo_quat, const double *vo_time_pre, const double *vo_time_now, const double *vo_rel_p,
                 const double *quat_in, double *quat_out, double *x_out, double *vb_out, uint8_t *contact_out,
                 int32_t *vo_dbg, int32_t *ekf_dbg, double *pvo_out, int32_t *status_out, double *arrP_out,
-                double *arrx_out) {
+                double *arrx_out, int32_t *qp_out) {
 #define ARGS *cfg, S, gyro, accel, imu_time, joint_pos, joint_vel, foot_force, vo_flag, vo_quat, vo_time_pre, \
              vo_time_now, vo_rel_p, quat_in, quat_out, x_out, vb_out, contact_out, vo_dbg, ekf_dbg, pvo_out,  \
-             status_out, arrP_out, arrx_out
+             status_out, arrP_out, arrx_out, qp_out
   const bool f32 = cfg->precision == DEKF_FP32;
   switch (cfg->robot) {
     case DEKF_ROBOT_GO1:

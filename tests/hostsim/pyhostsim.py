@@ -21,7 +21,7 @@ def build():
     so = os.path.join(HERE, "_build", "libhostsim.so")
     srcs = [os.path.join(HERE, "hostsim.cpp")] + [
         os.path.join(ROOT, "decentralized_ekf_mhe_b200", "csrc", f)
-        for f in ("estimator_core.cuh", "smallmat.cuh", "kinematics.cuh", "host_setup.hpp")] + [
+        for f in ("estimator_core.cuh", "smallmat.cuh", "kinematics.cuh", "host_setup.hpp", "box_solve.cuh")] + [
         os.path.join(ROOT, "include", "dekf_b200.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         os.makedirs(os.path.dirname(so), exist_ok=True)
@@ -47,7 +47,7 @@ def run(stream, cfg, quat_in=None):
     res = dict(quat=np.zeros((S, 4, n)), x=np.full((S, 9, n), np.nan), v_body=np.full((S, 3, n), np.nan),
                contact=np.zeros((S, nl, n), np.uint8), vo_dbg=np.zeros((S, 8, n), np.int32),
                ekf_dbg=np.zeros((S, 3, n), np.int32), p_vo=np.zeros((S, 3, n)), status=np.zeros((S, n), np.int32),
-               arr_P=np.zeros((45, n)), arr_x=np.zeros((9, n)))
+               arr_P=np.zeros((45, n)), arr_x=np.zeros((9, n)), qp=np.zeros((S, 2, n), np.int32))
     qi = None
     if quat_in is not None:
         qi = np.ascontiguousarray(quat_in, dtype=np.float64)
@@ -58,6 +58,6 @@ def run(stream, cfg, quat_in=None):
                          res["contact"].ctypes.data_as(up), res["vo_dbg"].ctypes.data_as(ip),
                          res["ekf_dbg"].ctypes.data_as(ip), res["p_vo"].ctypes.data_as(dp),
                          res["status"].ctypes.data_as(ip), res["arr_P"].ctypes.data_as(dp),
-                         res["arr_x"].ctypes.data_as(dp))
+                         res["arr_x"].ctypes.data_as(dp), res["qp"].ctypes.data_as(ip))
     assert rc == 0
     return res

@@ -204,6 +204,48 @@ def test_kf_alternative_vs_oracle(est_mod, oracle, n):
     est.close()
 
 
+@pytest.mark.parametrize("precision,tol", [("fp64", 1e-6), ("fp32", 1e-4)])
+def test_pogox_state_constrained_16384(est_mod, oracle, precision, tol):
+    """BASELINE config 4: PogoX, 16,384 instances, box on the velocity states of the whole window that binds in
+    >= 20 % of the steps (builder extension of MHEproblem::addConstraints(name, lb, ub), MheSrb.cpp:58-68).
+    Parity on the first 64 instances against the oracle's exact constrained optimum (itself certified by KKT
+    conditions and by the OSQP-style ADMM, tests/test_oracle_mhe.py); properties on all instances."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S, m = 16384, 50, 64
+    lo, hi = (-0.45, -0.03, -0.015), (0.55, 0.03, 0.015)
+    st_t = synth.make_stream(n, S, robot="pogox", vo_jitter=True, device="cuda")
+    d = {k: v.contiguous() for k, v in st_t.items()}
+    prm = E.robot_params("pogox", ekf_rate=200, v_box_enable=1, v_box_lo=lo, v_box_hi=hi)
+    est = E.BatchedEstimator(prm, n, precision=precision)
+    xs = np.full((S, 9, m), np.nan)
+    bind = 0.0
+    iters = []
+    lo_t = torch.tensor(lo, device="cuda", dtype=torch.float64)[:, None]
+    hi_t = torch.tensor(hi, device="cuda", dtype=torch.float64)[:, None]
+    for s in range(S):
+        est.step(s, E.robot_store.from_stream(d, s))
+        if s == 0:
+            continue
+        x = est.x_MHE_
+        v = x[3:6]
+        assert torch.isfinite(x).all()
+        assert (v <= hi_t + 1e-12).all() and (v >= lo_t - 1e-12).all()      # constraint violation: none
+        assert not (est.status_ & 64).any()                                  # active set converged everywhere
+        bind += float(((v == hi_t) | (v == lo_t)).any(dim=0).double().mean())
+        it, na = est.qp_info()
+        iters.append(float(it.double().mean()))
+        xs[s] = x[:, :m].cpu().numpy()
+    assert bind / (S - 1) > 0.2
+    assert np.mean(iters) < 6
+    sub = {k: np.ascontiguousarray(v[..., :m].cpu().numpy()) for k, v in st_t.items()}
+    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0))
+    ro, _, _ = oracle.run_batch(sub, oracle.go1_params(v_box_enable=1, v_box_lo=lo, v_box_hi=hi, **kw),
+                                oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1, want=("x",))
+    assert np.abs(xs[1:, 3:6] - ro["x"][1:, 3:6]).max() < tol
+    est.close()
+
+
 def test_run_and_run_host_equal_step_loop(est_mod, monkeypatch):
     """dekf_run (S ticks per call, device streams) and dekf_run_host (pinned host streams, pipelined copies) return
     bit-identical per-tick results to the tick-by-tick loop, on the large-batch kernel path."""

@@ -91,3 +91,26 @@ def test_kf_alternative_matches_oracle(oracle, go1_stream_small):
     assert np.abs(r["v_body"][1:] - ro["v_body"][1:]).max() < 1e-10
     assert np.abs(r["p_vo"] - ro["p_vo"]).max() < 1e-12
     assert np.abs(ro["p_vo"]).max() > 0.1  # VO messages were consumed
+
+
+BOX_LO, BOX_HI = (-0.45, -0.03, -0.015), (0.55, 0.03, 0.015)
+
+
+def test_state_constrained_solve_matches_oracle(oracle):
+    """BASELINE config 4 (PogoX, box on the velocity states that binds in >= 20 % of the steps): the kernel's
+    primal-dual active-set solve against the oracle's exact constrained optimum."""
+    import pyhostsim as hs
+    from decentralized_ekf_mhe_b200 import synth
+    st = synth.to_numpy(synth.make_stream(6, 140, robot="pogox", vo_jitter=True))
+    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0))
+    r = hs.run(st, _cfg(v_box_enable=1, v_box_lo=BOX_LO, v_box_hi=BOX_HI, **kw))
+    prm = oracle.go1_params(v_box_enable=1, v_box_lo=BOX_LO, v_box_hi=BOX_HI, **kw)
+    ro, _, _ = oracle.run_batch(st, prm, oracle.ekf_params(rate=200), nthreads=4, want=("x", "v_body"))
+    assert np.abs(r["x"][1:] - ro["x"][1:]).max() < 1e-8
+    assert np.abs(r["v_body"][1:] - ro["v_body"][1:]).max() < 1e-8
+    v = r["x"][1:, 3:6]
+    lo, hi = np.array(BOX_LO)[None, :, None], np.array(BOX_HI)[None, :, None]
+    assert (v <= hi + 1e-12).all() and (v >= lo - 1e-12).all()          # constraint violation: none
+    assert ((v == hi) | (v == lo)).any(axis=1).mean() > 0.2              # the box binds in >= 20 % of the steps
+    assert not (r["status"] & 64).any()                                  # active set always converged
+    assert r["qp"][1:, 0].mean() < 6                                     # warm start: few factorisations per tick

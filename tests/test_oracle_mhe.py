@@ -161,3 +161,55 @@ def test_kf_alternative_matches_mhe_without_vo(oracle):
     r_k = oracle.run_batch(st, oracle.go1_params(est_type=1), ep, nthreads=2, run_ekf=False, quat_in=quat,
                            want=("x",))[0]
     np.testing.assert_allclose(r_m["x"][2:, 3:6], r_k["x"][1:, 3:6], rtol=0, atol=1e-9)
+
+
+def test_box_constrained_optimum_certificate(oracle):
+    """The oracle's constrained solve (builder extension, PogoX config) is pinned by two independent checks:
+    (1) KKT certificate on the exported reference-ordered QP: stationarity with multipliers of the right sign on
+    the active box rows; (2) the OSQP-style ADMM restatement with the same rows converges to the same point."""
+    from decentralized_ekf_mhe_b200 import synth
+    lo, hi = np.array((-0.45, -0.03, -0.015)), np.array((0.55, 0.03, 0.015))
+    st = synth.to_numpy(synth.make_stream(1, 60, robot="pogox", vo_jitter=True, truth=True))
+    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0), v_box_enable=1,
+              v_box_lo=tuple(lo), v_box_hi=tuple(hi))
+    m = oracle.Mhe(oracle.go1_params(**kw))
+    ma = oracle.Mhe(oracle.go1_params(solve_mode=2, abs_tol=1e-9, relative_tol=1e-9, max_qp_iter=20000, time_limit=0.0, **kw))
+    n_active_seen = 0
+    worst_admm = 0.0
+    for s in range(60):
+        q = st["quat_true"][s, :, 0]
+        args = dict(imu_time=st["imu_time"][s, 0], accel=st["accel"][s, :, 0], gyro=st["gyro"][s, :, 0], quat=q,
+                    joint_pos=st["joint_pos"][s, :, 0], joint_vel=st["joint_vel"][s, :, 0],
+                    foot_force=st["foot_force"][s, :, 0],
+                    vo=(st["vo_time_pre"][s, 0], st["vo_time_now"][s, 0], st["vo_rel_p"][s, :, 0]) if st["vo_flag"][s, 0] else None)
+        m.step(s, **args)
+        ma.step(s, **args)
+        if s < 1:
+            continue
+        ds, dm, dc, nV, nC = m.dims()
+        H, g, A, l, u = m.export_qp()
+        z = m.solution()
+        K = (nV + ds + dc) // (2 * ds + dm + dc)
+        xi = [j * (2 * ds + dm + dc) for j in range(K)]
+        v = np.array([z[o + 3:o + 6] for o in xi])
+        assert (v <= hi + 1e-12).all() and (v >= lo - 1e-12).all()
+        eq = np.abs(u - l) < 1e-9
+        assert np.abs((A @ z - l)[eq]).max() < 1e-9 * max(1.0, np.abs(l[eq]).max())   # primal feasibility of the reference rows
+        act = [(j, c, +1 if v[j, c] >= hi[c] else -1) for j in range(K) for c in range(3) if v[j, c] >= hi[c] or v[j, c] <= lo[c]]
+        n_active_seen += len(act)
+        # stationarity: H z + g + A_eq' y + B_act' mu = 0 for some y and mu with sign(mu) = side of the bound
+        B = np.zeros((len(act), nV))
+        for r, (j, c, sgn) in enumerate(act):
+            B[r, xi[j] + 3 + c] = 1.0
+        G = np.vstack([A[eq], B]).T
+        rhs = -(H @ z + g)
+        scale = np.abs(rhs).max() + 1.0
+        sol, *_ = np.linalg.lstsq(G, rhs, rcond=None)
+        assert np.abs(G @ sol - rhs).max() < 1e-7 * scale
+        mu = sol[eq.sum():]
+        for (j, c, sgn), w in zip(act, mu):
+            assert sgn * w >= -1e-7 * scale
+        if ma.admm_iters() < 20000:
+            worst_admm = max(worst_admm, np.abs(ma.x()[3:6] - m.x()[3:6]).max())
+    assert n_active_seen > 20
+    assert worst_admm < 1e-6
