@@ -214,6 +214,9 @@ def main():
     ap.add_argument("--N", type=int, default=20)
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--window-solve", default="full", choices=["full", "incremental"],
+                    help="full: re-sweep the whole window every tick (tier A, the reference's semantics); "
+                         "incremental: restart at the first changed stage (tier B, bit-identical results)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-instances-per-thread", type=int, default=4)
@@ -251,7 +254,7 @@ def main():
     t_gen = time.time() - t_gen
     vo_steps = [bool(stream["vo_flag"][s].any()) for s in range(S)]
 
-    prm = estimator.robot_params("go1", ekf_rate=200, N=N)
+    prm = estimator.robot_params("go1", ekf_rate=200, N=N, window_solve=1 if args.window_solve == "incremental" else 0)
     est = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
 
     def barrier():

@@ -20,9 +20,20 @@ namespace dekf {
 // kernels: one thread per estimator instance
 // ------------------------------------------------------------------------------------------------
 constexpr int kBlock = 128;
+// resident CTAs per SM the small per-tick kernels are compiled for (register cap = 65536 / (128 * MINB)):
+// 65,536 instances are 512 CTAs; 4 CTAs/SM (592 slots) run them in ONE wave instead of 1.15 / 1.73 (profiles/r01_tick_kernels.md)
+#ifndef DEKF_MINB_EKF
+#define DEKF_MINB_EKF 4
+#endif
+#ifndef DEKF_MINB_ASM
+#define DEKF_MINB_ASM 4
+#endif
+#ifndef DEKF_MINB_INCR
+#define DEKF_MINB_INCR 2  // the sweep stage needs the full register file: 128 registers spill 944 B and lose (33 vs 26 us)
+#endif
 
 template <typename T>
-__global__ void __launch_bounds__(kBlock) k_ekf(const EkfConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
+__global__ void __launch_bounds__(kBlock, DEKF_MINB_EKF) k_ekf(const EkfConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
                                                 const Outputs out, int k, int32_t *status_state, int32_t *status_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
@@ -32,7 +43,7 @@ __global__ void __launch_bounds__(kBlock) k_ekf(const EkfConst<T> c, const Dims 
 }
 
 template <typename T, typename Model>
-__global__ void __launch_bounds__(kBlock) k_assemble(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
+__global__ void __launch_bounds__(kBlock, DEKF_MINB_ASM) k_assemble(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
                                                      const Outputs out, int Tk, const int32_t *prev_status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
@@ -53,6 +64,24 @@ __global__ void __launch_bounds__(kBlock) k_solve(const MheConst<T> c, const Dim
   if (Tk >= 1) st |= mhe_solve<T>(c, dm, b, in, out, Tk, i);
   b.status[i] = st;
   if (status_out != nullptr) status_out[i] = st;
+}
+
+// incremental window solve (cfg.window_solve == DEKF_SOLVE_INCREMENTAL): restart the sweep at the first changed stage
+template <typename T>
+__global__ void __launch_bounds__(kBlock, DEKF_MINB_INCR) k_solve_incr(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
+                                                       const Outputs out, int Tk, int32_t *status_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  int st = b.status[i];
+  if (Tk >= 1) st |= mhe_solve_incr<T>(c, dm, b, in, out, Tk, i);
+  b.status[i] = st;
+  if (status_out != nullptr) status_out[i] = st;
+}
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_arrival_from_ckpt(const MheConst<T> c, const Dims dm, const Buffers<T> b, int Tk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  arrival_from_checkpoint<T>(c, dm, b, Tk, i);
 }
 
 // state-constrained window solve (cfg.v_box_enable): marginalise + primal-dual active set on the block-tridiagonal QP
@@ -97,6 +126,8 @@ __global__ void __launch_bounds__(kBlock) k_fused(const EkfConst<T> ec, const Mh
   st |= mhe_assemble<T, Model>(mc, dm, b, in, out, Tk, i, q);
   if (mc.est_type == 1)
     st |= kf_update<T>(mc, dm, b, in, out, Tk, i);
+  else if (Tk >= 1 && mc.window_solve == 1)
+    st |= mhe_solve_incr<T>(mc, dm, b, in, out, Tk, i);
   else if (Tk >= 1)
     st |= mhe_solve<T>(mc, dm, b, in, out, Tk, i);
   b.status[i] = st;
@@ -232,6 +263,16 @@ struct StageSet {
   int32_t *status = nullptr;
 };
 
+// device staging of dekf_run_host: `cap` ticks of every stream
+struct ChunkSet {
+  int cap = 0;
+  double *in = nullptr;      // gyro accel imu_time joint_pos joint_vel foot_force | vo_quat vo_time_pre vo_time_now vo_rel_p, each [cap][rows][n]
+  uint8_t *flag = nullptr;   // [cap][n]
+  double *out = nullptr;     // quat [cap][4][n] | x [cap][9][n] | v_body [cap][3][n]
+  uint8_t *contact = nullptr;
+  int32_t *status = nullptr;
+};
+
 struct dekf_handle {
   dekf_config cfg;
   Dims dm;
@@ -245,10 +286,13 @@ struct dekf_handle {
   Buffers<float> b32;
   BoxConst bc;
   BoxBuffers bb = {nullptr, nullptr, nullptr, nullptr};
+  void *ckpt_mem = nullptr;       // incremental window solve: checkpoint ring
+  int32_t *resweep_mem = nullptr;
   void *slab = nullptr;
   size_t slab_bytes = 0;
   // device staging of the host-pointer entry points (set 1 and the copy streams only exist after dekf_run_host)
   StageSet stage[2];
+  ChunkSet chunk[2];
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   // dekf_run: the EKF ticks run ahead of the MHE on their own stream through a small ring of quaternions / status words
   static constexpr int kAhead = 4;
@@ -288,6 +332,8 @@ namespace {
 
 int alloc_stage_set(dekf_handle *h, StageSet &ss);
 void free_stage_set(StageSet &ss);
+int alloc_chunk_set(dekf_handle *h, ChunkSet &cs, int cap);
+void free_chunk_set(ChunkSet &cs);
 
 int fail(dekf_handle *h, int code, const char *what, cudaError_t ce = cudaSuccess) {
   if (h) {
@@ -333,6 +379,8 @@ size_t carve(Buffers<T> &b, const Dims &dm, char *base) {
   b.pend_flag = (uint8_t *)take(s.pend_flag, 1);
   b.pend = (double *)take(s.pend, sizeof(double));
   b.status = (int32_t *)take(s.status, sizeof(int32_t));
+  b.ckpt = nullptr;
+  b.resweep = nullptr;
   return off;
 }
 
@@ -453,6 +501,7 @@ int validate(const dekf_config *c, std::string &why) {
   if (c->leg_odom_type != 0) { why = "leg_odom_type 1 (foot-position states) is not built yet"; return DEKF_EINVAL; }
   if (c->est_type != 0 && c->est_type != 1) { why = "est_type must be 0 (MHE) or 1 (KF alternative)"; return DEKF_EINVAL; }
   if (c->ekf_hist_depth < 4) { why = "ekf_hist_depth < 4"; return DEKF_EINVAL; }
+  if (c->window_solve != DEKF_SOLVE_FULL && c->window_solve != DEKF_SOLVE_INCREMENTAL) { why = "window_solve"; return DEKF_EINVAL; }
   if (c->v_box_enable) {
     if (c->est_type != 0) { why = "v_box_enable needs est_type 0 (the KF alternative has no constraints)"; return DEKF_EINVAL; }
     for (int i = 0; i < 3; ++i)
@@ -533,6 +582,10 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
   ce = cudaFuncSetAttribute(k_solve_tma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_tma_smem_bytes<double>());
   if (ce == cudaSuccess)
     ce = cudaFuncSetAttribute(k_solve_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_tma_smem_bytes<float>());
+  if (ce == cudaSuccess)
+    ce = cudaFuncSetAttribute(k_solve_incr_tma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_tma_smem_bytes<double>());
+  if (ce == cudaSuccess)
+    ce = cudaFuncSetAttribute(k_solve_incr_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_tma_smem_bytes<float>());
   if (ce != cudaSuccess) {
     std::fprintf(stderr, "dekf_create: cudaFuncSetAttribute(k_solve_tma): %s\n", cudaGetErrorString(ce));
     delete h;
@@ -584,6 +637,17 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     }
   }
   h->extra_bytes = 0;
+  if (h->mc64.window_solve == 1) {
+    const size_t ns = (size_t)h->dm.ns, elt = h->f32 ? sizeof(float) : sizeof(double);
+    const size_t ck = (size_t)h->dm.NW * 54 * ns * elt;
+    if ((ce = cudaMalloc(&h->ckpt_mem, ck)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc(checkpoint ring)", ce);
+    if ((ce = cudaMalloc((void **)&h->resweep_mem, ns * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    if ((ce = cudaMemset(h->ckpt_mem, 0, ck)) != cudaSuccess) return bail(DEKF_ECUDA, "memset", ce);
+    h->b64.ckpt = (double *)h->ckpt_mem;
+    h->b32.ckpt = (float *)h->ckpt_mem;
+    h->b64.resweep = h->b32.resweep = h->resweep_mem;
+    h->extra_bytes += ck + ns * sizeof(int32_t);
+  }
   h->bc = make_box_const(*cfg);
   if (cfg->v_box_enable) {
     const size_t ns = (size_t)h->dm.ns;
@@ -619,12 +683,16 @@ int dekf_destroy(dekf_handle *h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->slab);
+  cudaFree(h->ckpt_mem);
+  cudaFree(h->resweep_mem);
   cudaFree(h->bb.fac);
   cudaFree(h->bb.act);
   cudaFree(h->bb.iters);
   cudaFree(h->bb.nactive);
   free_stage_set(h->stage[0]);
   free_stage_set(h->stage[1]);
+  free_chunk_set(h->chunk[0]);
+  free_chunk_set(h->chunk[1]);
   if (h->s_ekf) cudaStreamDestroy(h->s_ekf);
   if (h->s_mhe) cudaStreamDestroy(h->s_mhe);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -743,6 +811,10 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
       k_kf<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
     else if (h->bc.enable)
       k_solve_box<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->bc, h->dm, h->b32, h->bb, di, dout, T_, st);
+    else if (h->mc32.window_solve == 1 && tma && T_ >= 2 && di.vo_flag != nullptr)
+      k_solve_incr_tma<float><<<tiles, kTile, solve_tma_smem_bytes<float>(), h->stream>>>(h->tmap, h->mc32, h->dm, h->b32, di, dout, T_, st);
+    else if (h->mc32.window_solve == 1)
+      k_solve_incr<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
     else if (tma)
       k_solve_tma<float><<<tiles, kTile, solve_tma_smem_bytes<float>(), h->stream>>>(h->tmap, h->mc32, h->dm, h->b32, di, dout, T_, st);
     else
@@ -756,6 +828,10 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
       k_kf<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
     else if (h->bc.enable)
       k_solve_box<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->bc, h->dm, h->b64, h->bb, di, dout, T_, st);
+    else if (h->mc64.window_solve == 1 && tma && T_ >= 2 && di.vo_flag != nullptr)
+      k_solve_incr_tma<double><<<tiles, kTile, solve_tma_smem_bytes<double>(), h->stream>>>(h->tmap, h->mc64, h->dm, h->b64, di, dout, T_, st);
+    else if (h->mc64.window_solve == 1)
+      k_solve_incr<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
     else if (tma)
       k_solve_tma<double><<<tiles, kTile, solve_tma_smem_bytes<double>(), h->stream>>>(h->tmap, h->mc64, h->dm, h->b64, di, dout, T_, st);
     else
@@ -839,6 +915,28 @@ int alloc_stage_set(dekf_handle *h, StageSet &ss) {
   CK(cudaMalloc((void **)&ss.contact, (size_t)h->nl * n));
   CK(cudaMalloc((void **)&ss.status, n * sizeof(int32_t)));
   h->extra_bytes += (tot + 16 * n) * sizeof(double) + n + (size_t)h->nl * n + n * sizeof(int32_t);
+  return DEKF_OK;
+}
+void free_chunk_set(ChunkSet &cs) {
+  cudaFree(cs.in);
+  cudaFree(cs.flag);
+  cudaFree(cs.out);
+  cudaFree(cs.contact);
+  cudaFree(cs.status);
+  cs = ChunkSet();
+}
+int alloc_chunk_set(dekf_handle *h, ChunkSet &cs, int cap) {
+  if (cs.cap >= cap) return DEKF_OK;
+  free_chunk_set(cs);
+  const size_t n = (size_t)h->dm.n, c = (size_t)cap;
+  const size_t in_rows = 16 + 2 * (size_t)h->nq + (size_t)h->nl;  // 3+3+1+nq+nq+nl + 4+1+1+3
+  CK(cudaMalloc((void **)&cs.in, c * in_rows * n * sizeof(double)));
+  CK(cudaMalloc((void **)&cs.flag, c * n));
+  CK(cudaMalloc((void **)&cs.out, c * 16 * n * sizeof(double)));
+  CK(cudaMalloc((void **)&cs.contact, c * (size_t)h->nl * n));
+  CK(cudaMalloc((void **)&cs.status, c * n * sizeof(int32_t)));
+  cs.cap = cap;
+  h->extra_bytes += c * ((in_rows + 16) * n * sizeof(double) + n + (size_t)h->nl * n + n * sizeof(int32_t));
   return DEKF_OK;
 }
 void free_stage_set(StageSet &ss) {
@@ -1078,10 +1176,28 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
 int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const uint8_t *vo_steps, const dekf_outputs *out,
                   int32_t out_per_step) {
   if (!h || !in || S < 0) return fail(h, DEKF_EINVAL, "dekf_run_host: bad argument");
+  if (!in->gyro || !in->accel || !in->imu_time || !in->joint_pos || !in->joint_vel || !in->foot_force)
+    return fail(h, DEKF_EINVAL, "dekf_run_host: null input");
+  if (in->vo_flag && (!in->vo_quat || !in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
+    return fail(h, DEKF_EINVAL, "dekf_run_host: vo_flag without the VO arrays");
   CK(cudaSetDevice(h->cfg.device));
-  int rc = alloc_stage_set(h, h->stage[0]);
+  const size_t n = (size_t)h->dm.n;
+  // Ticks move in chunks of B: every field of the host streams is [S][rows][n], so B consecutive ticks of one field are
+  // ONE contiguous copy (6 input copies + the VO arrays of the ticks that carry a message per chunk, 5 result copies per
+  // chunk) and the chunk runs through dekf_run (EKF ticks ahead of the MHE).  Chunks are software-pipelined over three
+  // streams and two device staging sets: H2D of chunk c+1 | kernels of chunk c | D2H of chunk c-1.
+  int B = 8;
+  if (const char *e = std::getenv("DEKF_HOST_CHUNK")) B = std::atoi(e);
+  {
+    const size_t per_tick = (size_t)(16 + 2 * h->nq + h->nl + 16) * 8 * n;
+    const size_t cap = (size_t)384 << 20;  // staging budget per set
+    if ((size_t)B * per_tick > cap) B = (int)(cap / per_tick);
+  }
+  if (B < 1) B = 1;
+  if (B > S) B = S > 0 ? S : 1;
+  int rc = alloc_chunk_set(h, h->chunk[0], B);
   if (rc) return rc;
-  rc = alloc_stage_set(h, h->stage[1]);
+  rc = alloc_chunk_set(h, h->chunk[1], B);
   if (rc) return rc;
   if (!h->s_h2d) {
     CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
@@ -1092,30 +1208,76 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
       CK(cudaEventCreateWithFlags(&h->ev_d2h[k], cudaEventDisableTiming));
     }
   }
-  // software pipeline over ticks: H2D of tick s+1 | kernels of tick s | D2H of tick s-1 on three streams, two staging sets
   CK(cudaEventRecord(h->ev_comp[0], h->stream));  // order after whatever the caller queued on the handle's stream
   CK(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[0], 0));
   CK(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[0], 0));
-  for (int32_t s = 0; s < S; ++s) {
-    const int b = s & 1;
-    const bool want_out = out && (out_per_step || s == S - 1);
-    dekf_inputs is, din;
-    offset_inputs(h, in, (size_t)s, !vo_steps || vo_steps[s], &is);
-    if (s >= 2) CK(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));  // kernels of tick s-2 are done with staging set b
-    rc = stage_inputs(h, h->stage[b], &is, h->s_h2d, &din);
-    if (rc) return rc;
+  const size_t rows_in[6] = {3, 3, 1, (size_t)h->nq, (size_t)h->nq, (size_t)h->nl};
+  const double *src_in[6] = {in->gyro, in->accel, in->imu_time, in->joint_pos, in->joint_vel, in->foot_force};
+  const size_t rows_vo[4] = {4, 1, 1, 3};
+  const double *src_vo[4] = {in->vo_quat, in->vo_time_pre, in->vo_time_now, in->vo_rel_p};
+  int c = 0;
+  for (int32_t s0 = 0; s0 < S; s0 += B, ++c) {
+    const int b = c & 1;
+    const int Bc = (S - s0 < B) ? (S - s0) : B;
+    ChunkSet &cs = h->chunk[b];
+    const size_t cap = (size_t)cs.cap;
+    if (c >= 2) CK(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));  // kernels of chunk c-2 are done with staging set b
+    dekf_inputs din;
+    std::memset(&din, 0, sizeof(din));
+    {
+      double *d = cs.in;
+      const double **dp[6] = {&din.gyro, &din.accel, &din.imu_time, &din.joint_pos, &din.joint_vel, &din.foot_force};
+      for (int a = 0; a < 6; ++a) {
+        CK(cudaMemcpyAsync(d, src_in[a] + (size_t)s0 * rows_in[a] * n, (size_t)Bc * rows_in[a] * n * sizeof(double),
+                           cudaMemcpyHostToDevice, h->s_h2d));
+        *dp[a] = d;
+        d += cap * rows_in[a] * n;
+      }
+      bool any_vo = false;
+      if (in->vo_flag) {
+        const double **vp[4] = {&din.vo_quat, &din.vo_time_pre, &din.vo_time_now, &din.vo_rel_p};
+        for (int a = 0; a < 4; ++a) {
+          *vp[a] = d;
+          for (int j = 0; j < Bc; ++j)
+            if (!vo_steps || vo_steps[s0 + j]) {
+              CK(cudaMemcpyAsync(d + (size_t)j * rows_vo[a] * n, src_vo[a] + (size_t)(s0 + j) * rows_vo[a] * n,
+                                 rows_vo[a] * n * sizeof(double), cudaMemcpyHostToDevice, h->s_h2d));
+              any_vo = true;
+            }
+          d += cap * rows_vo[a] * n;
+        }
+        for (int j = 0; j < Bc; ++j)
+          if (!vo_steps || vo_steps[s0 + j])
+            CK(cudaMemcpyAsync(cs.flag + (size_t)j * n, in->vo_flag + (size_t)(s0 + j) * n, n, cudaMemcpyHostToDevice, h->s_h2d));
+        if (any_vo) din.vo_flag = cs.flag;
+      }
+    }
     CK(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
     CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[b], 0));
-    if (s >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_d2h[b], 0));  // results of tick s-2 have left staging set b
+    if (c >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_d2h[b], 0));  // results of chunk c-2 have left staging set b
+    const bool last = s0 + Bc >= S;
+    const bool want_out = out && (out_per_step || last);
     dekf_outputs dout;
-    stage_outputs(h, h->stage[b], want_out ? out : nullptr, &dout);
-    rc = dekf_step(h, T0 + s, &din, &dout);
+    std::memset(&dout, 0, sizeof(dout));
+    if (want_out) {
+      dout.quat = cs.out;
+      dout.x = cs.out + cap * 4 * n;
+      dout.v_body = cs.out + cap * 13 * n;
+      dout.contact = out->contact ? cs.contact : nullptr;
+      dout.status = out->status ? cs.status : nullptr;
+    }
+    // the chunk's own vo_steps mask (a tick whose VO arrays were not copied must not read them)
+    rc = dekf_run(h, T0 + s0, Bc, &din, vo_steps ? vo_steps + s0 : nullptr, want_out ? &dout : nullptr, out_per_step ? 1 : 0);
     if (rc) return rc;
     CK(cudaEventRecord(h->ev_comp[b], h->stream));
     CK(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
     if (want_out) {
-      rc = unstage_outputs(h, h->stage[b], out, out_per_step ? (size_t)s : 0, h->s_d2h, HK_STEP);
-      if (rc) return rc;
+      const size_t cnt = out_per_step ? (size_t)Bc : 1, so = out_per_step ? (size_t)s0 : 0;
+      if (out->quat) CK(cudaMemcpyAsync(out->quat + so * 4 * n, dout.quat, cnt * 4 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+      if (out->x) CK(cudaMemcpyAsync(out->x + so * 9 * n, dout.x, cnt * 9 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+      if (out->v_body) CK(cudaMemcpyAsync(out->v_body + so * 3 * n, dout.v_body, cnt * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+      if (out->contact) CK(cudaMemcpyAsync(out->contact + so * h->nl * n, cs.contact, cnt * h->nl * n, cudaMemcpyDeviceToHost, h->s_d2h));
+      if (out->status) CK(cudaMemcpyAsync(out->status + so * n, cs.status, cnt * n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_d2h));
     }
     CK(cudaEventRecord(h->ev_d2h[b], h->s_d2h));
   }
@@ -1128,6 +1290,13 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
 static int get_arrival(dekf_handle *h, double *P, double *x, int info) {
   if (!h || !P || !x) return fail(h, DEKF_EINVAL, "null argument");
   CK(cudaSetDevice(h->cfg.device));
+  if (h->mc64.window_solve == 1 && h->next_T >= 1) {  // marginalizeQP(T-N) on demand (see arrival_from_checkpoint)
+    if (h->f32)
+      k_arrival_from_ckpt<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, h->next_T - 1);
+    else
+      k_arrival_from_ckpt<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, h->next_T - 1);
+    h->launches++;
+  }
   if (h->f32)
     k_get_arrival<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->dm, h->b32, P, x, info);
   else

@@ -74,6 +74,7 @@ struct MheConst {
   double dt_d;
   int N;
   int est_type;  // 0: MHE (DecentralEst.cpp:156-187), 1: KF alternative (:189-196, :592-861)
+  int window_solve;  // 0: full window re-sweep every step (tier A), 1: incremental re-sweep from a checkpoint (tier B)
 };
 
 struct Dims {
@@ -105,6 +106,9 @@ struct Buffers {
   uint8_t *pend_flag;     // [n]   VO message latched at T==0 (robot_store.vo_new_ stays true)
   double *pend;           // [5][n]
   int32_t *status;        // [n]
+  // incremental window solve (window_solve == 1) only, else nullptr
+  T *ckpt;                // [NW][54][ns] filter state (P 45, x 9) of every window stage AFTER its leg-odometry update
+  int32_t *resweep;       // [ns] earliest stage whose VO row changed this tick (INT_MAX: none)
 };
 
 struct Inputs {
@@ -456,6 +460,7 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
   constexpr int NL = Model::NLEG, NJ = Model::NJ;
   const int n = dm.n, ns = dm.ns, N = dm.N, NW = dm.NW, HR = dm.HR;
   int status = 0;
+  if (b.resweep != nullptr) b.resweep[i] = 0x7fffffff;
 
   // ---- VO synchronisation against the history BEFORE this sample is pushed (:883-945)
   int vo_new = (in.vo_flag != nullptr) ? (int)in.vo_flag[i] : 0;
@@ -569,6 +574,7 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
         dbg[6] = num;
         dbg[7] = disc0;
         status |= ST_MHE_VO_BOUNDED;
+        if (b.resweep != nullptr) b.resweep[i] = disc0;
         // set_interval + interpolate_waypoint (Bezier_simple.cpp:29-71) + UpdateVOConstraints
         const double t_interval = wt[3] - wt[0];
         const double u_inc = c.dt_d / t_interval;
@@ -1306,6 +1312,154 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
                       int Tk, int i) {
   GlobalStageSource<T> src(dm, b, i);
   return mhe_solve<T>(c, dm, b, in, out, Tk, i, src);
+}
+
+// Incremental window solve (tier B of SURVEY.md 8d; legal because no row of the shipped QP is an inequality and only
+// x_T is read out).  The forward sweep of update(T) over the window differs from the sweep of update(T-1) only (a) by
+// the new stage T and (b) from the first stage whose VO row was turned into an equality this tick
+// (UpdateVOConstraints, DecentralEst.cpp:987-1009) onwards.  The filter state after the leg-odometry update of every
+// window stage is kept in a ring (`ckpt`), so update(T) restarts at stage ks = min(T-1, first changed stage) and runs
+// the SAME operations on the SAME operands as the full sweep would from there on: the results are bit-identical to
+// the full re-sweep (tests/test_gpu_parity.py::test_incremental_equals_full_resweep).  marginalizeQP(T-N) is not
+// needed on the step path any more: the arrival cost (M_p, n_p) is the time update of checkpoint T-N and is computed
+// when a getter asks for it (arrival_from_checkpoint).
+template <typename T>
+DEKF_HD void load_ckpt(const Dims &dm, const Buffers<T> &b, int k, int i, Cov9<T> &P, Vec9<T> &x) {
+  const T *base = b.ckpt + (size_t)(k % dm.NW) * 54 * dm.ns;
+  load_cov(base, dm.ns, i, P);
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    x.p[f] = base[(size_t)(45 + f) * dm.ns + i];
+    x.v[f] = base[(size_t)(48 + f) * dm.ns + i];
+    x.b[f] = base[(size_t)(51 + f) * dm.ns + i];
+  }
+}
+template <typename T>
+DEKF_HD void store_ckpt(const Dims &dm, const Buffers<T> &b, int k, int i, const Cov9<T> &P, const Vec9<T> &x) {
+  T *base = b.ckpt + (size_t)(k % dm.NW) * 54 * dm.ns;
+  store_cov(base, dm.ns, i, P);
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    base[(size_t)(45 + f) * dm.ns + i] = x.p[f];
+    base[(size_t)(48 + f) * dm.ns + i] = x.v[f];
+    base[(size_t)(51 + f) * dm.ns + i] = x.b[f];
+  }
+}
+
+// `ks`: restart stage (its checkpoint must be valid; any stage <= the instance's own first changed stage and >= the
+// window start will do, so a CTA may agree on a common one).  `src` as in mhe_solve; ordinal j is stage ks + j.
+template <typename T, typename Source, typename Math = DefaultMath<T>>
+DEKF_HD int mhe_solve_incr(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
+                           int Tk, int i, Source &src, int ks) {
+  const int n = dm.n;
+  Cov9<T> P;
+  Vec9<T> x;
+  if (Tk == 1) {
+    // Prior_0 (DecentralEst.cpp:232-253); the leg-odometry rows of stage 0 follow in the loop (j == 0 below)
+#pragma unroll
+    for (int f = 0; f < 6; ++f) P.pp.a[f] = P.vv.a[f] = P.bb.a[f] = T(0);
+#pragma unroll
+    for (int f = 0; f < 9; ++f) P.pv.a[f] = P.pb.a[f] = P.vb.a[f] = T(0);
+    P.pp.a[0] = c.P0[0];
+    P.pp.a[3] = c.P0[1];
+    P.pp.a[5] = c.P0[2];
+    P.vv.a[0] = c.P0[3];
+    P.vv.a[3] = c.P0[4];
+    P.vv.a[5] = c.P0[5];
+    P.bb.a[0] = c.P0[6];
+    P.bb.a[3] = c.P0[7];
+    P.bb.a[5] = c.P0[8];
+    x.p = x.v = x.b = v3<T>(T(0), T(0), T(0));
+  } else {
+    load_ckpt(dm, b, ks, i, P, x);
+  }
+  M3<T> RT;
+  for (int k = ks;; ++k) {
+    const int j = k - ks;
+    src.acquire(j);
+    if (j > 0 || Tk == 1) {  // the restart checkpoint already holds the leg-odometry update of stage ks
+      S3<T> Lam;
+      V3<T> eta;
+      src.meas(j, k, Lam, eta);
+      Math::meas(P, x, Lam, eta);
+      store_ckpt(dm, b, k, i, P, x);
+    }
+    src.rot(j, k, RT);
+    if (k == Tk) {
+      src.release(j);
+      break;
+    }
+    {
+      V3<T> as, dlt;
+      bool vo;
+      src.dyn(j, k, as, dlt, vo);
+      src.release(j);
+      Math::prop(c, P, x, RT, as, vo, dlt);
+    }
+  }
+  V3<T> om;
+#pragma unroll
+  for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
+  const V3<T> lever = v3<T>(T(0.016041), T(0.089061), T(0.0579875));
+  const V3<T> vb = mul(RT, add(x.v, cross(om, lever)));
+  int status = 0;
+  const T chk = x.p[0] + x.p[1] + x.p[2] + x.v[0] + x.v[1] + x.v[2] + x.b[0] + x.b[1] + x.b[2];
+  if (!(chk == chk) || !(chk - chk == T(0))) status |= ST_NONFINITE;
+  if (out.x != nullptr) {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) {
+      out.x[(size_t)f * n + i] = (double)x.p[f];
+      out.x[(size_t)(3 + f) * n + i] = (double)x.v[f];
+      out.x[(size_t)(6 + f) * n + i] = (double)x.b[f];
+    }
+  }
+  if (out.v_body != nullptr) {
+#pragma unroll
+    for (int f = 0; f < 3; ++f) out.v_body[(size_t)f * n + i] = (double)vb[f];
+  }
+  return status;
+}
+
+// restart stage of instance i at tick Tk: T-1, or the first stage whose VO row changed this tick
+template <typename T>
+DEKF_HD int incr_restart_stage(const Dims &dm, const Buffers<T> &b, int Tk, int i) {
+  if (Tk == 1) return 0;
+  int ks = Tk - 1;
+  const int rs = b.resweep[i];
+  if (rs < ks) ks = rs;
+  const int kmin = (Tk >= dm.N) ? Tk - dm.N : 0;  // VO bounds never reach below the window start (DecentralEst.cpp:917-918)
+  return ks < kmin ? kmin : ks;
+}
+
+template <typename T>
+DEKF_HD int mhe_solve_incr(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
+                           int Tk, int i) {
+  GlobalStageSource<T> src(dm, b, i);
+  return mhe_solve_incr<T>(c, dm, b, in, out, Tk, i, src, incr_restart_stage(dm, b, Tk, i));
+}
+
+// marginalizeQP(T-N) on demand for the incremental solve: arrival cost on x_{T-N+1} = time update (dynamics + VO row
+// of stage T-N as it stands now) of checkpoint T-N; written to arr_P / arr_x where the getters read it.
+template <typename T, typename Math = DefaultMath<T>>
+DEKF_HD void arrival_from_checkpoint(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, int Tk, int i) {
+  if (Tk < dm.N) return;  // still the initial prior (k_init_state)
+  GlobalStageSource<T> src(dm, b, i);
+  Cov9<T> P;
+  Vec9<T> x;
+  load_ckpt(dm, b, Tk - dm.N, i, P, x);
+  M3<T> R;
+  V3<T> as, dlt;
+  bool vo;
+  src.rot(0, Tk - dm.N, R);
+  src.dyn(0, Tk - dm.N, as, dlt, vo);
+  Math::prop(c, P, x, R, as, vo, dlt);
+  store_cov(b.arr_P, dm.ns, i, P);
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    b.arr_x[(size_t)f * dm.ns + i] = x.p[f];
+    b.arr_x[(size_t)(3 + f) * dm.ns + i] = x.v[f];
+    b.arr_x[(size_t)(6 + f) * dm.ns + i] = x.b[f];
+  }
 }
 
 // KF alternative, est_type_ == 1 (DecentralEst.cpp:592-861 InitializeKF / UpdateKF, :189-196 output): the same

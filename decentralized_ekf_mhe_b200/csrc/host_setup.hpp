@@ -114,6 +114,7 @@ inline MheConst<T> make_mhe_const(const dekf_config &c) {
   m.dt_d = dt;
   m.N = c.N;
   m.est_type = c.est_type;
+  m.window_solve = (c.est_type == 0 && !c.v_box_enable) ? c.window_solve : 0;
   m.thr = c.contact_effort_threshold;
   for (int i = 0; i < 3; ++i) {
     const double Cp = std::pow(c.p_process_std[i], 2), Ca = std::pow(c.accel_input_std[i], 2);

@@ -140,4 +140,49 @@ __global__ void __launch_bounds__(TILE, MINB) k_solve_tma(const __grid_constant_
   if (status_out != nullptr) status_out[i] = st;
 }
 
+// Incremental window solve on a tick that carries VO messages: the CTA agrees on the earliest restart stage of its 128
+// instances (re-sweeping from an earlier valid checkpoint gives the same bits) and streams the stage records
+// ks .. T through the same TMA ring as k_solve_tma.
+template <typename T, int TILE = kTile, int STAGES = kStages, typename Math = DefaultMath<T>>
+__global__ void __launch_bounds__(TILE, 1) k_solve_incr_tma(const __grid_constant__ CUtensorMap tmap, const MheConst<T> c,
+                                                            const Dims dm, const Buffers<T> b, const Inputs in,
+                                                            const Outputs out, int Tk, int32_t *status_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ int s_ks;
+  SmemStageSource<T, TILE, STAGES> src;
+  src.tiles = reinterpret_cast<T *>(smem_raw);
+  src.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * REC_SIZE * TILE * sizeof(T));
+  src.empty = src.full + STAGES;
+  src.map = &tmap;
+  src.NW = dm.NW;
+  src.i0 = blockIdx.x * TILE;
+  src.tid = threadIdx.x;
+  const int i = src.i0 + threadIdx.x;
+  const int active = min(TILE, dm.n - src.i0);
+  if (threadIdx.x == 0) {
+    s_ks = Tk - 1;
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&src.full[s], 1);
+      mbar_init(&src.empty[s], (uint32_t)active);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (i < dm.n) atomicMin(&s_ks, incr_restart_stage(dm, b, Tk, i));
+  __syncthreads();
+  const int ks = s_ks;
+  src.k0 = ks;
+  src.nst = Tk - ks + 1;
+  if (threadIdx.x == 0) {
+    const int pre = src.nst < STAGES ? src.nst : STAGES;
+    for (int j = 0; j < pre; ++j) src.issue(j);
+  }
+  if (i >= dm.n) return;
+  int st = b.status[i];
+  st |= mhe_solve_incr<T, SmemStageSource<T, TILE, STAGES>, Math>(c, dm, b, in, out, Tk, i, src, ks);
+  b.status[i] = st;
+  if (status_out != nullptr) status_out[i] = st;
+}
+
 }  // namespace dekf

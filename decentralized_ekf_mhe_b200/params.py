@@ -6,6 +6,7 @@ import ctypes as C
 
 ROBOT_GO1, ROBOT_CASSIE, ROBOT_POGOX = 0, 1, 2
 FP64, FP32 = 0, 1
+SOLVE_FULL, SOLVE_INCREMENTAL = 0, 1
 ROBOT_IDS = {"go1": ROBOT_GO1, "cassie": ROBOT_CASSIE, "pogox": ROBOT_POGOX}
 
 # per-instance status bits (include/dekf_b200.h)
@@ -25,7 +26,7 @@ class DekfConfig(C.Structure):
         ("contact_effort_threshold", C.c_double),
         ("p_init_std", C.c_double * 3), ("v_init_std", C.c_double * 3), ("foot_init_std", C.c_double * 3),
         ("accel_bias_init_std", C.c_double * 3), ("vo_p_std", C.c_double * 3),
-        ("rate", C.c_int32), ("N", C.c_int32), ("est_type", C.c_int32), ("reserved1", C.c_int32),
+        ("rate", C.c_int32), ("N", C.c_int32), ("est_type", C.c_int32), ("window_solve", C.c_int32),
         ("rho", C.c_double), ("alpha", C.c_double), ("delta", C.c_double), ("sigma", C.c_double),
         ("verbose", C.c_int32), ("adaptRho", C.c_int32), ("polish", C.c_int32), ("maxQPIter", C.c_int32),
         ("realtiveTol", C.c_double), ("absTol", C.c_double), ("primTol", C.c_double), ("dualTol", C.c_double),

@@ -63,6 +63,7 @@ enum {
 
 enum { DEKF_ROBOT_GO1 = 0, DEKF_ROBOT_CASSIE = 1, DEKF_ROBOT_POGOX = 2 };
 enum { DEKF_FP64 = 0, DEKF_FP32 = 1 };
+enum { DEKF_SOLVE_FULL = 0, DEKF_SOLVE_INCREMENTAL = 1 };
 
 /* per-instance status bits (OR-ed over the calls of one step) */
 enum {
@@ -94,7 +95,11 @@ typedef struct dekf_config {
   double contact_effort_threshold;
   double p_init_std[3], v_init_std[3], foot_init_std[3], accel_bias_init_std[3];
   double vo_p_std[3];
-  int32_t rate, N, est_type, reserved1;
+  int32_t rate, N, est_type;
+  /* DEKF_SOLVE_FULL: every update(T) re-sweeps the whole window, like the reference re-solves the whole QP
+   * (tier A of SURVEY.md 8d).  DEKF_SOLVE_INCREMENTAL: restart the sweep from the checkpoint of the first stage that
+   * changed (tier B; bit-identical results; ignored with v_box_enable or est_type 1). */
+  int32_t window_solve;
   /* OSQP settings are accepted for source compatibility and ignored: the window is solved
    * directly (exactly), see DESIGN.md section 4. */
   double rho, alpha, delta, sigma;

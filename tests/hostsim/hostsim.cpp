@@ -56,6 +56,8 @@ struct Sim {
     b.pend_flag = alloc<uint8_t>(s.pend_flag);
     b.pend = alloc<double>(s.pend);
     b.status = alloc<int32_t>(s.status);
+    b.ckpt = alloc<T>((size_t)dm.NW * 54 * dm.ns);
+    b.resweep = alloc<int32_t>(dm.ns);
     const int n = dm.ns;
     for (int i = 0; i < dm.n; ++i) {
       for (int f = 0; f < 4; ++f) {
@@ -114,6 +116,8 @@ void run(const dekf_config &cfg, int S, const double *gyro, const double *accel,
         st |= kf_update<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
       else if (s >= 1 && cfg.v_box_enable)
         st |= mhe_solve_box<T>(sim.mc, sim.bc, sim.dm, sim.b, sim.bb, in, out, s, i);
+      else if (s >= 1 && sim.mc.window_solve == 1)
+        st |= mhe_solve_incr<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
       else if (s >= 1)
         st |= mhe_solve<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
       if (qp_out) {
@@ -124,6 +128,8 @@ void run(const dekf_config &cfg, int S, const double *gyro, const double *accel,
       for (int f = 0; f < 3; ++f) pvo_out[((size_t)s * 3 + f) * n + i] = sim.b.p_vo[(size_t)f * sim.dm.ns + i];
     }
   }
+  if (sim.mc.window_solve == 1)
+    for (int i = 0; i < n; ++i) arrival_from_checkpoint<T>(sim.mc, sim.dm, sim.b, S - 1, i);
   for (int f = 0; f < 45; ++f)
     for (int i = 0; i < n; ++i) arrP_out[(size_t)f * n + i] = (double)sim.b.arr_P[(size_t)f * sim.dm.ns + i];
   for (int f = 0; f < 9; ++f)

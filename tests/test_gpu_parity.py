@@ -246,6 +246,38 @@ def test_pogox_state_constrained_16384(est_mod, oracle, precision, tol):
     est.close()
 
 
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("n", [200, 4500])  # fused single-launch path / split kernels (dekf_run pipeline)
+def test_incremental_equals_full_resweep(est_mod, precision, n):
+    """window_solve = DEKF_SOLVE_INCREMENTAL (tier B) restarts the sweep at the first changed stage; it performs the
+    same operations on the same operands as the full re-sweep from there on, so every output and the arrival cost
+    must be BIT-identical to DEKF_SOLVE_FULL (tier A), with ragged VO arrival and through the window fill."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    S = 120
+    st = synth.make_stream(n, S, vo_jitter=True, device="cuda")
+    d = {k: v.contiguous() for k, v in st.items()}
+    vo = [bool(st["vo_flag"][s].any()) for s in range(S)]
+    outs = []
+    for ws in (0, 1):
+        est = E.BatchedEstimator(E.robot_params("go1", ekf_rate=200, window_solve=ws), n, precision=precision)
+        o = dict(x=torch.zeros(S, 9, n, dtype=torch.float64, device="cuda"), v_body=torch.zeros(S, 3, n, dtype=torch.float64, device="cuda"),
+                 quat=torch.zeros(S, 4, n, dtype=torch.float64, device="cuda"), status=torch.zeros(S, n, dtype=torch.int32, device="cuda"))
+        est.run(0, 70, d, vo, out=o, out_per_step=True)
+        M1, n1 = est.mhe_qp_.arrival_cov()
+        for s in range(70, S):  # and tick by tick
+            est.step(s, E.robot_store.from_stream(d, s))
+            o["x"][s], o["v_body"][s], o["status"][s] = est.x_MHE_, est.v_MHE_b_, est.status_
+        M2, n2 = est.mhe_qp_.arrival_cov()
+        outs.append((o, M1.clone(), n1.clone(), M2.clone(), n2.clone()))
+        est.close()
+    (a, aM1, an1, aM2, an2), (b, bM1, bn1, bM2, bn2) = outs
+    assert torch.equal(a["x"][1:], b["x"][1:]) and torch.equal(a["v_body"][1:], b["v_body"][1:])
+    assert torch.equal(a["status"], b["status"])
+    assert torch.equal(aM1, bM1) and torch.equal(an1, bn1) and torch.equal(aM2, bM2) and torch.equal(an2, bn2)
+    assert (a["status"] & 16).any()  # VO bounds were inserted (re-sweeps happened)
+
+
 def test_run_and_run_host_equal_step_loop(est_mod, monkeypatch):
     """dekf_run (S ticks per call, device streams) and dekf_run_host (pinned host streams, pipelined copies) return
     bit-identical per-tick results to the tick-by-tick loop, on the large-batch kernel path."""
