@@ -14,7 +14,7 @@ ip = C.POINTER(C.c_int32)
 # every symbol include/dekf_b200.h declares
 SYMBOLS = [
     "dekf_config_default_go1", "dekf_config_default_cassie", "dekf_config_default_pogox", "dekf_create",
-    "dekf_destroy", "dekf_reset", "dekf_set_stream", "dekf_get_stream", "dekf_last_error", "dekf_num_joints",
+    "dekf_destroy", "dekf_reset", "dekf_set_stream", "dekf_get_stream", "dekf_last_error", "dekf_num_joints", "dekf_state_dim",
     "dekf_ekf_step", "dekf_mhe_step", "dekf_step", "dekf_step_host", "dekf_mhe_step_host", "dekf_ekf_step_host",
     "dekf_run", "dekf_run_host", "dekf_synchronize", "dekf_get_arrival_cost",
     "dekf_get_arrival_cov", "dekf_get_p_vo", "dekf_get_R_sb", "dekf_get_ekf_cov", "dekf_get_window_vo_count", "dekf_get_host", "dekf_debug_taps", "dekf_get_qp_info",
@@ -61,6 +61,7 @@ def load():
     L.dekf_last_error.argtypes = [hp]
     L.dekf_last_error.restype = C.c_char_p
     L.dekf_num_joints.argtypes = [hp]
+    L.dekf_state_dim.argtypes = [hp]
     L.dekf_ekf_step.argtypes = [hp, C.POINTER(DekfInputs), C.POINTER(DekfOutputs)]
     L.dekf_ekf_step_host.argtypes = [hp, C.POINTER(DekfInputs), C.POINTER(DekfOutputs)]
     for name in ("dekf_run", "dekf_run_host"):

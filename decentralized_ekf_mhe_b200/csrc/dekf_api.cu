@@ -97,6 +97,31 @@ __global__ void __launch_bounds__(kBlock) k_solve_box(const MheConst<T> c, const
   if (status_out != nullptr) status_out[i] = st;
 }
 
+// leg_odom_type 1 (foot-position states): information-form window sweep / KF step, footstate.cuh
+template <typename T, int L>
+__global__ void __launch_bounds__(kBlock) k_solve_foot(const FootConst fc, const Dims dm, const Buffers<T> b, const FootBuffers fb,
+                                                       const Inputs in, const Outputs out, int Tk, int32_t *status_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  int st = b.status[i];
+  if (Tk >= 1 || fc.est_type == 1) st |= foot_solve<T, L>(fc, dm, b, fb, in, out, Tk, i);
+  b.status[i] = st;
+  if (status_out != nullptr) status_out[i] = st;
+}
+// arrival cost of the foot-state model: (M_p, n_p) as the reference holds them (MheSrb.hpp:86-87)
+__global__ void k_get_arrival_foot(const Dims dm, const FootBuffers fb, int ds, double *Mout, double *nout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  int p = 0;
+  for (int r = 0; r < ds; ++r)
+    for (int c = 0; c <= r; ++c) {
+      const double v = fb.arr_M[(size_t)(p++) * dm.ns + i];
+      Mout[(size_t)(r * ds + c) * dm.n + i] = v;
+      Mout[(size_t)(c * ds + r) * dm.n + i] = v;
+    }
+  for (int r = 0; r < ds; ++r) nout[(size_t)r * dm.n + i] = -fb.arr_m[(size_t)r * dm.ns + i];
+}
+
 // KF alternative (est_type 1): one predict + correct per tick instead of the window solve
 template <typename T>
 __global__ void __launch_bounds__(kBlock) k_kf(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
@@ -277,6 +302,7 @@ struct dekf_handle {
   dekf_config cfg;
   Dims dm;
   int nl, nj, nq;
+  int ds;  // state dimension 9 + 3 * leg_odom_type * num_legs (DecentralEst.cpp:20) == rows of outputs.x
   bool f32;
   EkfConst<double> ec64;
   MheConst<double> mc64;
@@ -286,6 +312,8 @@ struct dekf_handle {
   Buffers<float> b32;
   BoxConst bc;
   BoxBuffers bb = {nullptr, nullptr, nullptr, nullptr};
+  FootConst fc;
+  FootBuffers fb = {nullptr, nullptr, nullptr};  // leg_odom_type 1
   void *ckpt_mem = nullptr;       // incremental window solve: checkpoint ring
   int32_t *resweep_mem = nullptr;
   void *slab = nullptr;
@@ -381,6 +409,7 @@ size_t carve(Buffers<T> &b, const Dims &dm, char *base) {
   b.status = (int32_t *)take(s.status, sizeof(int32_t));
   b.ckpt = nullptr;
   b.resweep = nullptr;
+  b.foot_leg = nullptr;
   return off;
 }
 
@@ -498,7 +527,9 @@ int validate(const dekf_config *c, std::string &why) {
   if (c->precision != DEKF_FP64 && c->precision != DEKF_FP32) { why = "precision"; return DEKF_EINVAL; }
   if (c->robot < DEKF_ROBOT_GO1 || c->robot > DEKF_ROBOT_POGOX) { why = "robot"; return DEKF_EINVAL; }
   if (c->num_legs != robot_num_legs(c->robot)) { why = "num_legs does not match the robot model"; return DEKF_EINVAL; }
-  if (c->leg_odom_type != 0) { why = "leg_odom_type 1 (foot-position states) is not built yet"; return DEKF_EINVAL; }
+  if (c->leg_odom_type != 0 && c->leg_odom_type != 1) { why = "leg_odom_type must be 0 or 1"; return DEKF_EINVAL; }
+  if (c->leg_odom_type == 1 && c->precision != DEKF_FP64) { why = "leg_odom_type 1 is carried in information form and needs DEKF_FP64"; return DEKF_EINVAL; }
+  if (c->leg_odom_type == 1 && c->v_box_enable) { why = "v_box_enable is built for leg_odom_type 0 only"; return DEKF_EINVAL; }
   if (c->est_type != 0 && c->est_type != 1) { why = "est_type must be 0 (MHE) or 1 (KF alternative)"; return DEKF_EINVAL; }
   if (c->ekf_hist_depth < 4) { why = "ekf_hist_depth < 4"; return DEKF_EINVAL; }
   if (c->window_solve != DEKF_SOLVE_FULL && c->window_solve != DEKF_SOLVE_INCREMENTAL) { why = "window_solve"; return DEKF_EINVAL; }
@@ -558,6 +589,7 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
   h->nl = robot_num_legs(cfg->robot);
   h->nj = robot_nj(cfg->robot);
   h->nq = h->nl * h->nj;
+  h->ds = state_dim(*cfg);
   h->f32 = cfg->precision == DEKF_FP32;
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -648,6 +680,19 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     h->b64.resweep = h->b32.resweep = h->resweep_mem;
     h->extra_bytes += ck + ns * sizeof(int32_t);
   }
+  h->fc = make_foot_const(*cfg);
+  if (cfg->leg_odom_type == 1) {
+    const size_t ns = (size_t)h->dm.ns, ds = (size_t)h->ds;
+    const size_t leg = (size_t)h->dm.NW * foot_rec_size(h->nl) * ns * sizeof(double), am = ds * (ds + 1) / 2 * ns * sizeof(double);
+    if ((ce = cudaMalloc((void **)&h->fb.leg, leg)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc(foot ring)", ce);
+    if ((ce = cudaMalloc((void **)&h->fb.arr_M, am)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    if ((ce = cudaMalloc((void **)&h->fb.arr_m, ds * ns * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    cudaMemset(h->fb.leg, 0, leg);
+    cudaMemset(h->fb.arr_M, 0, am);
+    cudaMemset(h->fb.arr_m, 0, ds * ns * sizeof(double));
+    h->b64.foot_leg = h->fb.leg;
+    h->extra_bytes += leg + am + ds * ns * sizeof(double);
+  }
   h->bc = make_box_const(*cfg);
   if (cfg->v_box_enable) {
     const size_t ns = (size_t)h->dm.ns;
@@ -683,6 +728,9 @@ int dekf_destroy(dekf_handle *h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   cudaFree(h->slab);
+  cudaFree(h->fb.leg);
+  cudaFree(h->fb.arr_M);
+  cudaFree(h->fb.arr_m);
   cudaFree(h->ckpt_mem);
   cudaFree(h->resweep_mem);
   cudaFree(h->bb.fac);
@@ -731,6 +779,10 @@ int dekf_reset(dekf_handle *h) {
   if (!h) return DEKF_EINVAL;
   CK(cudaSetDevice(h->cfg.device));
   CK(cudaMemsetAsync(h->slab, 0, h->slab_bytes, h->stream));
+  if (h->fb.arr_M) {
+    CK(cudaMemsetAsync(h->fb.arr_M, 0, (size_t)h->ds * (h->ds + 1) / 2 * h->dm.ns * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->fb.arr_m, 0, (size_t)h->ds * h->dm.ns * sizeof(double), h->stream));
+  }
   if (h->bb.act) {
     CK(cudaMemsetAsync(h->bb.act, 0, (size_t)h->dm.NW * h->dm.ns, h->stream));
     CK(cudaMemsetAsync(h->bb.iters, 0, (size_t)h->dm.ns * sizeof(int32_t), h->stream));
@@ -758,6 +810,7 @@ int dekf_set_stream(dekf_handle *h, void *cuda_stream) {
 void *dekf_get_stream(dekf_handle *h) { return h ? (void *)h->stream : nullptr; }
 const char *dekf_last_error(const dekf_handle *h) { return h ? h->err.c_str() : "null handle"; }
 int dekf_num_joints(const dekf_handle *h) { return h ? h->nq : DEKF_EINVAL; }
+int dekf_state_dim(const dekf_handle *h) { return h ? h->ds : DEKF_EINVAL; }
 int64_t dekf_launch_count(const dekf_handle *h) { return h ? h->launches : 0; }
 int64_t dekf_device_bytes(const dekf_handle *h) { return h ? (int64_t)(h->slab_bytes + h->extra_bytes) : 0; }
 
@@ -824,7 +877,15 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
     if (rc) return fail(h, rc, "assemble");
     if (after_assemble) cudaEventRecord(after_assemble, h->stream);
     ProfScope ps(h, 2);
-    if (kf)
+    if (h->cfg.leg_odom_type == 1) {
+      const int g = grid_for(h->dm.n);
+      if (h->nl == 4)
+        k_solve_foot<double, 4><<<g, kBlock, 0, h->stream>>>(h->fc, h->dm, h->b64, h->fb, di, dout, T_, st);
+      else if (h->nl == 2)
+        k_solve_foot<double, 2><<<g, kBlock, 0, h->stream>>>(h->fc, h->dm, h->b64, h->fb, di, dout, T_, st);
+      else
+        k_solve_foot<double, 1><<<g, kBlock, 0, h->stream>>>(h->fc, h->dm, h->b64, h->fb, di, dout, T_, st);
+    } else if (kf)
       k_kf<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
     else if (h->bc.enable)
       k_solve_box<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->bc, h->dm, h->b64, h->bb, di, dout, T_, st);
@@ -862,7 +923,7 @@ int dekf_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outp
   CK(cudaSetDevice(h->cfg.device));
   dekf_inputs in2 = *in;
   in2.quat = nullptr;  // lock-step: the MHE consumes this tick's EKF quaternion
-  if (h->dm.n <= h->fused_max && !h->bc.enable) {
+  if (h->dm.n <= h->fused_max && !h->bc.enable && h->cfg.leg_odom_type == 0) {
     const Inputs di = to_inputs(&in2);
     const Outputs dout = to_outputs(h, out);
     int32_t *st = out ? out->status : nullptr;
@@ -911,10 +972,10 @@ int alloc_stage_set(dekf_handle *h, StageSet &ss) {
   for (int a = 0; a < kNumIn; ++a) tot += cnt[a];
   CK(cudaMalloc((void **)&ss.in, tot * sizeof(double)));
   CK(cudaMalloc((void **)&ss.flag, n));
-  CK(cudaMalloc((void **)&ss.out, 16 * n * sizeof(double)));
+  CK(cudaMalloc((void **)&ss.out, (size_t)(7 + h->ds) * n * sizeof(double)));
   CK(cudaMalloc((void **)&ss.contact, (size_t)h->nl * n));
   CK(cudaMalloc((void **)&ss.status, n * sizeof(int32_t)));
-  h->extra_bytes += (tot + 16 * n) * sizeof(double) + n + (size_t)h->nl * n + n * sizeof(int32_t);
+  h->extra_bytes += (tot + (size_t)(7 + h->ds) * n) * sizeof(double) + n + (size_t)h->nl * n + n * sizeof(int32_t);
   return DEKF_OK;
 }
 void free_chunk_set(ChunkSet &cs) {
@@ -932,11 +993,11 @@ int alloc_chunk_set(dekf_handle *h, ChunkSet &cs, int cap) {
   const size_t in_rows = 16 + 2 * (size_t)h->nq + (size_t)h->nl;  // 3+3+1+nq+nq+nl + 4+1+1+3
   CK(cudaMalloc((void **)&cs.in, c * in_rows * n * sizeof(double)));
   CK(cudaMalloc((void **)&cs.flag, c * n));
-  CK(cudaMalloc((void **)&cs.out, c * 16 * n * sizeof(double)));
+  CK(cudaMalloc((void **)&cs.out, c * (size_t)(7 + h->ds) * n * sizeof(double)));
   CK(cudaMalloc((void **)&cs.contact, c * (size_t)h->nl * n));
   CK(cudaMalloc((void **)&cs.status, c * n * sizeof(int32_t)));
   cs.cap = cap;
-  h->extra_bytes += c * ((in_rows + 16) * n * sizeof(double) + n + (size_t)h->nl * n + n * sizeof(int32_t));
+  h->extra_bytes += c * ((in_rows + 7 + h->ds) * n * sizeof(double) + n + (size_t)h->nl * n + n * sizeof(int32_t));
   return DEKF_OK;
 }
 void free_stage_set(StageSet &ss) {
@@ -993,7 +1054,7 @@ void stage_outputs(const dekf_handle *h, const StageSet &ss, const dekf_outputs 
   std::memset(dout, 0, sizeof(*dout));
   dout->quat = ss.out;
   dout->x = ss.out + 4 * n;
-  dout->v_body = ss.out + 13 * n;
+  dout->v_body = ss.out + (size_t)(4 + h->ds) * n;
   dout->contact = (out && out->contact) ? ss.contact : nullptr;
   dout->status = (out && out->status) ? ss.status : nullptr;
 }
@@ -1003,15 +1064,16 @@ int unstage_outputs(dekf_handle *h, const StageSet &ss, const dekf_outputs *out,
   if (!out) return DEKF_OK;
   const size_t n = (size_t)h->dm.n;
   double *q = out->quat ? out->quat + step * 4 * n : nullptr;
-  double *x = (out->x && kind != HK_EKF) ? out->x + step * 9 * n : nullptr;
+  const size_t ds = (size_t)h->ds;
+  double *x = (out->x && kind != HK_EKF) ? out->x + step * ds * n : nullptr;
   double *v = (out->v_body && kind != HK_EKF) ? out->v_body + step * 3 * n : nullptr;
   if (kind == HK_MHE) q = nullptr;
-  if (q && x && v && x == q + 4 * n && v == x + 9 * n) {
-    CK(cudaMemcpyAsync(q, ss.out, 16 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (q && x && v && x == q + 4 * n && v == x + ds * n) {
+    CK(cudaMemcpyAsync(q, ss.out, (7 + ds) * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   } else {
     if (q) CK(cudaMemcpyAsync(q, ss.out, 4 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (x) CK(cudaMemcpyAsync(x, ss.out + 4 * n, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (v) CK(cudaMemcpyAsync(v, ss.out + 13 * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (x) CK(cudaMemcpyAsync(x, ss.out + 4 * n, ds * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (v) CK(cudaMemcpyAsync(v, ss.out + (4 + ds) * n, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
   if (out->contact && kind != HK_EKF)
     CK(cudaMemcpyAsync(out->contact + step * h->nl * n, ss.contact, (size_t)h->nl * n, cudaMemcpyDeviceToHost, st));
@@ -1089,14 +1151,14 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     if (out && (out_per_step || s == S - 1)) {
       const size_t o = out_per_step ? (size_t)s : 0;
       os->quat = out->quat ? out->quat + o * 4 * n : nullptr;
-      os->x = out->x ? out->x + o * 9 * n : nullptr;
+      os->x = out->x ? out->x + o * (size_t)h->ds * n : nullptr;
       os->v_body = out->v_body ? out->v_body + o * 3 * n : nullptr;
       os->contact = out->contact ? out->contact + o * h->nl * n : nullptr;
       os->status = out->status ? out->status + o * n : nullptr;
     }
   };
   // small batches (one fused launch per tick) and tapped handles: plain tick loop
-  if ((h->dm.n <= h->fused_max && !h->bc.enable) || h->cfg.debug_taps || S < 2) {
+  if ((h->dm.n <= h->fused_max && !h->bc.enable && h->cfg.leg_odom_type == 0) || h->cfg.debug_taps || S < 2) {
     for (int32_t s = 0; s < S; ++s) {
       dekf_inputs is;
       offset_inputs(h, in, (size_t)s, !vo_steps || vo_steps[s], &is);
@@ -1189,7 +1251,7 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
   int B = 8;
   if (const char *e = std::getenv("DEKF_HOST_CHUNK")) B = std::atoi(e);
   {
-    const size_t per_tick = (size_t)(16 + 2 * h->nq + h->nl + 16) * 8 * n;
+    const size_t per_tick = (size_t)(16 + 2 * h->nq + h->nl + 7 + h->ds) * 8 * n;
     const size_t cap = (size_t)384 << 20;  // staging budget per set
     if ((size_t)B * per_tick > cap) B = (int)(cap / per_tick);
   }
@@ -1262,7 +1324,7 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
     if (want_out) {
       dout.quat = cs.out;
       dout.x = cs.out + cap * 4 * n;
-      dout.v_body = cs.out + cap * 13 * n;
+      dout.v_body = cs.out + cap * (size_t)(4 + h->ds) * n;
       dout.contact = out->contact ? cs.contact : nullptr;
       dout.status = out->status ? cs.status : nullptr;
     }
@@ -1274,7 +1336,7 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
     if (want_out) {
       const size_t cnt = out_per_step ? (size_t)Bc : 1, so = out_per_step ? (size_t)s0 : 0;
       if (out->quat) CK(cudaMemcpyAsync(out->quat + so * 4 * n, dout.quat, cnt * 4 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
-      if (out->x) CK(cudaMemcpyAsync(out->x + so * 9 * n, dout.x, cnt * 9 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+      if (out->x) CK(cudaMemcpyAsync(out->x + so * (size_t)h->ds * n, dout.x, cnt * (size_t)h->ds * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
       if (out->v_body) CK(cudaMemcpyAsync(out->v_body + so * 3 * n, dout.v_body, cnt * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
       if (out->contact) CK(cudaMemcpyAsync(out->contact + so * h->nl * n, cs.contact, cnt * h->nl * n, cudaMemcpyDeviceToHost, h->s_d2h));
       if (out->status) CK(cudaMemcpyAsync(out->status + so * n, cs.status, cnt * n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_d2h));
@@ -1290,6 +1352,13 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
 static int get_arrival(dekf_handle *h, double *P, double *x, int info) {
   if (!h || !P || !x) return fail(h, DEKF_EINVAL, "null argument");
   CK(cudaSetDevice(h->cfg.device));
+  if (h->cfg.leg_odom_type == 1) {
+    if (!info) return fail(h, DEKF_EINVAL, "leg_odom_type 1 carries the arrival cost in information form: use dekf_get_arrival_cost");
+    k_get_arrival_foot<<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->dm, h->fb, h->ds, P, x);
+    h->launches++;
+    CK(cudaGetLastError());
+    return DEKF_OK;
+  }
   if (h->mc64.window_solve == 1 && h->next_T >= 1) {  // marginalizeQP(T-N) on demand (see arrival_from_checkpoint)
     if (h->f32)
       k_arrival_from_ckpt<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, h->next_T - 1);
@@ -1341,26 +1410,27 @@ int dekf_get_host(dekf_handle *h, int32_t what, void *host_out) {
   if (!h || !host_out) return fail(h, DEKF_EINVAL, "dekf_get_host: null argument");
   CK(cudaSetDevice(h->cfg.device));
   const size_t n = (size_t)h->dm.n;
-  const size_t rows[8] = {9, 3, 81, 9, 16, 1, 81, 9};
+  const size_t dsz = (size_t)h->ds;
+  const size_t rows[8] = {9, 3, dsz * dsz, dsz, 16, 1, dsz * dsz, dsz};
   if (what < 0 || what > DEKF_GET_ARRIVAL_MEAN) return fail(h, DEKF_EINVAL, "dekf_get_host: unknown selector");
   double *d = nullptr;
-  CK(cudaMalloc((void **)&d, (size_t)90 * n * sizeof(double)));
+  CK(cudaMalloc((void **)&d, (dsz * dsz + dsz) * n * sizeof(double)));
   int rc = DEKF_OK;
   const void *src = d;
   size_t bytes = rows[what] * n * sizeof(double);
   switch (what) {
     case DEKF_GET_R_SB: rc = dekf_get_R_sb(h, d); break;
     case DEKF_GET_P_VO: rc = dekf_get_p_vo(h, d); break;
-    case DEKF_GET_ARRIVAL_M: rc = dekf_get_arrival_cost(h, d, d + 81 * n); break;
+    case DEKF_GET_ARRIVAL_M: rc = dekf_get_arrival_cost(h, d, d + dsz * dsz * n); break;
     case DEKF_GET_ARRIVAL_N:
-      rc = dekf_get_arrival_cost(h, d, d + 81 * n);
-      src = d + 81 * n;
+      rc = dekf_get_arrival_cost(h, d, d + dsz * dsz * n);
+      src = d + dsz * dsz * n;
       break;
     case DEKF_GET_EKF_COV: rc = dekf_get_ekf_cov(h, d); break;
-    case DEKF_GET_ARRIVAL_COV: rc = dekf_get_arrival_cov(h, d, d + 81 * n); break;
+    case DEKF_GET_ARRIVAL_COV: rc = dekf_get_arrival_cov(h, d, d + dsz * dsz * n); break;
     case DEKF_GET_ARRIVAL_MEAN:
-      rc = dekf_get_arrival_cov(h, d, d + 81 * n);
-      src = d + 81 * n;
+      rc = dekf_get_arrival_cov(h, d, d + dsz * dsz * n);
+      src = d + dsz * dsz * n;
       break;
     default:
       rc = dekf_get_window_vo_count(h, (int32_t *)d);

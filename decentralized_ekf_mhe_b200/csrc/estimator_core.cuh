@@ -107,6 +107,8 @@ struct Buffers {
   double *pend;           // [5][n]
   int32_t *status;        // [n]
   // incremental window solve (window_solve == 1) only, else nullptr
+  // leg_odom_type 1 (foot-position states, footstate.cuh) only, else nullptr
+  double *foot_leg;       // [NW][9*legs+1][ns] per leg b_meas (3) + measurement covariance (6); contact bit mask
   T *ckpt;                // [NW][54][ns] filter state (P 45, x 9) of every window stage AFTER its leg-odometry update
   int32_t *resweep;       // [ns] earliest stage whose VO row changed this tick (INT_MAX: none)
 };
@@ -450,6 +452,32 @@ DEKF_HD void bezier_point(double out[3], double u, const double *P0, const doubl
   }
 }
 
+// stage data of the foot-state model (leg_odom_type 1, footstate.cuh) written by the assembly kernel:
+// b_i = R p_i, Q_i = R (J_i C_enc_pos J_i')^-1 R' (DecentralEst.cpp:550-564), always double
+template <typename T, int NJ>
+DEKF_HD void foot_leg_record(const T *cenc_p, const M3<T> &R, const V3<T> &p, const T *J /*3 x NJ*/, double *rec /*stride ns*/,
+                             size_t ns, int leg) {
+  double Rd[9], pd[3], JC[3 * NJ];
+  for (int f = 0; f < 9; ++f) Rd[f] = (double)R.a[f];
+  for (int f = 0; f < 3; ++f) pd[f] = (double)p[f];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < NJ; ++c) JC[r * NJ + c] = (double)J[r * NJ + c] * (double)cenc_p[c];
+  S3<double> JCJ;
+  for (int r = 0; r < 3; ++r)
+    for (int c = r; c < 3; ++c) {
+      double v = 0.0;
+      for (int k = 0; k < NJ; ++k) v += JC[r * NJ + k] * (double)J[c * NJ + k];
+      JCJ.a[S3<double>::idx(r, c)] = v;
+    }
+  const S3<double> Qb = inverse(JCJ);
+  M3<double> Rm;
+  for (int f = 0; f < 9; ++f) Rm.a[f] = Rd[f];
+  const S3<double> Qw = rsrt(Rm, Qb);
+  double *o = rec + (size_t)(9 * leg) * ns;
+  for (int r = 0; r < 3; ++r) o[(size_t)r * ns] = Rd[r * 3 + 0] * pd[0] + Rd[r * 3 + 1] * pd[1] + Rd[r * 3 + 2] * pd[2];
+  for (int f = 0; f < 6; ++f) o[(size_t)(3 + f) * ns] = Qw.a[f];
+}
+
 // GetMeasurement(T) + the Measurement_T / Dynamic_T / VO_T data of UpdateMHE (DecentralEst.cpp:
 // 374-424, 474-478, 496-572, 864-985) + UpdateVOConstraints (:987-1009) for instance i.
 // q_ext: orientation to use ([w,x,y,z]); written to the history ring un-normalised like the reference
@@ -619,11 +647,13 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
   V3<T> Qbeta_sum = v3<T>(T(0), T(0), T(0));  // sum over stance legs of (G C G')^-1 beta_i
   V3<T> beta_swing = v3<T>(T(0), T(0), T(0));  // sum over swing legs of beta_i
   int n_swing = 0;
+  int contact_mask = 0;
 #pragma unroll
   for (int leg = 0; leg < NL; ++leg) {
     const double force = in.foot_force[(size_t)leg * n + i];
     const bool contact = (force >= c.thr);  // go1Sub.cpp:74, exact
     if (out.contact != nullptr) out.contact[(size_t)leg * n + i] = contact ? 1 : 0;
+    contact_mask |= (contact ? 1 : 0) << leg;
     T q[NJ], dq[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
@@ -636,6 +666,8 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
     p[0] += c.p_ib[0];
     p[1] += c.p_ib[1];
     p[2] += c.p_ib[2];
+    if (b.foot_leg != nullptr)  // leg_odom_type 1: b_meas = R p, C_meas = R J C_enc_pos J' R' (:550-564)
+      foot_leg_record<T, NJ>(c.cenc_p, R, p, J, b.foot_leg + (size_t)(Tk % NW) * (9 * NL + 1) * ns + i, (size_t)ns, leg);
     // beta = -(J dq + omega x p)   (b_meas = R beta, :515-516)
     V3<T> Jdq = v3<T>(T(0), T(0), T(0));
 #pragma unroll
@@ -710,6 +742,7 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
     eta[2] += c.q_swing[2] * Rb[2];
   }
 
+  if (b.foot_leg != nullptr) b.foot_leg[((size_t)(Tk % NW) * (9 * NL + 1) + 9 * NL) * ns + i] = (double)contact_mask;
   // ---- push (:949-975): history ring + stage record of discrete time Tk
   b.hist_time[(size_t)(Tk % HR) * ns + i] = in.imu_time[i];
 #pragma unroll

@@ -8,6 +8,7 @@
 #include "../../include/dekf_b200.h"
 #include "estimator_core.cuh"
 #include "box_solve.cuh"
+#include "footstate.cuh"
 
 namespace dekf {
 
@@ -167,6 +168,26 @@ inline BoxConst make_box_const(const dekf_config &c) {
   }
   return b;
 }
+
+// constants of the foot-state model (leg_odom_type 1; always double)
+inline FootConst make_foot_const(const dekf_config &c) {
+  FootConst f;
+  std::memset(&f, 0, sizeof(f));
+  const double dt = 1.0 / c.rate;
+  f.bc = make_box_const(c);
+  f.N = c.N;
+  f.est_type = c.est_type;
+  for (int i = 0; i < 3; ++i) {
+    f.q_slide[i] = 1.0 / (dt * dt * std::pow(c.foot_slide_std[i], 2));  // R Q_foot_slide R' / dt^2, DecentralEst.cpp:438-448
+    f.q_swing[i] = 1.0 / (dt * dt * std::pow(c.foot_swing_std[i], 2));
+    f.M0[0 + i] = 1.0 / std::pow(c.p_init_std[i], 2);  // :239-253
+    f.M0[3 + i] = 1.0 / std::pow(c.v_init_std[i], 2);
+    f.M0[6 + i] = 1.0 / std::pow(c.accel_bias_init_std[i], 2);
+    f.M0_foot[i] = 1.0 / std::pow(c.foot_init_std[i], 2);  // :313-322
+  }
+  return f;
+}
+inline int state_dim(const dekf_config &c) { return 9 + 3 * c.leg_odom_type * robot_num_legs(c.robot); }
 
 // fields per instance of every state array, in units of elements
 struct StateSizes {

@@ -110,12 +110,13 @@ class _Handle:
             raise DekfError(f"dekf_create failed with code {rc}")
         self.nl = cfg.num_legs
         self.nq = self.L.dekf_num_joints(self.h)
+        self.ds = self.L.dekf_state_dim(self.h)
         # run the library on torch's current stream of that device so tensor lifetimes stay simple
         self.stream = torch.cuda.current_stream(self.device)
         self.L.dekf_set_stream(self.h, C.c_void_p(self.stream.cuda_stream))
         f64 = dict(dtype=torch.float64, device=self.device)
         self.quat = torch.zeros(4, self.n, **f64)
-        self.x = torch.full((9, self.n), float("nan"), **f64)
+        self.x = torch.full((self.ds, self.n), float("nan"), **f64)
         self.v_body = torch.full((3, self.n), float("nan"), **f64)
         self.contact = torch.zeros(self.nl, self.n, dtype=torch.uint8, device=self.device)
         self.status = torch.zeros(self.n, dtype=torch.int32, device=self.device)
@@ -171,11 +172,11 @@ class _MheQpView:
 
     def _get(self, info):
         h = self._o._hd
-        M = torch.empty(81, h.n, dtype=torch.float64, device=h.device)
-        v = torch.empty(9, h.n, dtype=torch.float64, device=h.device)
+        M = torch.empty(h.ds * h.ds, h.n, dtype=torch.float64, device=h.device)
+        v = torch.empty(h.ds, h.n, dtype=torch.float64, device=h.device)
         fn = h.L.dekf_get_arrival_cost if info else h.L.dekf_get_arrival_cov
         h.check(fn(h.h, _ptr(M), _ptr(v)), "dekf_get_arrival")
-        return M.view(9, 9, h.n), v
+        return M.view(h.ds, h.ds, h.n), v
 
     @property
     def M_p(self):

@@ -136,7 +136,8 @@ typedef struct dekf_inputs {
 
 typedef struct dekf_outputs {
   double *quat;     /* [4][n] EKF quaternion after the tick (may be NULL) */
-  double *x;        /* [9][n] x_MHE_ = [p_s, v_s, accel bias] (valid for T>=1; may be NULL) */
+  double *x;        /* [ds][n] x_MHE_ = [p_s, v_s, accel bias (, foot positions if leg_odom_type 1)], ds = dekf_state_dim()
+                     * (valid for T>=1; may be NULL) */
   double *v_body;   /* [3][n] v_MHE_b_ (may be NULL) */
   uint8_t *contact; /* [num_legs][n] contact flags (may be NULL) */
   int32_t *status;  /* [n] status bits of this call (may be NULL) */
@@ -158,6 +159,7 @@ int dekf_set_stream(dekf_handle *h, void *cuda_stream);
 void *dekf_get_stream(dekf_handle *h);
 const char *dekf_last_error(const dekf_handle *h);
 int dekf_num_joints(const dekf_handle *h); /* num_legs * joints per leg */
+int dekf_state_dim(const dekf_handle *h);  /* dim_state_ = 9 + 3 * leg_odom_type * num_legs (DecentralEst.cpp:20) = rows of dekf_outputs.x */
 
 /* Device-pointer, stream-ordered entry points. */
 int dekf_ekf_step(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out);
@@ -184,8 +186,8 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
 int dekf_synchronize(dekf_handle *h);
 
 /* Getters (device pointers, stream-ordered). */
-int dekf_get_arrival_cost(dekf_handle *h, double *M_p /*[81][n]*/, double *n_p /*[9][n]*/);
-int dekf_get_arrival_cov(dekf_handle *h, double *P /*[81][n]*/, double *x /*[9][n]*/);
+int dekf_get_arrival_cost(dekf_handle *h, double *M_p /*[ds*ds][n]*/, double *n_p /*[ds][n]*/);
+int dekf_get_arrival_cov(dekf_handle *h, double *P /*[81][n]*/, double *x /*[9][n]*/); /* leg_odom_type 0 only */
 int dekf_get_p_vo(dekf_handle *h, double *p /*[3][n]*/);
 int dekf_get_R_sb(dekf_handle *h, double *R /*[9][n]*/);
 int dekf_get_ekf_cov(dekf_handle *h, double *P /*[16][n]*/);

@@ -248,9 +248,10 @@ class DecentralizedEstimation {
     nl_ = cfg.num_legs;
     nq_ = dekf_num_joints(h_);
     kf_ = cfg.est_type == 1;
-    x_MHE_.assign(kf_ ? 0 : 9 * (size_t)n_, 0.0);
+    ds_ = dekf_state_dim(h_);
+    x_MHE_.assign(kf_ ? 0 : ds_ * (size_t)n_, 0.0);
     v_MHE_b_.assign(kf_ ? 0 : 3 * (size_t)n_, 0.0);
-    x_KF_.assign(kf_ ? 9 * (size_t)n_ : 0, 0.0);
+    x_KF_.assign(kf_ ? ds_ * (size_t)n_ : 0, 0.0);
     v_KF_b_.assign(kf_ ? 3 * (size_t)n_ : 0, 0.0);
     R_sb_.assign(9 * (size_t)n_, 0.0);
     p_vo_accmulate_.assign(3 * (size_t)n_, 0.0);
@@ -270,13 +271,13 @@ class DecentralizedEstimation {
   // results (DecentralEst.hpp:278-285), `[rows][n]`
   std::vector<double> R_sb_;            // [9][n] row-major 3x3 per instance
   std::vector<double> p_vo_accmulate_;  // [3][n]
-  std::vector<double> x_MHE_;           // [9][n]  p_s, v_s, accel bias
+  std::vector<double> x_MHE_;           // [ds][n]  p_s, v_s, accel bias (, foot positions if leg_odom_type_ == 1)
   std::vector<double> v_MHE_b_;         // [3][n]
   // KF alternative, est_type_ == 1 (DecentralEst.hpp:286-291): filled instead of x_MHE_ / v_MHE_b_
   std::vector<double> x_KF_;            // [9][n]
   std::vector<double> v_KF_b_;          // [3][n]
   std::vector<double> C_KF_() const {   // [81][n] row-major 9x9 per instance
-    std::vector<double> c(81 * (size_t)n_);
+    std::vector<double> c((size_t)ds_ * ds_ * n_);
     detail::check(dekf_get_host(h_, DEKF_GET_ARRIVAL_COV, c.data()), h_, "dekf_get_host");
     return c;
   }
@@ -286,12 +287,12 @@ class DecentralizedEstimation {
   struct MheQp {
     DecentralizedEstimation *o;
     std::vector<double> M_p() const {
-      std::vector<double> m(81 * (size_t)o->n_);
+      std::vector<double> m((size_t)o->ds_ * o->ds_ * o->n_);
       detail::check(dekf_get_host(o->h_, DEKF_GET_ARRIVAL_M, m.data()), o->h_, "dekf_get_host");
       return m;
     }
     std::vector<double> n_p() const {
-      std::vector<double> v(9 * (size_t)o->n_);
+      std::vector<double> v((size_t)o->ds_ * o->n_);
       detail::check(dekf_get_host(o->h_, DEKF_GET_ARRIVAL_N, v.data()), o->h_, "dekf_get_host");
       return v;
     }
@@ -336,6 +337,7 @@ class DecentralizedEstimation {
   dekf_handle *h_ = nullptr;
   int n_ = 0, nl_ = 0, nq_ = 0;
   bool kf_ = false;
+  int ds_ = 9;
 };
 
 }  // namespace dekf

@@ -22,6 +22,8 @@ struct Sim {
   MheConst<T> mc;
   BoxConst bc;
   BoxBuffers bb;
+  FootConst fc;
+  FootBuffers fb;
   Buffers<T> b;
   std::vector<std::vector<char>> store;
 
@@ -56,6 +58,14 @@ struct Sim {
     b.pend_flag = alloc<uint8_t>(s.pend_flag);
     b.pend = alloc<double>(s.pend);
     b.status = alloc<int32_t>(s.status);
+    fc = make_foot_const(c);
+    {
+      const int L = robot_num_legs(c.robot), DS = 9 + 3 * L;
+      fb.leg = alloc<double>((size_t)dm.NW * (9 * L + 1) * dm.ns);
+      fb.arr_M = alloc<double>((size_t)(DS * (DS + 1) / 2) * dm.ns);
+      fb.arr_m = alloc<double>((size_t)DS * dm.ns);
+      b.foot_leg = c.leg_odom_type == 1 ? fb.leg : nullptr;
+    }
     b.ckpt = alloc<T>((size_t)dm.NW * 54 * dm.ns);
     b.resweep = alloc<int32_t>(dm.ns);
     const int n = dm.ns;
@@ -101,7 +111,8 @@ void run(const dekf_config &cfg, int S, const double *gyro, const double *accel,
     Outputs out;
     std::memset(&out, 0, sizeof(out));
     out.quat = quat_out + (size_t)s * 4 * n;
-    out.x = x_out + (size_t)s * 9 * n;
+    const int xr = cfg.leg_odom_type == 1 ? 9 + 3 * nl : 9;
+    out.x = x_out + (size_t)s * xr * n;
     out.v_body = vb_out + (size_t)s * 3 * n;
     out.contact = contact_out + (size_t)s * nl * n;
     out.dbg_vo = vo_dbg + (size_t)s * 8 * n;
@@ -112,7 +123,9 @@ void run(const dekf_config &cfg, int S, const double *gyro, const double *accel,
       for (int f = 0; f < 4; ++f)
         q[f] = in.quat ? in.quat[(size_t)f * n + i] : (double)sim.b.ekf_q[(size_t)f * sim.dm.ns + i];
       st |= mhe_assemble<T, Model>(sim.mc, sim.dm, sim.b, in, out, s, i, q);
-      if (cfg.est_type == 1)
+      if (cfg.leg_odom_type == 1) {
+        if (cfg.est_type == 1 || s >= 1) st |= foot_solve<T, Model::NLEG>(sim.fc, sim.dm, sim.b, sim.fb, in, out, s, i);
+      } else if (cfg.est_type == 1)
         st |= kf_update<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
       else if (s >= 1 && cfg.v_box_enable)
         st |= mhe_solve_box<T>(sim.mc, sim.bc, sim.dm, sim.b, sim.bb, in, out, s, i);

@@ -21,7 +21,7 @@ def build():
     so = os.path.join(HERE, "_build", "libhostsim.so")
     srcs = [os.path.join(HERE, "hostsim.cpp")] + [
         os.path.join(ROOT, "decentralized_ekf_mhe_b200", "csrc", f)
-        for f in ("estimator_core.cuh", "smallmat.cuh", "kinematics.cuh", "host_setup.hpp", "box_solve.cuh")] + [
+        for f in ("estimator_core.cuh", "smallmat.cuh", "kinematics.cuh", "host_setup.hpp", "box_solve.cuh", "footstate.cuh")] + [
         os.path.join(ROOT, "include", "dekf_b200.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         os.makedirs(os.path.dirname(so), exist_ok=True)
@@ -44,7 +44,8 @@ def run(stream, cfg, quat_in=None):
         return a.ctypes.data_as(dp)
 
     flag = np.ascontiguousarray(stream["vo_flag"], dtype=np.uint8)
-    res = dict(quat=np.zeros((S, 4, n)), x=np.full((S, 9, n), np.nan), v_body=np.full((S, 3, n), np.nan),
+    xr = 9 + 3 * nl * int(cfg.leg_odom_type)
+    res = dict(quat=np.zeros((S, 4, n)), x=np.full((S, xr, n), np.nan), v_body=np.full((S, 3, n), np.nan),
                contact=np.zeros((S, nl, n), np.uint8), vo_dbg=np.zeros((S, 8, n), np.int32),
                ekf_dbg=np.zeros((S, 3, n), np.int32), p_vo=np.zeros((S, 3, n)), status=np.zeros((S, n), np.int32),
                arr_P=np.zeros((45, n)), arr_x=np.zeros((9, n)), qp=np.zeros((S, 2, n), np.int32))

@@ -278,6 +278,51 @@ def test_incremental_equals_full_resweep(est_mod, precision, n):
     assert (a["status"] & 16).any()  # VO bounds were inserted (re-sweeps happened)
 
 
+def test_foot_state_model_vs_oracle(est_mod, oracle):
+    """leg_odom_type 1: 21-state model, information-form sweep (csrc/footstate.cuh).
+    Exact reference = the oracle solving the whole history in one banded system (no marginalisation); the literal
+    N = 20 oracle (reference-form marginalizeQP) is only accurate to 2.5e-6 here, see tests/test_hostsim.py."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S = 200, 110
+    nth = os.cpu_count() or 1
+
+    def run(st, **over):
+        d = _to_dev(st)
+        est = E.BatchedEstimator(E.robot_params("go1", ekf_rate=200, leg_odom_type=1, **over), n)
+        xs = np.full((S, 21, n), np.nan)
+        vb = np.full((S, 3, n), np.nan)
+        qs = np.zeros((S, 4, n))
+        for s in range(S):
+            est.step(s, E.robot_store.from_stream(d, s))
+            xs[s], vb[s], qs[s] = est.x_MHE_.cpu().numpy(), est.v_MHE_b_.cpu().numpy(), est.quaternion_.cpu().numpy()
+        return est, xs, vb, qs
+
+    st = synth.to_numpy(synth.make_stream(n, S, vo=False))
+    est, xs, vb, _ = run(st)
+    ex, _, _ = oracle.run_batch(st, oracle.go1_params(leg_odom_type=1, N=400), oracle.ekf_params(rate=200), nthreads=nth, i1=32, want=("x", "v_body"))
+    assert np.abs(xs[1:, :, :32] - ex["x"][1:, :, :32]).max() < 1e-8
+    assert np.abs(vb[1:, :, :32] - ex["v_body"][1:, :, :32]).max() < 1e-8
+    M, nv = est.mhe_qp_.M_p, est.mhe_qp_.n_p   # arrival cost in the reference's own (M_p, n_p) form
+    assert M.shape == (21, 21, n) and torch.isfinite(M).all() and torch.equal(M, M.transpose(0, 1))
+    est.close()
+    st = synth.to_numpy(synth.make_stream(n, S, vo_jitter=True))
+    est, xs, _, _ = run(st)
+    ro, _, _ = oracle.run_batch(st, oracle.go1_params(leg_odom_type=1), oracle.ekf_params(rate=200), nthreads=nth, i1=32, want=("x",))
+    assert np.abs(xs[1:, :9, :32] - ro["x"][1:, :9, :32]).max() < 1e-6      # base states: north-star tolerance
+    assert np.abs(xs[1:, :, :32] - ro["x"][1:, :, :32]).max() < 1e-5        # feet: noise floor of the literal marginalisation
+    assert (est.status_ & 32).sum() == 0
+    est.close()
+    # KF alternative on the foot-state model
+    st = synth.to_numpy(synth.make_stream(n, S, vo=False))
+    est, xs, _, qs = run(st, est_type=1)
+    dup = {k: np.concatenate([v[:1], v], axis=0) for k, v in st.items()}
+    ex, _, _ = oracle.run_batch(dup, oracle.go1_params(leg_odom_type=1, N=400), oracle.ekf_params(rate=200), nthreads=nth, i1=32,
+                                run_ekf=False, quat_in=np.concatenate([qs[:1], qs], axis=0), want=("x",))
+    assert np.abs(xs[1:, :, :32] - ex["x"][2:, :, :32]).max() < 1e-8
+    est.close()
+
+
 def test_run_and_run_host_equal_step_loop(est_mod, monkeypatch):
     """dekf_run (S ticks per call, device streams) and dekf_run_host (pinned host streams, pipelined copies) return
     bit-identical per-tick results to the tick-by-tick loop, on the large-batch kernel path."""

@@ -114,3 +114,43 @@ def test_state_constrained_solve_matches_oracle(oracle):
     assert ((v == hi) | (v == lo)).any(axis=1).mean() > 0.2              # the box binds in >= 20 % of the steps
     assert not (r["status"] & 64).any()                                  # active set always converged
     assert r["qp"][1:, 0].mean() < 6                                     # warm start: few factorisations per tick
+
+
+def _dup_first(st):
+    """Stream with sample 0 delivered twice: the KF alternative runs InitializeKF + UpdateKF on the same sample at
+    T == 0 (DecentralEst.cpp:139-141), so x_KF_(T) is the MHE/filter estimate of this stream at T + 1."""
+    return {k: np.concatenate([v[:1], v], axis=0) for k, v in st.items()}
+
+
+def test_foot_state_model_matches_exact_solution(oracle):
+    """leg_odom_type 1 (foot-position states, DecentralEst.cpp:101-111, :310-325, :432-452, :550-564).
+    The kernel math carries the sweep in information form and matches the EXACT optimum -- the oracle solving the
+    whole history in one banded system (N larger than the run: no marginalisation) -- to 1e-8.  The oracle with
+    N = 20 restates the reference's marginalizeQP literally (MheSrb.cpp:475-713: dense inverse of the stacked
+    observation covariance, which holds the swing-foot variance dt^2 * 1e14 here) and is itself only 2.5e-6 away
+    from that optimum; the same bound is asserted for it."""
+    import pyhostsim as hs
+    from decentralized_ekf_mhe_b200 import synth
+    st = synth.to_numpy(synth.make_stream(4, 150, vo=False))
+    r = hs.run(st, _cfg(leg_odom_type=1))
+    exact, _, _ = oracle.run_batch(st, oracle.go1_params(leg_odom_type=1, N=400), oracle.ekf_params(rate=200), nthreads=4, want=("x", "v_body"))
+    ref20, _, _ = oracle.run_batch(st, oracle.go1_params(leg_odom_type=1, N=20), oracle.ekf_params(rate=200), nthreads=4, want=("x",))
+    assert r["x"].shape[1] == 21
+    assert np.abs(r["x"][1:] - exact["x"][1:]).max() < 1e-8
+    assert np.abs(r["v_body"][1:] - exact["v_body"][1:]).max() < 1e-8
+    assert np.abs(ref20["x"][1:] - exact["x"][1:]).max() < 1e-5      # noise floor of the reference-form marginalisation
+    assert np.abs(r["x"][1:] - ref20["x"][1:]).max() < 1e-5
+    # with delayed VO the window matters, so only the literal (N = 20) oracle applies
+    st = synth.to_numpy(synth.make_stream(4, 120, vo_jitter=True))
+    r = hs.run(st, _cfg(leg_odom_type=1))
+    ro, _, _ = oracle.run_batch(st, oracle.go1_params(leg_odom_type=1), oracle.ekf_params(rate=200), nthreads=4, want=("x", "vo_dbg"))
+    assert np.abs(r["x"][1:, :9] - ro["x"][1:, :9]).max() < 1e-6 and np.abs(r["x"][1:] - ro["x"][1:]).max() < 1e-5
+    assert np.array_equal(r["vo_dbg"], ro["vo_dbg"][:, :8])
+    # KF alternative on the same model: exact reference through the duplicated-first-sample stream
+    st = synth.to_numpy(synth.make_stream(4, 100, vo=False))
+    r = hs.run(st, _cfg(leg_odom_type=1, est_type=1))
+    ex, _, _ = oracle.run_batch(_dup_first(st), oracle.go1_params(leg_odom_type=1, N=400), oracle.ekf_params(rate=200), nthreads=4,
+                                run_ekf=False, quat_in=_dup_first({"q": r["quat"]})["q"], want=("x",))
+    assert np.abs(r["x"][1:] - ex["x"][2:]).max() < 1e-8
+    okf, _, _ = oracle.run_batch(st, oracle.go1_params(leg_odom_type=1, est_type=1), oracle.ekf_params(rate=200), nthreads=4, want=("x",))
+    assert np.abs(r["x"][1:] - okf["x"][1:]).max() < 1e-5           # the literal covariance-form KF has the same noise floor

@@ -213,3 +213,30 @@ def test_box_constrained_optimum_certificate(oracle):
             worst_admm = max(worst_admm, np.abs(ma.x()[3:6] - m.x()[3:6]).max())
     assert n_active_seen > 20
     assert worst_admm < 1e-6
+
+
+def test_foot_state_oracle_consistency(oracle):
+    """leg_odom_type 1 in the oracle: the exact banded solve equals the dense KKT solution of the exported
+    reference-ordered QP (nVar/nCon as MheSrb.cpp would count them), and the literal reference-form marginalisation
+    stays within its 1e-5 noise floor of the no-marginalisation optimum (see tests/test_hostsim.py)."""
+    from decentralized_ekf_mhe_b200 import synth
+    st = synth.to_numpy(synth.make_stream(1, 30, vo_jitter=True, truth=True))
+    m = oracle.Mhe(oracle.go1_params(leg_odom_type=1))
+    for s in range(30):
+        m.step(s, imu_time=st["imu_time"][s, 0], accel=st["accel"][s, :, 0], gyro=st["gyro"][s, :, 0], quat=st["quat_true"][s, :, 0],
+               joint_pos=st["joint_pos"][s, :, 0], joint_vel=st["joint_vel"][s, :, 0], foot_force=st["foot_force"][s, :, 0],
+               vo=(st["vo_time_pre"][s, 0], st["vo_time_now"][s, 0], st["vo_rel_p"][s, :, 0]) if st["vo_flag"][s, 0] else None)
+        if s in (1, 5, 19, 20, 29):
+            ds, dm, dc, nV, nC = m.dims()
+            assert ds == 21 and dm == 12
+            K = min(s + 1, 20)
+            assert nV == K * (ds + dm) + (K - 1) * (ds + dc) and nC == K * dm + (K - 1) * (ds + dc)
+            H, g, A, l, u = m.export_qp()
+            eq = np.abs(u - l) < 1e-9
+            Ae, be = A[eq], l[eq]
+            KKT = np.block([[H, Ae.T], [Ae, np.zeros((Ae.shape[0], Ae.shape[0]))]])
+            sol = np.linalg.solve(KKT, np.concatenate([-g, be]))[:nV]
+            z = m.solution()
+            xT, xk = z[nV - ds - dm:nV - dm], sol[nV - ds - dm:nV - dm]
+            assert np.abs(xT - m.x()).max() == 0.0
+            assert np.abs(xT - xk).max() < 1e-7, (s, np.abs(xT - xk).max())
