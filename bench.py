@@ -34,17 +34,73 @@ FLOPS = dict(meas_update=657, propagate=656, propagate_vo=1496, ekf_predict=432,
              ekf_vo_correct=450, assemble_go1=1401, solve_epilogue=30)
 
 
-def algorithmic_work(N, n_vo_mean, elt=8):
-    """Per instance-step algorithmic bytes / flops of each kernel (tier A = full-window re-solve)."""
+def algorithmic_work(N, n_vo_mean, elt=8, depth_mean=None, depth_vo_mean=None):
+    """Per instance-step algorithmic (bytes, flops) of each kernel.  Tier A (full window re-solve every
+    tick): `solve` sweeps N+1 stages.  Tier B (incremental): `solve` is ONE stage from the newest checkpoint, `resweep`
+    (ticks that carry VO bounds) restarts `depth_mean` stages back, `depth_vo_mean` of which carry a VO row."""
     rec = 25 * elt
-    solve_bytes = 2 * 54 * elt + (N + 1) * rec + 3 * 8 + 12 * 8 + 8
-    solve_flops = (N + 1) * FLOPS["meas_update"] + N * FLOPS["propagate"] + n_vo_mean * (
-        FLOPS["propagate_vo"] - FLOPS["propagate"]) + FLOPS["solve_epilogue"]
-    ekf_bytes = 7 * 8 + 2 * 20 * elt + 26 * elt + 8 + 4 * 8 + 4
-    ekf_flops = FLOPS["ekf_predict"] + FLOPS["ekf_correct"]
-    asm_bytes = 4 * elt + 7 * 8 + 24 * 8 + 4 * 8 + 1 + rec + 5 * 8 + 4 + 8
-    asm_flops = FLOPS["assemble_go1"]
-    return dict(solve=(solve_bytes, solve_flops), ekf=(ekf_bytes, ekf_flops), assemble=(asm_bytes, asm_flops))
+    io = 3 * 8 + 12 * 8 + 8  # gyro in, x + v_body out, status
+    w = {}
+    if depth_mean is None:
+        w["solve"] = (2 * 54 * elt + (N + 1) * rec + io,
+                      (N + 1) * FLOPS["meas_update"] + N * FLOPS["propagate"] + n_vo_mean * (
+                          FLOPS["propagate_vo"] - FLOPS["propagate"]) + FLOPS["solve_epilogue"])
+    else:
+        w["solve"] = ((54 + 54 + 16 + 18) * elt + io + 4,
+                      FLOPS["meas_update"] + FLOPS["propagate"] + FLOPS["solve_epilogue"])
+        w["resweep"] = ((54 + depth_mean * 54 + (depth_mean + 1) * 25) * elt + io + 4,
+                        depth_mean * (FLOPS["meas_update"] + FLOPS["propagate"]) + depth_vo_mean * (
+                            FLOPS["propagate_vo"] - FLOPS["propagate"]) + FLOPS["solve_epilogue"])
+    w["ekf"] = (7 * 8 + 2 * 20 * elt + 26 * elt + 8 + 4 * 8 + 4, FLOPS["ekf_predict"] + FLOPS["ekf_correct"])
+    w["assemble"] = (4 * elt + 7 * 8 + 24 * 8 + 4 * 8 + 1 + rec + 5 * 8 + 4 + 8, FLOPS["assemble_go1"])
+    return w
+
+
+KERNEL_NAMES = {"full": {"solve": "k_solve_tma", "ekf": "k_ekf", "assemble": "k_assemble"},
+                "incremental": {"solve": "k_solve_incr", "resweep": "k_solve_incr_tma", "ekf": "k_ekf", "assemble": "k_assemble"}}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
+    of this workload (profiles/r01_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel)
+    except Exception:
+        return None
+
+
+def kernel_report(mode, work, pms, pcnt, n, hbm_peak, hbm_src, fma_peak, precision, extra_alg):
+    """Per-kernel achieved GB/s and TFLOP/s from the event-pair times, and the roofline object of the dominant one."""
+    kern = {}
+    for name, (by, fl) in work.items():
+        if pcnt.get(name, 0) == 0:
+            continue
+        dur = pms[name] / pcnt[name] * 1e-3
+        kern[name] = {"kernel": KERNEL_NAMES[mode][name], "ms": dur * 1e3, "launches": pcnt[name], "total_ms": pms[name],
+                      "gbs": by * n / dur / 1e9, "tflops": fl * n / dur / 1e12, "bytes_per_instance": by, "flops_per_instance": fl}
+    tot = sum(v["total_ms"] for v in kern.values()) or 1.0
+    dom = max(kern, key=lambda k: kern[k]["total_ms"]) if kern else "solve"
+    kd = kern.get(dom, {"gbs": 0.0, "tflops": 0.0, "ms": 0.0, "total_ms": 0.0})
+    t_hbm = work[dom][0] / (hbm_peak * 1e9)
+    t_fma = work[dom][1] / (fma_peak * 1e12) if fma_peak > 0 else 0.0
+    if t_fma >= t_hbm:
+        roof = {"bound": "fp64" if precision == "fp64" else "fp32", "achieved": kd["tflops"], "peak": fma_peak,
+                "unit": "TFLOP/s", "frac": kd["tflops"] / fma_peak if fma_peak else None}
+    else:
+        roof = {"bound": "hbm", "achieved": kd["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": kd["gbs"] / hbm_peak}
+    alg = {"bytes_per_instance_step": work[dom][0], "flops_per_instance_step": work[dom][1]}
+    alg.update(extra_alg)
+    roof.update({
+        "kernel": KERNEL_NAMES[mode][dom], "kernel_ms": kd["ms"], "kernel_share_of_step": kd["total_ms"] / tot,
+        "kernel_ms_source": "CUDA event pair around every launch on the launching stream (dekf_profile_*), mean over a "
+                            "separate tick-by-tick pass of the same workload, no host sync between launches",
+        "traffic": ncu_traffic(KERNEL_NAMES[mode][dom]),
+        "hbm": {"achieved": kd["gbs"], "peak": hbm_peak, "frac": kd["gbs"] / hbm_peak, "peak_source": hbm_src},
+        "fma": {"achieved": kd["tflops"], "peak": fma_peak, "frac": kd["tflops"] / fma_peak if fma_peak else None,
+                "peak_source": "measured in this run (dekf_measure_fma_peak, non-tensor FMA)"},
+        "algorithmic": alg, "all_kernels": kern})
+    return roof
 
 
 class ClockSampler(threading.Thread):
@@ -214,7 +270,7 @@ def main():
     ap.add_argument("--N", type=int, default=20)
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--e2e-steps", type=int, default=100)
-    ap.add_argument("--window-solve", default="full", choices=["full", "incremental"],
+    ap.add_argument("--window-solve", default="incremental", choices=["full", "incremental"],
                     help="full: re-sweep the whole window every tick (tier A, the reference's semantics); "
                          "incremental: restart at the first changed stage (tier B, bit-identical results)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -244,7 +300,7 @@ def main():
     lo, hi = shard_range(n_total, rank, world)
     assert hi - lo == n
     N = args.N
-    S = FILL_STEPS + W + K + Ke + 20
+    S = FILL_STEPS + W + K + Ke + 8 + 20 + 24
     dev = torch.device("cuda", local_rank)
 
     # ---- synthetic stream, resident in HBM before any timed region (each rank: its own instance range)
@@ -254,56 +310,95 @@ def main():
     t_gen = time.time() - t_gen
     vo_steps = [bool(stream["vo_flag"][s].any()) for s in range(S)]
 
-    prm = estimator.robot_params("go1", ekf_rate=200, N=N, window_solve=1 if args.window_solve == "incremental" else 0)
-    est = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def sub(a, b):
-        d = {k: v[a:b] for k, v in stream.items() if torch.is_tensor(v) and v.shape[0] == S}
-        return d
+        return {k: v[a:b] for k, v in stream.items() if torch.is_tensor(v) and v.shape[0] == S}
 
-    T = 0
-    est.run(T, FILL_STEPS + W, sub(0, FILL_STEPS + W), vo_steps[:FILL_STEPS + W])
-    T += FILL_STEPS + W
-    # ---- value: K ticks in one dekf_run call, inputs resident in HBM, CUDA events on the launching stream, max over ranks
+    T0 = FILL_STEPS + W
+
+    def timed_pass(mode):
+        """K ticks in one dekf_run call, inputs resident in HBM, CUDA events on the launching stream, max over ranks;
+        then a tick-by-tick pass of a fresh handle over the same ticks with an event pair around every launch."""
+        prm = estimator.robot_params("go1", ekf_rate=200, N=N, window_solve=1 if mode == "incremental" else 0)
+        est = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
+        est.run(0, T0, sub(0, T0), vo_steps[:T0])
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        timed = sub(T0, T0 + K)
+        barrier()
+        l0 = est.launch_count()
+        ev0.record()
+        est.run(T0, K, timed, vo_steps[T0:T0 + K])
+        ev1.record()
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        launches = est.launch_count() - l0
+        n_vo_mean = float(est.window_vo_count().double().mean().item())
+        # per-kernel device time
+        Kp = min(K, 60)
+        est2 = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
+        est2.run(0, T0, sub(0, T0), vo_steps[:T0])
+        est2.profile(True)
+        dsum = torch.zeros((), dtype=torch.float64, device=dev)
+        vsum = torch.zeros((), dtype=torch.float64, device=dev)
+        nvo_ticks = 0
+        for s in range(T0, T0 + Kp):
+            est2.step(s, estimator.robot_store.from_stream(stream, s, with_vo=vo_steps[s]))
+            if mode == "incremental" and vo_steps[s]:
+                d, v = est2.resweep_info()
+                dsum += d.double().mean()
+                vsum += v.double().mean()
+                nvo_ticks += 1
+        pms, pcnt = est2.profile_read()
+        est2.close()
+        depth = float(dsum.item()) / max(nvo_ticks, 1)
+        depth_vo = float(vsum.item()) / max(nvo_ticks, 1)
+        return est, dict(ms=ms, launches=launches, n_vo_mean=n_vo_mean, pms=pms, pcnt=pcnt, depth=depth, depth_vo=depth_vo,
+                         vo_tick_share=nvo_ticks / Kp)
+
     sampler = ClockSampler(local_rank)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    timed = sub(T, T + K)
-    barrier()
-    launches0 = est.launch_count()
     sampler.start()
-    ev0.record()
-    est.run(T, K, timed, vo_steps[T:T + K])
-    T += K
-    ev1.record()
-    barrier()
-    ms_value = ev0.elapsed_time(ev1)
-    launches = est.launch_count() - launches0
-    ms_value = max_over_ranks(ms_value)
+    mode = args.window_solve
+    est, main = timed_pass(mode)
+    other_mode = "full" if mode == "incremental" else "incremental"
+    est_o, other = timed_pass(other_mode)
+    est_o.close()
+    ms_value, launches = main["ms"], main["launches"]
     value = n_total * K / (ms_value * 1e-3)
-    n_vo_mean = float(est.window_vo_count().double().mean().item())
+    T = T0 + K
 
     # ---- e2e: the same metric through dekf_run_host with pinned HOST streams: every tick's inputs are copied H2D and
     # every tick's results (quat, x_MHE, v_body, contact, status) are copied D2H inside the timed region
     keys = ["gyro", "accel", "imu_time", "joint_pos", "joint_vel", "foot_force", "vo_quat", "vo_time_pre",
             "vo_time_now", "vo_rel_p"]
     rows = {k: (stream[k][0].numel() // n) for k in keys}
-    hst = {k: stream[k][T:T + Ke].reshape(Ke, rows[k], n).cpu().pin_memory() for k in keys}
-    hst["vo_flag"] = stream["vo_flag"][T:T + Ke].cpu().pin_memory()
-    hout = {"quat": torch.empty(Ke, 4, n, dtype=torch.float64).pin_memory(),
-            "x": torch.empty(Ke, 9, n, dtype=torch.float64).pin_memory(),
-            "v_body": torch.empty(Ke, 3, n, dtype=torch.float64).pin_memory(),
-            "contact": torch.empty(Ke, 4, n, dtype=torch.uint8).pin_memory(),
-            "status": torch.empty(Ke, n, dtype=torch.int32).pin_memory()}
+    Kw = 8  # untimed warm-up ticks of the host path (first call allocates the device staging and the copy streams)
+    Ke = max(1, min(Ke, S - T - Kw - 20))
+
+    def host_slice(a, b):
+        h = {k: stream[k][a:b].reshape(b - a, rows[k], n).cpu().pin_memory() for k in keys}
+        h["vo_flag"] = stream["vo_flag"][a:b].cpu().pin_memory()
+        return h
+
+    def host_out(k):
+        return {"quat": torch.empty(k, 4, n, dtype=torch.float64).pin_memory(),
+                "x": torch.empty(k, 9, n, dtype=torch.float64).pin_memory(),
+                "v_body": torch.empty(k, 3, n, dtype=torch.float64).pin_memory(),
+                "contact": torch.empty(k, 4, n, dtype=torch.uint8).pin_memory(),
+                "status": torch.empty(k, n, dtype=torch.int32).pin_memory()}
+
+    est.run_host(T, Kw, host_slice(T, T + Kw), vo_steps[T:T + Kw], out=host_out(Kw), out_per_step=True)
+    T += Kw
+    hst, hout = host_slice(T, T + Ke), host_out(Ke)
     h2d = 0
     for j in range(Ke):
         has_vo = vo_steps[T + j]
         h2d += (sum(rows[k] for k in keys[:6]) * 8 * n) + ((sum(rows[k] for k in keys[6:]) * 8 + 1) * n if has_vo else 0)
     d2h = 16 * 8 * n + 4 * n + 4 * n
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t0 = time.perf_counter()
     ev0.record()
@@ -318,8 +413,7 @@ def main():
     # single-tick host path (dekf_step_host: copy in, step, copy out, sync) for comparison
     Ks = min(20, S - T)
     one_out = {"quat": hout["quat"][0], "x": hout["x"][0], "v_body": hout["v_body"][0]}
-    hs1 = {k: stream[k][T:T + Ks].reshape(Ks, rows[k], n).cpu().pin_memory() for k in keys}
-    hs1["vo_flag"] = stream["vo_flag"][T:T + Ks].cpu().pin_memory()
+    hs1 = host_slice(T, T + Ks)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for j in range(Ks):
@@ -329,16 +423,26 @@ def main():
         T += 1
     ms_step_host = (time.perf_counter() - t0) * 1e3 / max(Ks, 1)
     clocks = sampler.stop()
-
-    # ---- per-kernel device time: event pairs around every launch of a second handle (no host sync between launches),
-    # over Kp ticks of the same stream (a fresh handle re-plays the stream from T=0)
-    Kp = min(K, 50)
-    est2 = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
-    est2.run(0, FILL_STEPS + W, sub(0, FILL_STEPS + W), vo_steps[:FILL_STEPS + W])
-    est2.profile(True)
-    est2.run(FILL_STEPS + W, Kp, sub(FILL_STEPS + W, FILL_STEPS + W + Kp), vo_steps[FILL_STEPS + W:FILL_STEPS + W + Kp])
-    pms, pcnt = est2.profile_read()
-    est2.close()
+    # pinned-host copy bandwidth of this box (the roofline of the e2e path): one large H2D and D2H, both directions at once
+    pcie = None
+    try:
+        nb = 256 << 20
+        hb, hb2 = torch.empty(nb, dtype=torch.uint8).pin_memory(), torch.empty(nb, dtype=torch.uint8).pin_memory()
+        db, db2 = torch.empty(nb, dtype=torch.uint8, device=dev), torch.empty(nb, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        best = 0.0
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s1):
+                db.copy_(hb, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hb2.copy_(db2, non_blocking=True)
+            torch.cuda.synchronize()
+            best = max(best, nb / (time.perf_counter() - t0) / 1e9)
+        pcie = best
+    except Exception:
+        pcie = None
 
     # ---- batch-1 step latency (BASELINE metric, second half): one instance, lock-step tick
     lat = batch1_latency(estimator, synth, local_rank, args.precision, N) if rank == 0 else None
@@ -348,41 +452,23 @@ def main():
         hbm_peak, hbm_src = measured_peaks()
         peaks = estimator.measure_peaks(local_rank)
         elt = 8 if args.precision == "fp64" else 4
-        work = algorithmic_work(N, n_vo_mean, elt)
         fma_peak = peaks["fp64_tflops"] if args.precision == "fp64" else peaks["fp32_tflops"]
-        kern = {}
-        for name in ("ekf", "assemble", "solve"):
-            if pcnt[name] == 0:
-                continue
-            dur = pms[name] / pcnt[name] * 1e-3
-            by, fl = work[name]
-            kern[name] = {"ms": dur * 1e3, "gbs": by * n / dur / 1e9, "tflops": fl * n / dur / 1e12,
-                          "bytes_per_instance": by, "flops_per_instance": fl}
-        share = {k: v["ms"] for k, v in kern.items()}
-        tot = sum(share.values()) or 1.0
-        dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else "solve"
-        kd = kern.get(dom, {"gbs": 0.0, "tflops": 0.0, "ms": 0.0})
-        t_hbm = work[dom][0] / (hbm_peak * 1e9)
-        t_fma = work[dom][1] / (fma_peak * 1e12) if fma_peak > 0 else 0.0
-        if t_fma >= t_hbm:
-            roof = {"bound": "fp64" if args.precision == "fp64" else "fp32", "achieved": kd["tflops"], "peak": fma_peak,
-                    "unit": "TFLOP/s", "frac": kd["tflops"] / fma_peak if fma_peak else None}
-        else:
-            roof = {"bound": "hbm", "achieved": kd["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": kd["gbs"] / hbm_peak}
-        roof.update({
-            "kernel": {"solve": "k_solve_tma", "ekf": "k_ekf", "assemble": "k_assemble"}[dom],
-            "kernel_ms": kd["ms"], "kernel_share_of_step": kd["ms"] / tot,
-            "kernel_ms_source": "CUDA event pair around every launch on the launching stream, mean over the ticks of a "
-                                "separate pass of the same workload (no host sync between launches)",
-            "step_ms_sum_of_kernels": tot,
-            "traffic": None,
-            "hbm": {"achieved": kd["gbs"], "peak": hbm_peak, "frac": kd["gbs"] / hbm_peak, "peak_source": hbm_src},
-            "fma": {"achieved": kd["tflops"], "peak": fma_peak, "frac": kd["tflops"] / fma_peak if fma_peak else None,
-                    "peak_source": "measured in this run (dekf_measure_fma_peak, non-tensor FMA)"},
-            "algorithmic": {"tier": "A (full-window re-solve every step)", "bytes_per_instance_step": work[dom][0],
-                            "flops_per_instance_step": work[dom][1], "vo_stages_in_window_mean": n_vo_mean},
-            "all_kernels": kern, "measured_copy_gbs": peaks["copy_gbs"],
-        })
+
+        def report(md, res):
+            if md == "incremental":
+                work = algorithmic_work(N, res["n_vo_mean"], elt, depth_mean=res["depth"], depth_vo_mean=res["depth_vo"])
+                extra = {"tier": "B (incremental: restart the sweep at the first changed stage; bit-identical to tier A)",
+                         "resweep_depth_mean_on_vo_ticks": res["depth"], "vo_rows_in_resweep_mean": res["depth_vo"],
+                         "vo_tick_share": res["vo_tick_share"]}
+            else:
+                work = algorithmic_work(N, res["n_vo_mean"], elt)
+                extra = {"tier": "A (full-window re-solve every step)", "vo_stages_in_window_mean": res["n_vo_mean"]}
+            return kernel_report(md, work, res["pms"], res["pcnt"], n, hbm_peak, hbm_src, fma_peak, args.precision, extra)
+
+        roof = report(mode, main)
+        roof["measured_copy_gbs"] = peaks["copy_gbs"]
+        alt = {"window_solve": other_mode, "value": n_total * K / (other["ms"] * 1e-3), "unit": UNIT,
+               "ms_per_step": other["ms"] / K, "gpu_launches": other["launches"], "roofline": report(other_mode, other)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -391,18 +477,23 @@ def main():
                        f"go1_ekf_mhe_{n}x_N{N}_{args.precision}",
                        "robot": "go1", "instances_per_gpu": n, "instances_total": n_total, "N": N, "rate_hz": 200,
                        "vo": "30 Hz, 40 ms latency, lock-step arrival", "parallelism": f"instance-shard x{world}",
-                       "cache": "per-step working set (window ring + inputs, >400 MB at 65,536 instances) exceeds the 126 MB L2; "
-                                "every step reads distinct input arrays",
+                       "window_solve": mode + (" (library default; every tick's outputs are bit-identical to the full re-sweep, "
+                                               "reported beside it under full_resweep)" if mode == "incremental" else ""),
+                       "cache": "per-step working set (window ring + checkpoints + inputs, >400 MB at 65,536 instances) exceeds the "
+                                "126 MB L2; every step reads distinct input arrays",
                        "fill_steps": FILL_STEPS, "stream_gen_s": round(t_gen, 2)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // Ke, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "ms_per_step": ms_e2e / Ke,
-                    "api": "dekf_run_host (pinned host streams; H2D | kernels | D2H pipelined over ticks, every tick's "
-                           "inputs copied in and results copied out)",
+                    "steps": Ke, "warmup_steps": Kw, "ms_per_step": ms_e2e / Ke,
+                    "h2d_gbs": (h2d / Ke) / (ms_e2e / Ke * 1e-3) / 1e9, "d2h_gbs": d2h / (ms_e2e / Ke * 1e-3) / 1e9,
+                    "pinned_copy_gbs_each_way_measured": pcie,
+                    "api": "dekf_run_host (pinned host streams; H2D | kernels | D2H pipelined over chunks of ticks, every "
+                           "tick's inputs copied in and results copied out)",
                     "single_tick_host_call_ms": ms_step_host, "host_checksum": chk},
             "latency_batch1": lat,
             "gpu_launches": launches,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "roofline": roof,
+            ("full_resweep" if other_mode == "full" else "incremental"): alt,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1

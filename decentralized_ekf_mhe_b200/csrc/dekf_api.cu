@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(kBlock, DEKF_MINB_ASM) k_assemble(const MheCon
   for (int f = 0; f < 4; ++f)
     q[f] = (in.quat != nullptr) ? in.quat[(size_t)f * dm.n + i] : (double)b.ekf_q[(size_t)f * dm.ns + i];
   const int st = mhe_assemble<T, Model>(c, dm, b, in, out, Tk, i, q);
-  b.status[i] = (prev_status != nullptr) ? (prev_status[i] | st) : st;  // prev_status: this tick's EKF status bits
+  tick_status(dm, b, Tk, i) = (prev_status != nullptr) ? (prev_status[i] | st) : st;  // prev_status: this tick's EKF status bits
 }
 
 template <typename T>
@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(kBlock) k_solve(const MheConst<T> c, const Dim
                                                   const Outputs out, int Tk, int32_t *status_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
-  int st = b.status[i];
+  int st = tick_status(dm, b, Tk, i);
   if (Tk >= 1) st |= mhe_solve<T>(c, dm, b, in, out, Tk, i);
-  b.status[i] = st;
+  tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
 
@@ -72,9 +72,9 @@ __global__ void __launch_bounds__(kBlock, DEKF_MINB_INCR) k_solve_incr(const Mhe
                                                        const Outputs out, int Tk, int32_t *status_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
-  int st = b.status[i];
+  int st = tick_status(dm, b, Tk, i);
   if (Tk >= 1) st |= mhe_solve_incr<T>(c, dm, b, in, out, Tk, i);
-  b.status[i] = st;
+  tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
 template <typename T>
@@ -91,9 +91,9 @@ __global__ void __launch_bounds__(kBlock) k_solve_box(const MheConst<T> c, const
                                                       int32_t *status_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
-  int st = b.status[i];
+  int st = tick_status(dm, b, Tk, i);
   if (Tk >= 1) st |= mhe_solve_box<T>(c, bc, dm, b, bb, in, out, Tk, i);
-  b.status[i] = st;
+  tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
 
@@ -103,9 +103,9 @@ __global__ void __launch_bounds__(kBlock) k_solve_foot(const FootConst fc, const
                                                        const Inputs in, const Outputs out, int Tk, int32_t *status_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
-  int st = b.status[i];
+  int st = tick_status(dm, b, Tk, i);
   if (Tk >= 1 || fc.est_type == 1) st |= foot_solve<T, L>(fc, dm, b, fb, in, out, Tk, i);
-  b.status[i] = st;
+  tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
 // arrival cost of the foot-state model: (M_p, n_p) as the reference holds them (MheSrb.hpp:86-87)
@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(kBlock) k_kf(const MheConst<T> c, const Dims d
                                                const Outputs out, int Tk, int32_t *status_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
-  int st = b.status[i];
+  int st = tick_status(dm, b, Tk, i);
   st |= kf_update<T>(c, dm, b, in, out, Tk, i);
-  b.status[i] = st;
+  tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
 
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kBlock) k_fused(const EkfConst<T> ec, const Mh
     st |= mhe_solve_incr<T>(mc, dm, b, in, out, Tk, i);
   else if (Tk >= 1)
     st |= mhe_solve<T>(mc, dm, b, in, out, Tk, i);
-  b.status[i] = st;
+  tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
 
@@ -184,6 +184,7 @@ __global__ void k_init_state(const EkfConst<T> ec, const MheConst<T> mc, const D
   b.wp_count[i] = 0;
   b.pend_flag[i] = 0;
   b.status[i] = 0;
+  b.status[(size_t)dm.ns + i] = 0;
 }
 
 // arrival cost getters: (P, x) -> dense 9x9 P, and (M_p, n_p) = (P^-1, -P^-1 x) (MheSrb.hpp:86-87)
@@ -263,6 +264,18 @@ __global__ void k_get_misc(const Dims dm, const Buffers<T> b, int Tk, double *p_
     for (int f = 0; f < 16; ++f) ekfP[(size_t)f * n + i] = (double)b.ekf_P[(size_t)f * ns + i];
 }
 
+// incremental solve bookkeeping of the last tick: re-swept stages (T - restart stage) and how many of them carry a VO row
+template <typename T>
+__global__ void k_resweep_info(const Dims dm, const Buffers<T> b, int Tk, int32_t *depth, int32_t *n_vo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n) return;
+  const int ks = incr_restart_stage(dm, b, Tk, i);
+  int c = 0;
+  for (int k = ks; k < Tk; ++k) c += b.win[((size_t)(k % dm.NW) * REC_SIZE + REC_FLAG) * dm.ns + i] != T(0);
+  if (depth) depth[i] = Tk - ks;
+  if (n_vo) n_vo[i] = c;
+}
+
 template <typename T>
 __global__ void k_vo_count(const Dims dm, const Buffers<T> b, int Tk, int32_t *count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,11 +337,12 @@ struct dekf_handle {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   // dekf_run: the EKF ticks run ahead of the MHE on their own stream through a small ring of quaternions / status words
   static constexpr int kAhead = 4;
-  cudaStream_t s_ekf = nullptr, s_mhe = nullptr;  // lowest / highest stream priority
+  cudaStream_t s_ekf = nullptr, s_asm = nullptr, s_mhe = nullptr;  // lowest / medium / highest stream priority
   cudaEvent_t ev_join = nullptr;
   double *quat_ring = nullptr;      // [kAhead][4][n]
   int32_t *status_ring = nullptr;   // [kAhead][n]
   cudaEvent_t ev_ekf[kAhead] = {nullptr, nullptr, nullptr, nullptr}, ev_mhe[kAhead] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_sol[kAhead] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   // debug taps
@@ -351,8 +365,8 @@ struct dekf_handle {
   };
   std::vector<ProfRec> prof_recs;   // pairs recorded since the last read
   std::vector<ProfRec> prof_free;   // recycled pairs
-  double prof_ms[3] = {0, 0, 0};
-  int64_t prof_n[3] = {0, 0, 0};
+  double prof_ms[4] = {0, 0, 0, 0};
+  int64_t prof_n[4] = {0, 0, 0, 0};
   std::string err;
 };
 
@@ -673,12 +687,12 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     const size_t ns = (size_t)h->dm.ns, elt = h->f32 ? sizeof(float) : sizeof(double);
     const size_t ck = (size_t)h->dm.NW * 54 * ns * elt;
     if ((ce = cudaMalloc(&h->ckpt_mem, ck)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc(checkpoint ring)", ce);
-    if ((ce = cudaMalloc((void **)&h->resweep_mem, ns * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    if ((ce = cudaMalloc((void **)&h->resweep_mem, 2 * ns * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
     if ((ce = cudaMemset(h->ckpt_mem, 0, ck)) != cudaSuccess) return bail(DEKF_ECUDA, "memset", ce);
     h->b64.ckpt = (double *)h->ckpt_mem;
     h->b32.ckpt = (float *)h->ckpt_mem;
     h->b64.resweep = h->b32.resweep = h->resweep_mem;
-    h->extra_bytes += ck + ns * sizeof(int32_t);
+    h->extra_bytes += ck + 2 * ns * sizeof(int32_t);
   }
   h->fc = make_foot_const(*cfg);
   if (cfg->leg_odom_type == 1) {
@@ -743,12 +757,14 @@ int dekf_destroy(dekf_handle *h) {
   free_chunk_set(h->chunk[1]);
   if (h->s_ekf) cudaStreamDestroy(h->s_ekf);
   if (h->s_mhe) cudaStreamDestroy(h->s_mhe);
+  if (h->s_asm) cudaStreamDestroy(h->s_asm);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->quat_ring);
   cudaFree(h->status_ring);
   for (int k = 0; k < dekf_handle::kAhead; ++k) {
     if (h->ev_ekf[k]) cudaEventDestroy(h->ev_ekf[k]);
     if (h->ev_mhe[k]) cudaEventDestroy(h->ev_mhe[k]);
+    if (h->ev_sol[k]) cudaEventDestroy(h->ev_sol[k]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -842,8 +858,9 @@ int dekf_ekf_step(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out
   return ekf_launch(h, in, out, nullptr, h->stream);
 }
 
+// phases: 1 = stage assembly, 2 = window solve, 3 = both (on h->stream)
 static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outputs *out, const int32_t *acc,
-                         cudaEvent_t after_assemble = nullptr) {
+                         int phases = 3) {
   if (!in->gyro || !in->accel || !in->imu_time || !in->joint_pos || !in->joint_vel || !in->foot_force)
     return fail(h, DEKF_EINVAL, "dekf_mhe_step: null input");
   if (in->vo_flag && (!in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
@@ -855,16 +872,22 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
   const bool tma = h->use_tma && T_ >= 1;
   const bool kf = h->cfg.est_type == 1;
   const int tiles = h->dm.ns / kTile;
-  if (h->f32) {
-    rc = do_assemble<float>(h, h->mc32, h->b32, di, dout, T_, acc);
+  // incremental solve on a tick that carries VO messages: TMA-staged re-sweep from the CTA's earliest restart stage
+  const bool resweep_tick = h->mc64.window_solve == 1 && tma && T_ >= 2 && di.vo_flag != nullptr && !kf && !h->bc.enable &&
+                            h->cfg.leg_odom_type == 0;
+  if (phases & 1) {
+    rc = h->f32 ? do_assemble<float>(h, h->mc32, h->b32, di, dout, T_, acc) : do_assemble<double>(h, h->mc64, h->b64, di, dout, T_, acc);
     if (rc) return fail(h, rc, "assemble");
-    if (after_assemble) cudaEventRecord(after_assemble, h->stream);
-    ProfScope ps(h, 2);
+    CK(cudaGetLastError());
+  }
+  if (!(phases & 2)) return DEKF_OK;
+  if (h->f32) {
+    ProfScope ps(h, resweep_tick ? 3 : 2);
     if (kf)
       k_kf<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
     else if (h->bc.enable)
       k_solve_box<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->bc, h->dm, h->b32, h->bb, di, dout, T_, st);
-    else if (h->mc32.window_solve == 1 && tma && T_ >= 2 && di.vo_flag != nullptr)
+    else if (resweep_tick)
       k_solve_incr_tma<float><<<tiles, kTile, solve_tma_smem_bytes<float>(), h->stream>>>(h->tmap, h->mc32, h->dm, h->b32, di, dout, T_, st);
     else if (h->mc32.window_solve == 1)
       k_solve_incr<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
@@ -873,10 +896,7 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
     else
       k_solve<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
   } else {
-    rc = do_assemble<double>(h, h->mc64, h->b64, di, dout, T_, acc);
-    if (rc) return fail(h, rc, "assemble");
-    if (after_assemble) cudaEventRecord(after_assemble, h->stream);
-    ProfScope ps(h, 2);
+    ProfScope ps(h, resweep_tick ? 3 : 2);
     if (h->cfg.leg_odom_type == 1) {
       const int g = grid_for(h->dm.n);
       if (h->nl == 4)
@@ -889,7 +909,7 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
       k_kf<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
     else if (h->bc.enable)
       k_solve_box<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->bc, h->dm, h->b64, h->bb, di, dout, T_, st);
-    else if (h->mc64.window_solve == 1 && tma && T_ >= 2 && di.vo_flag != nullptr)
+    else if (resweep_tick)
       k_solve_incr_tma<double><<<tiles, kTile, solve_tma_smem_bytes<double>(), h->stream>>>(h->tmap, h->mc64, h->dm, h->b64, di, dout, T_, st);
     else if (h->mc64.window_solve == 1)
       k_solve_incr<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
@@ -940,9 +960,10 @@ int dekf_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outp
   dekf_outputs o_ekf;
   std::memset(&o_ekf, 0, sizeof(o_ekf));
   if (out) o_ekf.quat = out->quat;
-  rc = dekf_ekf_step(h, &in2, &o_ekf);
+  int32_t *slot = (h->f32 ? h->b32.status : h->b64.status) + (size_t)(T_ & 1) * h->dm.ns;  // tick_status(T_)
+  rc = ekf_launch(h, &in2, &o_ekf, slot, h->stream);
   if (rc) return rc;
-  return mhe_step_impl(h, T_, &in2, out, h->f32 ? h->b32.status : h->b64.status);
+  return mhe_step_impl(h, T_, &in2, out, slot);
 }
 
 int dekf_synchronize(dekf_handle *h) {
@@ -1169,10 +1190,13 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     }
     return DEKF_OK;
   }
-  // Large batches.  The orientation EKF does not depend on the MHE, so its ticks run ahead (up to kAhead ticks) on a
-  // LOW-priority stream and hand each tick's quaternion / status word over through a ring, while k_assemble / k_solve
-  // run on a HIGH-priority stream: the block scheduler only dispatches EKF CTAs when no window-solve CTA is pending,
-  // i.e. into the SMs the solve kernel leaves idle in its last wave (1.73 waves at 65,536 instances).
+  // Large batches: three streams.  The orientation EKF does not depend on the MHE, so its ticks run ahead (up to kAhead
+  // ticks) on a LOW-priority stream and hand each tick's quaternion / status word over through a ring.  The stage assembly
+  // of tick s+1 does not depend on the window solve of tick s either (per-tick scratch words are double-buffered by tick
+  // parity, the stage ring has one slot more than the window), unless tick s+1 inserts VO bounds into stages the solve
+  // of tick s is reading: it runs one tick ahead on a MEDIUM-priority stream and is serialised behind the solve only on
+  // ticks that carry VO messages.  The window solves run on a HIGH-priority stream: the block scheduler dispatches
+  // EKF / assembly CTAs into the SMs the solve kernel leaves idle (1.73 waves at 65,536 instances).
   constexpr int QA = dekf_handle::kAhead;
   int rc = check_T(h, T0);
   if (rc) return rc;
@@ -1184,6 +1208,7 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = numerically largest = lowest priority
     CK(cudaStreamCreateWithPriority(&h->s_ekf, cudaStreamNonBlocking, lo));
+    CK(cudaStreamCreateWithPriority(&h->s_asm, cudaStreamNonBlocking, (lo + hi) / 2));
     CK(cudaStreamCreateWithPriority(&h->s_mhe, cudaStreamNonBlocking, hi));
     CK(cudaMalloc((void **)&h->quat_ring, (size_t)QA * 4 * n * sizeof(double)));
     CK(cudaMalloc((void **)&h->status_ring, (size_t)QA * n * sizeof(int32_t)));
@@ -1191,19 +1216,23 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     for (int k = 0; k < QA; ++k) {
       CK(cudaEventCreateWithFlags(&h->ev_ekf[k], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_mhe[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_sol[k], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   }
-  // fork both internal streams off the caller-visible stream, join back at the end
+  // the assembly may only run ahead of the solve where the solve is the plain window sweep (full or incremental)
+  const bool asm_ahead = h->cfg.est_type == 0 && !h->bc.enable && h->cfg.leg_odom_type == 0 && !h->prof;
+  // fork the internal streams off the caller-visible stream, join back at the end
   cudaStream_t user = h->stream;
   CK(cudaEventRecord(h->ev_fork, user));
   CK(cudaStreamWaitEvent(h->s_ekf, h->ev_fork, 0));
+  CK(cudaStreamWaitEvent(h->s_asm, h->ev_fork, 0));
   CK(cudaStreamWaitEvent(h->s_mhe, h->ev_fork, 0));
-  h->stream = h->s_mhe;  // mhe_step_impl launches on h->stream
   for (int32_t s = 0; s < S && rc == DEKF_OK; ++s) {
     const int slot = s % QA;
     dekf_inputs is;
+    const bool vo_tick = (!vo_steps || vo_steps[s]) && in->vo_flag != nullptr;
     offset_inputs(h, in, (size_t)s, !vo_steps || vo_steps[s], &is);
     is.quat = nullptr;
     dekf_outputs os;
@@ -1218,17 +1247,43 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     if (ce == cudaSuccess) rc = ekf_launch(h, &is, &oe, sslot, h->s_ekf);
     if (rc) break;
     if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_ekf[slot], h->s_ekf);
-    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(h->s_mhe, h->ev_ekf[slot], 0);
-    if (ce == cudaSuccess && os.quat) ce = cudaMemcpyAsync(os.quat, qslot, 4 * n * sizeof(double), cudaMemcpyDeviceToDevice, h->s_mhe);
+    // ---- stage assembly of tick s
+    cudaStream_t sa = asm_ahead ? h->s_asm : h->s_mhe;
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sa, h->ev_ekf[slot], 0);
+    if (asm_ahead) {
+      // parity-buffered scratch + the spare ring slot allow ONE tick of lead: wait for the solve of tick s-2, and for the
+      // solve of tick s-1 too when this tick rewrites VO rows inside the window that solve is reading
+      if (ce == cudaSuccess && s >= 2) ce = cudaStreamWaitEvent(sa, h->ev_sol[(s - 2) % QA], 0);
+      if (ce == cudaSuccess && s >= 1 && vo_tick) ce = cudaStreamWaitEvent(sa, h->ev_sol[(s - 1) % QA], 0);
+    }
     if (ce != cudaSuccess) {
       rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
       break;
     }
     is.quat = qslot;
-    rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, h->ev_mhe[slot]);
+    h->stream = sa;
+    rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 1);
+    h->stream = user;
+    if (rc) break;
+    ce = cudaEventRecord(h->ev_mhe[slot], sa);
+    // ---- window solve of tick s
+    if (ce == cudaSuccess && asm_ahead) ce = cudaStreamWaitEvent(h->s_mhe, h->ev_mhe[slot], 0);
+    if (ce == cudaSuccess && os.quat) ce = cudaMemcpyAsync(os.quat, qslot, 4 * n * sizeof(double), cudaMemcpyDeviceToDevice, h->s_mhe);
+    if (ce != cudaSuccess) {
+      rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
+      break;
+    }
+    h->stream = h->s_mhe;
+    rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 2);
+    h->stream = user;
+    if (rc) break;
+    ce = cudaEventRecord(h->ev_sol[slot], h->s_mhe);
+    if (ce != cudaSuccess) rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
   }
   h->stream = user;
   cudaEventRecord(h->ev_join, h->s_mhe);
+  cudaStreamWaitEvent(user, h->ev_join, 0);
+  cudaEventRecord(h->ev_join, h->s_asm);
   cudaStreamWaitEvent(user, h->ev_join, 0);
   cudaEventRecord(h->ev_join, h->s_ekf);
   cudaStreamWaitEvent(user, h->ev_join, 0);
@@ -1406,6 +1461,19 @@ int dekf_get_window_vo_count(dekf_handle *h, int32_t *count) {
   return DEKF_OK;
 }
 
+int dekf_get_resweep_info(dekf_handle *h, int32_t *depth, int32_t *n_vo) {
+  if (!h) return DEKF_EINVAL;
+  if (h->mc64.window_solve != 1 || h->next_T < 2) return fail(h, DEKF_EINVAL, "dekf_get_resweep_info: needs DEKF_SOLVE_INCREMENTAL and T >= 1");
+  CK(cudaSetDevice(h->cfg.device));
+  if (h->f32)
+    k_resweep_info<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->dm, h->b32, h->next_T - 1, depth, n_vo);
+  else
+    k_resweep_info<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->dm, h->b64, h->next_T - 1, depth, n_vo);
+  h->launches++;
+  CK(cudaGetLastError());
+  return DEKF_OK;
+}
+
 int dekf_get_host(dekf_handle *h, int32_t what, void *host_out) {
   if (!h || !host_out) return fail(h, DEKF_EINVAL, "dekf_get_host: null argument");
   CK(cudaSetDevice(h->cfg.device));
@@ -1485,7 +1553,7 @@ int dekf_profile_read(dekf_handle *h, double *ms, int64_t *count) {
     h->prof_free.push_back(r);
   }
   h->prof_recs.clear();
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 4; ++k) {
     ms[k] = h->prof_ms[k];
     count[k] = h->prof_n[k];
     h->prof_ms[k] = 0;

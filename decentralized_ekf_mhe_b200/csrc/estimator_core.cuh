@@ -110,8 +110,15 @@ struct Buffers {
   // leg_odom_type 1 (foot-position states, footstate.cuh) only, else nullptr
   double *foot_leg;       // [NW][9*legs+1][ns] per leg b_meas (3) + measurement covariance (6); contact bit mask
   T *ckpt;                // [NW][54][ns] filter state (P 45, x 9) of every window stage AFTER its leg-odometry update
-  int32_t *resweep;       // [ns] earliest stage whose VO row changed this tick (INT_MAX: none)
+  int32_t *resweep;       // [2][ns] earliest stage whose VO row changed at tick T (INT_MAX: none), slot = T & 1
 };
+
+// Per-tick scratch words are double-buffered by tick parity so that the assembly kernel of tick T+1 may run while the
+// window solve of tick T is still in flight (dekf_run).
+template <typename T>
+DEKF_HD int32_t &tick_status(const Dims &dm, const Buffers<T> &b, int Tk, int i) { return b.status[(size_t)(Tk & 1) * dm.ns + i]; }
+template <typename T>
+DEKF_HD int32_t &tick_resweep(const Dims &dm, const Buffers<T> &b, int Tk, int i) { return b.resweep[(size_t)(Tk & 1) * dm.ns + i]; }
 
 struct Inputs {
   const double *gyro, *accel, *imu_time, *joint_pos, *joint_vel, *foot_force;
@@ -488,7 +495,7 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
   constexpr int NL = Model::NLEG, NJ = Model::NJ;
   const int n = dm.n, ns = dm.ns, N = dm.N, NW = dm.NW, HR = dm.HR;
   int status = 0;
-  if (b.resweep != nullptr) b.resweep[i] = 0x7fffffff;
+  if (b.resweep != nullptr) tick_resweep(dm, b, Tk, i) = 0x7fffffff;
 
   // ---- VO synchronisation against the history BEFORE this sample is pushed (:883-945)
   int vo_new = (in.vo_flag != nullptr) ? (int)in.vo_flag[i] : 0;
@@ -602,7 +609,7 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
         dbg[6] = num;
         dbg[7] = disc0;
         status |= ST_MHE_VO_BOUNDED;
-        if (b.resweep != nullptr) b.resweep[i] = disc0;
+        if (b.resweep != nullptr) tick_resweep(dm, b, Tk, i) = disc0;
         // set_interval + interpolate_waypoint (Bezier_simple.cpp:29-71) + UpdateVOConstraints
         const double t_interval = wt[3] - wt[0];
         const double u_inc = c.dt_d / t_interval;
@@ -1458,7 +1465,7 @@ template <typename T>
 DEKF_HD int incr_restart_stage(const Dims &dm, const Buffers<T> &b, int Tk, int i) {
   if (Tk == 1) return 0;
   int ks = Tk - 1;
-  const int rs = b.resweep[i];
+  const int rs = tick_resweep(dm, b, Tk, i);
   if (rs < ks) ks = rs;
   const int kmin = (Tk >= dm.N) ? Tk - dm.N : 0;  // VO bounds never reach below the window start (DecentralEst.cpp:917-918)
   return ks < kmin ? kmin : ks;

@@ -53,6 +53,7 @@ inline void fill_go1_defaults(dekf_config *c) {
   c->rate = 200;
   c->N = 20;
   c->est_type = 0;
+  c->window_solve = DEKF_SOLVE_INCREMENTAL;  // bit-identical to the full re-sweep, see estimator_core.cuh: mhe_solve_incr
   c->rho = 0.1;
   c->alpha = 1.6;
   c->delta = 0.00001;
@@ -82,7 +83,7 @@ inline Dims make_dims(const dekf_config &c) {
   d.n = c.n_instances;
   d.ns = (c.n_instances + 127) / 128 * 128;
   d.N = c.N;
-  d.NW = c.N + 1;
+  d.NW = c.N + 2;  // window stages T-N .. T plus one slot so that stage T+1 can be assembled while update(T) is in flight
   d.HR = 4 * c.N + 1;
   d.D = c.ekf_hist_depth;
   return d;
@@ -212,7 +213,7 @@ inline StateSizes state_sizes(const Dims &d) {
   s.p_vo = 3 * n;
   s.pend_flag = n;
   s.pend = 5 * n;
-  s.status = n;
+  s.status = 2 * n;
   return s;
 }
 

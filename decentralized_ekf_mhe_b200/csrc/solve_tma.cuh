@@ -134,9 +134,9 @@ __global__ void __launch_bounds__(TILE, MINB) k_solve_tma(const __grid_constant_
   }
   const int i = src.i0 + threadIdx.x;
   if (i >= dm.n) return;
-  int st = b.status[i];
+  int st = tick_status(dm, b, Tk, i);
   st |= mhe_solve<T, SmemStageSource<T, TILE, STAGES>, Math>(c, dm, b, in, out, Tk, i, src);
-  b.status[i] = st;
+  tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
 
@@ -179,9 +179,9 @@ __global__ void __launch_bounds__(TILE, 1) k_solve_incr_tma(const __grid_constan
     for (int j = 0; j < pre; ++j) src.issue(j);
   }
   if (i >= dm.n) return;
-  int st = b.status[i];
+  int st = tick_status(dm, b, Tk, i);
   st |= mhe_solve_incr<T, SmemStageSource<T, TILE, STAGES>, Math>(c, dm, b, in, out, Tk, i, src, ks);
-  b.status[i] = st;
+  tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
 

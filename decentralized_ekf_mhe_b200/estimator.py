@@ -446,15 +446,23 @@ class BatchedEstimator:
         h.check(h.L.dekf_get_qp_info(h.h, _ptr(it), _ptr(na)), "dekf_get_qp_info")
         return it, na
 
+    def resweep_info(self):
+        """(stages re-swept, VO rows among them) [n] int32 of the last tick (incremental window solve)."""
+        h = self._hd
+        d = torch.empty(h.n, dtype=torch.int32, device=h.device)
+        v = torch.empty(h.n, dtype=torch.int32, device=h.device)
+        h.check(h.L.dekf_get_resweep_info(h.h, _ptr(d), _ptr(v)), "dekf_get_resweep_info")
+        return d, v
+
     def profile(self, enable):
         self._hd.check(self._hd.L.dekf_profile_enable(self._hd.h, int(bool(enable))), "dekf_profile_enable")
 
     def profile_read(self):
-        """({'ekf','assemble','solve'} -> total ms, launch counts) since the last read."""
-        ms = (C.c_double * 3)()
-        cnt = (C.c_int64 * 3)()
+        """({'ekf','assemble','solve','resweep'} -> total ms, launch counts) since the last read."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
         self._hd.check(self._hd.L.dekf_profile_read(self._hd.h, ms, cnt), "dekf_profile_read")
-        names = ("ekf", "assemble", "solve")
+        names = ("ekf", "assemble", "solve", "resweep")
         return {k: ms[i] for i, k in enumerate(names)}, {k: cnt[i] for i, k in enumerate(names)}
 
     def device_bytes(self):

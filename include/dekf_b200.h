@@ -215,10 +215,14 @@ int dekf_debug_taps(dekf_handle *h, double *b_meas /*[3*legs][n]*/, double *Q_me
                     int32_t *vo_idx /*[8][n]*/, int32_t *ekf_idx /*[3][n]*/);
 
 /* Per-kernel device time of the step kernels (CUDA events on the handle's stream around every launch while
- * enabled).  ms[3] / count[3]: 0 = EKF tick, 1 = stage assembly, 2 = window solve (or the fused kernel).
+ * enabled).  ms[4] / count[4]: 0 = EKF tick, 1 = stage assembly, 2 = window solve (full sweep, one-stage incremental
+ * step, KF step, constrained solve or the fused kernel), 3 = incremental re-sweep on a VO tick (k_solve_incr_tma).
  * Reading synchronises the stream and clears the accumulators. */
 int dekf_profile_enable(dekf_handle *h, int32_t enable);
-int dekf_profile_read(dekf_handle *h, double *ms /*[3]*/, int64_t *count /*[3]*/);
+int dekf_profile_read(dekf_handle *h, double *ms /*[4]*/, int64_t *count /*[4]*/);
+/* Incremental solve bookkeeping of the last tick (device pointers, either may be NULL): stages re-swept per instance
+ * (1 on a tick without VO bounds) and how many of them carry a VO row -- the operands of the algorithmic flop tally. */
+int dekf_get_resweep_info(dekf_handle *h, int32_t *depth /*[n]*/, int32_t *n_vo /*[n]*/);
 
 /* Roofline denominators measured on the device (the driver's MEASURED_PEAKS.json has no FP64/FP32 FMA figure):
  * dense non-tensor FMA throughput in TFLOP/s (FMA = 2 flop) and a device-to-device copy in GB/s (read+write). */

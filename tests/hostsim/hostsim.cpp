@@ -67,7 +67,7 @@ struct Sim {
       b.foot_leg = c.leg_odom_type == 1 ? fb.leg : nullptr;
     }
     b.ckpt = alloc<T>((size_t)dm.NW * 54 * dm.ns);
-    b.resweep = alloc<int32_t>(dm.ns);
+    b.resweep = alloc<int32_t>(2 * (size_t)dm.ns);
     const int n = dm.ns;
     for (int i = 0; i < dm.n; ++i) {
       for (int f = 0; f < 4; ++f) {

@@ -95,14 +95,15 @@ def test_go1_fp64_lockstep_vs_oracle(est_mod, oracle):
 @pytest.mark.parametrize("env", [{"DEKF_FUSED_MAX_N": "0"}, {"DEKF_FUSED_MAX_N": "0", "DEKF_NO_TMA": "1"}],
                          ids=["split+tma", "split+global-loads"])
 @pytest.mark.parametrize("precision,n", [("fp64", 300), ("fp32", 129)])
-def test_go1_split_kernel_paths_vs_oracle(est_mod, oracle, monkeypatch, env, precision, n):
-    """The large-batch path (k_ekf, k_assemble, k_solve_tma: TMA-staged stage tiles) on parity-sized batches,
-    including a ragged last tile, and the plain-global-load solve kernel it replaced."""
+@pytest.mark.parametrize("window_solve", [0, 1], ids=["full-resweep", "incremental"])
+def test_go1_split_kernel_paths_vs_oracle(est_mod, oracle, monkeypatch, env, precision, n, window_solve):
+    """The large-batch path (k_ekf, k_assemble, k_solve_tma / k_solve_incr + k_solve_incr_tma: TMA-staged stage
+    tiles) on parity-sized batches, including a ragged last tile, and the plain-global-load kernels."""
     from decentralized_ekf_mhe_b200 import synth
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     st = synth.to_numpy(synth.make_stream(n, 150, vo_jitter=True))
-    est, r = _run_lockstep(est_mod, st, precision=precision)
+    est, r = _run_lockstep(est_mod, st, precision=precision, window_solve=window_solve)
     ro, _, _ = oracle.run_batch(st, oracle.go1_params(), oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1)
     tol = TOL_V if precision == "fp64" else TOL_V32
     assert np.abs(r["x"][1:, 3:6] - ro["x"][1:, 3:6]).max() < tol
