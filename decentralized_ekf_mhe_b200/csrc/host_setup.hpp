@@ -53,7 +53,7 @@ inline void fill_go1_defaults(dekf_config *c) {
   c->rate = 200;
   c->N = 20;
   c->est_type = 0;
-  c->window_solve = DEKF_SOLVE_INCREMENTAL;  // bit-identical to the full re-sweep, see estimator_core.cuh: mhe_solve_incr
+  c->window_solve = DEKF_SOLVE_FULL;  // the reference's semantics: every update(T) re-solves the whole window
   c->rho = 0.1;
   c->alpha = 1.6;
   c->delta = 0.00001;

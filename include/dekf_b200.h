@@ -96,9 +96,10 @@ typedef struct dekf_config {
   double p_init_std[3], v_init_std[3], foot_init_std[3], accel_bias_init_std[3];
   double vo_p_std[3];
   int32_t rate, N, est_type;
-  /* DEKF_SOLVE_FULL: every update(T) re-sweeps the whole window, like the reference re-solves the whole QP
+  /* DEKF_SOLVE_FULL (default): every update(T) re-sweeps the whole window, like the reference re-solves the whole QP
    * (tier A of SURVEY.md 8d).  DEKF_SOLVE_INCREMENTAL: restart the sweep from the checkpoint of the first stage that
-   * changed (tier B; bit-identical results; ignored with v_box_enable or est_type 1). */
+   * changed (tier B; bit-identical results, about twice the throughput; ignored with v_box_enable, est_type 1 or
+   * leg_odom_type 1). */
   int32_t window_solve;
   /* OSQP settings are accepted for source compatibility and ignored: the window is solved
    * directly (exactly), see DESIGN.md section 4. */

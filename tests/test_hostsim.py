@@ -154,3 +154,17 @@ def test_foot_state_model_matches_exact_solution(oracle):
     assert np.abs(r["x"][1:] - ex["x"][2:]).max() < 1e-8
     okf, _, _ = oracle.run_batch(st, oracle.go1_params(leg_odom_type=1, est_type=1), oracle.ekf_params(rate=200), nthreads=4, want=("x",))
     assert np.abs(r["x"][1:] - okf["x"][1:]).max() < 1e-5           # the literal covariance-form KF has the same noise floor
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_incremental_solve_is_bit_identical_to_full_resweep(precision):
+    """window_solve = DEKF_SOLVE_INCREMENTAL (tier B): restart at the first changed stage from the checkpoint ring.
+    Same operations on the same operands => every output and the arrival cost equal the full re-sweep bit for bit."""
+    import pyhostsim as hs
+    from decentralized_ekf_mhe_b200 import synth
+    st = synth.to_numpy(synth.make_stream(8, 260, vo_jitter=True))
+    a = hs.run(st, _cfg(window_solve=0, precision=precision))
+    b = hs.run(st, _cfg(window_solve=1, precision=precision))
+    assert np.array_equal(a["x"][1:], b["x"][1:]) and np.array_equal(a["v_body"][1:], b["v_body"][1:])
+    assert np.array_equal(a["arr_P"], b["arr_P"]) and np.array_equal(a["arr_x"], b["arr_x"])
+    assert np.array_equal(a["status"], b["status"]) and (a["status"] & 16).any()

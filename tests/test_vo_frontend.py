@@ -1,0 +1,53 @@
+"""Host-side VO front-end (include/dekf_b200/vo_frontend.hpp) against a numpy restatement of the reference node's pose
+arithmetic (visual_odometry/orbslam3_ros2/src/stereo-decentralized/stereo-pub-node.cpp:153-192) on a synthetic camera
+trajectory, and against the synthetic stream generator's own VO messages."""
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _rot(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _T(R, t):
+    M = np.eye(4)
+    M[:3, :3], M[:3, 3] = R, t
+    return M
+
+
+def test_vo_frontend_matches_reference_pose_arithmetic(tmp_path):
+    exe = tmp_path / "vo_frontend"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", str(exe), os.path.join(HERE, "cpp", "vo_frontend_main.cpp")])
+    rng = np.random.default_rng(7)
+    q_ic = rng.normal(size=4)
+    q_ic /= np.linalg.norm(q_ic)
+    R_ic, p_ic = _rot(q_ic), np.array([0.12, -0.03, 0.05])
+    n = 40
+    qs = rng.normal(size=(n, 4)) * 0.2 + np.array([1.0, 0, 0, 0])
+    qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    ts = np.cumsum(rng.normal(size=(n, 3)) * 0.02, axis=0)
+    stamps = np.arange(n) / 30.0
+    lines = [" ".join(f"{v:.17g}" for v in list(R_ic.reshape(-1)) + list(p_ic)), str(n)]
+    lines += [" ".join(f"{v:.17g}" for v in [stamps[k], *qs[k], *ts[k]]) for k in range(n)]
+    out = subprocess.run([str(exe)], input="\n".join(lines) + "\n", text=True, capture_output=True, check=True).stdout
+    got = np.array([[float(v) for v in ln.split()] for ln in out.strip().splitlines()])
+    assert got.shape == (n - 1, 12)
+    Tbc = _T(R_ic, p_ic)
+    Twc = [_T(_rot(qs[k]), ts[k]) for k in range(n)]
+    Twb0 = Twc[0] @ np.linalg.inv(Tbc)
+    for k in range(1, n):
+        rel = Tbc @ np.linalg.inv(Twc[k - 1]) @ Twc[k] @ np.linalg.inv(Tbc)       # stereo-pub-node.cpp:161
+        Twb = np.linalg.inv(Twb0) @ Twc[k] @ np.linalg.inv(Tbc)                  # :163
+        g = got[k - 1]
+        assert g[0] == stamps[k - 1] and g[1] == stamps[k]
+        np.testing.assert_allclose(g[2:5], rel[:3, 3], atol=1e-13)
+        np.testing.assert_allclose(_rot(g[5:9]), Twb[:3, :3], atol=1e-13)          # quaternion <-> rotation
+        assert abs(np.linalg.norm(g[5:9]) - 1.0) < 1e-13
+        np.testing.assert_allclose(g[9:12], Twb[:3, 3], atol=1e-13)
