@@ -184,7 +184,7 @@ def cpu_port_baseline(N, threads, steps_timed, instances_per_thread, mode="admm"
     return n * steps_timed / t, t, n, S
 
 
-def batch1_latency(estimator, synth, device, precision, N, steps=300):
+def batch1_latency(estimator, synth, device, precision, N, steps=300, window_solve=0):
     """Batch-1 lock-step tick latency: device time per tick (dekf_run over a resident stream, CUDA events) and host
     wall clock of one dekf_step_host call (pinned host buffers in and out, synchronised)."""
     import torch
@@ -192,7 +192,7 @@ def batch1_latency(estimator, synth, device, precision, N, steps=300):
     S = N + 8 + steps
     st = synth.make_stream(1, S, seed=777, device=dev, device_rng=True)
     vo = [bool(st["vo_flag"][s].any()) for s in range(S)]
-    prm = estimator.robot_params("go1", ekf_rate=200, N=N)
+    prm = estimator.robot_params("go1", ekf_rate=200, N=N, window_solve=window_solve)
     est = estimator.BatchedEstimator(prm, 1, device=device, precision=precision)
     cut = {k: v for k, v in st.items() if torch.is_tensor(v) and v.shape[0] == S}
     est.run(0, N + 8, cut, vo[:N + 8])
@@ -220,7 +220,8 @@ def batch1_latency(estimator, synth, device, precision, N, steps=300):
     est.close()
     ts.sort()
     return {"device_us_per_tick": dev_us, "host_call_us_median": 1e6 * ts[len(ts) // 2], "host_call_us_p99": 1e6 * ts[int(len(ts) * 0.99)],
-            "ticks": len(ts), "api": "dekf_step_host, n_instances=1 (k_fused: one launch per tick)"}
+            "ticks": len(ts), "window_solve": "incremental" if window_solve else "full",
+            "api": "dekf_step_host, n_instances=1 (k_fused: one launch per tick)"}
 
 
 def run_reference(args):
@@ -344,9 +345,11 @@ def main():
         est2.profile(True)
         dsum = torch.zeros((), dtype=torch.float64, device=dev)
         vsum = torch.zeros((), dtype=torch.float64, device=dev)
+        wsum = torch.zeros((), dtype=torch.float64, device=dev)
         nvo_ticks = 0
         for s in range(T0, T0 + Kp):
             est2.step(s, estimator.robot_store.from_stream(stream, s, with_vo=vo_steps[s]))
+            wsum += est2.window_vo_count().double().mean()  # VO rows in the window of THIS tick (flop tally operand)
             if mode == "incremental" and vo_steps[s]:
                 d, v = est2.resweep_info()
                 dsum += d.double().mean()
@@ -354,6 +357,7 @@ def main():
                 nvo_ticks += 1
         pms, pcnt = est2.profile_read()
         est2.close()
+        n_vo_mean = float(wsum.item()) / Kp
         depth = float(dsum.item()) / max(nvo_ticks, 1)
         depth_vo = float(vsum.item()) / max(nvo_ticks, 1)
         return est, dict(ms=ms, launches=launches, n_vo_mean=n_vo_mean, pms=pms, pcnt=pcnt, depth=depth, depth_vo=depth_vo,
@@ -445,7 +449,10 @@ def main():
         pcie = None
 
     # ---- batch-1 step latency (BASELINE metric, second half): one instance, lock-step tick
-    lat = batch1_latency(estimator, synth, local_rank, args.precision, N) if rank == 0 else None
+    lat = lat_o = None
+    if rank == 0:
+        lat = batch1_latency(estimator, synth, local_rank, args.precision, N, window_solve=1 if mode == "incremental" else 0)
+        lat_o = batch1_latency(estimator, synth, local_rank, args.precision, N, window_solve=0 if mode == "incremental" else 1)
 
     line = None
     if rank == 0:
@@ -468,7 +475,8 @@ def main():
         roof = report(mode, main)
         roof["measured_copy_gbs"] = peaks["copy_gbs"]
         alt = {"window_solve": other_mode, "value": n_total * K / (other["ms"] * 1e-3), "unit": UNIT,
-               "ms_per_step": other["ms"] / K, "gpu_launches": other["launches"], "roofline": report(other_mode, other)}
+               "ms_per_step": other["ms"] / K, "gpu_launches": other["launches"], "latency_batch1": lat_o,
+               "roofline": report(other_mode, other)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -15,15 +15,15 @@ est = estimator.BatchedEstimator(estimator.robot_params("go1", ekf_rate=200, N=N
 sub = {k: v for k, v in stream.items() if torch.is_tensor(v) and v.shape[0] == S}
 est.run(0, 30, sub, vo[:30])
 torch.cuda.synchronize()
-acc = {True: {"ekf": 0, "assemble": 0, "solve": 0, "n": 0}, False: {"ekf": 0, "assemble": 0, "solve": 0, "n": 0}}
+acc = {v: {"ekf": 0, "assemble": 0, "solve": 0, "resweep": 0, "n": 0} for v in (True, False)}
 est.profile(True)
 for s in range(30, S):
     est.step(s, estimator.robot_store.from_stream(sub, s, with_vo=vo[s]))
     ms, cnt = est.profile_read()
     a = acc[vo[s]]
-    for k in ("ekf", "assemble", "solve"):
+    for k in ("ekf", "assemble", "solve", "resweep"):
         a[k] += ms[k]
     a["n"] += 1
 for v in (False, True):
     a = acc[v]
-    print(f"window_solve={ws} {prec} vo_tick={v}: ticks {a['n']}  ekf {1e3*a['ekf']/a['n']:.1f} us  assemble {1e3*a['assemble']/a['n']:.1f} us  solve {1e3*a['solve']/a['n']:.1f} us")
+    print(f"window_solve={ws} {prec} vo_tick={v}: ticks {a['n']}  ekf {1e3*a['ekf']/a['n']:.1f} us  assemble {1e3*a['assemble']/a['n']:.1f} us  solve {1e3*(a['solve']+a['resweep'])/a['n']:.1f} us")
