@@ -519,3 +519,52 @@ def test_full_size_properties(est_mod, oracle):
     ro, _, _ = oracle.run_batch({k: v.cpu().numpy() for k, v in sub.items()}, oracle.go1_params(),
                                 oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1)
     assert np.abs(xs[1:, 3:6] - ro["x"][1:, 3:6]).max() < TOL_V
+
+
+@pytest.mark.parametrize("precision,tol", [("fp64", TOL_V), ("fp32", TOL_V32)])
+def test_cassie_full_size_properties(est_mod, oracle, precision, tol):
+    """BASELINE config 3 size (Cassie, 65,536 instances, fp64 and fp32; builder-defined 2-leg x 5-joint model):
+    contact sets equal the threshold compare on the raw input for every instance, everything stays finite, and the
+    first 64 instances match the generalised oracle (the builder's own restatement: not reference parity)."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S, m = 65536, 70, 64
+    stt = synth.make_stream(n, S, robot="cassie", vo_jitter=True, device="cuda")
+    est = E.BatchedEstimator(E.robot_params("cassie", ekf_rate=200), n, precision=precision)
+    xs = np.zeros((S, 9, m))
+    double_support = 0
+    for s in range(S):
+        est.step(s, E.robot_store.from_stream(stt, s))
+        c = (stt["foot_force"][s] >= 150.0).to(torch.uint8)
+        assert torch.equal(est.contact_, c)
+        double_support += int((c.sum(dim=0) == 2).sum())
+        if s >= 1:
+            xs[s] = est.x_MHE_[:, :m].cpu().numpy()
+    assert double_support > 0                                # the walk gait has double-support phases
+    assert torch.isfinite(est.x_MHE_).all() and not (est.status_ & 32).any()
+    sub = {k: np.ascontiguousarray(v[..., :m].cpu().numpy()) for k, v in stt.items()}
+    prm = oracle.go1_params(robot=1, num_legs=2, contact_effort_threshold=150.0, p_ib=(0.0, 0.0, 0.0))
+    ro, _, _ = oracle.run_batch(sub, prm, oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1, want=("x",))
+    assert np.abs(xs[1:, 3:6] - ro["x"][1:, 3:6]).max() < tol
+    est.close()
+
+
+@pytest.mark.parametrize("window_solve", [0, 1], ids=["full-resweep", "incremental"])
+def test_long_horizon_sweep_shard_size(est_mod, oracle, window_solve):
+    """BASELINE config 5 shape: N = 100 (0.5 s window) at the per-GPU shard size of the 1 M-instance sweep on 8 GPUs
+    (131,072 instances), per-instance amplitude jitter.  Properties on all instances, parity on the first 16."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S, m = 131072, 125, 16
+    stt = synth.make_stream(n, S, vo_jitter=True, amp_jitter=True, device="cuda", device_rng=True)
+    vo = [bool(stt["vo_flag"][s].any()) for s in range(S)]
+    sub_t = {k: v for k, v in stt.items() if torch.is_tensor(v) and v.shape[0] == S}
+    est = E.BatchedEstimator(E.robot_params("go1", ekf_rate=200, N=100, window_solve=window_solve), n)
+    out = {"x": torch.zeros(S, 9, n, dtype=torch.float64, device="cuda")}
+    est.run(0, S, sub_t, vo, out=out, out_per_step=True)
+    assert torch.isfinite(out["x"][1:]).all() and not (est.status_ & 32).any()
+    assert est.device_bytes() < 20e9
+    sub = {k: np.ascontiguousarray(v[..., :m].cpu().numpy()) for k, v in sub_t.items()}
+    ro, _, _ = oracle.run_batch(sub, oracle.go1_params(N=100), oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1, want=("x",))
+    assert np.abs(out["x"][1:, 3:6, :m].cpu().numpy() - ro["x"][1:, 3:6]).max() < TOL_V
+    est.close()
