@@ -11,7 +11,7 @@
  * (updateConstraintBound, MheSrb.cpp:233-243).
  * OSQP itself is not in /root/reference (unpinned dependency): solve_mode 0 returns
  * the unique optimum of the assembled QP by slack elimination + banded Cholesky, solve_mode 2 runs
- * the OSQP-style ADMM restated in admm.c.  "parity unpinned" (see oracle.h). */
+ * the OSQP-style ADMM restated in admm.c.  Parity status: see oracle.h (pinned against the compiled reference sources; OSQP's own iterates unpinned). */
 #include "oracle.h"
 #include "la.h"
 #include <math.h>

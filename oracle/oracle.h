@@ -7,10 +7,20 @@
  * and bench.py's cpu_baseline / --impl reference legs may load this library; the product path
  * (decentralized_ekf_mhe_b200/ + libdekf_b200.so) never does.
  *
- * PARITY STATUS: the reference ships no tests, golden vectors or fixtures and cannot be built in
- * this image (needs rclcpp, Eigen3, osqp, OsqpEigen) => "parity unpinned" for the EKF/MHE
- * arithmetic.  The Go1 kinematics part IS pinned: oracle/_ref/libfrost_go1.so is compiled from the
- * reference's own FROST sources and checked against orc_go1_* (tests/test_oracle_kinematics.py,
+ * PARITY STATUS: the reference ships no tests, golden vectors or fixtures, and Eigen3 / OSQP / osqp-eigen / rclcpp are
+ * absent from this image.  The restatement is pinned against THE REFERENCE'S OWN SOURCES instead:
+ *   - oracle/_ref/libref_nodes.so = orien_ekf.cpp, go1Sub.cpp, EstSub.cpp, DecentralEst.cpp, MheSrb.cpp,
+ *     Bezier_simple.cpp and the FROST expressions, compiled UNMODIFIED where they lie under /root/reference against
+ *     stand-in headers (oracle/ref_stub/: eager dense linear algebra for Eigen, exact KKT solve or oracle/admm.c for
+ *     OSQP, a synchronous topic bus for rclcpp) and driven through their own ROS callbacks by oracle/ref_nodes.cc;
+ *   - tests/golden/go1_refnodes_golden.npz = its outputs on synthetic streams (tests/golden/make_refnodes_golden.py);
+ *   - tests/test_refnodes_pin.py: oracle == reference (quaternion 7e-18, x_MHE 5e-11, contact sets / VO index
+ *     bookkeeping / accumulated VO translation exact, the QP handed to OSQP equal entry by entry, KF alternative 3e-17,
+ *     foot-state model 1e-10).
+ * NOT pinned ("parity unpinned" for these): the floating-point rounding inside Eigen's own kernels (PartialPivLU,
+ * SimplicialLLT) and OSQP's ADMM iterates -- the stand-ins replace them; BASELINE.json defines parity on the converged
+ * optimum (eps 1e-8), which is what both stand-in solvers return.
+ * The Go1 kinematics are additionally pinned through oracle/_ref/libfrost_go1.so (tests/test_oracle_kinematics.py,
  * tests/golden/go1_kin_golden.npz).
  */
 #ifndef ORC_ORACLE_H

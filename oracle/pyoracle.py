@@ -84,8 +84,9 @@ def build(force=False):
         os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if stale:
         subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
-    ref = os.path.join(_HERE, "_ref", "libfrost_go1.so")
-    if not os.path.exists(ref) and os.path.isdir("/root/reference/src/go1_example/src/Expressions"):
+    # oracle/_ref: the reference's own sources compiled where they lie (build container only; the GPU box uses the
+    # prebuilt files and the committed golden vectors)
+    if os.path.isdir("/root/reference/src/go1_example/src/Expressions"):
         subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
     return so
 
@@ -296,6 +297,15 @@ class Mhe:
         Q = np.zeros(dm * dm)
         lib().orc_mhe_get_meas(self.h, _p(b), _p(Q))
         return b, Q.reshape(dm, dm)
+
+    def kin(self):
+        """p_imu_2_foot_ (3*legs) and J_imu_2_foot_ (3*legs x joints-per-leg, row-major) of the last sample."""
+        dm = self.dims()[1]
+        nj = lib().orc_robot_joints_per_leg(self.prm.robot)
+        p = np.zeros(dm)
+        J = np.zeros(dm * nj)
+        lib().orc_mhe_get_kin(self.h, _p(p), _p(J))
+        return p, J.reshape(dm, nj)
 
     def vo_debug(self):
         a = (C.c_int * 10)()

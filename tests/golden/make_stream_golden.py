@@ -2,10 +2,9 @@
 steps, ragged VO arrival) together with the ORACLE's outputs on it (quaternions, x_MHE, v_MHE_b,
 contact flags, VO / EKF index bookkeeping, final arrival cost).
 
-These vectors are produced by oracle/ (the CPU restatement), NOT by the reference itself -- the
-reference cannot be built in this image (no rclcpp/Eigen/OSQP) and ships no fixtures, so they pin
-"CUDA path == oracle" and guard the oracle against regressions; parity vs the reference stays
-"unpinned" (see oracle/oracle.h).
+These vectors are produced by oracle/ (the CPU restatement): they pin "CUDA path == oracle" including the integer
+debug taps of the VO / EKF-replay index logic and guard the oracle against regressions.  The vectors produced by the
+REFERENCE'S OWN sources are tests/golden/go1_refnodes_golden.npz (make_refnodes_golden.py).
 
     python tests/golden/make_stream_golden.py
 """
