@@ -58,9 +58,15 @@ struct Nodes {
   sensor_msgs::msg::Imu last_filter;
 };
 
+// the reference prints timing / diagnostics on every tick: swallow them while its code runs
+struct NullBuf : std::streambuf {
+  int overflow(int c) override { return traits_type::not_eof(c); }
+  std::streamsize xsputn(const char *, std::streamsize n) override { return n; }
+};
 struct CoutMute {
+  NullBuf nb;
   std::streambuf *old;
-  CoutMute() : old(std::cout.rdbuf(nullptr)) {}
+  CoutMute() : old(std::cout.rdbuf(&nb)) {}
   ~CoutMute() { std::cout.rdbuf(old); }
 };
 bool g_mute = true;

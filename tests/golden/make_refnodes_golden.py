@@ -15,6 +15,7 @@ This script needs /root/reference and runs in the build container only; the GPU 
 """
 import os
 import sys
+import tempfile
 import time
 
 import numpy as np
@@ -58,6 +59,24 @@ def main():
         for k, v in ref.items():
             out[f"{name}/out_{k}"] = v
         out[f"{name}/params"] = np.array([prm.N, prm.est_type, prm.leg_odom_type, rate], dtype=np.int32)
+        if name in ("mhe", "kf"):
+            # what the reference's Data_Logger (data_logger.hpp) writes for instance 0: robotSub::init_logging /
+            # spin_logging (EstSub.cpp:77-121) into $HOME/log_exp/<log_name>_{Data,Name.csv}
+            home = os.environ.get("HOME")
+            with tempfile.TemporaryDirectory() as tmp:
+                os.makedirs(os.path.join(tmp, "log_exp"))
+                os.environ["HOME"] = tmp
+                try:
+                    pr.run_stream(st, prm, ep, i0=0, i1=1, want=())
+                finally:
+                    if home is None:
+                        del os.environ["HOME"]
+                    else:
+                        os.environ["HOME"] = home
+                out[f"{name}/log_data"] = np.fromfile(os.path.join(tmp, "log_exp", "refnodes_Data"), dtype=np.float64)
+                out[f"{name}/log_names"] = np.frombuffer(open(os.path.join(tmp, "log_exp", "refnodes_Name.csv"), "rb").read(), dtype=np.uint8)
+            print(f"  reference log: {out[f'{name}/log_data'].size} doubles, names:",
+                  bytes(out[f"{name}/log_names"]).decode().replace("\n", " | "))
         print(f"{name}: {n} instances x {S} ticks in {time.time() - t0:.1f} s", flush=True)
     path = os.path.join(os.path.dirname(__file__), "go1_refnodes_golden.npz")
     np.savez_compressed(path, **out)
