@@ -167,6 +167,34 @@ DEKF_HD bool box_chol9(double *S) {
 DEKF_HD double box_bound(const BoxConst &bc, int mask, int c) { return (mask & (8 << c)) ? bc.hi[c] : bc.lo[c]; }
 DEKF_HD bool box_is_active(int mask, int c) { return (mask & ((1 << c) | (8 << c))) != 0; }
 
+// Gaussian prior (Pa, xa) in information form: M = Pa^-1 (by Cholesky), m = sym(M) xa.  Returns status bits.
+DEKF_HD int box_prior_info(const double *Pa /*81*/, const double *xa /*9*/, double *M /*81*/, double *mv /*9*/) {
+  int status = 0;
+  double L[81];
+  for (int f = 0; f < 81; ++f) L[f] = Pa[f];
+  if (!box_chol9(L)) status |= ST_NONFINITE;
+  for (int c = 0; c < 9; ++c) {
+    double y[9];
+    for (int r = 0; r < 9; ++r) {
+      double v = (r == c) ? 1.0 : 0.0;
+      for (int k = 0; k < r; ++k) v -= L[r * 9 + k] * y[k];
+      y[r] = v / L[r * 9 + r];
+    }
+    for (int r = 8; r >= 0; --r) {
+      double v = y[r];
+      for (int k = r + 1; k < 9; ++k) v -= L[k * 9 + r] * y[k];
+      y[r] = v / L[r * 9 + r];
+    }
+    for (int r = 0; r < 9; ++r) M[r * 9 + c] = y[r];
+  }
+  for (int r = 0; r < 9; ++r) {
+    double v = 0.0;
+    for (int k = 0; k < 9; ++k) v += 0.5 * (M[r * 9 + k] + M[k * 9 + r]) * xa[k];
+    mv[r] = v;
+  }
+  return status;
+}
+
 // Constrained solve over the window states k0 .. Tk (K = Tk - k0 + 1 <= N) with the Gaussian prior
 // (Pa, xa) on x_k0.  Returns status bits; writes x_T to xT.
 template <typename T>
@@ -177,30 +205,7 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
   int status = 0;
   // prior in information form: M = Pa^-1, m = M xa
   double M[81], mv[9];
-  {
-    double L[81];
-    for (int f = 0; f < 81; ++f) L[f] = Pa[f];
-    if (!box_chol9(L)) status |= ST_NONFINITE;
-    for (int c = 0; c < 9; ++c) {
-      double y[9];
-      for (int r = 0; r < 9; ++r) {
-        double v = (r == c) ? 1.0 : 0.0;
-        for (int k = 0; k < r; ++k) v -= L[r * 9 + k] * y[k];
-        y[r] = v / L[r * 9 + r];
-      }
-      for (int r = 8; r >= 0; --r) {
-        double v = y[r];
-        for (int k = r + 1; k < 9; ++k) v -= L[k * 9 + r] * y[k];
-        y[r] = v / L[r * 9 + r];
-      }
-      for (int r = 0; r < 9; ++r) M[r * 9 + c] = y[r];
-    }
-    for (int r = 0; r < 9; ++r) {
-      double v = 0.0;
-      for (int k = 0; k < 9; ++k) v += 0.5 * (M[r * 9 + k] + M[k * 9 + r]) * xa[k];
-      mv[r] = v;
-    }
-  }
+  status |= box_prior_info(Pa, xa, M, mv);
   // warm start: masks of the previous tick stay attached to their stage (ring slot), the new state starts free
   bb.act[(size_t)(Tk % dm.NW) * ns + i] = 0;
   int iters = 0, nact = 0;
@@ -409,16 +414,14 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
   return status;
 }
 
-// update(T) with the box rows: marginalizeQP(T-N) as one stage of the unconstrained covariance-form sweep
-// (MheSrb.cpp:475-713), then the constrained solve over the states that remain in the window, getsolution(T) and the
-// body-velocity read-out (DecentralEst.cpp:179-185).
+// marginalizeQP(T-N) as one stage of the unconstrained covariance-form sweep (MheSrb.cpp:475-713; arrival cost updated
+// in place), leaving the Gaussian prior (Pa, xa) on the first state k0 that remains in the window.
 template <typename T, typename Math = DefaultMath<T>>
-DEKF_HD int mhe_solve_box(const MheConst<T> &c, const BoxConst &bc, const Dims &dm, const Buffers<T> &b, const BoxBuffers &bb,
-                          const Inputs &in, const Outputs &out, int Tk, int i) {
-  const int n = dm.n, ns = dm.ns, N = dm.N;
+DEKF_HD void box_prepare(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, int Tk, int i, double *Pa /*81*/, double *xa /*9*/,
+                         int &k0) {
+  const int ns = dm.ns, N = dm.N;
   Cov9<T> P;
   Vec9<T> x;
-  int k0;
   GlobalStageSource<T> src(dm, b, i);
   if (Tk < N) {
 #pragma unroll
@@ -463,7 +466,6 @@ DEKF_HD int mhe_solve_box(const MheConst<T> &c, const BoxConst &bc, const Dims &
     }
     k0 = km + 1;
   }
-  double Pa[81], xa[9], xT[9];
   for (int r = 0; r < 3; ++r)
     for (int cc = 0; cc < 3; ++cc) {
       Pa[(0 + r) * 9 + 0 + cc] = (double)P.pp(r, cc);
@@ -478,6 +480,19 @@ DEKF_HD int mhe_solve_box(const MheConst<T> &c, const BoxConst &bc, const Dims &
     xa[3 + f] = (double)x.v[f];
     xa[6 + f] = (double)x.b[f];
   }
+}
+
+// update(T) with the box rows: marginalizeQP(T-N) as one stage of the unconstrained covariance-form sweep
+// (MheSrb.cpp:475-713), then the constrained solve over the states that remain in the window, getsolution(T) and the
+// body-velocity read-out (DecentralEst.cpp:179-185).
+template <typename T, typename Math = DefaultMath<T>>
+DEKF_HD int mhe_solve_box(const MheConst<T> &c, const BoxConst &bc, const Dims &dm, const Buffers<T> &b, const BoxBuffers &bb,
+                          const Inputs &in, const Outputs &out, int Tk, int i) {
+  const int n = dm.n;
+  double Pa[81], xa[9], xT[9];
+  int k0;
+  box_prepare<T, Math>(c, dm, b, Tk, i, Pa, xa, k0);
+  GlobalStageSource<T> src(dm, b, i);
   int status = box_solve<T>(bc, dm, b, bb, k0, Tk, i, Pa, xa, xT);
   M3<T> RT;
   src.rot(0, Tk, RT);

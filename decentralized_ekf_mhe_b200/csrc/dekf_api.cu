@@ -13,6 +13,7 @@
 #include "../../include/dekf_b200.h"
 #include "estimator_core.cuh"
 #include "host_setup.hpp"
+#include "box_team.cuh"
 
 namespace dekf {
 
@@ -95,6 +96,63 @@ __global__ void __launch_bounds__(kBlock) k_solve_box(const MheConst<T> c, const
   if (Tk >= 1) st |= mhe_solve_box<T>(c, bc, dm, b, bb, in, out, Tk, i);
   tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
+}
+
+// state-constrained window solve, team form (box_team.cuh): k_box_prior (one thread per instance: marginalisation +
+// information-form prior) then k_box_team (9 lanes per instance, 3 instances per warp: the active-set iteration)
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_box_prior(const MheConst<T> c, const Dims dm, const Buffers<T> b, const BoxBuffers bb,
+                                                      const BoxTeamBuffers tb, int Tk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dm.n || Tk < 1) return;
+  const int st = box_team_prior<T>(c, dm, b, bb, tb, Tk, i);
+  if (st) tick_status(dm, b, Tk, i) |= st;
+}
+
+constexpr int kTeamsPerWarp = 3, kTeamBlock = 128;
+#ifndef DEKF_MINB_BOXTEAM
+#define DEKF_MINB_BOXTEAM 4
+#endif
+template <typename T>
+__global__ void __launch_bounds__(kTeamBlock, DEKF_MINB_BOXTEAM) k_box_team(const BoxConst bc, const Dims dm, const Buffers<T> b, const BoxBuffers bb,
+                                                         const BoxTeamBuffers tb, const Inputs in, const Outputs out, int Tk,
+                                                         int32_t *status_out) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int team = lane / 9;  // 3 = the five idle lanes of the warp
+  const int r = lane - 9 * team, base = 9 * team;
+  int i = warp * kTeamsPerWarp + team;
+  const bool valid = team < kTeamsPerWarp && i < dm.n;
+  if (i > dm.n - 1) i = dm.n - 1;  // idle teams shadow a real instance (loads only)
+  const int n = dm.n;
+  int st = 0;
+  double xT = 0.0;
+  if (Tk >= 1) {
+    const int k0 = Tk < dm.N ? 0 : Tk - dm.N + 1;
+    st = box_team_solve<T>(bc, dm, b, bb, tb, k0, Tk, i, valid, base, r, xT);
+    // getsolution(T) and the body-velocity read-out (DecentralEst.cpp:179-185)
+    const unsigned bad = __ballot_sync(0xffffffffu, !(xT == xT) || !(xT - xT == 0.0));
+    if ((bad >> base) & 0x1ffu) st |= ST_NONFINITE;
+    const double v0 = bt_shfl(xT, base + 3), v1 = bt_shfl(xT, base + 4), v2 = bt_shfl(xT, base + 5);
+    if (valid) {
+      if (out.x != nullptr) out.x[(size_t)r * n + i] = xT;
+      if (out.v_body != nullptr && r < 3) {
+        const T *rec = b.win + (size_t)(Tk % dm.NW) * REC_SIZE * dm.ns + i;
+        const double om0 = in.gyro[(size_t)0 * n + i], om1 = in.gyro[(size_t)1 * n + i], om2 = in.gyro[(size_t)2 * n + i];
+        const double lever[3] = {0.016041, 0.089061, 0.0579875};
+        const double u0 = v0 + (om1 * lever[2] - om2 * lever[1]), u1 = v1 + (om2 * lever[0] - om0 * lever[2]),
+                     u2 = v2 + (om0 * lever[1] - om1 * lever[0]);
+        const double R0 = (double)rec[(size_t)(REC_R + r * 3 + 0) * dm.ns], R1 = (double)rec[(size_t)(REC_R + r * 3 + 1) * dm.ns],
+                     R2 = (double)rec[(size_t)(REC_R + r * 3 + 2) * dm.ns];
+        out.v_body[(size_t)r * n + i] = R0 * u0 + R1 * u1 + R2 * u2;
+      }
+    }
+  }
+  if (valid && r == 0) {
+    st |= tick_status(dm, b, Tk, i);
+    tick_status(dm, b, Tk, i) = st;
+    if (status_out != nullptr) status_out[i] = st;
+  }
 }
 
 // leg_odom_type 1 (foot-position states): information-form window sweep / KF step, footstate.cuh
@@ -325,6 +383,8 @@ struct dekf_handle {
   Buffers<float> b32;
   BoxConst bc;
   BoxBuffers bb = {nullptr, nullptr, nullptr, nullptr};
+  BoxTeamBuffers tb = {nullptr, nullptr};
+  bool box_team = true;           // team form of the constrained solve (DEKF_BOX_SERIAL=1 selects one thread per instance)
   FootConst fc;
   FootBuffers fb = {nullptr, nullptr, nullptr};  // leg_odom_type 1
   void *ckpt_mem = nullptr;       // incremental window solve: checkpoint ring
@@ -496,6 +556,18 @@ int launch_assemble(dekf_handle *h, const MheConst<T> &mc, const Buffers<T> &b, 
   h->launches++;
   return 0;
 }
+template <typename T>
+void launch_box(dekf_handle *h, const MheConst<T> &mc, const Buffers<T> &b, const Inputs &in, const Outputs &out, int T_, int32_t *st) {
+  if (!h->box_team) {
+    k_solve_box<T><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(mc, h->bc, h->dm, b, h->bb, in, out, T_, st);
+    return;
+  }
+  k_box_prior<T><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(mc, h->dm, b, h->bb, h->tb, T_);
+  const int warps = (h->dm.n + kTeamsPerWarp - 1) / kTeamsPerWarp, wpb = kTeamBlock / 32;
+  k_box_team<T><<<(warps + wpb - 1) / wpb, kTeamBlock, 0, h->stream>>>(h->bc, h->dm, b, h->bb, h->tb, in, out, T_, st);
+  h->launches += 1;  // the caller counts one launch per window solve
+}
+
 template <typename T, typename Model>
 int launch_fused(dekf_handle *h, const EkfConst<T> &ec, const MheConst<T> &mc, const Buffers<T> &b, const Inputs &in,
                  const Outputs &out, int k, int T_, int32_t *status) {
@@ -716,6 +788,13 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     if ((ce = cudaMalloc((void **)&h->bb.iters, ns * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
     if ((ce = cudaMalloc((void **)&h->bb.nactive, ns * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
     h->extra_bytes += fac + act + 2 * ns * sizeof(int32_t);
+    if (const char *e = std::getenv("DEKF_BOX_SERIAL")) h->box_team = std::atoi(e) == 0;
+    if (h->box_team) {
+      const size_t tfac = (size_t)h->dm.N * BOX_TFAC * ns * sizeof(double);
+      if ((ce = cudaMalloc((void **)&h->tb.prior, ns * BOX_PRIOR * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+      if ((ce = cudaMalloc((void **)&h->tb.fac, tfac)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc(box team scratch)", ce);
+      h->extra_bytes += ns * BOX_PRIOR * sizeof(double) + tfac;
+    }
   }
   if (cfg->debug_taps) {
     if ((ce = cudaMalloc((void **)&h->tap_b_meas, (size_t)3 * h->nl * n * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
@@ -748,6 +827,8 @@ int dekf_destroy(dekf_handle *h) {
   cudaFree(h->ckpt_mem);
   cudaFree(h->resweep_mem);
   cudaFree(h->bb.fac);
+  cudaFree(h->tb.prior);
+  cudaFree(h->tb.fac);
   cudaFree(h->bb.act);
   cudaFree(h->bb.iters);
   cudaFree(h->bb.nactive);
@@ -886,7 +967,7 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
     if (kf)
       k_kf<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
     else if (h->bc.enable)
-      k_solve_box<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->bc, h->dm, h->b32, h->bb, di, dout, T_, st);
+      launch_box<float>(h, h->mc32, h->b32, di, dout, T_, st);
     else if (resweep_tick)
       k_solve_incr_tma<float><<<tiles, kTile, solve_tma_smem_bytes<float>(), h->stream>>>(h->tmap, h->mc32, h->dm, h->b32, di, dout, T_, st);
     else if (h->mc32.window_solve == 1)
@@ -908,7 +989,7 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
     } else if (kf)
       k_kf<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
     else if (h->bc.enable)
-      k_solve_box<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->bc, h->dm, h->b64, h->bb, di, dout, T_, st);
+      launch_box<double>(h, h->mc64, h->b64, di, dout, T_, st);
     else if (resweep_tick)
       k_solve_incr_tma<double><<<tiles, kTile, solve_tma_smem_bytes<double>(), h->stream>>>(h->tmap, h->mc64, h->dm, h->b64, di, dout, T_, st);
     else if (h->mc64.window_solve == 1)

@@ -244,8 +244,41 @@ def test_kf_alternative_vs_oracle(est_mod, oracle, n):
     est.close()
 
 
+def test_pogox_team_kernel_equals_serial_kernel(est_mod, monkeypatch):
+    """k_box_team (9 lanes per instance, csrc/box_team.cuh) against k_solve_box (one thread per instance, DEKF_BOX_SERIAL=1):
+    same algorithm on the same operands -> same active sets, same number of factorisations, x_T equal to rounding.
+    2,000 instances: a ragged last warp (3 instances per warp) and the T < N start-up."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S = 2000, 45
+    lo, hi = (-0.45, -0.03, -0.015), (0.55, 0.03, 0.015)
+    d = {k: v.contiguous() for k, v in synth.make_stream(n, S, robot="pogox", vo_jitter=True, device="cuda").items()}
+    res = {}
+    for serial in ("0", "1"):
+        monkeypatch.setenv("DEKF_BOX_SERIAL", serial)
+        est = E.BatchedEstimator(E.robot_params("pogox", ekf_rate=200, v_box_enable=1, v_box_lo=lo, v_box_hi=hi), n)
+        xs, its, nas, sts = [], [], [], []
+        for s in range(S):
+            est.step(s, E.robot_store.from_stream(d, s))
+            it, na = est.qp_info()
+            xs.append(est.x_MHE_.clone()), its.append(it.clone()), nas.append(na.clone()), sts.append(est.status_.clone())
+        res[serial] = [torch.stack(a).cpu().numpy() for a in (xs, its, nas, sts)]
+        est.close()
+    (xa, ia, na_, sa), (xb, ib, nb, sb) = res["0"], res["1"]
+    assert np.abs(xa[1:] - xb[1:]).max() < 1e-9
+    assert np.array_equal(sa, sb)
+    # the multipliers are evaluated in a different operation order: allow a handful of razor-edge sign decisions
+    assert (ia[1:] != ib[1:]).mean() < 1e-3 and (na_[1:] != nb[1:]).mean() < 1e-3
+
+
+@pytest.mark.parametrize("serial", ["0", "1"], ids=["team-kernel", "serial-kernel"])
 @pytest.mark.parametrize("precision,tol", [("fp64", 1e-6), ("fp32", 1e-4)])
-def test_pogox_state_constrained_16384(est_mod, oracle, precision, tol):
+def test_pogox_state_constrained_16384(est_mod, oracle, monkeypatch, precision, tol, serial):
+    monkeypatch.setenv("DEKF_BOX_SERIAL", serial)
+    _pogox_state_constrained_16384(est_mod, oracle, precision, tol)
+
+
+def _pogox_state_constrained_16384(est_mod, oracle, precision, tol):
     """BASELINE config 4: PogoX, 16,384 instances, box on the velocity states of the whole window that binds in
     >= 20 % of the steps (builder extension of MHEproblem::addConstraints(name, lb, ub), MheSrb.cpp:58-68).
     Parity on the first 64 instances against the oracle's exact constrained optimum (itself certified by KKT
