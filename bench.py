@@ -229,11 +229,61 @@ def batch1_latency(estimator, synth, device, precision, N, steps=300, window_sol
             "api": "dekf_step_host, n_instances=1 (k_fused: one launch per tick)"}
 
 
+def _ref_sources_worker(job):
+    """One process = one instance stepped through oracle/_ref/libref_nodes.so (the reference's own sources compiled against
+    the stand-in Eigen/OSQP/rclcpp headers; its topic bus is process-global, hence processes, not threads)."""
+    path, idx, t_steady = job
+    import numpy as np
+    from oracle import pyoracle as po, pyref as pr
+    st = dict(np.load(path))
+    prm = po.go1_params(N=int(st.pop("N")))
+    rn = pr.RefNodes(prm, po.ekf_params(rate=200))
+    S = st["gyro"].shape[0]
+    t0 = 0.0
+    for s in range(S):
+        if s == t_steady:
+            t0 = time.perf_counter()
+        rn.tick_from_stream(st, s, idx)
+    dt = time.perf_counter() - t0
+    del rn
+    return dt
+
+
+def time_reference_sources(cores, N, ticks=40):
+    """instance-steps/s of the reference's OWN sources (oracle/_ref/libref_nodes.so) with every host core, or None when the
+    library did not travel.  Reported beside the port, never as the headline baseline: Eigen and OSQP are stand-ins there
+    (dense eager linear algebra, exact KKT solve), so its speed says little about the real reference."""
+    try:
+        import tempfile
+        from concurrent.futures import ProcessPoolExecutor
+        import numpy as np
+        from oracle import pyref as pr
+        if not os.path.exists(pr._SO):
+            return None
+        from decentralized_ekf_mhe_b200 import synth
+        t_steady = N + 4
+        st = pr.quantize_stream(synth.to_numpy(synth.make_stream(cores, t_steady + ticks)))
+        with tempfile.TemporaryDirectory() as tmp:
+            path = os.path.join(tmp, "stream.npz")
+            np.savez(path, N=N, **st)
+            import multiprocessing as mp
+            with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("spawn")) as ex:
+                dts = list(ex.map(_ref_sources_worker, [(path, i, t_steady) for i in range(cores)]))
+        return {"value": cores * ticks / max(dts), "unit": UNIT, "cores": cores, "kind": "reference sources + stand-in libraries",
+                "sample": f"{cores} instances (one process each) x {ticks} steady-state ticks; exact KKT solve in the OSQP stand-in",
+                "note": "correctness artefact (pins the oracle); NOT the headline baseline: the stand-in linear algebra is dense"}
+    except Exception as e:  # never fail the bench on the optional leg
+        return {"unavailable": repr(e)[:200]}
+
+
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path on the host cores.  The reference
-    cannot be compiled in this image (needs rclcpp, Eigen3, osqp, OsqpEigen), so this
-    times the oracle port in its reference-faithful mode (OSQP-style ADMM with a cold setup every step,
-    the shipped eps 1e-6, no wall-clock limit) with every host thread, one instance per thread."""
+    """Reference arm: the reference's own CPU implementation of the path on the host cores.  The reference's own build
+    (colcon + Eigen3 + OSQP + osqp-eigen + rclcpp) is impossible in this image; its sources do compile against stand-in
+    headers into oracle/_ref/ (DESIGN.md 3), but with dense stand-in linear algebra and an exact KKT solve instead of OSQP
+    that build is ~15x SLOWER than the real reference would be, so timing it would flatter our arm.  The headline of this
+    arm is therefore the faster oracle port in its reference-faithful mode (OSQP-style ADMM with a cold setup every step,
+    the shipped eps 1e-6, no wall-clock limit) with every host thread, one instance per thread; the compiled reference
+    sources are timed beside it (`reference_sources`) for transparency."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -262,6 +312,9 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    rs = time_reference_sources(cores, N)
+    if rs is not None:
+        line["reference_sources"] = rs
     print(json.dumps(line))
     return 0
 
@@ -505,6 +558,9 @@ def main():
                            "tick's inputs copied in and results copied out)",
                     "single_tick_host_call_ms": ms_step_host, "host_checksum": chk},
             "latency_batch1": lat,
+            "ekf_only": {"value": n_total / (roof["all_kernels"]["ekf"]["ms"] * 1e-3) if "ekf" in roof.get("all_kernels", {}) else None,
+                         "unit": "EKF ticks/s", "note": "orien_ekf::timerCallback alone (k_ekf, event pairs, incl. the VO rewind/"
+                         "replay ticks): the reference runs this filter as its own 500 Hz process"},
             "gpu_launches": launches,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
             "roofline": roof,
