@@ -114,47 +114,72 @@ void ref_nodes_destroy(void *h) {
   delete mute;
 }
 
-// vo_*_ns: integer-nanosecond header stamps of the VO messages (as ROS carries them); quat_in (or NULL): orientation
-// published on imu/filter when the EKF node is not instantiated.
+// ---- single events (any schedule of messages and timers; ref_nodes_tick below is the 1:1 lock-step schedule)
+void ref_nodes_set_clock(long long t_ns) { refstub::now_ns() = t_ns; }
+// /unitree/imu at the current clock -> orien_ekf::imu_callback and go1Sub::imu_callback
+void ref_nodes_msg_imu(void *h, const double *gyro, const double *accel) {
+  (void)h;
+  sensor_msgs::msg::Imu imu;
+  stamp_from_ns(refstub::now_ns(), imu.header.stamp);
+  imu.angular_velocity.x = gyro[0]; imu.angular_velocity.y = gyro[1]; imu.angular_velocity.z = gyro[2];
+  imu.linear_acceleration.x = accel[0]; imu.linear_acceleration.y = accel[1]; imu.linear_acceleration.z = accel[2];
+  refstub::deliver<sensor_msgs::msg::Imu>("unitree/imu", imu);
+}
+// /unitree/joint_state -> go1Sub::lo_callback (positions = joints then foot forces, go1Sub.cpp:68-75)
+void ref_nodes_msg_joint(void *h, const double *joint_pos, int n_pos, const double *joint_vel, int n_vel) {
+  (void)h;
+  sensor_msgs::msg::JointState js;
+  stamp_from_ns(refstub::now_ns(), js.header.stamp);
+  js.position.assign(joint_pos, joint_pos + n_pos);
+  js.velocity.assign(joint_vel, joint_vel + n_vel);
+  refstub::deliver<sensor_msgs::msg::JointState>("unitree/joint_state", js);
+}
+// orb/pos -> orien_ekf::vo_pose_callback, orb/vo -> robotSub::vo_callback; stamps are integer nanoseconds as ROS carries them
+void ref_nodes_msg_vo(void *h, const double *vo_quat_wxyz, long long vo_now_ns, long long vo_pre_ns, const double *vo_rel_p) {
+  (void)h;
+  geometry_msgs::msg::PoseStamped ps;
+  stamp_from_ns(vo_now_ns, ps.header.stamp);
+  ps.pose.orientation.w = vo_quat_wxyz[0]; ps.pose.orientation.x = vo_quat_wxyz[1];
+  ps.pose.orientation.y = vo_quat_wxyz[2]; ps.pose.orientation.z = vo_quat_wxyz[3];
+  refstub::deliver<geometry_msgs::msg::PoseStamped>("orb/pos", ps);
+  custom_msgs::msg::VoRealtiveTransform vt;
+  stamp_from_ns(vo_now_ns, vt.header.stamp);
+  stamp_from_ns(vo_pre_ns, vt.header_pre.stamp);
+  vt.x_relative = vo_rel_p[0]; vt.y_relative = vo_rel_p[1]; vt.z_relative = vo_rel_p[2];
+  refstub::deliver<custom_msgs::msg::VoRealtiveTransform>("orb/vo", vt);
+}
+// imu/filter published by something else than the EKF node (runs without it)
+void ref_nodes_msg_filter(void *h, const double *quat_wxyz) {
+  (void)h;
+  sensor_msgs::msg::Imu f;
+  f.orientation.w = quat_wxyz[0]; f.orientation.x = quat_wxyz[1]; f.orientation.y = quat_wxyz[2]; f.orientation.z = quat_wxyz[3];
+  refstub::deliver<sensor_msgs::msg::Imu>("imu/filter", f);
+}
+void ref_nodes_fire_ekf(void *h) {  // orien_ekf::timerCallback; publishes imu/filter -> robotSub::orien_filter_callback
+  Nodes *nd = (Nodes *)h;
+  CoutMute *mute = g_mute ? new CoutMute : nullptr;
+  if (nd->ekf) nd->ekf->fire_timers();
+  delete mute;
+}
+void ref_nodes_fire_est(void *h) {  // robotSub::timerCallback: initialize at discrete time 0, update(T) afterwards
+  Nodes *nd = (Nodes *)h;
+  CoutMute *mute = g_mute ? new CoutMute : nullptr;
+  if (nd->est) nd->est->fire_timers();
+  delete mute;
+}
+
+// One lock-step tick.  quat_in (or NULL): orientation published on imu/filter when the EKF node is not instantiated.
 void ref_nodes_tick(void *h, long long t_ns, const double *gyro, const double *accel, const double *joint_pos, int n_pos,
                     const double *joint_vel, int n_vel, int vo_new, const double *vo_quat_wxyz, long long vo_now_ns,
                     long long vo_pre_ns, const double *vo_rel_p, const double *quat_in_wxyz) {
   Nodes *nd = (Nodes *)h;
-  CoutMute *mute = g_mute ? new CoutMute : nullptr;
-  refstub::now_ns() = t_ns;
-  sensor_msgs::msg::Imu imu;
-  stamp_from_ns(t_ns, imu.header.stamp);
-  imu.angular_velocity.x = gyro[0]; imu.angular_velocity.y = gyro[1]; imu.angular_velocity.z = gyro[2];
-  imu.linear_acceleration.x = accel[0]; imu.linear_acceleration.y = accel[1]; imu.linear_acceleration.z = accel[2];
-  refstub::deliver<sensor_msgs::msg::Imu>("unitree/imu", imu);
-  if (nd->est) {
-    sensor_msgs::msg::JointState js;
-    stamp_from_ns(t_ns, js.header.stamp);
-    js.position.assign(joint_pos, joint_pos + n_pos);
-    js.velocity.assign(joint_vel, joint_vel + n_vel);
-    refstub::deliver<sensor_msgs::msg::JointState>("unitree/joint_state", js);
-  }
-  if (vo_new) {
-    geometry_msgs::msg::PoseStamped ps;
-    stamp_from_ns(vo_now_ns, ps.header.stamp);
-    ps.pose.orientation.w = vo_quat_wxyz[0]; ps.pose.orientation.x = vo_quat_wxyz[1];
-    ps.pose.orientation.y = vo_quat_wxyz[2]; ps.pose.orientation.z = vo_quat_wxyz[3];
-    refstub::deliver<geometry_msgs::msg::PoseStamped>("orb/pos", ps);
-    custom_msgs::msg::VoRealtiveTransform vt;
-    stamp_from_ns(vo_now_ns, vt.header.stamp);
-    stamp_from_ns(vo_pre_ns, vt.header_pre.stamp);
-    vt.x_relative = vo_rel_p[0]; vt.y_relative = vo_rel_p[1]; vt.z_relative = vo_rel_p[2];
-    refstub::deliver<custom_msgs::msg::VoRealtiveTransform>("orb/vo", vt);
-  }
-  if (nd->ekf) nd->ekf->fire_timers();  // publishes imu/filter
-  else if (quat_in_wxyz) {
-    sensor_msgs::msg::Imu f;
-    f.orientation.w = quat_in_wxyz[0]; f.orientation.x = quat_in_wxyz[1];
-    f.orientation.y = quat_in_wxyz[2]; f.orientation.z = quat_in_wxyz[3];
-    refstub::deliver<sensor_msgs::msg::Imu>("imu/filter", f);
-  }
-  if (nd->est) nd->est->fire_timers();
-  delete mute;
+  ref_nodes_set_clock(t_ns);
+  ref_nodes_msg_imu(h, gyro, accel);
+  if (nd->est) ref_nodes_msg_joint(h, joint_pos, n_pos, joint_vel, n_vel);
+  if (vo_new) ref_nodes_msg_vo(h, vo_quat_wxyz, vo_now_ns, vo_pre_ns, vo_rel_p);
+  if (nd->ekf) ref_nodes_fire_ekf(h);
+  else if (quat_in_wxyz) ref_nodes_msg_filter(h, quat_in_wxyz);
+  ref_nodes_fire_est(h);
 }
 
 void ref_nodes_get_quat(void *h, double *q4, double *P16) {
