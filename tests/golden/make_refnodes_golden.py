@@ -78,6 +78,20 @@ def main():
             print(f"  reference log: {out[f'{name}/log_data'].size} doubles, names:",
                   bytes(out[f"{name}/log_names"]).decode().replace("\n", " | "))
         print(f"{name}: {n} instances x {S} ticks in {time.time() - t0:.1f} s", flush=True)
+    # the reference's deployment schedule: EKF timer at 500 Hz, estimator timer at 200 Hz (tests/mixed_rate.py)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mixed_rate as mr
+    t0 = time.time()
+    n, S = 4, 300
+    st = pr.quantize_stream(synth.to_numpy(synth.make_stream(n, S, dt=0.002, vo_jitter=True, seed=23)))
+    prm, ep = po.go1_params(), po.ekf_params(rate=500)
+    runs = [mr.run_reference(pr, st, i, prm, ep) for i in range(n)]
+    for k in IN_KEYS:
+        out[f"mixed/in_{k}"] = st[k]
+    for k in runs[0]:
+        out[f"mixed/out_{k}"] = np.stack([r[k] for r in runs], axis=-1)
+    out["mixed/params"] = np.array([prm.N, prm.est_type, prm.leg_odom_type, 500], dtype=np.int32)
+    print(f"mixed (EKF 500 Hz / MHE 200 Hz): {n} instances x {S} IMU samples, {runs[0]['x'].shape[0]} estimator ticks in {time.time() - t0:.1f} s", flush=True)
     path = os.path.join(os.path.dirname(__file__), "go1_refnodes_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -212,6 +212,27 @@ def test_go1_matches_reference_golden(est_mod, name, tol9, tol_all, window_solve
     est.close()
 
 
+def test_go1_matches_reference_at_the_deployment_rates(est_mod):
+    """The reference's shipped rates -- orientation EKF at 500 Hz, estimator at 200 Hz, two timers over the same topics --
+    replayed through the reference's class API of the CUDA path (E.orien_ekf.timerCallback, E.DecentralizedEstimation.
+    initialize/update: dekf_ekf_step / dekf_mhe_step) against the outputs of the reference's own nodes (tests/mixed_rate.py,
+    golden case "mixed")."""
+    import sys
+    sys.path.insert(0, HERE)
+    import mixed_rate as mr
+    g = np.load(os.path.join(HERE, "golden", "go1_refnodes_golden.npz"))
+    st = {k.split("/in_")[1]: g[k] for k in g.files if k.startswith("mixed/in_")}
+    ref = {k.split("/out_")[1]: g[k] for k in g.files if k.startswith("mixed/out_")}
+    N, est_type, leg_odom_type, rate = (int(v) for v in g["mixed/params"])
+    r = mr.run_cuda(est_mod, torch, st, dict(N=N), ekf_rate=rate)
+    assert np.abs(r["quat"] - ref["quat"]).max() < TOL_Q
+    assert np.abs(r["x"][1:, 3:6] - ref["x"][1:, 3:6]).max() < TOL_V
+    assert np.abs(r["x"][1:] - ref["x"][1:]).max() < 1e-9
+    assert np.abs(r["v_body"][1:] - ref["v_body"][1:]).max() < 1e-9
+    assert np.abs(r["p_vo"] - ref["p_vo"]).max() < 1e-12
+    assert np.array_equal(r["contact"], ref["contact"])
+
+
 @pytest.mark.parametrize("n", [96, 5000])  # fused single-launch path / split k_assemble + k_kf path
 def test_kf_alternative_vs_oracle(est_mod, oracle, n):
     """est_type 1 (DecentralEst.cpp:592-861): x_KF_, v_KF_b_, C_KF_, p_vo_accmulate_."""

@@ -15,6 +15,7 @@ import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "hostsim"))
+sys.path.insert(0, HERE)
 GOLDEN = os.path.join(HERE, "golden", "go1_refnodes_golden.npz")
 
 
@@ -88,6 +89,25 @@ def test_kernel_math_matches_reference_golden(name, tol9, tol_all):
     assert d[:, :9].max() < tol9 and d.max() < tol_all
     assert np.array_equal(r["contact"], ref["contact"])              # contact sets bit-exact
     assert np.abs(r["p_vo"] - ref["p_vo"]).max() < 1e-12
+
+
+def test_oracle_matches_reference_at_the_deployment_rates(oracle):
+    """EKF timer at 500 Hz, estimator timer at 200 Hz (the reference's shipped rates; tests/mixed_rate.py): the estimator then
+    reads the latest of the 500 Hz samples, the orientation of the latest EKF tick and the VO message latched since its
+    previous tick, and assumes dt = 5 ms between samples that are 4 or 6 ms apart -- all of it reproduced."""
+    import mixed_rate as mr
+    st, ref, pkw, rate = _case("mixed")
+    assert rate == 500
+    prm, ep = oracle.go1_params(**pkw), oracle.ekf_params(rate=rate)
+    n = st["gyro"].shape[2]
+    for i in range(n):
+        o = mr.run_oracle(oracle, st, i, prm, ep)
+        assert np.abs(o["quat"] - ref["quat"][..., i]).max() < 1e-12
+        assert np.abs(o["x"][1:] - ref["x"][1:, :, i]).max() < 1e-9
+        assert np.abs(o["v_body"][1:] - ref["v_body"][1:, :, i]).max() < 1e-9
+        assert np.abs(o["p_vo"] - ref["p_vo"][..., i]).max() < 1e-13
+        assert np.array_equal(o["contact"], ref["contact"][..., i])
+    assert np.abs(ref["p_vo"]).max() > 1e-3  # VO messages were consumed
 
 
 # ------------------------------------------------------------------------------------------------ live (container only)
