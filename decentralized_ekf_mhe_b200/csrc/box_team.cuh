@@ -22,9 +22,10 @@
 namespace dekf {
 
 enum { BOX_PRIOR = 90 };  // per instance: symmetrised M = Pa^-1 (81, row-major) + m = M xa (9)
-// per instance and stage: L (45, packed lower, inverse diagonal) + F (81) + y / x (9) + the v rows of the UNMODIFIED
-// blocks for the multipliers: 3 x [D0 row (9), E row (9), E' row (9), r0 (1)]
-enum { BOX_TFAC_GRAD = 135, BOX_TFAC = 135 + 3 * 28 + 1 };
+// per instance and stage: L (45, packed lower, inverse diagonal) + F (81) + y (9) + x (9) + the v rows of the UNMODIFIED
+// blocks for the multipliers: 3 x [D0 row (9), E row (9), E' row (9), r0 (1)] + the carry INTO the stage for a restarted
+// forward pass: 9 x [Dc row (9), rc, rc0]
+enum { BOX_TFAC_Y = 126, BOX_TFAC_X = 135, BOX_TFAC_GRAD = 144, BOX_TFAC_CARRY = 144 + 3 * 28, BOX_TFAC = 144 + 3 * 28 + 9 * 11 + 1 };
 
 struct BoxTeamBuffers {
   double *prior;  // [ns][90]
@@ -98,6 +99,7 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
   int status = 0;
   int iters = 0, nact = 0;
   bool done = false;
+  int first_changed = 0;  // first stage whose active set the previous iteration changed
   xT_r = 0.0;
   const double qa_m = bt_sel3(m, bc.qa[0], bc.qa[1], bc.qa[2]), qb_m = bt_sel3(m, bc.qb[0], bc.qb[1], bc.qb[2]);
   const double qc_m = bt_sel3(m, bc.qc[0], bc.qc[1], bc.qc[2]), qab_m = bt_sel3(m, bc.qab[0], bc.qab[1], bc.qab[2]);
@@ -106,15 +108,32 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
     if (__all_sync(0xffffffffu, done || !valid)) break;
     if (!done) iters = it + 1;
     // ------------------------------------------------------------------ forward: assemble, active set, factor
+    // Stage j's factor depends on the active sets of stages <= j + 1 only: an iteration after the first restarts the
+    // forward pass at the stage before the first changed set (warp-uniform: the earliest restart of the warp's teams; a
+    // team that restarts earlier than it needs to recomputes what it already has).
+    const int j_start = __reduce_min_sync(0xffffffffu, (done || !valid) ? K : (first_changed > 0 ? first_changed - 1 : 0));
     double Dc[9], rc, rc0, Fp[9], yp = 0.0;  // rc0: carry of the right-hand side without the active-set terms
+    if (j_start == 0) {
 #pragma unroll
-    for (int c = 0; c < 9; ++c) {
-      Dc[c] = pri[r * 9 + c];
-      Fp[c] = 0.0;
+      for (int c = 0; c < 9; ++c) {
+        Dc[c] = pri[r * 9 + c];
+        Fp[c] = 0.0;
+      }
+      rc = rc0 = pri[81 + r];
+    } else {
+      const double *cj = fac + (size_t)j_start * BOX_TFAC + BOX_TFAC_CARRY + r * 11;
+      const double *fp = fac + (size_t)(j_start - 1) * BOX_TFAC;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        Dc[c] = cj[c];
+        Fp[c] = fp[45 + r * 9 + c];
+      }
+      rc = cj[9];
+      rc0 = cj[10];
+      yp = fp[BOX_TFAC_Y + r];
     }
-    rc = rc0 = pri[81 + r];
-    int slot = slot0;
-    for (int j = 0; j < K; ++j) {
+    int slot = (slot0 + j_start) % dm.NW;
+    for (int j = j_start; j < K; ++j) {
       const int slot_n = slot + 1 == dm.NW ? 0 : slot + 1;
       const T *rec = b.win + (size_t)slot * REC_SIZE * ns + i;
       double R[9], as[3], dlt[3];
@@ -128,6 +147,13 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
       const bool vo = rec[(size_t)REC_FLAG * ns] != T(0);
       const int mask = bb.act[(size_t)slot * ns + i];
       const bool last = j + 1 >= K;
+      if (valid && j > 0) {  // carry into this stage, for a restart of the forward pass here
+        double *cj = fac + (size_t)j * BOX_TFAC + BOX_TFAC_CARRY + r * 11;
+#pragma unroll
+        for (int c = 0; c < 9; ++c) cj[c] = Dc[c];
+        cj[9] = rc;
+        cj[10] = rc0;
+      }
       if (!last) {
         const T *nrec = b.win + (size_t)slot_n * REC_SIZE * ns + i;
         bt_prefetch(nrec + (size_t)r * ns);
@@ -296,7 +322,7 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
 #pragma unroll
           for (int c = 0; c < 9; ++c) fj[45 + r * 9 + c] = F[c];
         }
-        fj[126 + r] = ymine;
+        fj[BOX_TFAC_Y + r] = ymine;
       }
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
@@ -314,7 +340,7 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
     for (int j = K - 1; j >= 0; --j) {
       double *fj = fac + (size_t)j * BOX_TFAC;
       if (j > 0) bt_prefetch(fj - BOX_TFAC + 16 * r);
-      double tt = fj[126 + r];
+      double tt = fj[BOX_TFAC_Y + r];
       if (j + 1 < K) {
 #pragma unroll
         for (int kk = 0; kk < 9; ++kk) tt -= fj[45 + kk * 9 + r] * bt_shfl(xn, base + kk);
@@ -329,8 +355,7 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
         if (r == rr) xmine = xrr;
         if (r < rr) tt -= Lcol[rr] * xrr;
       }
-      __syncwarp();  // every lane has read y_j before it is overwritten by x_j
-      if (valid) fj[126 + r] = xmine;
+      if (valid) fj[BOX_TFAC_X + r] = xmine;
       xn = xmine;
       if (j == K - 1) xT_r = xmine;
     }
@@ -345,18 +370,17 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
 #pragma unroll
     for (int f = 0; f < 9; ++f) {
       xm[f] = 0.0;
-      xj[f] = fac[126 + f];
+      xj[f] = fac[BOX_TFAC_X + f];
     }
     slot = slot0;
     for (int j = 0; j < K; ++j) {
       const double *gj = fac + (size_t)j * BOX_TFAC + BOX_TFAC_GRAD + q * 28;
       const bool more = j + 1 < K;
-      if (more) bt_prefetch(fac + (size_t)(j + 1) * BOX_TFAC + 126 + 16 * r < fac + (size_t)(j + 2) * BOX_TFAC ? fac + (size_t)(j + 1) * BOX_TFAC + 126 + 16 * r
-                                                                                                  : fac + (size_t)(j + 1) * BOX_TFAC + 126);
+      if (more && r < 6) bt_prefetch(fac + (size_t)(j + 1) * BOX_TFAC + BOX_TFAC_X + 16 * r);  // x and gradient rows of the next stage
       double g = -gj[27];
 #pragma unroll
       for (int f = 0; f < 9; ++f) {
-        x1[f] = more ? fac[(size_t)(j + 1) * BOX_TFAC + 126 + f] : 0.0;
+        x1[f] = more ? fac[(size_t)(j + 1) * BOX_TFAC + BOX_TFAC_X + f] : 0.0;
         g += gj[f] * xj[f] + gj[9 + f] * x1[f];
       }
       if (j > 0) {
@@ -379,6 +403,7 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
       na += __popc((unsigned)nm);
       __syncwarp();  // every lane of the team has read the mask before lane 0 replaces it
       if (nm != mask) {
+        if (!changed) first_changed = j;
         changed = true;
         if (valid && r == 0) *mp = (uint8_t)nm;
       }

@@ -242,7 +242,6 @@ inline void CommaInit::put_block(const double *cm, int br, int bc) {
 }
 inline CommaInit &CommaInit::operator,(const Mat &b) {
   // a vector of the other orientation filling a vector target is accepted (Eigen transposes vectors on assignment)
-  if (b.rows() != 1 && c_ == 1 + 0 * r_ && false) {}
   if ((r_ == 1 && b.cols() == 1 && b.rows() > 1)) { Mat t = b.transpose(); put_block(t.data(), t.rows(), t.cols()); }
   else if ((c_ == 1 && b.rows() == 1 && b.cols() > 1)) { Mat t = b.transpose(); put_block(t.data(), t.rows(), t.cols()); }
   else put_block(b.data(), b.rows(), b.cols());
