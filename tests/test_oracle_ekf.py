@@ -1,6 +1,6 @@
-"""Oracle pinning, EKF part: known-answer values of a literal restatement (the
-reference ships no tests, so these pin the oracle against hand-derived numbers, not against
-reference fixtures -> "parity unpinned")."""
+"""Oracle pinning, EKF part: known-answer values of a literal restatement (the reference ships
+no tests, so these are hand-derived numbers).  The pin against the reference's OWN compiled sources -- including the EKF
+with its VO rewind/replay -- is tests/test_refnodes_pin.py."""
 import numpy as np
 
 
