@@ -360,7 +360,7 @@ def main():
     assert hi - lo == n
     N = args.N
     FILL = fill_steps(N)
-    S = FILL + W + K + Ke + 8 + 20 + 24
+    S = FILL + W + K + 2 * (Ke + 8) + 20 + 24
     dev = torch.device("cuda", local_rank)
 
     # ---- synthetic stream, resident in HBM before any timed region (each rank: its own instance range)
@@ -485,6 +485,38 @@ def main():
         est.step_host(T, d, one_out)
         T += 1
     ms_step_host = (time.perf_counter() - t0) * 1e3 / max(Ks, 1)
+    # the same host path with the five sensor streams delivered as float32 (dekf_run_host_f32: what a robot's SDK produces;
+    # widened on the device, arithmetic unchanged) -- reported BESIDE e2e, not instead of it
+    e2e_f32 = None
+    try:
+        Kf = max(1, min(Ke, S - T - 8))
+        def host_slice_f32(a, b):
+            h = host_slice(a, b)
+            for k in estimator.BatchedEstimator.F32_KEYS:
+                h[k] = h[k].float().pin_memory()
+            return h
+        est.run_host_f32(T, 8, host_slice_f32(T, T + 8), vo_steps[T:T + 8], out=host_out(8), out_per_step=True)
+        T += 8
+        hf, hfo = host_slice_f32(T, T + Kf), host_out(Kf)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        tw = time.perf_counter()
+        f0.record()
+        est.run_host_f32(T, Kf, hf, vo_steps[T:T + Kf], out=hfo, out_per_step=True)
+        chk_f = float(hfo["x"][:, 3, 0].sum())
+        f1.record()
+        barrier()
+        tw = time.perf_counter() - tw
+        ms_f = max_over_ranks(max(f0.elapsed_time(f1), tw * 1e3))
+        h2d_f = sum((sum(rows[k] for k in estimator.BatchedEstimator.F32_KEYS) * 4 + 8) * n
+                    + ((sum(rows[k] for k in keys[6:]) * 8 + 1) * n if vo_steps[T + j] else 0) for j in range(Kf))
+        T += Kf
+        e2e_f32 = {"value": n_total * Kf / (ms_f * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_f // Kf, "d2h_bytes_per_step": d2h,
+                   "steps": Kf, "ms_per_step": ms_f / Kf, "host_checksum": chk_f,
+                   "api": "dekf_run_host_f32 (gyro, accel, joint_pos, joint_vel, foot_force as float32 host streams; time stamps, "
+                          "VO messages and all arithmetic double)"}
+    except Exception as e:
+        e2e_f32 = {"unavailable": repr(e)[:200]}
     clocks = sampler.stop()
     # pinned-host copy bandwidth of this box (the roofline of the e2e path): one large H2D and D2H, both directions at once
     pcie = None
@@ -557,6 +589,7 @@ def main():
                     "api": "dekf_run_host (pinned host streams; H2D | kernels | D2H pipelined over chunks of ticks, every "
                            "tick's inputs copied in and results copied out)",
                     "single_tick_host_call_ms": ms_step_host, "host_checksum": chk},
+            "e2e_f32_inputs": e2e_f32,
             "latency_batch1": lat,
             "ekf_only": {"value": n_total / (roof["all_kernels"]["ekf"]["ms"] * 1e-3) if "ekf" in roof.get("all_kernels", {}) else None,
                          "unit": "EKF ticks/s", "note": "orien_ekf::timerCallback alone (k_ekf, event pairs, incl. the VO rewind/"

@@ -363,6 +363,8 @@ struct StageSet {
 struct ChunkSet {
   int cap = 0;
   double *in = nullptr;      // gyro accel imu_time joint_pos joint_vel foot_force | vo_quat vo_time_pre vo_time_now vo_rel_p, each [cap][rows][n]
+  float *in_f32 = nullptr;   // dekf_run_host_f32: gyro accel joint_pos joint_vel foot_force as float, each [cap][rows][n]
+  int cap_f32 = 0;
   uint8_t *flag = nullptr;   // [cap][n]
   double *out = nullptr;     // quat [cap][4][n] | x [cap][9][n] | v_body [cap][3][n]
   uint8_t *contact = nullptr;
@@ -1082,6 +1084,7 @@ int alloc_stage_set(dekf_handle *h, StageSet &ss) {
 }
 void free_chunk_set(ChunkSet &cs) {
   cudaFree(cs.in);
+  cudaFree(cs.in_f32);
   cudaFree(cs.flag);
   cudaFree(cs.out);
   cudaFree(cs.contact);
@@ -1346,10 +1349,12 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 1);
     h->stream = user;
     if (rc) break;
-    ce = cudaEventRecord(h->ev_mhe[slot], sa);
+    // the tick's quaternion leaves the ring slot BEFORE ev_mhe releases the slot to the EKF of tick s+QA (copying it on the
+    // solve stream raced with that EKF tick whenever the solves lagged behind the assembly)
+    ce = os.quat ? cudaMemcpyAsync(os.quat, qslot, 4 * n * sizeof(double), cudaMemcpyDeviceToDevice, sa) : cudaSuccess;
+    if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_mhe[slot], sa);
     // ---- window solve of tick s
     if (ce == cudaSuccess && asm_ahead) ce = cudaStreamWaitEvent(h->s_mhe, h->ev_mhe[slot], 0);
-    if (ce == cudaSuccess && os.quat) ce = cudaMemcpyAsync(os.quat, qslot, 4 * n * sizeof(double), cudaMemcpyDeviceToDevice, h->s_mhe);
     if (ce != cudaSuccess) {
       rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
       break;
@@ -1371,13 +1376,14 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
   return rc;
 }
 
-int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const uint8_t *vo_steps, const dekf_outputs *out,
-                  int32_t out_per_step) {
-  if (!h || !in || S < 0) return fail(h, DEKF_EINVAL, "dekf_run_host: bad argument");
-  if (!in->gyro || !in->accel || !in->imu_time || !in->joint_pos || !in->joint_vel || !in->foot_force)
-    return fail(h, DEKF_EINVAL, "dekf_run_host: null input");
-  if (in->vo_flag && (!in->vo_quat || !in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
-    return fail(h, DEKF_EINVAL, "dekf_run_host: vo_flag without the VO arrays");
+// float32 sensor streams -> the double staging arrays the kernels read (dekf_run_host_f32)
+__global__ void __launch_bounds__(256) k_widen(const float *__restrict__ src, double *__restrict__ dst, size_t count) {
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (size_t)gridDim.x * blockDim.x) dst[k] = (double)src[k];
+}
+
+// in: all-double host streams; inf (non-null: dekf_run_host_f32): the five sensor arrays as float, the rest from inf too
+static int run_host_impl(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const dekf_inputs_f32 *inf, const uint8_t *vo_steps,
+                         const dekf_outputs *out, int32_t out_per_step) {
   CK(cudaSetDevice(h->cfg.device));
   const size_t n = (size_t)h->dm.n;
   // Ticks move in chunks of B: every field of the host streams is [S][rows][n], so B consecutive ticks of one field are
@@ -1397,6 +1403,16 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
   if (rc) return rc;
   rc = alloc_chunk_set(h, h->chunk[1], B);
   if (rc) return rc;
+  const size_t rows_f32 = 6 + 2 * (size_t)h->nq + (size_t)h->nl;  // gyro accel joint_pos joint_vel foot_force
+  if (inf)
+    for (int k = 0; k < 2; ++k)
+      if (h->chunk[k].cap_f32 < h->chunk[k].cap) {
+        cudaFree(h->chunk[k].in_f32);
+        h->chunk[k].in_f32 = nullptr;
+        CK(cudaMalloc((void **)&h->chunk[k].in_f32, (size_t)h->chunk[k].cap * rows_f32 * n * sizeof(float)));
+        h->chunk[k].cap_f32 = h->chunk[k].cap;
+        h->extra_bytes += (size_t)h->chunk[k].cap * rows_f32 * n * sizeof(float);
+      }
   if (!h->s_h2d) {
     CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
@@ -1411,6 +1427,8 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
   CK(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[0], 0));
   const size_t rows_in[6] = {3, 3, 1, (size_t)h->nq, (size_t)h->nq, (size_t)h->nl};
   const double *src_in[6] = {in->gyro, in->accel, in->imu_time, in->joint_pos, in->joint_vel, in->foot_force};
+  const float *src_f32[6] = {inf ? inf->gyro : nullptr, inf ? inf->accel : nullptr, nullptr, inf ? inf->joint_pos : nullptr,
+                             inf ? inf->joint_vel : nullptr, inf ? inf->foot_force : nullptr};
   const size_t rows_vo[4] = {4, 1, 1, 3};
   const double *src_vo[4] = {in->vo_quat, in->vo_time_pre, in->vo_time_now, in->vo_rel_p};
   int c = 0;
@@ -1425,9 +1443,17 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
     {
       double *d = cs.in;
       const double **dp[6] = {&din.gyro, &din.accel, &din.imu_time, &din.joint_pos, &din.joint_vel, &din.foot_force};
+      float *df = cs.in_f32;
       for (int a = 0; a < 6; ++a) {
-        CK(cudaMemcpyAsync(d, src_in[a] + (size_t)s0 * rows_in[a] * n, (size_t)Bc * rows_in[a] * n * sizeof(double),
-                           cudaMemcpyHostToDevice, h->s_h2d));
+        const size_t cnt = (size_t)Bc * rows_in[a] * n;
+        if (src_f32[a]) {  // half the PCIe bytes; widened on the copy stream so that ev_h2d covers it
+          CK(cudaMemcpyAsync(df, src_f32[a] + (size_t)s0 * rows_in[a] * n, cnt * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
+          k_widen<<<148 * 4, 256, 0, h->s_h2d>>>(df, d, cnt);
+          h->launches++;
+          df += cap * rows_in[a] * n;
+        } else {
+          CK(cudaMemcpyAsync(d, src_in[a] + (size_t)s0 * rows_in[a] * n, cnt * sizeof(double), cudaMemcpyHostToDevice, h->s_h2d));
+        }
         *dp[a] = d;
         d += cap * rows_in[a] * n;
       }
@@ -1483,6 +1509,34 @@ int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, 
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaStreamSynchronize(h->s_d2h));
   return DEKF_OK;
+}
+
+int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const uint8_t *vo_steps, const dekf_outputs *out,
+                  int32_t out_per_step) {
+  if (!h || !in || S < 0) return fail(h, DEKF_EINVAL, "dekf_run_host: bad argument");
+  if (!in->gyro || !in->accel || !in->imu_time || !in->joint_pos || !in->joint_vel || !in->foot_force)
+    return fail(h, DEKF_EINVAL, "dekf_run_host: null input");
+  if (in->vo_flag && (!in->vo_quat || !in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
+    return fail(h, DEKF_EINVAL, "dekf_run_host: vo_flag without the VO arrays");
+  return run_host_impl(h, T0, S, in, nullptr, vo_steps, out, out_per_step);
+}
+
+int dekf_run_host_f32(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs_f32 *inf, const uint8_t *vo_steps, const dekf_outputs *out,
+                      int32_t out_per_step) {
+  if (!h || !inf || S < 0) return fail(h, DEKF_EINVAL, "dekf_run_host_f32: bad argument");
+  if (!inf->gyro || !inf->accel || !inf->imu_time || !inf->joint_pos || !inf->joint_vel || !inf->foot_force)
+    return fail(h, DEKF_EINVAL, "dekf_run_host_f32: null input");
+  if (inf->vo_flag && (!inf->vo_quat || !inf->vo_time_pre || !inf->vo_time_now || !inf->vo_rel_p))
+    return fail(h, DEKF_EINVAL, "dekf_run_host_f32: vo_flag without the VO arrays");
+  dekf_inputs in;  // the double fields; the five sensor arrays are taken from inf
+  std::memset(&in, 0, sizeof(in));
+  in.imu_time = inf->imu_time;
+  in.vo_flag = inf->vo_flag;
+  in.vo_quat = inf->vo_quat;
+  in.vo_time_pre = inf->vo_time_pre;
+  in.vo_time_now = inf->vo_time_now;
+  in.vo_rel_p = inf->vo_rel_p;
+  return run_host_impl(h, T0, S, &in, inf, vo_steps, out, out_per_step);
 }
 
 static int get_arrival(dekf_handle *h, double *P, double *x, int info) {

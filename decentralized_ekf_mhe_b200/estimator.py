@@ -425,6 +425,33 @@ class BatchedEstimator:
         """Same with pinned HOST tensors: pipelined H2D | kernels | D2H, returns when the results are in host memory."""
         self._run(self._hd.L.dekf_run_host, "dekf_run_host", T0, S, stream, vo_steps, out, out_per_step)
 
+    F32_KEYS = ("gyro", "accel", "joint_pos", "joint_vel", "foot_force")
+
+    def run_host_f32(self, T0, S, stream, vo_steps=None, out=None, out_per_step=False):
+        """run_host for sensor streams delivered in single precision (dekf_run_host_f32): ``stream[k]`` for k in F32_KEYS are
+        pinned float32 host tensors (half the PCIe bytes, widened to double on the device), everything else as in run_host."""
+        import torch
+        h = self._hd
+        s0 = int(stream.get("_offset", 0))
+        ptrs = []
+        for k in self._IN_KEYS:
+            t = stream.get(k)
+            if t is None:
+                ptrs.append(None)
+                continue
+            want = torch.float32 if k in self.F32_KEYS else (torch.uint8 if k == "vo_flag" else torch.float64)
+            if t.dtype != want or t.shape[0] < s0 + S or not t.is_contiguous():
+                raise DekfError(f"stream[{k!r}] must be contiguous {want} with at least {s0 + S} ticks")
+            ptrs.append(_ptr(t[s0]))
+        inp = _lib.DekfInputsF32(*ptrs)
+        o = out or {}
+        outs = _lib.DekfOutputs(*[_ptr(o.get(k)) for k in self._OUT_KEYS]) if out is not None else _lib.DekfOutputs(None, None, None, None, None)
+        mask = None
+        if vo_steps is not None:
+            mask = (C.c_uint8 * S)(*[1 if v else 0 for v in vo_steps[:S]])
+        h.check(h.L.dekf_run_host_f32(h.h, int(T0), int(S), C.byref(inp), mask, C.byref(outs), int(bool(out_per_step))),
+                "dekf_run_host_f32")
+
     def reset(self):
         self._hd.check(self._hd.L.dekf_reset(self._hd.h), "dekf_reset")
 

@@ -184,6 +184,26 @@ int dekf_ekf_step_host(dekf_handle *h, const dekf_inputs *in, const dekf_outputs
  * over two device staging sets; returns after the last result has landed in host memory. */
 int dekf_run_host(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const uint8_t *vo_steps,
                   const dekf_outputs *out, int32_t out_per_step);
+/* dekf_run_host for sensor streams delivered in single precision -- what the robot's SDK produces (Unitree LowState: float
+ * IMU, joint and foot-force fields; the reference's callbacks widen them into the double members of robot_store,
+ * go1Sub.cpp:30-75).  The five sensor arrays travel over PCIe as float32 (136 instead of 272 bytes per instance-tick) and are
+ * widened to double on the device; time stamps and VO messages stay double; ALL arithmetic is unchanged, so for values
+ * representable in float32 the results equal dekf_run_host bit for bit. */
+typedef struct dekf_inputs_f32 {
+  const float *gyro;        /* [S][3][n] */
+  const float *accel;       /* [S][3][n] */
+  const double *imu_time;   /* [S][n] */
+  const float *joint_pos;   /* [S][num_legs*nj][n] */
+  const float *joint_vel;   /* [S][num_legs*nj][n] */
+  const float *foot_force;  /* [S][num_legs][n] */
+  const uint8_t *vo_flag;    /* [S][n] or NULL */
+  const double *vo_quat;     /* [S][4][n] */
+  const double *vo_time_pre; /* [S][n] */
+  const double *vo_time_now; /* [S][n] */
+  const double *vo_rel_p;    /* [S][3][n] */
+} dekf_inputs_f32;
+int dekf_run_host_f32(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs_f32 *in, const uint8_t *vo_steps,
+                      const dekf_outputs *out, int32_t out_per_step);
 int dekf_synchronize(dekf_handle *h);
 
 /* Getters (device pointers, stream-ordered). */

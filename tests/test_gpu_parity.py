@@ -212,6 +212,42 @@ def test_go1_matches_reference_golden(est_mod, name, tol9, tol_all, window_solve
     est.close()
 
 
+def test_run_host_f32_equals_run_host_bit_for_bit(est_mod, oracle):
+    """dekf_run_host_f32 (sensor streams as float32 over PCIe, widened on the device) against dekf_run_host fed the same
+    values as doubles: identical results, bit for bit (5,000 instances: split kernels, chunked pipeline, ragged VO)."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S = 5000, 70
+    st = synth.make_stream(n, S, vo_jitter=True)
+    f32 = {k: st[k].float() for k in E.BatchedEstimator.F32_KEYS}
+    host64 = {k: (f32[k].double() if k in f32 else st[k]).contiguous().pin_memory() for k in E.BatchedEstimator._IN_KEYS}
+    host32 = {k: (f32[k] if k in f32 else st[k]).contiguous().pin_memory() for k in E.BatchedEstimator._IN_KEYS}
+    vo = [bool(st["vo_flag"][s].any()) for s in range(S)]
+    res = []
+    for fn, host in (("run_host", host64), ("run_host_f32", host32)):
+        est = E.BatchedEstimator(E.robot_params("go1", ekf_rate=200), n)
+        out = {"quat": torch.empty(S, 4, n, dtype=torch.float64).pin_memory(), "x": torch.empty(S, 9, n, dtype=torch.float64).pin_memory(),
+               "v_body": torch.empty(S, 3, n, dtype=torch.float64).pin_memory(), "contact": torch.empty(S, 4, n, dtype=torch.uint8).pin_memory(),
+               "status": torch.empty(S, n, dtype=torch.int32).pin_memory()}
+        getattr(est, fn)(0, S, host, vo, out=out, out_per_step=True)
+        res.append({k: v.clone() for k, v in out.items()})
+        est.close()
+    for k in ("quat", "contact", "status"):
+        assert torch.equal(res[0][k], res[1][k]), k
+    for k in ("x", "v_body"):  # defined from tick 1 on (tick 0 is initialize())
+        assert torch.equal(res[0][k][1:], res[1][k][1:]), k
+    # and the per-tick output STREAMS of the pipelined host path are the right ticks' results (EKF ticks run ahead of the MHE
+    # through a ring: the quaternion of tick s must leave its slot before tick s + 4 overwrites it)
+    m = 32
+    sub = {k: np.ascontiguousarray(v[..., :m].numpy()) for k, v in host64.items()}
+    ro, _, _ = oracle.run_batch(sub, oracle.go1_params(), oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1,
+                                want=("quat", "x", "contact"))
+    assert np.abs(res[1]["quat"][..., :m].numpy() - ro["quat"]).max() < TOL_Q
+    assert np.abs(res[1]["x"][1:, 3:6, :m].numpy() - ro["x"][1:, 3:6]).max() < TOL_V
+    assert np.array_equal(res[1]["contact"][..., :m].numpy(), ro["contact"])
+    assert torch.isfinite(res[1]["x"][1:]).all()
+
+
 def test_go1_matches_reference_at_the_deployment_rates(est_mod):
     """The reference's shipped rates -- orientation EKF at 500 Hz, estimator at 200 Hz, two timers over the same topics --
     replayed through the reference's class API of the CUDA path (E.orien_ekf.timerCallback, E.DecentralizedEstimation.
