@@ -212,6 +212,47 @@ def test_go1_matches_reference_golden(est_mod, name, tol9, tol_all, window_solve
     est.close()
 
 
+@pytest.mark.parametrize("precision,window_solve,n,S,CH", [("fp64", 0, 20000, 150, 37), ("fp64", 1, 20000, 150, 37),
+                                                          ("fp32", 0, 20000, 150, 37), ("fp32", 1, 20000, 150, 37),
+                                                          ("fp64", 0, 65536, 72, 72), ("fp64", 1, 65536, 72, 72)],
+                         ids=["fp64-full", "fp64-incr", "fp32-full", "fp32-incr", "fp64-full-65536", "fp64-incr-65536"])
+def test_dekf_run_pipeline_equals_tick_by_tick(est_mod, precision, window_solve, n, S, CH):
+    """dekf_run (three streams: EKF ticks ahead through a ring, assembly one tick ahead, solves) against the same handle type
+    stepped tick by tick on ONE stream: the same kernels on the same operands, so every per-tick output must be identical
+    bit for bit -- any difference is a stream-ordering hazard.  20,000 instances, 150 ticks in calls of 37 (ring wrap-around,
+    call boundaries), ragged VO arrival; and the benchmark size (65,536 instances, where the solves lag furthest)."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    st = {k: v.contiguous() for k, v in synth.make_stream(n, S, vo_jitter=True, device="cuda", device_rng=n > 30000).items()}
+    vo = [bool(st["vo_flag"][s].any()) for s in range(S)]
+    prm = E.robot_params("go1", ekf_rate=200, window_solve=window_solve)
+
+    def outs():
+        return {"quat": torch.zeros(S, 4, n, dtype=torch.float64, device="cuda"), "x": torch.zeros(S, 9, n, dtype=torch.float64, device="cuda"),
+                "v_body": torch.zeros(S, 3, n, dtype=torch.float64, device="cuda"), "contact": torch.zeros(S, 4, n, dtype=torch.uint8, device="cuda"),
+                "status": torch.zeros(S, n, dtype=torch.int32, device="cuda")}
+
+    a = outs()
+    est = E.BatchedEstimator(prm, n, precision=precision)
+    for s0 in range(0, S, CH):
+        c = min(CH, S - s0)
+        est.run(s0, c, {k: v[s0:s0 + c] for k, v in st.items()}, vo[s0:s0 + c],
+                out={k: v[s0:s0 + c] for k, v in a.items()}, out_per_step=True)
+    torch.cuda.synchronize()
+    est.close()
+    b = outs()
+    est = E.BatchedEstimator(prm, n, precision=precision)
+    for s in range(S):
+        est.step(s, E.robot_store.from_stream(st, s))
+        b["quat"][s], b["x"][s], b["v_body"][s] = est.quaternion_, est.x_MHE_, est.v_MHE_b_
+        b["contact"][s], b["status"][s] = est.contact_, est.status_
+    est.close()
+    for k in ("quat", "contact", "status"):
+        assert torch.equal(a[k], b[k]), k
+    for k in ("x", "v_body"):
+        assert torch.equal(a[k][1:], b[k][1:]), k
+
+
 def test_run_host_f32_equals_run_host_bit_for_bit(est_mod, oracle):
     """dekf_run_host_f32 (sensor streams as float32 over PCIe, widened on the device) against dekf_run_host fed the same
     values as doubles: identical results, bit for bit (5,000 instances: split kernels, chunked pipeline, ragged VO)."""
