@@ -253,6 +253,33 @@ def test_dekf_run_pipeline_equals_tick_by_tick(est_mod, precision, window_solve,
         assert torch.equal(a[k][1:], b[k][1:]), k
 
 
+def test_run_host_equals_device_run_at_benchmark_size(est_mod):
+    """dekf_run_host (H2D of chunk c+1 | kernels of chunk c | D2H of chunk c-1 over two staging sets) against dekf_run on
+    device-resident streams at the benchmark size: every per-tick result identical bit for bit (staging-set reuse hazards)."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S = 65536, 44
+    st = {k: v.contiguous() for k, v in synth.make_stream(n, S, vo_jitter=True, device="cuda", device_rng=True).items()}
+    vo = [bool(st["vo_flag"][s].any()) for s in range(S)]
+    prm = E.robot_params("go1", ekf_rate=200)
+    shapes = {"quat": (S, 4, n, torch.float64), "x": (S, 9, n, torch.float64), "v_body": (S, 3, n, torch.float64),
+              "contact": (S, 4, n, torch.uint8), "status": (S, n, torch.int32)}
+    dev_out = {k: torch.zeros(*v[:-1], dtype=v[-1], device="cuda") for k, v in shapes.items()}
+    est = E.BatchedEstimator(prm, n)
+    est.run(0, S, st, vo, out=dev_out, out_per_step=True)
+    torch.cuda.synchronize()
+    est.close()
+    host_in = {k: v.cpu().pin_memory() for k, v in st.items()}
+    host_out = {k: torch.zeros(*v[:-1], dtype=v[-1]).pin_memory() for k, v in shapes.items()}
+    est = E.BatchedEstimator(prm, n)
+    est.run_host(0, S, host_in, vo, out=host_out, out_per_step=True)
+    est.close()
+    for k in ("quat", "contact", "status"):
+        assert torch.equal(dev_out[k].cpu(), host_out[k]), k
+    for k in ("x", "v_body"):
+        assert torch.equal(dev_out[k][1:].cpu(), host_out[k][1:]), k
+
+
 def test_run_host_f32_equals_run_host_bit_for_bit(est_mod, oracle):
     """dekf_run_host_f32 (sensor streams as float32 over PCIe, widened on the device) against dekf_run_host fed the same
     values as doubles: identical results, bit for bit (5,000 instances: split kernels, chunked pipeline, ragged VO)."""
