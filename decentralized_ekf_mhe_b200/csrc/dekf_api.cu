@@ -1440,16 +1440,23 @@ static int run_host_impl(dekf_handle *h, int32_t T0, int32_t S, const dekf_input
     if (c >= 2) CK(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));  // kernels of chunk c-2 are done with staging set b
     dekf_inputs din;
     std::memset(&din, 0, sizeof(din));
+    const float *wsrc[6];
+    double *wdst[6];
+    size_t wcnt[6];
+    int nw = 0;
     {
       double *d = cs.in;
       const double **dp[6] = {&din.gyro, &din.accel, &din.imu_time, &din.joint_pos, &din.joint_vel, &din.foot_force};
       float *df = cs.in_f32;
+      nw = 0;
       for (int a = 0; a < 6; ++a) {
         const size_t cnt = (size_t)Bc * rows_in[a] * n;
-        if (src_f32[a]) {  // half the PCIe bytes; widened on the copy stream so that ev_h2d covers it
+        if (src_f32[a]) {  // half the PCIe bytes; widened on the COMPUTE stream below (a kernel on the copy stream would queue
+                           // behind the running solves and stall the copies that follow it)
           CK(cudaMemcpyAsync(df, src_f32[a] + (size_t)s0 * rows_in[a] * n, cnt * sizeof(float), cudaMemcpyHostToDevice, h->s_h2d));
-          k_widen<<<148 * 4, 256, 0, h->s_h2d>>>(df, d, cnt);
-          h->launches++;
+          wsrc[nw] = df;
+          wdst[nw] = d;
+          wcnt[nw++] = cnt;
           df += cap * rows_in[a] * n;
         } else {
           CK(cudaMemcpyAsync(d, src_in[a] + (size_t)s0 * rows_in[a] * n, cnt * sizeof(double), cudaMemcpyHostToDevice, h->s_h2d));
@@ -1479,6 +1486,10 @@ static int run_host_impl(dekf_handle *h, int32_t T0, int32_t S, const dekf_input
     CK(cudaEventRecord(h->ev_h2d[b], h->s_h2d));
     CK(cudaStreamWaitEvent(h->stream, h->ev_h2d[b], 0));
     if (c >= 2) CK(cudaStreamWaitEvent(h->stream, h->ev_d2h[b], 0));  // results of chunk c-2 have left staging set b
+    for (int w = 0; w < nw; ++w) {
+      k_widen<<<148 * 4, 256, 0, h->stream>>>(wsrc[w], wdst[w], wcnt[w]);
+      h->launches++;
+    }
     const bool last = s0 + Bc >= S;
     const bool want_out = out && (out_per_step || last);
     dekf_outputs dout;
