@@ -14,6 +14,7 @@
 #include "estimator_core.cuh"
 #include "host_setup.hpp"
 #include "box_team.cuh"
+#include "foot_team.cuh"
 
 namespace dekf {
 
@@ -165,6 +166,22 @@ __global__ void __launch_bounds__(kBlock) k_solve_foot(const FootConst fc, const
   if (Tk >= 1 || fc.est_type == 1) st |= foot_solve<T, L>(fc, dm, b, fb, in, out, Tk, i);
   tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
+}
+// the same with one WARP per instance (foot_team.cuh): rows of the 21 x 21 blocks in registers, shuffles between lanes
+template <typename T, int L>
+__global__ void __launch_bounds__(kTeamBlock) k_foot_team(const FootConst fc, const Dims dm, const Buffers<T> b, const FootBuffers fb,
+                                                          const Inputs in, const Outputs out, int Tk, int32_t *status_out) {
+  const int lane = threadIdx.x & 31;
+  int i = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const bool valid = i < dm.n;
+  if (!valid) i = dm.n - 1;  // idle warps shadow a real instance (loads only)
+  int st = 0;
+  if (Tk >= 1 || fc.est_type == 1) st = foot_team_solve<T, L>(fc, dm, b, fb, in, out, Tk, i, valid, lane);
+  if (valid && lane == 0) {
+    st |= tick_status(dm, b, Tk, i);
+    tick_status(dm, b, Tk, i) = st;
+    if (status_out != nullptr) status_out[i] = st;
+  }
 }
 // arrival cost of the foot-state model: (M_p, n_p) as the reference holds them (MheSrb.hpp:86-87)
 __global__ void k_get_arrival_foot(const Dims dm, const FootBuffers fb, int ds, double *Mout, double *nout) {
@@ -387,6 +404,7 @@ struct dekf_handle {
   BoxBuffers bb = {nullptr, nullptr, nullptr, nullptr};
   BoxTeamBuffers tb = {nullptr, nullptr};
   bool box_team = true;           // team form of the constrained solve (DEKF_BOX_SERIAL=1 selects one thread per instance)
+  bool foot_team = true;          // one warp per instance for the foot-state model (DEKF_FOOT_SERIAL=1: one thread per instance)
   FootConst fc;
   FootBuffers fb = {nullptr, nullptr, nullptr};  // leg_odom_type 1
   void *ckpt_mem = nullptr;       // incremental window solve: checkpoint ring
@@ -782,6 +800,7 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     h->extra_bytes += leg + am + ds * ns * sizeof(double);
   }
   h->bc = make_box_const(*cfg);
+  if (const char *e = std::getenv("DEKF_FOOT_SERIAL")) h->foot_team = std::atoi(e) == 0;
   if (cfg->v_box_enable) {
     const size_t ns = (size_t)h->dm.ns;
     const size_t fac = (size_t)h->dm.N * BOX_FAC * ns * sizeof(double), act = (size_t)h->dm.NW * ns;
@@ -982,7 +1001,14 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
     ProfScope ps(h, resweep_tick ? 3 : 2);
     if (h->cfg.leg_odom_type == 1) {
       const int g = grid_for(h->dm.n);
-      if (h->nl == 4)
+      const int gt = (h->dm.n + kTeamBlock / 32 - 1) / (kTeamBlock / 32);  // one warp per instance
+      if (h->foot_team && h->nl == 4)
+        k_foot_team<double, 4><<<gt, kTeamBlock, 0, h->stream>>>(h->fc, h->dm, h->b64, h->fb, di, dout, T_, st);
+      else if (h->foot_team && h->nl == 2)
+        k_foot_team<double, 2><<<gt, kTeamBlock, 0, h->stream>>>(h->fc, h->dm, h->b64, h->fb, di, dout, T_, st);
+      else if (h->foot_team)
+        k_foot_team<double, 1><<<gt, kTeamBlock, 0, h->stream>>>(h->fc, h->dm, h->b64, h->fb, di, dout, T_, st);
+      else if (h->nl == 4)
         k_solve_foot<double, 4><<<g, kBlock, 0, h->stream>>>(h->fc, h->dm, h->b64, h->fb, di, dout, T_, st);
       else if (h->nl == 2)
         k_solve_foot<double, 2><<<g, kBlock, 0, h->stream>>>(h->fc, h->dm, h->b64, h->fb, di, dout, T_, st);

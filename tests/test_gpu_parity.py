@@ -369,6 +369,35 @@ def test_kf_alternative_vs_oracle(est_mod, oracle, n):
     est.close()
 
 
+@pytest.mark.parametrize("est_type", [0, 1], ids=["mhe", "kf"])
+def test_foot_team_kernel_equals_serial_kernel(est_mod, monkeypatch, est_type):
+    """k_foot_team (one warp per instance, csrc/foot_team.cuh) against k_solve_foot (one thread per instance,
+    DEKF_FOOT_SERIAL=1) for the foot-position-state model: same information-form sweep on the same operands.  1,003
+    instances: a ragged last CTA, the T <= N start-up and the marginalisation steady state."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S = 1003, 48
+    d = {k: v.contiguous() for k, v in synth.make_stream(n, S, vo_jitter=True, device="cuda").items()}
+    res = {}
+    for serial in ("0", "1"):
+        monkeypatch.setenv("DEKF_FOOT_SERIAL", serial)
+        est = E.BatchedEstimator(E.robot_params("go1", ekf_rate=200, leg_odom_type=1, est_type=est_type), n)
+        xs, vs, sts = [], [], []
+        for s in range(S):
+            est.step(s, E.robot_store.from_stream(d, s))
+            xs.append(est.x_MHE_.clone()), vs.append(est.v_MHE_b_.clone()), sts.append(est.status_.clone())
+        M = est.mhe_qp_.M_p.clone() if est_type == 0 else None
+        res[serial] = [torch.stack(a).cpu().numpy() for a in (xs, vs, sts)] + [None if M is None else M.cpu().numpy()]
+        est.close()
+    (xa, va, sa, Ma), (xb, vb, sb, Mb) = res["0"], res["1"]
+    assert xa.shape[1] == 21
+    assert np.abs(xa[1:, :9] - xb[1:, :9]).max() < 1e-9 and np.abs(xa[1:] - xb[1:]).max() < 1e-8
+    assert np.abs(va[1:] - vb[1:]).max() < 1e-9
+    assert np.array_equal(sa, sb) and not (sa & 32).any()
+    if Ma is not None:  # the arrival cost both kernels hand to the next tick
+        assert np.abs(Ma - Mb).max() <= 1e-9 * np.abs(Mb).max()
+
+
 def test_pogox_team_kernel_equals_serial_kernel(est_mod, monkeypatch):
     """k_box_team (9 lanes per instance, csrc/box_team.cuh) against k_solve_box (one thread per instance, DEKF_BOX_SERIAL=1):
     same algorithm on the same operands -> same active sets, same number of factorisations, x_T equal to rounding.
