@@ -28,14 +28,17 @@ struct FtFactor {
     const double yk = bt_shfl(m * inv, K);
     if (r == K) m = yk;
     if (r > K) m -= Lrk * yk;
-    double Yk[DS], ykr = 0.0;
+    // Hxp is block diagonal (base block 9 x 9, one 3 x 3 block per foot) and L^-1 is lower triangular: row K of Y is zero
+    // to the right of the block that contains K
+    constexpr int CE = K < 9 ? 9 : 9 + 3 * ((K - 9) / 3 + 1);
+    double Yk[CE], ykr = 0.0;
 #pragma unroll
-    for (int c = 0; c < DS; ++c) {
+    for (int c = 0; c < CE; ++c) {
       Yk[c] = bt_shfl(X[c] * inv, K);  // row K of Y (final: rows < K have been eliminated from it)
       if (c == r) ykr = Yk[c];         // Y[K][r]
     }
 #pragma unroll
-    for (int c = 0; c < DS; ++c) {
+    for (int c = 0; c < CE; ++c) {
       if (r > K) X[c] -= Lrk * Yk[c];
       Mp[c] -= ykr * Yk[c];
     }
