@@ -38,6 +38,23 @@ __device__ __forceinline__ double bt_shfl(double v, int src) { return __shfl_syn
 // the three passes are chains of dependent stages with one global-memory round trip at the head of each stage: the data
 // of the NEXT stage is requested while the current one computes (no registers held)
 __device__ __forceinline__ void bt_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// asynchronous global -> shared copy of one element (4 or 8 bytes): the stage record of the NEXT stage is staged while the
+// current stage computes, without holding registers (LDGSTS)
+template <typename T>
+__device__ __forceinline__ void bt_cp_async(T *smem_dst, const T *gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc));
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void bt_cp_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void bt_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <typename T>
+__device__ __forceinline__ void bt_stage_record(T *dst /*[REC_SIZE]*/, const T *rec, size_t ns, int r) {
+  bt_cp_async(dst + r, rec + (size_t)r * ns);
+  bt_cp_async(dst + r + 9, rec + (size_t)(r + 9) * ns);
+  if (r + 18 < REC_SIZE) bt_cp_async(dst + r + 18, rec + (size_t)(r + 18) * ns);
+  bt_cp_commit();
+}
 __device__ __forceinline__ double bt_sel3(int m, double a0, double a1, double a2) { return m == 0 ? a0 : (m == 1 ? a1 : a2); }
 
 // v (row vector, 9) times A = [[I, dt I, -h R],[0, I, -dt R],[0, 0, I]]
@@ -88,7 +105,8 @@ struct BtFactor<9> {
 // Returns status bits (identical in every lane of the team); x_T[r] in xT_r.
 template <typename T>
 __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, const BoxBuffers &bb, const BoxTeamBuffers &tb,
-                              int k0, int Tk, int i, bool valid, int base, int r, double &xT_r) {
+                              int k0, int Tk, int i, bool valid, int base, int r, T *srec /*shared, [2][REC_SIZE] of this team*/,
+                              double &xT_r) {
   const size_t ns = (size_t)dm.ns;
   const int K = Tk - k0 + 1;
   const int slot0 = k0 % dm.NW;
@@ -133,20 +151,27 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
       yp = fp[BOX_TFAC_Y + r];
     }
     int slot = (slot0 + j_start) % dm.NW;
+    // the stage record of the NEXT stage travels global -> shared (cp.async) while the current stage computes
+    __syncwarp();
+    bt_stage_record(srec, b.win + (size_t)slot * REC_SIZE * ns + i, ns, r);
+    int mask_carry = bb.act[(size_t)slot * ns + i];
     for (int j = j_start; j < K; ++j) {
       const int slot_n = slot + 1 == dm.NW ? 0 : slot + 1;
-      const T *rec = b.win + (size_t)slot * REC_SIZE * ns + i;
+      const bool last = j + 1 >= K;
+      const T *rec = srec + ((j - j_start) & 1) * REC_SIZE;  // this stage's record, staged in shared memory
+      bt_cp_wait_all();
+      __syncwarp();
+      if (!last) bt_stage_record(srec + ((j - j_start + 1) & 1) * REC_SIZE, b.win + (size_t)slot_n * REC_SIZE * ns + i, ns, r);
       double R[9], as[3], dlt[3];
 #pragma unroll
-      for (int f = 0; f < 9; ++f) R[f] = (double)rec[(size_t)(REC_R + f) * ns];
+      for (int f = 0; f < 9; ++f) R[f] = (double)rec[REC_R + f];
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
-        as[f] = (double)rec[(size_t)(REC_AS + f) * ns];
-        dlt[f] = (double)rec[(size_t)(REC_DLT + f) * ns];
+        as[f] = (double)rec[REC_AS + f];
+        dlt[f] = (double)rec[REC_DLT + f];
       }
-      const bool vo = rec[(size_t)REC_FLAG * ns] != T(0);
-      const int mask = bb.act[(size_t)slot * ns + i];
-      const bool last = j + 1 >= K;
+      const bool vo = rec[REC_FLAG] != T(0);
+      const int mask = mask_carry;
       if (valid && j > 0) {  // carry into this stage, for a restart of the forward pass here
         double *cj = fac + (size_t)j * BOX_TFAC + BOX_TFAC_CARRY + r * 11;
 #pragma unroll
@@ -154,13 +179,8 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
         cj[9] = rc;
         cj[10] = rc0;
       }
-      if (!last) {
-        const T *nrec = b.win + (size_t)slot_n * REC_SIZE * ns + i;
-        bt_prefetch(nrec + (size_t)r * ns);
-        bt_prefetch(nrec + (size_t)(r + 9) * ns);
-        if (r + 18 < REC_SIZE) bt_prefetch(nrec + (size_t)(r + 18) * ns);
-      }
       const int mask_n = last ? 0 : bb.act[(size_t)slot_n * ns + i];
+      mask_carry = mask_n;
       double D[9], rhs = rc, rhs0 = rc0, G[9], Dn[9], rn = 0.0, rn0 = 0.0, Erow[9];
 #pragma unroll
       for (int c = 0; c < 9; ++c) {
@@ -173,13 +193,12 @@ __device__ int box_team_solve(const BoxConst &bc, const Dims &dm, const Buffers<
       if (t == 1) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          const double l0 = (double)rec[(size_t)(REC_LAM + S3<double>::idx(0, c)) * ns];
-          const double l1 = (double)rec[(size_t)(REC_LAM + S3<double>::idx(1, c)) * ns];
-          const double l2 = (double)rec[(size_t)(REC_LAM + S3<double>::idx(2, c)) * ns];
+          const double l0 = (double)rec[REC_LAM + S3<double>::idx(0, c)];
+          const double l1 = (double)rec[REC_LAM + S3<double>::idx(1, c)];
+          const double l2 = (double)rec[REC_LAM + S3<double>::idx(2, c)];
           D[3 + c] += bt_sel3(m, l0, l1, l2);
         }
-        const double eta_m = bt_sel3(m, (double)rec[(size_t)(REC_ETA + 0) * ns], (double)rec[(size_t)(REC_ETA + 1) * ns],
-                                     (double)rec[(size_t)(REC_ETA + 2) * ns]);
+        const double eta_m = bt_sel3(m, (double)rec[REC_ETA + 0], (double)rec[REC_ETA + 1], (double)rec[REC_ETA + 2]);
         rhs += eta_m;
         rhs0 += eta_m;
       }

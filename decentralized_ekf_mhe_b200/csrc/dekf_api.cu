@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(kTeamBlock, DEKF_MINB_BOXTEAM) k_box_team(cons
   double xT = 0.0;
   if (Tk >= 1) {
     const int k0 = Tk < dm.N ? 0 : Tk - dm.N + 1;
-    st = box_team_solve<T>(bc, dm, b, bb, tb, k0, Tk, i, valid, base, r, xT);
+    __shared__ T s_rec[kTeamBlock / 32 * 4][2 * REC_SIZE];  // per team (3 + the idle lanes' slot per warp): two stage records
+    st = box_team_solve<T>(bc, dm, b, bb, tb, k0, Tk, i, valid, base, r, s_rec[(threadIdx.x >> 5) * 4 + team], xT);
     // getsolution(T) and the body-velocity read-out (DecentralEst.cpp:179-185)
     const unsigned bad = __ballot_sync(0xffffffffu, !(xT == xT) || !(xT - xT == 0.0));
     if ((bad >> base) & 0x1ffu) st |= ST_NONFINITE;
