@@ -110,9 +110,9 @@ __global__ void __launch_bounds__(kBlock) k_box_prior(const MheConst<T> c, const
   if (st) tick_status(dm, b, Tk, i) |= st;
 }
 
-constexpr int kTeamsPerWarp = 3, kTeamBlock = 128;
+constexpr int kTeamsPerWarp = 3, kTeamBlock = 64;  // 64-thread CTAs: finer tail of the 2.3-wave grid (128: 4.3 ms, 64: 4.0 ms, 32: 3.95 / foot 4.5 ms)
 #ifndef DEKF_MINB_BOXTEAM
-#define DEKF_MINB_BOXTEAM 4
+#define DEKF_MINB_BOXTEAM 8
 #endif
 template <typename T>
 __global__ void __launch_bounds__(kTeamBlock, DEKF_MINB_BOXTEAM) k_box_team(const BoxConst bc, const Dims dm, const Buffers<T> b, const BoxBuffers bb,
