@@ -419,6 +419,10 @@ struct dekf_handle {
   // dekf_run: the EKF ticks run ahead of the MHE on their own stream through a small ring of quaternions / status words
   static constexpr int kAhead = 4;
   cudaStream_t s_ekf = nullptr, s_asm = nullptr, s_mhe = nullptr;  // lowest / medium / highest stream priority
+  cudaStream_t s_mhe_b = nullptr;  // second solve stream: the tiles beyond the last full wave (dekf_run, full re-sweep)
+  cudaEvent_t ev_solb[kAhead] = {nullptr, nullptr, nullptr, nullptr};
+  int solve_tile0 = 0, solve_tiles = -1;  // tile range of the next k_solve_tma launch (-1: the whole batch)
+  int solve_slots = 0;                    // CTAs of k_solve_tma resident on the whole device (occupancy x SM count)
   cudaEvent_t ev_join = nullptr;
   double *quat_ring = nullptr;      // [kAhead][4][n]
   int32_t *status_ring = nullptr;   // [kAhead][n]
@@ -801,6 +805,15 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     h->extra_bytes += leg + am + ds * ns * sizeof(double);
   }
   h->bc = make_box_const(*cfg);
+  {
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+    if (h->f32)
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_tma<float>, kTile, solve_tma_smem_bytes<float>());
+    else
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_tma<double>, kTile, solve_tma_smem_bytes<double>());
+    h->solve_slots = sms * per_sm;
+  }
   if (const char *e = std::getenv("DEKF_FOOT_SERIAL")) h->foot_team = std::atoi(e) == 0;
   if (cfg->v_box_enable) {
     const size_t ns = (size_t)h->dm.ns;
@@ -860,6 +873,9 @@ int dekf_destroy(dekf_handle *h) {
   free_chunk_set(h->chunk[1]);
   if (h->s_ekf) cudaStreamDestroy(h->s_ekf);
   if (h->s_mhe) cudaStreamDestroy(h->s_mhe);
+  if (h->s_mhe_b) cudaStreamDestroy(h->s_mhe_b);
+  for (int k = 0; k < dekf_handle::kAhead; ++k)
+    if (h->ev_solb[k]) cudaEventDestroy(h->ev_solb[k]);
   if (h->s_asm) cudaStreamDestroy(h->s_asm);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->quat_ring);
@@ -975,6 +991,9 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
   const bool tma = h->use_tma && T_ >= 1;
   const bool kf = h->cfg.est_type == 1;
   const int tiles = h->dm.ns / kTile;
+  Dims rdm = h->dm;  // k_solve_tma may cover a tile range only (dekf_run splits the batch at the last full wave)
+  rdm.tile0 = h->solve_tiles >= 0 ? h->solve_tile0 : 0;
+  const int rtiles = h->solve_tiles >= 0 ? h->solve_tiles : tiles;
   // incremental solve on a tick that carries VO messages: TMA-staged re-sweep from the CTA's earliest restart stage
   const bool resweep_tick = h->mc64.window_solve == 1 && tma && T_ >= 2 && di.vo_flag != nullptr && !kf && !h->bc.enable &&
                             h->cfg.leg_odom_type == 0;
@@ -995,7 +1014,7 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
     else if (h->mc32.window_solve == 1)
       k_solve_incr<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
     else if (tma)
-      k_solve_tma<float><<<tiles, kTile, solve_tma_smem_bytes<float>(), h->stream>>>(h->tmap, h->mc32, h->dm, h->b32, di, dout, T_, st);
+      k_solve_tma<float><<<rtiles, kTile, solve_tma_smem_bytes<float>(), h->stream>>>(h->tmap, h->mc32, rdm, h->b32, di, dout, T_, st);
     else
       k_solve<float><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc32, h->dm, h->b32, di, dout, T_, st);
   } else {
@@ -1024,7 +1043,7 @@ static int mhe_step_impl(dekf_handle *h, int32_t T_, const dekf_inputs *in, cons
     else if (h->mc64.window_solve == 1)
       k_solve_incr<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
     else if (tma)
-      k_solve_tma<double><<<tiles, kTile, solve_tma_smem_bytes<double>(), h->stream>>>(h->tmap, h->mc64, h->dm, h->b64, di, dout, T_, st);
+      k_solve_tma<double><<<rtiles, kTile, solve_tma_smem_bytes<double>(), h->stream>>>(h->tmap, h->mc64, rdm, h->b64, di, dout, T_, st);
     else
       k_solve<double><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(h->mc64, h->dm, h->b64, di, dout, T_, st);
   }
@@ -1321,6 +1340,7 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     CK(cudaStreamCreateWithPriority(&h->s_ekf, cudaStreamNonBlocking, lo));
     CK(cudaStreamCreateWithPriority(&h->s_asm, cudaStreamNonBlocking, (lo + hi) / 2));
     CK(cudaStreamCreateWithPriority(&h->s_mhe, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&h->s_mhe_b, cudaStreamNonBlocking, hi));
     CK(cudaMalloc((void **)&h->quat_ring, (size_t)QA * 4 * n * sizeof(double)));
     CK(cudaMalloc((void **)&h->status_ring, (size_t)QA * n * sizeof(int32_t)));
     h->extra_bytes += (size_t)QA * n * (4 * sizeof(double) + sizeof(int32_t));
@@ -1328,6 +1348,7 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
       CK(cudaEventCreateWithFlags(&h->ev_ekf[k], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_mhe[k], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_sol[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->ev_solb[k], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -1340,6 +1361,17 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
   CK(cudaStreamWaitEvent(h->s_ekf, h->ev_fork, 0));
   CK(cudaStreamWaitEvent(h->s_asm, h->ev_fork, 0));
   CK(cudaStreamWaitEvent(h->s_mhe, h->ev_fork, 0));
+  CK(cudaStreamWaitEvent(h->s_mhe_b, h->ev_fork, 0));
+  // Full re-sweep with the TMA kernel: 65,536 instances are 512 tiles on 2 x 148 CTA slots = 1.73 waves.  The tiles beyond
+  // the last full wave run as a second launch on their own stream; the two tile ranges are independent instances, so the
+  // partial wave of tick s overlaps the full wave of tick s + 1 instead of leaving slots idle (DEKF_NO_SPLIT=1 disables).
+  int split_tiles = 0;
+  {
+    static const bool no_split = std::getenv("DEKF_NO_SPLIT") && std::atoi(std::getenv("DEKF_NO_SPLIT")) != 0;
+    const int tiles = h->dm.ns / kTile, slots = h->solve_slots;
+    if (asm_ahead && !no_split && h->use_tma && h->mc64.window_solve == 0 && slots > 0 && tiles > slots && tiles % slots != 0)
+      split_tiles = tiles / slots * slots;
+  }
   for (int32_t s = 0; s < S && rc == DEKF_OK; ++s) {
     const int slot = s % QA;
     dekf_inputs is;
@@ -1365,7 +1397,9 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
       // parity-buffered scratch + the spare ring slot allow ONE tick of lead: wait for the solve of tick s-2, and for the
       // solve of tick s-1 too when this tick rewrites VO rows inside the window that solve is reading
       if (ce == cudaSuccess && s >= 2) ce = cudaStreamWaitEvent(sa, h->ev_sol[(s - 2) % QA], 0);
+      if (ce == cudaSuccess && s >= 2 && split_tiles) ce = cudaStreamWaitEvent(sa, h->ev_solb[(s - 2) % QA], 0);
       if (ce == cudaSuccess && s >= 1 && vo_tick) ce = cudaStreamWaitEvent(sa, h->ev_sol[(s - 1) % QA], 0);
+      if (ce == cudaSuccess && s >= 1 && vo_tick && split_tiles) ce = cudaStreamWaitEvent(sa, h->ev_solb[(s - 1) % QA], 0);
     }
     if (ce != cudaSuccess) {
       rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
@@ -1386,15 +1420,40 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
       rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
       break;
     }
+    const bool split = split_tiles > 0 && T0 + s >= 1;  // tick 0 has no window solve (the non-TMA kernel handles it)
+    if (split) {
+      h->solve_tile0 = 0;
+      h->solve_tiles = split_tiles;
+    }
     h->stream = h->s_mhe;
     rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 2);
     h->stream = user;
+    h->solve_tiles = -1;
     if (rc) break;
     ce = cudaEventRecord(h->ev_sol[slot], h->s_mhe);
+    if (ce == cudaSuccess && split_tiles) {
+      if (split) {
+        ce = cudaStreamWaitEvent(h->s_mhe_b, h->ev_mhe[slot], 0);
+        if (ce == cudaSuccess) {
+          h->solve_tile0 = split_tiles;
+          h->solve_tiles = h->dm.ns / kTile - split_tiles;
+          h->stream = h->s_mhe_b;
+          rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 2);
+          h->stream = user;
+          h->solve_tiles = -1;
+          if (rc) break;
+        }
+      } else {
+        ce = cudaStreamWaitEvent(h->s_mhe_b, h->ev_sol[slot], 0);  // tick 0: the one launch covered every instance
+      }
+      if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_solb[slot], h->s_mhe_b);
+    }
     if (ce != cudaSuccess) rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
   }
   h->stream = user;
   cudaEventRecord(h->ev_join, h->s_mhe);
+  cudaStreamWaitEvent(user, h->ev_join, 0);
+  cudaEventRecord(h->ev_join, h->s_mhe_b);
   cudaStreamWaitEvent(user, h->ev_join, 0);
   cudaEventRecord(h->ev_join, h->s_asm);
   cudaStreamWaitEvent(user, h->ev_join, 0);

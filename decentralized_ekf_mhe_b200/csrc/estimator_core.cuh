@@ -84,6 +84,7 @@ struct Dims {
   int NW;  // window ring slots  = N + 1
   int HR;  // MHE history ring   = 4N + 1   (DecentralEst.cpp:963)
   int D;   // EKF history ring depth
+  int tile0 = 0;  // first 128-instance tile of a k_solve_tma launch that covers only part of the batch (dekf_run)
 };
 
 template <typename T>

@@ -86,6 +86,7 @@ inline Dims make_dims(const dekf_config &c) {
   d.NW = c.N + 2;  // window stages T-N .. T plus one slot so that stage T+1 can be assembled while update(T) is in flight
   d.HR = 4 * c.N + 1;
   d.D = c.ekf_hist_depth;
+  d.tile0 = 0;
   return d;
 }
 

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_solve_tma(const __grid_constant_
   src.empty = src.full + STAGES;
   src.map = &tmap;
   src.NW = dm.NW;
-  src.i0 = blockIdx.x * TILE;
+  src.i0 = (blockIdx.x + dm.tile0) * TILE;
   src.tid = threadIdx.x;
   src.k0 = (Tk < dm.N) ? 0 : Tk - dm.N;
   src.nst = Tk - src.k0 + 1;
