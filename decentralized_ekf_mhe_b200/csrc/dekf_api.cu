@@ -1371,6 +1371,11 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     const int tiles = h->dm.ns / kTile, slots = h->solve_slots;
     if (asm_ahead && !no_split && h->use_tma && h->mc64.window_solve == 0 && slots > 0 && tiles > slots && tiles % slots != 0)
       split_tiles = tiles / slots * slots;
+    if (split_tiles > 0)
+      if (const char *e = std::getenv("DEKF_SPLIT_TILES")) {  // tuning: size of the first tile range
+        const int v = std::atoi(e);
+        if (v > 0 && v < tiles) split_tiles = v;
+      }
   }
   for (int32_t s = 0; s < S && rc == DEKF_OK; ++s) {
     const int slot = s % QA;
