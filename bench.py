@@ -35,8 +35,8 @@ def fill_steps(N):
 
 # Exact operation tally of the committed algorithm (tests/hostsim/flopcount.cpp; mul and add counted
 # separately, FMA = 2; tests/test_flop_tally.py keeps these in sync with the kernels)
-FLOPS = dict(meas_update=657, propagate=656, propagate_vo=1496, ekf_predict=432, ekf_correct=641,
-             ekf_vo_correct=450, assemble_go1=1401, solve_epilogue=30)
+FLOPS = dict(meas_update=486, propagate=407, propagate_vo=1049, meas_update_pp=597, propagate_pp=503, propagate_vo_pp=1103,
+             ekf_predict=432, ekf_correct=641, ekf_vo_correct=450, assemble_go1=1401, solve_epilogue=30)
 
 
 def algorithmic_work(N, n_vo_mean, elt=8, depth_mean=None, depth_vo_mean=None):
@@ -47,15 +47,18 @@ def algorithmic_work(N, n_vo_mean, elt=8, depth_mean=None, depth_vo_mean=None):
     io = 3 * 8 + 12 * 8 + 8  # gyro in, x + v_body out, status
     w = {}
     if depth_mean is None:
+        # full re-sweep: P_pp is carried through the arrival stage only (the "_pp" figures), not through the other N - 1
         w["solve"] = (2 * 54 * elt + (N + 1) * rec + io,
                       (N + 1) * FLOPS["meas_update"] + N * FLOPS["propagate"] + n_vo_mean * (
-                          FLOPS["propagate_vo"] - FLOPS["propagate"]) + FLOPS["solve_epilogue"])
+                          FLOPS["propagate_vo"] - FLOPS["propagate"]) + (FLOPS["meas_update_pp"] - FLOPS["meas_update"]) + (
+                          FLOPS["propagate_pp"] - FLOPS["propagate"]) + FLOPS["solve_epilogue"])
     else:
+        # incremental sweep: every stage carries P_pp (any checkpoint may become the arrival cost)
         w["solve"] = ((54 + 54 + 16 + 18) * elt + io + 4,
-                      FLOPS["meas_update"] + FLOPS["propagate"] + FLOPS["solve_epilogue"])
+                      FLOPS["meas_update_pp"] + FLOPS["propagate_pp"] + FLOPS["solve_epilogue"])
         w["resweep"] = ((54 + depth_mean * 54 + (depth_mean + 1) * 25) * elt + io + 4,
-                        depth_mean * (FLOPS["meas_update"] + FLOPS["propagate"]) + depth_vo_mean * (
-                            FLOPS["propagate_vo"] - FLOPS["propagate"]) + FLOPS["solve_epilogue"])
+                        depth_mean * (FLOPS["meas_update_pp"] + FLOPS["propagate_pp"]) + depth_vo_mean * (
+                            FLOPS["propagate_vo_pp"] - FLOPS["propagate_pp"]) + FLOPS["solve_epilogue"])
     w["ekf"] = (7 * 8 + 2 * 20 * elt + 26 * elt + 8 + 4 * 8 + 4, FLOPS["ekf_predict"] + FLOPS["ekf_correct"])
     w["assemble"] = (4 * elt + 7 * 8 + 24 * 8 + 4 * 8 + 1 + rec + 5 * 8 + 4 + 8, FLOPS["assemble_go1"])
     return w

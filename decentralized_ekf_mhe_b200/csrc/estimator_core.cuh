@@ -66,6 +66,9 @@ struct MheConst {
   T cvo[3];  // vo_p_std^2                       (Q_cam^-1 before rotation)
   // the same four diagonals as (d[0], d[1]-d[0], d[2]-d[0]) for the two-term form R diag(d) R' = d0 I + e1 r1r1' + e2 r2r2'
   T n1[3], n2[3], n3[3], nvo[3];
+  // version-4 sweep: C_accel and dt^2 C_p in the same (e0, e1-e0, e2-e0) form; the rotated noise blocks are
+  // h^2, h dt, dt^2 times R C_accel R' (+ dt^2 R C_p R' on pp)
+  T ae[3], pe[3];
   T cenc_v[8], cenc_p[8], cgy[3];
   T q_swing[3];
   T P0[9];   // prior covariance diag (p,v,b init std^2), prior mean 0
@@ -785,6 +788,20 @@ struct Vec9 {
   V3<T> p, v, b;
 };
 
+// The same 9-vector kept outside the register file (k_solve_tma's XS variant: one column of a [9][STRIDE] shared-memory
+// array per thread).  Same member syntax as Vec9 (x.p[r], x.v[r], x.b[r]); every access is a shared-memory access.
+template <typename T, int STRIDE>
+struct MemV3 {
+  T *q;
+  DEKF_HD T &operator[](int i) { return q[i * STRIDE]; }
+  DEKF_HD const T &operator[](int i) const { return q[i * STRIDE]; }
+};
+template <typename T, int STRIDE>
+struct MemVec9 {
+  MemV3<T, STRIDE> p, v, b;
+  DEKF_HD explicit MemVec9(T *base) : p{base}, v{base + 3 * STRIDE}, b{base + 6 * STRIDE} {}
+};
+
 template <typename T>
 DEKF_HD void load_cov(const T *base, int n, int i, Cov9<T> &P) {
 #pragma unroll
@@ -1177,34 +1194,484 @@ DEKF_HD void meas_update3(Cov9<T> &P, Vec9<T> &x, const S3<T> &Lam, const V3<T> 
   }
 }
 
+// ---- version 4 (round 2): the sweep stages re-derived for the fewest FP64 instructions ----------------------------------
+// Every multiply-add is an explicit fma (deterministic contraction: the full re-sweep, the incremental sweep and the host
+// build of this header perform bit-identical operations).  Differences to versions 1-3:
+//  * leg-odometry update through Z^-1 = (I + Lam P_vv)^-1 only:  P_vv+ = P_vv Z^-1,  P_vb+ = Z^-T P_vb,  P_pv+ = P_pv Z^-1,
+//    P_pb+ = P_pb - P_pv G,  P_bb+ = P_bb - P_vb' G  with  G = Z^-1 (Lam P_vb)  -- no gain matrices K_v, K_b;
+//    (Lam P_vb) and adj(Z) r do not depend on 1/det(Z) and overlap its latency.
+//  * the accelerometer noise R C_a R' enters the time update only as an addend of R P_bb R' (Q_dyn^-1 = G C G' with
+//    G = [h R; dt R], DecentralEst.cpp:409-418), so the three rotated noise blocks C1, C2, C3 cost one.
+//  * the VO row re-uses the blocks of the time update: U_v = (P_pv+ - P_pv + dt P_pb R')', U_b = (P_pb+ - P_pb)',
+//    U_p - PL_p = Cov(d) - C_vo = the increment of P_pp+.
+//  * PP = false leaves P_pp untouched.  P_pp feeds nothing but itself (p is observed only through differences
+//    p_{k+1} - p_k, whose statistics involve P_pv, P_pb alone), so the full re-sweep carries it through the first stage only,
+//    where the arrival cost of the next tick is produced (marginalizeQP, MheSrb.cpp:475-713).
+template <typename T>
+DEKF_HD T fm(T a, T b, T c) { return a * b + c; }
+#if defined(__CUDA_ARCH__)
+template <>
+DEKF_HD double fm<double>(double a, double b, double c) { return fma(a, b, c); }
+template <>
+DEKF_HD float fm<float>(float a, float b, float c) { return fmaf(a, b, c); }
+#else
+template <>
+DEKF_HD double fm<double>(double a, double b, double c) { return ::fma(a, b, c); }
+template <>
+DEKF_HD float fm<float>(float a, float b, float c) { return ::fmaf(a, b, c); }
+#endif
+
+// R diag(e0, e0+e1, e0+e2) R' = e0 I + e1 r1 r1' + e2 r2 r2' added onto S (r1, r2: 2nd / 3rd column of R); branch-free
+template <typename T>
+DEKF_HD void add_rot_diag(S3<T> &S, const M3<T> &R, const T e[3]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const T s1 = e[1] * R(r, 1), s2 = e[2] * R(r, 2);
+#pragma unroll
+    for (int cc = r; cc < 3; ++cc)
+      S.a[S3<T>::idx(r, cc)] = fm(s2, R(cc, 2), fm(s1, R(cc, 1), S.a[S3<T>::idx(r, cc)] + ((r == cc) ? e[0] : T(0))));
+  }
+}
+
+// PPM selects how P_pp is carried: 0 not at all, 1 in P.pp (registers), 2 read-modify-written at ppm[f * pps] (f = 0..5)
+// when ppm != nullptr (the first stage of the full re-sweep works directly on the arrival cost in HBM).
+template <typename T>
+DEKF_HD void pp_load(S3<T> &pp, const T *ppm, size_t pps) {
+#pragma unroll
+  for (int f = 0; f < 6; ++f) pp.a[f] = ppm[f * pps];
+}
+template <typename T>
+DEKF_HD void pp_store(const S3<T> &pp, T *ppm, size_t pps) {
+#pragma unroll
+  for (int f = 0; f < 6; ++f) ppm[f * pps] = pp.a[f];
+}
+
+template <int PPM, typename T, typename X>
+DEKF_HD void meas_update4(Cov9<T> &P, X &x, const S3<T> &Lam, const V3<T> &eta, T *ppm = nullptr, size_t pps = 0) {
+  M3<T> Z;  // I + Lam P_vv
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      Z(r, c) = fm(Lam(r, 2), P.vv(2, c), fm(Lam(r, 1), P.vv(1, c), fm(Lam(r, 0), P.vv(0, c), (r == c) ? T(1) : T(0))));
+  T det;
+  M3<T> Zi = adjugate(Z, det);
+  const T id = T(1) / det;
+  V3<T> rr;  // eta - Lam v
+#pragma unroll
+  for (int r = 0; r < 3; ++r) rr[r] = fm(-Lam(r, 2), x.v[2], fm(-Lam(r, 1), x.v[1], fm(-Lam(r, 0), x.v[0], eta[r])));
+  M3<T> LP;  // Lam P_vb
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) LP(r, c) = fm(Lam(r, 2), P.vb(2, c), fm(Lam(r, 1), P.vb(1, c), Lam(r, 0) * P.vb(0, c)));
+  V3<T> t;  // Z^-1 (eta - Lam v)
+#pragma unroll
+  for (int r = 0; r < 3; ++r) t[r] = fm(Zi(r, 2), rr[2], fm(Zi(r, 1), rr[1], Zi(r, 0) * rr[0]));
+#pragma unroll
+  for (int f = 0; f < 9; ++f) Zi.a[f] *= id;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) t[r] *= id;
+  M3<T> G;  // Z^-1 Lam P_vb = W P_vb
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) G(r, c) = fm(Zi(r, 2), LP(2, c), fm(Zi(r, 1), LP(1, c), Zi(r, 0) * LP(0, c)));
+  // mean
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    x.p[r] = fm(P.pv(r, 2), t[2], fm(P.pv(r, 1), t[1], fm(P.pv(r, 0), t[0], x.p[r])));
+    x.b[r] = fm(P.vb(2, r), t[2], fm(P.vb(1, r), t[1], fm(P.vb(0, r), t[0], x.b[r])));
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) x.v[r] = fm(P.vv(r, 2), t[2], fm(P.vv(r, 1), t[1], fm(P.vv(r, 0), t[0], x.v[r])));
+  if (PPM == 1 || (PPM == 2 && ppm != nullptr)) {
+    // P_pp -= (P_pv W) P_pv',  W = Z^-1 Lam (symmetric)
+    S3<T> pp;
+    if constexpr (PPM == 1) pp = P.pp; else pp_load(pp, ppm, pps);
+    S3<T> W;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = r; c < 3; ++c) W.a[S3<T>::idx(r, c)] = fm(Zi(r, 2), Lam(2, c), fm(Zi(r, 1), Lam(1, c), Zi(r, 0) * Lam(0, c)));
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      T kp[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) kp[c] = fm(P.pv(r, 2), W(2, c), fm(P.pv(r, 1), W(1, c), P.pv(r, 0) * W(0, c)));
+#pragma unroll
+      for (int c = r; c < 3; ++c)
+        pp.a[S3<T>::idx(r, c)] = fm(-kp[2], P.pv(c, 2), fm(-kp[1], P.pv(c, 1), fm(-kp[0], P.pv(c, 0), pp.a[S3<T>::idx(r, c)])));
+    }
+    if constexpr (PPM == 1) P.pp = pp; else pp_store(pp, ppm, pps);
+  }
+  // blocks that read the OLD P_pv / P_vb first
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) P.pb(r, c) = fm(-P.pv(r, 2), G(2, c), fm(-P.pv(r, 1), G(1, c), fm(-P.pv(r, 0), G(0, c), P.pb(r, c))));
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = r; c < 3; ++c)
+      P.bb.a[S3<T>::idx(r, c)] =
+          fm(-P.vb(2, r), G(2, c), fm(-P.vb(1, r), G(1, c), fm(-P.vb(0, r), G(0, c), P.bb.a[S3<T>::idx(r, c)])));
+  {
+    M3<T> n;  // P_pv Z^-1
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) n(r, c) = fm(P.pv(r, 2), Zi(2, c), fm(P.pv(r, 1), Zi(1, c), P.pv(r, 0) * Zi(0, c)));
+    P.pv = n;
+  }
+  {
+    M3<T> n;  // Z^-T P_vb
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) n(r, c) = fm(Zi(2, r), P.vb(2, c), fm(Zi(1, r), P.vb(1, c), Zi(0, r) * P.vb(0, c)));
+    P.vb = n;
+  }
+  {
+    S3<T> n;  // P_vv Z^-1 (symmetric)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = r; c < 3; ++c) n.a[S3<T>::idx(r, c)] = fm(P.vv(r, 2), Zi(2, c), fm(P.vv(r, 1), Zi(1, c), P.vv(r, 0) * Zi(0, c)));
+    P.vv = n;
+  }
+}
+
+template <int PPM, typename T, typename X>
+DEKF_HD void propagate4(const MheConst<T> &c, Cov9<T> &P, X &x, const M3<T> &R, const V3<T> &as, bool vo,
+                        const V3<T> &dlt, T *ppm = nullptr, size_t pps = 0) {
+  const bool pp_on = PPM == 1 || (PPM == 2 && ppm != nullptr);
+  const T dt = c.dt, h = T(0.5) * c.dt * c.dt;
+  const T dt2 = dt * dt, hdt = h * dt, hh = h * h;
+  // mean: acc = a_s - R b,  d = p+ - p = dt v + h acc,  v+ = v + dt acc
+  V3<T> hmean;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const T acc = fm(-R(r, 2), x.b[2], fm(-R(r, 1), x.b[1], fm(-R(r, 0), x.b[0], as[r])));
+    hmean[r] = fm(h, acc, dt * x.v[r]);
+    x.p[r] += hmean[r];
+    x.v[r] = fm(dt, acc, x.v[r]);
+  }
+  // position rows first: Ep = P_pb R' is only needed for P_pv (and PL_p = Cov(p, d) = dt P_pv - h Ep)
+  M3<T> PLp;
+  {
+    M3<T> Ep;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) Ep(r, cc) = fm(P.pb(r, 2), R(cc, 2), fm(P.pb(r, 1), R(cc, 1), P.pb(r, 0) * R(cc, 0)));
+    if (pp_on || vo) {
+#pragma unroll
+      for (int f = 0; f < 9; ++f) PLp.a[f] = fm(-h, Ep.a[f], dt * P.pv.a[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < 9; ++f) P.pv.a[f] = fm(-dt, Ep.a[f], P.pv.a[f]);
+  }
+  // B = R P_bb,  Ev = P_vb R',  BRn = R P_bb R' + R C_a R'
+  M3<T> B, Ev;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      B(r, cc) = fm(R(r, 2), P.bb(2, cc), fm(R(r, 1), P.bb(1, cc), R(r, 0) * P.bb(0, cc)));
+      Ev(r, cc) = fm(P.vb(r, 2), R(cc, 2), fm(P.vb(r, 1), R(cc, 1), P.vb(r, 0) * R(cc, 0)));
+    }
+  S3<T> BRn;
+#pragma unroll
+  for (int f = 0; f < 6; ++f) BRn.a[f] = T(0);
+  add_rot_diag(BRn, R, c.ae);
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = r; cc < 3; ++cc)
+      BRn.a[S3<T>::idx(r, cc)] = fm(B(r, 2), R(cc, 2), fm(B(r, 1), R(cc, 1), fm(B(r, 0), R(cc, 0), BRn.a[S3<T>::idx(r, cc)])));
+  P.bb.a[0] += c.cab[0];
+  P.bb.a[3] += c.cab[1];
+  P.bb.a[5] += c.cab[2];
+  // U_v = Cov(v+, d) = dt P_vv - h Ev - dt^2 Ev' + h dt BRn (old P_vv);  P_pv+ = P_pv - dt Ep + U_v'
+  M3<T> Uv;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) Uv(r, cc) = fm(hdt, BRn(r, cc), fm(-dt2, Ev(cc, r), fm(-h, Ev(r, cc), dt * P.vv(r, cc))));
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) P.pv(r, cc) += Uv(cc, r);
+  // Cov(d) without the camera noise: Vn = dt^2 P_vv - h dt (Ev + Ev') + h^2 BRn + dt^2 R C_p R'
+  S3<T> Vn;
+  if (pp_on || vo) {
+#pragma unroll
+    for (int f = 0; f < 6; ++f) Vn.a[f] = T(0);
+    add_rot_diag(Vn, R, c.pe);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = r; cc < 3; ++cc) {
+        const int k = S3<T>::idx(r, cc);
+        Vn.a[k] = fm(dt2, P.vv.a[k], fm(-hdt, Ev(r, cc) + Ev(cc, r), fm(hh, BRn.a[k], Vn.a[k])));
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = r; cc < 3; ++cc) {
+      const int k = S3<T>::idx(r, cc);
+      P.vv.a[k] = fm(dt2, BRn.a[k], fm(-dt, Ev(r, cc) + Ev(cc, r), P.vv.a[k]));
+    }
+  M3<T> Xb;  // dt P_vb - h B = P_pb+ - P_pb = U_b'
+#pragma unroll
+  for (int f = 0; f < 9; ++f) {
+    Xb.a[f] = fm(-h, B.a[f], dt * P.vb.a[f]);
+    P.pb.a[f] += Xb.a[f];
+    P.vb.a[f] = fm(-dt, B.a[f], P.vb.a[f]);
+  }
+  S3<T> pp;
+  if (pp_on) {
+    if constexpr (PPM == 1) pp = P.pp; else pp_load(pp, ppm, pps);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = r; cc < 3; ++cc) {
+        const int k = S3<T>::idx(r, cc);
+        pp.a[k] += (PLp(r, cc) + PLp(cc, r)) + Vn.a[k];
+      }
+    if (!vo) {
+      if constexpr (PPM == 1) P.pp = pp; else pp_store(pp, ppm, pps);
+    }
+  }
+  if (vo) {
+    // p_{k+1} - p_k = Delta + vcam, cov(vcam) = R diag(vo_p_std^2) R' (DecentralEst.cpp:477, :1004-1005)
+    S3<T> Si;
+    T id;
+    {
+      S3<T> Sinn = Vn;
+      add_rot_diag(Sinn, R, c.nvo);
+      T det;
+      Si = adjugate(Sinn, det);
+      id = T(1) / det;
+    }
+    // U_p = PL_p + Vn,  U_b = Xb'
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) PLp(r, cc) += Vn(r, cc);
+    V3<T> t;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      // innovation Delta - (predicted d); hmean was already added to x.p
+      t[r] = dlt[r] - hmean[r];
+    }
+    {
+      const V3<T> nu = t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) t[r] = fm(Si(r, 2), nu[2], fm(Si(r, 1), nu[1], Si(r, 0) * nu[0]));
+    }
+#pragma unroll
+    for (int f = 0; f < 6; ++f) Si.a[f] *= id;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) t[r] *= id;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      x.p[r] = fm(PLp(r, 2), t[2], fm(PLp(r, 1), t[1], fm(PLp(r, 0), t[0], x.p[r])));
+      x.v[r] = fm(Uv(r, 2), t[2], fm(Uv(r, 1), t[1], fm(Uv(r, 0), t[0], x.v[r])));
+      x.b[r] = fm(Xb(2, r), t[2], fm(Xb(1, r), t[1], fm(Xb(0, r), t[0], x.b[r])));
+    }
+    // P -= U S^-1 U', one row of K = U S^-1 at a time
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      T k[3];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) k[cc] = fm(PLp(r, 2), Si(2, cc), fm(PLp(r, 1), Si(1, cc), PLp(r, 0) * Si(0, cc)));
+      if (pp_on) {
+#pragma unroll
+        for (int cc = r; cc < 3; ++cc)
+          pp.a[S3<T>::idx(r, cc)] = fm(-k[2], PLp(cc, 2), fm(-k[1], PLp(cc, 1), fm(-k[0], PLp(cc, 0), pp.a[S3<T>::idx(r, cc)])));
+      }
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        P.pv(r, cc) = fm(-k[2], Uv(cc, 2), fm(-k[1], Uv(cc, 1), fm(-k[0], Uv(cc, 0), P.pv(r, cc))));
+        P.pb(r, cc) = fm(-k[2], Xb(2, cc), fm(-k[1], Xb(1, cc), fm(-k[0], Xb(0, cc), P.pb(r, cc))));
+      }
+    }
+    if (pp_on) {
+      if constexpr (PPM == 1) P.pp = pp; else pp_store(pp, ppm, pps);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      T k[3];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) k[cc] = fm(Uv(r, 2), Si(2, cc), fm(Uv(r, 1), Si(1, cc), Uv(r, 0) * Si(0, cc)));
+#pragma unroll
+      for (int cc = r; cc < 3; ++cc)
+        P.vv.a[S3<T>::idx(r, cc)] =
+            fm(-k[2], Uv(cc, 2), fm(-k[1], Uv(cc, 1), fm(-k[0], Uv(cc, 0), P.vv.a[S3<T>::idx(r, cc)])));
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc)
+        P.vb(r, cc) = fm(-k[2], Xb(2, cc), fm(-k[1], Xb(1, cc), fm(-k[0], Xb(0, cc), P.vb(r, cc))));
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      T k[3];
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) k[cc] = fm(Xb(2, r), Si(2, cc), fm(Xb(1, r), Si(1, cc), Xb(0, r) * Si(0, cc)));
+#pragma unroll
+      for (int cc = r; cc < 3; ++cc)
+        P.bb.a[S3<T>::idx(r, cc)] =
+            fm(-k[2], Xb(2, cc), fm(-k[1], Xb(1, cc), fm(-k[0], Xb(0, cc), P.bb.a[S3<T>::idx(r, cc)])));
+    }
+  }
+}
+
+// ---- version 5 of the propagation: stages WITHOUT a VO row take an in-place path with the shortest live ranges
+// (A = T1 T2 with T2: p += dt v and T1: p -= h R b, v -= dt R b; each rotated product is consumed right after it is formed);
+// stages WITH a VO row need Cov(x+, p+ - p) from the pre-update blocks and take the version-4 path.  Which path a stage takes
+// depends only on its own VO flag, so the full re-sweep, the incremental sweep and the KF alternative stay bit-identical.
+template <int PPM, typename T, typename X>
+DEKF_HD void propagate5(const MheConst<T> &c, Cov9<T> &P, X &x, const M3<T> &R, const V3<T> &as, bool vo, const V3<T> &dlt,
+                        T *ppm = nullptr, size_t pps = 0) {
+  if (vo) {
+    propagate4<PPM>(c, P, x, R, as, true, dlt, ppm, pps);
+    return;
+  }
+  const bool pp_on = PPM == 1 || (PPM == 2 && ppm != nullptr);
+  const T dt = c.dt, h = T(0.5) * c.dt * c.dt;
+  const T dt2 = dt * dt, hdt = h * dt, hh = h * h;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const T acc = fm(-R(r, 2), x.b[2], fm(-R(r, 1), x.b[1], fm(-R(r, 0), x.b[0], as[r])));
+    x.p[r] += fm(h, acc, dt * x.v[r]);
+    x.v[r] = fm(dt, acc, x.v[r]);
+  }
+  S3<T> pp;
+  if (pp_on) {
+    if constexpr (PPM == 1) pp = P.pp; else pp_load(pp, ppm, pps);
+    // T2 on P_pp: += dt (P_pv + P_pv') + dt^2 P_vv;  noise dt^2 R C_p R'
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = r; cc < 3; ++cc) {
+        const int k = S3<T>::idx(r, cc);
+        pp.a[k] = fm(dt, P.pv(r, cc) + P.pv(cc, r), fm(dt2, P.vv.a[k], pp.a[k]));
+      }
+    add_rot_diag(pp, R, c.pe);
+  }
+  // T2: P_pv += dt P_vv, P_pb += dt P_vb
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      P.pv(r, cc) = fm(dt, P.vv(r, cc), P.pv(r, cc));
+      P.pb(r, cc) = fm(dt, P.vb(r, cc), P.pb(r, cc));
+    }
+  // T1, position rows: Ep = P_pb R';  P_pv -= dt Ep  (P_pp -= h (Ep + Ep'))
+  {
+    M3<T> Ep;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        Ep(r, cc) = fm(P.pb(r, 2), R(cc, 2), fm(P.pb(r, 1), R(cc, 1), P.pb(r, 0) * R(cc, 0)));
+        P.pv(r, cc) = fm(-dt, Ep(r, cc), P.pv(r, cc));
+      }
+    if (pp_on) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int cc = r; cc < 3; ++cc) pp.a[S3<T>::idx(r, cc)] = fm(-h, Ep(r, cc) + Ep(cc, r), pp.a[S3<T>::idx(r, cc)]);
+    }
+  }
+  // T1, velocity rows: Ev = P_vb R';  P_pv -= h Ev',  P_vv -= dt (Ev + Ev')
+  {
+    M3<T> Ev;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        Ev(r, cc) = fm(P.vb(r, 2), R(cc, 2), fm(P.vb(r, 1), R(cc, 1), P.vb(r, 0) * R(cc, 0)));
+        P.pv(cc, r) = fm(-h, Ev(r, cc), P.pv(cc, r));
+      }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = r; cc < 3; ++cc) P.vv.a[S3<T>::idx(r, cc)] = fm(-dt, Ev(r, cc) + Ev(cc, r), P.vv.a[S3<T>::idx(r, cc)]);
+  }
+  // T1, bias column: B = R P_bb;  P_pb -= h B,  P_vb -= dt B;  BRn = B R' + R C_a R' enters P_pv, P_vv (and P_pp)
+  {
+    M3<T> B;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        B(r, cc) = fm(R(r, 2), P.bb(2, cc), fm(R(r, 1), P.bb(1, cc), R(r, 0) * P.bb(0, cc)));
+        P.pb(r, cc) = fm(-h, B(r, cc), P.pb(r, cc));
+        P.vb(r, cc) = fm(-dt, B(r, cc), P.vb(r, cc));
+      }
+    S3<T> BRn;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) BRn.a[f] = T(0);
+    add_rot_diag(BRn, R, c.ae);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = r; cc < 3; ++cc) {
+        const int k = S3<T>::idx(r, cc);
+        BRn.a[k] = fm(B(r, 2), R(cc, 2), fm(B(r, 1), R(cc, 1), fm(B(r, 0), R(cc, 0), BRn.a[k])));
+        P.vv.a[k] = fm(dt2, BRn.a[k], P.vv.a[k]);
+        if (pp_on) pp.a[k] = fm(hh, BRn.a[k], pp.a[k]);
+      }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) P.pv(r, cc) = fm(hdt, BRn(r, cc), P.pv(r, cc));
+  }
+  P.bb.a[0] += c.cab[0];
+  P.bb.a[3] += c.cab[1];
+  P.bb.a[5] += c.cab[2];
+  if (pp_on) {
+    if constexpr (PPM == 1) P.pp = pp; else pp_store(pp, ppm, pps);
+  }
+}
+
 // Math policy of the sweep: MV / PV select the version of the measurement / propagation stage.
 template <int MV, int PV>
 struct MathSel {
-  template <typename T>
-  DEKF_HD static void meas(Cov9<T> &P, Vec9<T> &x, const S3<T> &Lam, const V3<T> &eta) {
+  // PPM (version 4 only; versions 1-3 always carry P_pp in P.pp): see meas_update4
+  template <int PPM = 1, typename T, typename X>
+  DEKF_HD static void meas(Cov9<T> &P, X &x, const S3<T> &Lam, const V3<T> &eta, T *ppm = nullptr, size_t pps = 0) {
     if constexpr (MV == 1)
       meas_update(P, x, Lam, eta);
     else if constexpr (MV == 2)
       meas_update2(P, x, Lam, eta);
-    else
+    else if constexpr (MV == 3)
       meas_update3(P, x, Lam, eta);
+    else
+      meas_update4<PPM>(P, x, Lam, eta, ppm, pps);
   }
-  template <typename T>
-  DEKF_HD static void prop(const MheConst<T> &c, Cov9<T> &P, Vec9<T> &x, const M3<T> &R, const V3<T> &as, bool vo,
-                           const V3<T> &dlt) {
+  template <int PPM = 1, typename T, typename X>
+  DEKF_HD static void prop(const MheConst<T> &c, Cov9<T> &P, X &x, const M3<T> &R, const V3<T> &as, bool vo,
+                           const V3<T> &dlt, T *ppm = nullptr, size_t pps = 0) {
     if constexpr (PV == 1)
       propagate(c, P, x, R, as, vo, dlt);
-    else
+    else if constexpr (PV == 2)
       propagate2(c, P, x, R, as, vo, dlt);
+    else if constexpr (PV == 4)
+      propagate4<PPM>(c, P, x, R, as, vo, dlt, ppm, pps);
+    else
+      propagate5<PPM>(c, P, x, R, as, vo, dlt, ppm, pps);
   }
+  static constexpr bool kLazyPP = (MV == 4 && PV >= 4);
 };
 // Measured on B200 (tools/tune_solve.cu, profiles/r01_tune_solve.md): fp64 is register-bound at 255 registers, the
 // in-place propagation of version 2 spills more there (139 vs 121 us/launch); fp32 has registers to spare and takes
 // the version with the fewest instructions (67.7 vs 77.4 us/launch).
 template <typename T>
-struct DefaultMath : MathSel<2, 1> {};
-template <>
-struct DefaultMath<float> : MathSel<2, 2> {};
+struct DefaultMath : MathSel<4, 5> {};
 
 template <typename T>
 struct StageRec {
@@ -1256,13 +1723,12 @@ struct GlobalStageSource {
 // reference re-solves the whole QP every step.  `src` hands out the stage records: ordinal j = 0.. is
 // the position in the sweep (stage k0 + j), acquire/release bracket the use of one record (the TMA
 // path maps them onto the full/empty mbarriers of its shared-memory ring).
-template <typename T, typename Source, typename Math = DefaultMath<T>>
-DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
-                      int Tk, int i, Source &src) {
-  const int n = dm.n, ns = dm.ns, N = dm.N;
-  Cov9<T> P;
-  Vec9<T> x;
-  int k0;
+// Start of the sweep of update(T): the prior at stage 0 while the window is still growing, else the arrival cost at stage
+// T-N.  Returns the first stage k0.  Separate from the sweep so that the TMA kernel can issue these loads before it sets
+// up its barriers and tiles.
+template <typename T, typename X>
+DEKF_HD int mhe_solve_start(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, int Tk, int i, Cov9<T> &P, X &x) {
+  const int ns = dm.ns, N = dm.N;
   if (Tk < N) {
     // Prior_0: Q_prior = blkdiag(Q_p0, Q_v0, Q_b0), x_prior = 0 (DecentralEst.cpp:232-253)
 #pragma unroll
@@ -1278,28 +1744,70 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
     P.bb.a[0] = c.P0[6];
     P.bb.a[3] = c.P0[7];
     P.bb.a[5] = c.P0[8];
-    x.p = x.v = x.b = v3<T>(T(0), T(0), T(0));
-    k0 = 0;
-  } else {
-    load_cov(b.arr_P, ns, i, P);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) x.p[f] = x.v[f] = x.b[f] = T(0);
+    return 0;
+  }
+  load_cov(b.arr_P, ns, i, P);
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    x.p[f] = b.arr_x[(size_t)f * ns + i];
+    x.v[f] = b.arr_x[(size_t)(3 + f) * ns + i];
+    x.b[f] = b.arr_x[(size_t)(6 + f) * ns + i];
+  }
+  return Tk - N;
+}
+
+template <typename T, typename Source, typename Math = DefaultMath<T>, typename X = Vec9<T>>
+DEKF_HD int mhe_solve_sweep(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
+                            int Tk, int i, Source &src, Cov9<T> &P, X &x, const int k0) {
+  const int n = dm.n, ns = dm.ns, N = dm.N;
+  // Version-4 math: P_pp is only needed where the arrival cost of the next tick is produced, i.e. in stage T-N.  That
+  // stage is peeled off (it carries P_pp in registers); the loop over the remaining stages does not carry P_pp at all.
+  // Otherwise: one copy of the stage body in the instruction stream (the loop is ~2k instructions; the I-cache matters).
+  constexpr bool LZ = Math::kLazyPP;
+  constexpr int PPM = LZ ? 0 : 1;
+  M3<T> RT;
+  V3<T> om = v3<T>(T(0), T(0), T(0));
+  int k = k0;
+  if (LZ && Tk >= N) {
+    src.acquire(0);
+    {
+      S3<T> Lam;
+      V3<T> eta;
+      src.meas(0, k, Lam, eta);
+      Math::template meas<1>(P, x, Lam, eta);
+    }
+    src.rot(0, k, RT);
+    {
+      V3<T> as, dlt;
+      bool vo;
+      src.dyn(0, k, as, dlt, vo);
+      src.release(0);
+      Math::template prop<1>(c, P, x, RT, as, vo, dlt);
+    }
+    // marginalizeQP(T-N): the arrival cost moves to x_{T-N+1} (MheSrb.cpp:475-713)
+    store_cov(b.arr_P, ns, i, P);
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
-      x.p[f] = b.arr_x[(size_t)f * ns + i];
-      x.v[f] = b.arr_x[(size_t)(3 + f) * ns + i];
-      x.b[f] = b.arr_x[(size_t)(6 + f) * ns + i];
+      b.arr_x[(size_t)f * ns + i] = x.p[f];
+      b.arr_x[(size_t)(3 + f) * ns + i] = x.v[f];
+      b.arr_x[(size_t)(6 + f) * ns + i] = x.b[f];
     }
-    k0 = Tk - N;
+    if (k == Tk - 1) {
+#pragma unroll
+      for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
+    }
+    ++k;
   }
-  // one copy of each stage body in the instruction stream (the loop is ~2.4k instructions; the I-cache matters)
-  M3<T> RT;
-  for (int k = k0;; ++k) {
+  for (;; ++k) {
     const int j = k - k0;
     src.acquire(j);
     {
       S3<T> Lam;
       V3<T> eta;
       src.meas(j, k, Lam, eta);
-      Math::meas(P, x, Lam, eta);
+      Math::template meas<PPM>(P, x, Lam, eta);
     }
     src.rot(j, k, RT);
     if (k == Tk) {
@@ -1311,10 +1819,14 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
       bool vo;
       src.dyn(j, k, as, dlt, vo);
       src.release(j);
-      Math::prop(c, P, x, RT, as, vo, dlt);
+      Math::template prop<PPM>(c, P, x, RT, as, vo, dlt);
     }
-    if (k == Tk - N) {
-      // marginalizeQP(T-N): the arrival cost moves to x_{T-N+1} (MheSrb.cpp:475-713)
+    if (k == Tk - 1) {
+      // angular velocity of the newest sample for the read-out below: fetched one stage ahead of its use
+#pragma unroll
+      for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
+    }
+    if (!LZ && k == Tk - N) {
       store_cov(b.arr_P, ns, i, P);
 #pragma unroll
       for (int f = 0; f < 3; ++f) {
@@ -1325,20 +1837,28 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
     }
   }
   // getsolution(T) + v_MHE_b = R_sb (v + omega x p_imu_2_opti) (DecentralEst.cpp:181-185)
-  V3<T> om;
+  if (k0 == Tk) {  // (not reachable from update(T >= 1); keeps the read-out defined)
 #pragma unroll
-  for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
+    for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
+  }
   const V3<T> lever = v3<T>(T(0.016041), T(0.089061), T(0.0579875));
-  const V3<T> vb = mul(RT, add(x.v, cross(om, lever)));
+  Vec9<T> xr;
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    xr.p[f] = x.p[f];
+    xr.v[f] = x.v[f];
+    xr.b[f] = x.b[f];
+  }
+  const V3<T> vb = mul(RT, add(xr.v, cross(om, lever)));
   int status = 0;
-  const T chk = x.p[0] + x.p[1] + x.p[2] + x.v[0] + x.v[1] + x.v[2] + x.b[0] + x.b[1] + x.b[2];
+  const T chk = xr.p[0] + xr.p[1] + xr.p[2] + xr.v[0] + xr.v[1] + xr.v[2] + xr.b[0] + xr.b[1] + xr.b[2];
   if (!(chk == chk) || !(chk - chk == T(0))) status |= ST_NONFINITE;
   if (out.x != nullptr) {
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
-      out.x[(size_t)f * n + i] = (double)x.p[f];
-      out.x[(size_t)(3 + f) * n + i] = (double)x.v[f];
-      out.x[(size_t)(6 + f) * n + i] = (double)x.b[f];
+      out.x[(size_t)f * n + i] = (double)xr.p[f];
+      out.x[(size_t)(3 + f) * n + i] = (double)xr.v[f];
+      out.x[(size_t)(6 + f) * n + i] = (double)xr.b[f];
     }
   }
   if (out.v_body != nullptr) {
@@ -1346,6 +1866,15 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
     for (int f = 0; f < 3; ++f) out.v_body[(size_t)f * n + i] = (double)vb[f];
   }
   return status;
+}
+
+template <typename T, typename Source, typename Math = DefaultMath<T>>
+DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
+                      int Tk, int i, Source &src) {
+  Cov9<T> P;
+  Vec9<T> x;
+  const int k0 = mhe_solve_start(c, dm, b, Tk, i, P, x);
+  return mhe_solve_sweep<T, Source, Math>(c, dm, b, in, out, Tk, i, src, P, x, k0);
 }
 
 template <typename T>

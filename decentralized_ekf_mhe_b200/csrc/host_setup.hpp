@@ -140,6 +140,10 @@ inline MheConst<T> make_mhe_const(const dekf_config &c) {
     m.n2[i] = (i == 0) ? m.d2[0] : m.d2[i] - m.d2[0];
     m.n3[i] = (i == 0) ? m.d3[0] : m.d3[i] - m.d3[0];
     m.nvo[i] = (i == 0) ? m.cvo[0] : m.cvo[i] - m.cvo[0];
+    const double Ca0 = std::pow(c.accel_input_std[0], 2), Cai = std::pow(c.accel_input_std[i], 2);
+    const double Cp0 = dt * dt * std::pow(c.p_process_std[0], 2), Cpi = dt * dt * std::pow(c.p_process_std[i], 2);
+    m.ae[i] = (T)((i == 0) ? Ca0 : Cai - Ca0);
+    m.pe[i] = (T)((i == 0) ? Cp0 : Cpi - Cp0);
   }
   for (int i = 0; i < 8; ++i) {
     m.cenc_v[i] = (T)std::pow(c.joint_velocity_std[i], 2);

@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "estimator_core.cuh"
 
 namespace dekf {
@@ -17,7 +19,18 @@ namespace dekf {
 // is signalled on a "full" mbarrier (expect_tx), consumers hand the buffer back through an "empty" mbarrier.
 // The stage record is read from shared memory at the point of use instead of being parked in registers.
 constexpr int kTile = 128;
-constexpr int kStages = 3;
+// Ring depth and CTAs per SM per element type (measured, profiles/r02_tune_solve.md).  fp64: the sweep needs ~250 registers,
+// i.e. 2 CTAs/SM; 4 stage tiles of 25.6 KB each per CTA.  fp32: 128 registers and 4 CTAs/SM without spills.
+template <typename T>
+struct SolveCfg {
+  static constexpr int kStages = 3, kMinB = 1;
+  static constexpr bool kXS = false;
+};
+template <>
+struct SolveCfg<float> {
+  static constexpr int kStages = 3, kMinB = 4;
+  static constexpr bool kXS = false;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -51,7 +64,15 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
       : "memory");
 }
 
-template <typename T, int TILE = kTile, int STAGES = kStages>
+template <typename T, int TILE, bool XS>
+__device__ __forceinline__ typename std::conditional<XS, MemVec9<T, TILE>, Vec9<T>>::type make_x(T *col) {
+  if constexpr (XS)
+    return MemVec9<T, TILE>(col);
+  else
+    return Vec9<T>();
+}
+
+template <typename T, int TILE = kTile, int STAGES = SolveCfg<T>::kStages>
 struct SmemStageSource {
   T *tiles;         // [STAGES][REC_SIZE][TILE]
   uint64_t *full;   // [STAGES]
@@ -98,12 +119,14 @@ struct SmemStageSource {
   }
 };
 
-template <typename T, int TILE = kTile, int STAGES = kStages>
+template <typename T, int TILE = kTile, int STAGES = SolveCfg<T>::kStages, bool XS = SolveCfg<T>::kXS>
 constexpr size_t solve_tma_smem_bytes() {
-  return (size_t)STAGES * REC_SIZE * TILE * sizeof(T) + 2 * STAGES * sizeof(uint64_t);
+  return (size_t)STAGES * REC_SIZE * TILE * sizeof(T) + 2 * STAGES * sizeof(uint64_t) + (XS ? (size_t)9 * TILE * sizeof(T) : 0);
 }
 
-template <typename T, int TILE = kTile, int STAGES = kStages, int MINB = 1, typename Math = DefaultMath<T>>
+// XS: keep the state mean x (9 scalars per instance) in shared memory instead of registers ([9][TILE] behind the ring)
+template <typename T, int TILE = kTile, int STAGES = SolveCfg<T>::kStages, int MINB = SolveCfg<T>::kMinB, typename Math = DefaultMath<T>,
+          bool XS = SolveCfg<T>::kXS>
 __global__ void __launch_bounds__(TILE, MINB) k_solve_tma(const __grid_constant__ CUtensorMap tmap, const MheConst<T> c, const Dims dm,
                                                      const Buffers<T> b, const Inputs in, const Outputs out, int Tk,
                                                      int32_t *status_out) {
@@ -119,6 +142,12 @@ __global__ void __launch_bounds__(TILE, MINB) k_solve_tma(const __grid_constant_
   src.k0 = (Tk < dm.N) ? 0 : Tk - dm.N;
   src.nst = Tk - src.k0 + 1;
   const int active = min(TILE, dm.n - src.i0);  // consumers in this CTA (thread 0 is always one of them)
+  // the arrival-cost loads are in flight while the barriers are set up and the first tiles are requested
+  const int i = src.i0 + threadIdx.x;
+  Cov9<T> P;
+  using XT = typename std::conditional<XS, MemVec9<T, TILE>, Vec9<T>>::type;
+  XT x = make_x<T, TILE, XS>(reinterpret_cast<T *>(smem_raw + (size_t)STAGES * REC_SIZE * TILE * sizeof(T) + 2 * STAGES * sizeof(uint64_t)) + threadIdx.x);
+  if (i < dm.n) mhe_solve_start(c, dm, b, Tk, i, P, x);
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int s = 0; s < STAGES; ++s) {
@@ -132,10 +161,9 @@ __global__ void __launch_bounds__(TILE, MINB) k_solve_tma(const __grid_constant_
     const int pre = src.nst < STAGES ? src.nst : STAGES;
     for (int j = 0; j < pre; ++j) src.issue(j);
   }
-  const int i = src.i0 + threadIdx.x;
   if (i >= dm.n) return;
   int st = tick_status(dm, b, Tk, i);
-  st |= mhe_solve<T, SmemStageSource<T, TILE, STAGES>, Math>(c, dm, b, in, out, Tk, i, src);
+  st |= mhe_solve_sweep<T, SmemStageSource<T, TILE, STAGES>, Math, XT>(c, dm, b, in, out, Tk, i, src, P, x, src.k0);
   tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
@@ -143,7 +171,7 @@ __global__ void __launch_bounds__(TILE, MINB) k_solve_tma(const __grid_constant_
 // Incremental window solve on a tick that carries VO messages: the CTA agrees on the earliest restart stage of its 128
 // instances (re-sweeping from an earlier valid checkpoint gives the same bits) and streams the stage records
 // ks .. T through the same TMA ring as k_solve_tma.
-template <typename T, int TILE = kTile, int STAGES = kStages, typename Math = DefaultMath<T>>
+template <typename T, int TILE = kTile, int STAGES = SolveCfg<T>::kStages, typename Math = DefaultMath<T>>
 __global__ void __launch_bounds__(TILE, 1) k_solve_incr_tma(const __grid_constant__ CUtensorMap tmap, const MheConst<T> c,
                                                             const Dims dm, const Buffers<T> b, const Inputs in,
                                                             const Outputs out, int Tk, int32_t *status_out) {

@@ -28,6 +28,8 @@ inline CT operator/(CT a, CT b) { Cnt::div++; return CT(a.v / b.v); }
 inline CT operator-(CT a) { return CT(-a.v); }
 inline CT &operator+=(CT &a, CT b) { Cnt::add++; a.v += b.v; return a; }
 inline CT &operator-=(CT &a, CT b) { Cnt::add++; a.v -= b.v; return a; }
+inline CT &operator*=(CT &a, CT b) { Cnt::mul++; a.v *= b.v; return a; }
+inline bool operator!=(CT a, CT b) { return a.v != b.v; }
 inline bool operator==(CT a, CT b) { return a.v == b.v; }
 inline CT sqrt(CT a) { Cnt::sq++; return CT(std::sqrt(a.v)); }
 
@@ -60,15 +62,27 @@ int main() {
   V3<CT> eta = v3<CT>(CT(1.0), CT(2.0), CT(3.0));
   M3<CT> R = quat_to_rot<CT>(CT(0.9), CT(0.1), CT(0.2), CT(0.3));
   V3<CT> as = v3<CT>(CT(0.1), CT(0.0), CT(0.2)), dlt = v3<CT>(CT(0.002), CT(0.0), CT(0.0));
+  // the committed sweep: DefaultMath = version-4 measurement stage + version-5 propagation; PPM 0 = the loop body of the
+  // full re-sweep (P_pp not carried), PPM 1 = the peeled arrival stage / incremental sweep / KF alternative
+  using Mth = DefaultMath<CT>;
   Cnt::reset();
-  meas_update(P, x, Lam, eta);
+  Mth::meas<0>(P, x, Lam, eta);
   long f_meas = Cnt::flops(), d_meas = Cnt::div;
   Cnt::reset();
-  propagate(mc, P, x, R, as, false, dlt);
+  Mth::prop<0>(mc, P, x, R, as, false, dlt);
   long f_prop = Cnt::flops();
   Cnt::reset();
-  propagate(mc, P, x, R, as, true, dlt);
+  Mth::prop<0>(mc, P, x, R, as, true, dlt);
   long f_prop_vo = Cnt::flops();
+  Cnt::reset();
+  Mth::meas<1>(P, x, Lam, eta);
+  long f_meas_pp = Cnt::flops();
+  Cnt::reset();
+  Mth::prop<1>(mc, P, x, R, as, false, dlt);
+  long f_prop_pp = Cnt::flops();
+  Cnt::reset();
+  Mth::prop<1>(mc, P, x, R, as, true, dlt);
+  long f_prop_vo_pp = Cnt::flops();
   // EKF
   EkfState<CT> s;
   for (int f = 0; f < 4; ++f) s.q[f] = CT(f == 0 ? 1.0 : 0.01);
@@ -120,7 +134,7 @@ int main() {
   long f_asm = Cnt::flops(), t_asm = Cnt::trig;
   std::printf("{\"meas_update\": %ld, \"propagate\": %ld, \"propagate_vo\": %ld, \"ekf_predict\": %ld, "
               "\"ekf_correct\": %ld, \"ekf_vo_correct\": %ld, \"assemble_go1\": %ld, \"assemble_go1_sincos\": %ld, "
-              "\"meas_update_div\": %ld}\n",
-              f_meas, f_prop, f_prop_vo, f_pred, f_corr, f_vo, f_asm, t_asm, d_meas);
+              "\"meas_update_div\": %ld, \"meas_update_pp\": %ld, \"propagate_pp\": %ld, \"propagate_vo_pp\": %ld}\n",
+              f_meas, f_prop, f_prop_vo, f_pred, f_corr, f_vo, f_asm, t_asm, d_meas, f_meas_pp, f_prop_pp, f_prop_vo_pp);
   return 0;
 }

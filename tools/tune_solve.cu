@@ -93,10 +93,10 @@ struct Ctx {
   int reps;
 };
 
-template <typename T, int TILE, int STAGES, int MINB, typename Math = DefaultMath<T>>
+template <typename T, int TILE, int STAGES, int MINB, typename Math = DefaultMath<T>, bool XS = false>
 void run_variant(Ctx<T> &c, const char *name) {
-  auto kern = k_solve_tma<T, TILE, STAGES, MINB, Math>;
-  const size_t smem = solve_tma_smem_bytes<T, TILE, STAGES>();
+  auto kern = k_solve_tma<T, TILE, STAGES, MINB, Math, XS>;
+  const size_t smem = solve_tma_smem_bytes<T, TILE, STAGES, XS>();
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, kern));
@@ -175,15 +175,12 @@ void run_all(int n, int N, int reps) {
     cudaEventElapsedTime(&ms, e0, e1);
     std::printf("%-28s %8.2f us/launch\n", "global-load kernel", 1e3 * ms / reps);
   }
-  run_variant<T, 128, 3, 1>(c, "tma 128x3 default math");
-  run_variant<T, 128, 3, 1, MathSel<1, 1>>(c, "tma 128x3 meas1 prop1");
-  run_variant<T, 128, 3, 1, MathSel<2, 2>>(c, "tma 128x3 meas2 prop2");
-  run_variant<T, 128, 3, 1, MathSel<3, 1>>(c, "tma 128x3 meas3 prop1");
-  run_variant<T, 128, 3, 1, MathSel<1, 2>>(c, "tma 128x3 meas1 prop2");
-  run_variant<T, 128, 3, 1, MathSel<2, 1>>(c, "tma 128x3 meas2 prop1");
-  run_variant<T, 128, 3, 1, MathSel<3, 2>>(c, "tma 128x3 meas3 prop2");
-  run_variant<T, 128, 2, 4, MathSel<2, 2>>(c, "tma 128x2 minb4 meas2 prop2");
-  run_variant<T, 64, 3, 4, MathSel<1, 1>>(c, "tma 64x3 minb4 meas1 prop1");
+  run_variant<T, 128, SolveCfg<T>::kStages, SolveCfg<T>::kMinB>(c, "product config (meas4 prop5)");
+  run_variant<T, 128, 3, 1, MathSel<4, 4>>(c, "tma 128x3 minb1 meas4 prop4");
+  run_variant<T, 128, 3, 1, DefaultMath<T>, true>(c, "tma 128x3 minb1 x-in-smem");
+  run_variant<T, 128, 2, 3, DefaultMath<T>, true>(c, "tma 128x2 minb3 x-in-smem");
+  run_variant<T, 128, 2, 3, DefaultMath<T>, false>(c, "tma 128x2 minb3");
+  run_variant<T, 128, 3, 1, MathSel<2, 1>>(c, "tma 128x3 meas2 prop1 (r01)");
   cudaFree(c.b.arr_P);
   cudaFree(c.b.arr_x);
   cudaFree(c.b.win);
