@@ -175,21 +175,58 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_port_baseline(N, threads, steps_timed, instances_per_thread, mode="admm", seed=20240510):
-    """Times the oracle (CPU restatement) on a bounded sample of the same workload, one instance per thread."""
+def shared_config(n, world, N, precision, robot="go1", box=False, leg_odom_type=0, est_type=0, window_solve="full"):
+    """The `config` object of the JSON line: a pure function of the workload, identical for our arm and the reference arm."""
+    std = (robot == "go1" and n == 65536 and N == 20 and precision == "fp64" and not box and leg_odom_type == 0 and est_type == 0)
+    return {"workload": WORKLOAD if std else f"{robot}_ekf_mhe_{n}x_N{N}_{precision}" + ("_box" if box else "") +
+            ("_footstates" if leg_odom_type else "") + ("_kf" if est_type else ""),
+            "robot": robot, "instances_per_gpu": n, "instances_total": n * world, "N": N, "rate_hz": 200,
+            "vo": "30 Hz, 40 ms latency, lock-step arrival", "parallelism": f"instance-shard x{world}",
+            "window_solve": window_solve, "est_type": est_type, "leg_odom_type": leg_odom_type, "v_box": bool(box),
+            "cache": "per-step working set (window ring + inputs + per-tick outputs, > 300 MB at 65,536 instances) exceeds the 126 MB L2; "
+                     "every step reads distinct input arrays and writes distinct output arrays"}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(N, K, W, min_seconds=5.0, max_seconds=150.0, mode="admm", ipt_min=64, seed=20240510):
+    """The reference's CPU algorithm (oracle port) on the host cores: one instance at a time per thread, threads pinned,
+    every thread stepping `ipt` instances through FILL + W warm-up + K timed steady-state ticks.  BASELINE.md section 2
+    protocol: OSQP-style ADMM with a cold setup every tick, eps_abs = eps_rel = 1e-8, no wall-clock limit.  `ipt` is
+    calibrated so that the timed region lasts at least `min_seconds` whatever K is (stable numbers), capped by
+    `max_seconds` for the whole run.  Returns (instance-steps/s, timed seconds, instances, ipt, cores)."""
     from decentralized_ekf_mhe_b200 import synth
     from oracle import pyoracle as po
-    n = threads * instances_per_thread
-    S = N + 4 + steps_timed
-    st = synth.to_numpy(synth.make_stream(n, S, seed=seed))
-    if mode == "admm":
-        # reference-faithful: OSQP-style ADMM, cold setup every step, shipped tolerances, no wall-clock limit
-        prm = po.go1_params(N=N, solve_mode=2, time_limit=0.0)
-    else:
-        prm = po.go1_params(N=N, solve_mode=0)
-    res, wall, busy = po.run_batch(st, prm, po.ekf_params(rate=200), nthreads=threads, t_steady=N + 4, want=())
-    t = max(res["_busy_max"], 1e-9)
-    return n * steps_timed / t, t, n, S
+    cores = host_cores()
+    po.pin_threads(True)
+    fill = fill_steps(N)
+
+    def params():
+        if mode == "admm":
+            return po.go1_params(N=N, solve_mode=2, time_limit=0.0, abs_tol=1e-8, relative_tol=1e-8)
+        return po.go1_params(N=N, solve_mode=0)
+
+    def run(ipt, ticks_timed, warm):
+        n = cores * ipt
+        S = fill + warm + ticks_timed
+        st = synth.to_numpy(synth.make_stream(n, S, seed=seed))
+        res, wall, busy = po.run_batch(st, params(), po.ekf_params(rate=200), nthreads=cores, t_steady=fill + warm, want=())
+        return max(res["_busy_max"], 1e-9), n
+
+    # calibration: 2 instances per thread x 6 timed ticks
+    t_cal, n_cal = run(2, 6, 0)
+    per_step = t_cal / (2 * 6)  # seconds per instance-step on the slowest thread
+    ipt = max(ipt_min, int(min_seconds / max(K * per_step, 1e-9)) + 1)
+    total_est = ipt * (fill + W + K) * per_step
+    if total_est > max_seconds:
+        ipt = max(1, int(max_seconds / ((fill + W + K) * per_step)))
+    t, n = run(ipt, K, W)
+    return n * K / t, t, n, ipt, cores
 
 
 def batch1_latency(estimator, synth, device, precision, N, steps=300, window_solve=0):
@@ -284,42 +321,86 @@ def run_reference(args):
     (colcon + Eigen3 + OSQP + osqp-eigen + rclcpp) is impossible in this image; its sources do compile against stand-in
     headers into oracle/_ref/ (DESIGN.md 3), but with dense stand-in linear algebra and an exact KKT solve instead of OSQP
     that build is ~15x SLOWER than the real reference would be, so timing it would flatter our arm.  The headline of this
-    arm is therefore the faster oracle port in its reference-faithful mode (OSQP-style ADMM with a cold setup every step,
-    the shipped eps 1e-6, no wall-clock limit) with every host thread, one instance per thread; the compiled reference
-    sources are timed beside it (`reference_sources`) for transparency."""
+    arm is therefore the faster oracle port in its reference-faithful mode (OSQP-style ADMM, cold
+    setup every step, eps_abs = eps_rel = 1e-8, no wall-clock limit) with every host thread pinned, one instance at a time
+    per thread; the compiled reference sources are timed beside it (`reference_sources`) for transparency.  A "step" is one
+    tick of the bounded sample batch (cores x ipt instances); ipt >= 64 and the timed region lasts >= 5 s whatever --steps."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cores = os.cpu_count() or 1
-    K, W = args.steps, args.warmup
+    world = int(os.environ.get("WORLD_SIZE", args.gpus))
+    K, W = args.steps, max(args.warmup, 3)
     N = args.N
-    ipt = args.ref_instances_per_thread
-    from decentralized_ekf_mhe_b200 import synth
-    from oracle import pyoracle as po
-    n = cores * ipt
-    S = N + 4 + W + K
-    st = synth.to_numpy(synth.make_stream(n, S))
-    prm = po.go1_params(N=N, solve_mode=2, time_limit=0.0)
-    res, wall, busy = po.run_batch(st, prm, po.ekf_params(rate=200), nthreads=cores, t_steady=N + 4 + W, want=())
-    t = max(res["_busy_max"], 1e-9)
-    value = n * K / t
-    sample = (f"{n} instances ({ipt}/thread) x {K} steady-state ticks each per step-batch; oracle port, "
-              f"ADMM eps_abs=eps_rel=1e-6, cold setup every tick, time_limit=0")
+    value, t, n, ipt, cores = cpu_reference_run(N, K, W, min_seconds=5.0, mode="admm", ipt_min=args.ref_instances_per_thread)
+    sample = (f"{n} instances ({ipt}/thread, {cores} pinned threads) x {K} steady-state ticks after {fill_steps(N)} fill + {W} warm-up "
+              f"ticks; oracle port, OSQP-style ADMM eps_abs=eps_rel=1e-8, cold setup every tick, time_limit=0; timed {t:.1f} s")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": W, "ms_per_step": 1e3 * t / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "N": N, "rate_hz": 200, "robot": "go1",
-                   "batch_per_step": n, "note": "CPU path; a step is one tick of a bounded sample batch"},
+        "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
+        "config": shared_config(args.instances, world, N, args.precision, args.robot, args.box, args.leg_odom_type, args.est_type,
+                                args.window_solve),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    rs = time_reference_sources(cores, N)
+    rs = time_reference_sources(min(cores, 16), N)
     if rs is not None:
         line["reference_sources"] = rs
     print(json.dumps(line))
     return 0
+
+
+BOX = dict(v_box_enable=1, v_box_lo=(-0.45, -0.03, -0.015), v_box_hi=(0.55, 0.03, 0.015))  # binds in ~50 % of the PogoX steps
+
+
+def bind_rank_to_host(local_rank, local_world):
+    """One process per GPU: give every rank its own slice of the host cores -- the cores of its GPU's NUMA node when sysfs
+    says which that is -- and prefer that node for the pinned buffers it allocates afterwards (first touch happens on these
+    cores; set_mempolicy(MPOL_PREFERRED) when the node is allowed).  Returns what was done, for the JSON line."""
+    info = {"cores": None, "numa_node": None, "mempolicy": None}
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        node = None
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(local_rank)
+            bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            v = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+            node = v if v >= 0 else None
+        except Exception:
+            node = None
+        pool = allowed
+        if node is not None:
+            try:
+                cl = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+                cpus = set()
+                for part in cl.split(","):
+                    lo, _, hi = part.partition("-")
+                    cpus.update(range(int(lo), int(hi or lo) + 1))
+                near = [c for c in allowed if c in cpus]
+                if len(near) >= 2:
+                    pool = near
+            except Exception:
+                pass
+        k = max(1, len(pool) // max(1, local_world))
+        mine = pool[(local_rank * k) % len(pool):][:k] or pool
+        os.sched_setaffinity(0, mine)
+        info["cores"] = [mine[0], mine[-1], len(mine)]
+        info["numa_node"] = node
+        if node is not None:
+            try:
+                import ctypes
+                libc = ctypes.CDLL(None, use_errno=True)
+                mask = ctypes.c_ulong(1 << node)
+                MPOL_PREFERRED = 1
+                rc = libc.syscall(238, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(8 * ctypes.sizeof(mask)))
+                info["mempolicy"] = "preferred" if rc == 0 else f"errno {ctypes.get_errno()}"
+            except Exception as e:
+                info["mempolicy"] = repr(e)[:60]
+    except Exception as e:
+        info["error"] = repr(e)[:80]
+    return info
 
 
 def main():
@@ -331,13 +412,18 @@ def main():
     ap.add_argument("--instances", type=int, default=65536, help="instances per GPU")
     ap.add_argument("--N", type=int, default=20)
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--robot", default="go1", choices=["go1", "cassie", "pogox"])
+    ap.add_argument("--box", action="store_true", help="state constraints lo <= v_s <= hi on every window state (BASELINE config 4)")
+    ap.add_argument("--leg-odom-type", type=int, default=0, choices=[0, 1])
+    ap.add_argument("--est-type", type=int, default=0, choices=[0, 1])
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--window-solve", default="full", choices=["full", "incremental"],
                     help="full: re-sweep the whole window every tick (tier A, the reference's semantics); "
                          "incremental: restart at the first changed stage (tier B, bit-identical results)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--ref-instances-per-thread", type=int, default=4)
+    ap.add_argument("--no-configs", action="store_true", help="skip the compact objects of BASELINE configs 3/4/5 and the ragged-VO stream")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--ref-instances-per-thread", type=int, default=64)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -353,6 +439,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (our arm) needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    binding = bind_rank_to_host(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W, K = max(args.warmup, 3), args.steps
@@ -363,123 +450,170 @@ def main():
     assert hi - lo == n
     N = args.N
     FILL = fill_steps(N)
+    robot = args.robot
+    plain = not (args.box or args.leg_odom_type or args.est_type)  # the 9-state MHE: both solve modes exist
+    base_over = dict(est_type=args.est_type, leg_odom_type=args.leg_odom_type, **(BOX if args.box else {}))
     S = FILL + W + K + 2 * (Ke + 8) + 20 + 24
     dev = torch.device("cuda", local_rank)
-
-    # ---- synthetic stream, resident in HBM before any timed region (each rank: its own instance range)
-    t_gen = time.time()
-    stream = synth.make_stream(n, S, seed=20240510 + 7919 * rank, device=dev, device_rng=True)
-    torch.cuda.synchronize()
-    t_gen = time.time() - t_gen
-    vo_steps = [bool(stream["vo_flag"][s].any()) for s in range(S)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def sub(a, b):
-        return {k: v[a:b] for k, v in stream.items() if torch.is_tensor(v) and v.shape[0] == S}
+    def gen_stream(rb, nn, SS, jitter=False, seed=20240510 + 7919 * rank, amp=False):
+        st = synth.make_stream(nn, SS, robot=rb, seed=seed, device=dev, device_rng=True, vo_jitter=jitter, amp_jitter=amp)
+        vo = [bool(st["vo_flag"][s].any()) for s in range(SS)]
+        return st, vo
 
-    T0 = FILL + W
+    def sub(st, a, b_, SS):
+        return {k: v[a:b_] for k, v in st.items() if torch.is_tensor(v) and v.shape[0] == SS}
 
-    def timed_pass(mode):
-        """K ticks in one dekf_run call, inputs resident in HBM, CUDA events on the launching stream, max over ranks;
-        then a tick-by-tick pass of a fresh handle over the same ticks with an event pair around every launch."""
-        prm = estimator.robot_params("go1", ekf_rate=200, N=N, window_solve=1 if mode == "incremental" else 0)
-        est = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
-        est.run(0, T0, sub(0, T0), vo_steps[:T0])
+    def step_outputs(est, kk, nn):
+        """Per-tick result arrays of the timed region: every tick writes quat, x, v_body, contact, status."""
+        ds, nl = est._hd.ds, est._hd.nl
+        return {"quat": torch.empty(kk, 4, nn, dtype=torch.float64, device=dev), "x": torch.empty(kk, ds, nn, dtype=torch.float64, device=dev),
+                "v_body": torch.empty(kk, 3, nn, dtype=torch.float64, device=dev), "contact": torch.empty(kk, nl, nn, dtype=torch.uint8, device=dev),
+                "status": torch.empty(kk, nn, dtype=torch.int32, device=dev)}
+
+    def device_pass(rb, nn, NN, precision, over, st, vo, SS, t0, kk, profile_ticks=0, keep=False):
+        """kk ticks in one dekf_run call, inputs resident in HBM, every tick's results written to per-tick arrays, CUDA events
+        on the launching stream, max over ranks; optionally a tick-by-tick pass of a fresh handle with an event pair around
+        every launch (per-kernel device time)."""
+        prm = estimator.robot_params(rb, ekf_rate=200, N=NN, **over)
+        est = estimator.BatchedEstimator(prm, nn, device=local_rank, precision=precision)
+        est.run(0, t0, sub(st, 0, t0, SS), vo[:t0])
+        outs = step_outputs(est, kk, nn)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        timed = sub(T0, T0 + K)
+        timed = sub(st, t0, t0 + kk, SS)
         barrier()
         l0 = est.launch_count()
         ev0.record()
-        est.run(T0, K, timed, vo_steps[T0:T0 + K])
+        est.run(t0, kk, timed, vo[t0:t0 + kk], out=outs, out_per_step=True)
         ev1.record()
         barrier()
         ms = max_over_ranks(ev0.elapsed_time(ev1))
-        launches = est.launch_count() - l0
-        n_vo_mean = float(est.window_vo_count().double().mean().item())
-        # per-kernel device time
-        Kp = min(K, 60)
-        est2 = estimator.BatchedEstimator(prm, n, device=local_rank, precision=args.precision)
-        est2.run(0, T0, sub(0, T0), vo_steps[:T0])
-        est2.profile(True)
-        dsum = torch.zeros((), dtype=torch.float64, device=dev)
-        vsum = torch.zeros((), dtype=torch.float64, device=dev)
-        wsum = torch.zeros((), dtype=torch.float64, device=dev)
-        nvo_ticks = 0
-        for s in range(T0, T0 + Kp):
-            est2.step(s, estimator.robot_store.from_stream(stream, s, with_vo=vo_steps[s]))
-            wsum += est2.window_vo_count().double().mean()  # VO rows in the window of THIS tick (flop tally operand)
-            if mode == "incremental" and vo_steps[s]:
-                d, v = est2.resweep_info()
-                dsum += d.double().mean()
-                vsum += v.double().mean()
-                nvo_ticks += 1
-        pms, pcnt = est2.profile_read()
-        est2.close()
-        n_vo_mean = float(wsum.item()) / Kp
-        depth = float(dsum.item()) / max(nvo_ticks, 1)
-        depth_vo = float(vsum.item()) / max(nvo_ticks, 1)
-        return est, dict(ms=ms, launches=launches, n_vo_mean=n_vo_mean, pms=pms, pcnt=pcnt, depth=depth, depth_vo=depth_vo,
-                         vo_tick_share=nvo_ticks / Kp)
+        res = dict(ms=ms, launches=est.launch_count() - l0, checksum=float(outs["x"][:, 3].double().sum().item()),
+                   finite=bool(torch.isfinite(outs["x"]).all().item()), bytes=est.device_bytes())
+        if over.get("v_box_enable"):
+            it, na = est.qp_info()
+            res["factorisations_mean"] = float(it.double().mean())
+            res["active_bounds_mean"] = float(na.double().mean())
+        del outs
+        if profile_ticks:
+            Kp = min(kk, profile_ticks)
+            est2 = estimator.BatchedEstimator(prm, nn, device=local_rank, precision=precision)
+            est2.run(0, t0, sub(st, 0, t0, SS), vo[:t0])
+            est2.profile(True)
+            dsum = torch.zeros((), dtype=torch.float64, device=dev)
+            vsum = torch.zeros((), dtype=torch.float64, device=dev)
+            wsum = torch.zeros((), dtype=torch.float64, device=dev)
+            nvo_ticks = 0
+            incr = over.get("window_solve", 0) == 1
+            for s_ in range(t0, t0 + Kp):
+                est2.step(s_, estimator.robot_store.from_stream(st, s_, with_vo=vo[s_]))
+                if rb != "pogox" or not over.get("v_box_enable"):
+                    wsum += est2.window_vo_count().double().mean()  # VO rows in the window of THIS tick (flop tally operand)
+                if incr and vo[s_]:
+                    d_, v_ = est2.resweep_info()
+                    dsum += d_.double().mean()
+                    vsum += v_.double().mean()
+                    nvo_ticks += 1
+            pms, pcnt = est2.profile_read()
+            est2.close()
+            res.update(pms=pms, pcnt=pcnt, n_vo_mean=float(wsum.item()) / Kp, depth=float(dsum.item()) / max(nvo_ticks, 1),
+                       depth_vo=float(vsum.item()) / max(nvo_ticks, 1), vo_tick_share=nvo_ticks / Kp)
+        if keep:
+            return est, res
+        est.close()
+        return None, res
+
+    # ---- synthetic stream, resident in HBM before any timed region (each rank: its own instance range)
+    t_gen = time.time()
+    stream, vo_steps = gen_stream(robot, n, S)
+    torch.cuda.synchronize()
+    t_gen = time.time() - t_gen
+    T0 = FILL + W
 
     sampler = ClockSampler(local_rank)
     sampler.start()
-    mode = args.window_solve
-    est, main = timed_pass(mode)
+    mode = args.window_solve if plain else "full"
     other_mode = "full" if mode == "incremental" else "incremental"
-    est_o, other = timed_pass(other_mode)
-    est_o.close()
+
+    def over_for(md):
+        o = dict(base_over)
+        if plain:
+            o["window_solve"] = 1 if md == "incremental" else 0
+        return o
+
+    est, main = device_pass(robot, n, N, args.precision, over_for(mode), stream, vo_steps, S, T0, K, profile_ticks=60 if plain else 0, keep=True)
+    other = None
+    if plain:
+        _, other = device_pass(robot, n, N, args.precision, over_for(other_mode), stream, vo_steps, S, T0, K, profile_ticks=60)
     ms_value, launches = main["ms"], main["launches"]
     value = n_total * K / (ms_value * 1e-3)
     T = T0 + K
 
-    # ---- e2e: the same metric through dekf_run_host with pinned HOST streams: every tick's inputs are copied H2D and
-    # every tick's results (quat, x_MHE, v_body, contact, status) are copied D2H inside the timed region
+    # ---- e2e: the same metric through the host-buffer entry point with pinned HOST streams: every tick's inputs are copied
+    # H2D and every tick's results (quat, x_MHE, v_body, contact, status) are copied D2H inside the timed region.
+    # Headline contract: dekf_run_host_f32io -- sensor streams as float32 (what the robot SDK delivers), results as float32;
+    # time stamps, VO messages and ALL arithmetic double.  The all-double contract (dekf_run_host) is timed beside it.
     keys = ["gyro", "accel", "imu_time", "joint_pos", "joint_vel", "foot_force", "vo_quat", "vo_time_pre",
             "vo_time_now", "vo_rel_p"]
+    F32 = estimator.BatchedEstimator.F32_KEYS
     rows = {k: (stream[k][0].numel() // n) for k in keys}
+    ds_rows, nl = est._hd.ds, est._hd.nl
     Kw = 8  # untimed warm-up ticks of the host path (first call allocates the device staging and the copy streams)
-    Ke = max(1, min(Ke, S - T - Kw - 20))
 
-    def host_slice(a, b):
-        h = {k: stream[k][a:b].reshape(b - a, rows[k], n).cpu().pin_memory() for k in keys}
-        h["vo_flag"] = stream["vo_flag"][a:b].cpu().pin_memory()
+    def host_slice(a, b_, f32):
+        h = {k: stream[k][a:b_].reshape(b_ - a, rows[k], n).cpu() for k in keys}
+        if f32:
+            for k in F32:
+                h[k] = h[k].float()
+        h = {k: v.pin_memory() for k, v in h.items()}
+        h["vo_flag"] = stream["vo_flag"][a:b_].cpu().pin_memory()
         return h
 
-    def host_out(k):
-        return {"quat": torch.empty(k, 4, n, dtype=torch.float64).pin_memory(),
-                "x": torch.empty(k, 9, n, dtype=torch.float64).pin_memory(),
-                "v_body": torch.empty(k, 3, n, dtype=torch.float64).pin_memory(),
-                "contact": torch.empty(k, 4, n, dtype=torch.uint8).pin_memory(),
+    def host_out(k, dt):
+        return {"quat": torch.empty(k, 4, n, dtype=dt).pin_memory(), "x": torch.empty(k, ds_rows, n, dtype=dt).pin_memory(),
+                "v_body": torch.empty(k, 3, n, dtype=dt).pin_memory(), "contact": torch.empty(k, nl, n, dtype=torch.uint8).pin_memory(),
                 "status": torch.empty(k, n, dtype=torch.int32).pin_memory()}
 
-    est.run_host(T, Kw, host_slice(T, T + Kw), vo_steps[T:T + Kw], out=host_out(Kw), out_per_step=True)
-    T += Kw
-    hst, hout = host_slice(T, T + Ke), host_out(Ke)
-    h2d = 0
-    for j in range(Ke):
-        has_vo = vo_steps[T + j]
-        h2d += (sum(rows[k] for k in keys[:6]) * 8 * n) + ((sum(rows[k] for k in keys[6:]) * 8 + 1) * n if has_vo else 0)
-    d2h = 16 * 8 * n + 4 * n + 4 * n
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.perf_counter()
-    ev0.record()
-    est.run_host(T, Ke, hst, vo_steps[T:T + Ke], out=hout, out_per_step=True)
-    chk = float(hout["x"][:, 3, 0].sum())  # read the results on the host
-    T += Ke
-    ev1.record()
-    barrier()
-    wall_e2e = time.perf_counter() - t0
-    ms_e2e = max_over_ranks(max(ev0.elapsed_time(ev1), wall_e2e * 1e3))  # device events vs host wall clock: the slower
-    e2e_value = n_total * Ke / (ms_e2e * 1e-3)
+    def e2e_pass(f32_in, f32_out, T, kk):
+        fn = est.run_host_f32 if f32_in else est.run_host
+        odt = torch.float32 if f32_out else torch.float64
+        fn(T, Kw, host_slice(T, T + Kw, f32_in), vo_steps[T:T + Kw], out=host_out(Kw, odt), out_per_step=True)
+        T += Kw
+        hst, hout = host_slice(T, T + kk, f32_in), host_out(kk, odt)
+        in_b = sum(rows[k] * (4 if (f32_in and k in F32) else 8) for k in keys[:6])
+        h2d = sum(in_b * n + ((sum(rows[k] for k in keys[6:]) * 8 + 1) * n if vo_steps[T + j] else 0) for j in range(kk))
+        d2h = (7 + ds_rows) * (4 if f32_out else 8) * n + nl * n + 4 * n
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        fn(T, kk, hst, vo_steps[T:T + kk], out=hout, out_per_step=True)
+        chk = float(hout["x"][:, 3, 0].double().sum())  # read the results on the host
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = max_over_ranks(max(ev0.elapsed_time(ev1), wall * 1e3))  # device events vs host wall clock: the slower
+        T += kk
+        return T, {"value": n_total * kk / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d // kk, "d2h_bytes_per_step": d2h,
+                   "steps": kk, "warmup_steps": Kw, "ms_per_step": ms / kk, "h2d_gbs": (h2d / kk) / (ms / kk * 1e-3) / 1e9,
+                   "d2h_gbs": d2h / (ms / kk * 1e-3) / 1e9, "host_checksum": chk}
+
+    Ke = max(1, min(Ke, (S - T - 2 * Kw - 44) // 2))
+    T, e2e = e2e_pass(True, True, T, Ke)
+    e2e["api"] = ("dekf_run_host_f32io: gyro, accel, joint_pos, joint_vel, foot_force travel as float32 pinned host streams (the robot SDK's "
+                  "type), quat / x / v_body come back as float32; time stamps, VO messages and all arithmetic are double; H2D | kernels | "
+                  "D2H pipelined over chunks of ticks, every tick's inputs copied in and results copied out")
+    T, e2e64 = e2e_pass(False, False, T, Ke)
+    e2e64["api"] = "dekf_run_host: all-double host streams and results (19.1 MB in + 8.9 MB out per tick at 65,536 Go1 instances)"
     # single-tick host path (dekf_step_host: copy in, step, copy out, sync) for comparison
     Ks = min(20, S - T)
-    one_out = {"quat": hout["quat"][0], "x": hout["x"][0], "v_body": hout["v_body"][0]}
-    hs1 = host_slice(T, T + Ks)
+    hs1 = host_slice(T, T + Ks, False)
+    one_out = {k: v[0] for k, v in host_out(1, torch.float64).items() if k in ("quat", "x", "v_body")}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for j in range(Ks):
@@ -487,40 +621,68 @@ def main():
         d["vo_flag"] = hs1["vo_flag"][j] if vo_steps[T] else None
         est.step_host(T, d, one_out)
         T += 1
-    ms_step_host = (time.perf_counter() - t0) * 1e3 / max(Ks, 1)
-    # the same host path with the five sensor streams delivered as float32 (dekf_run_host_f32: what a robot's SDK produces;
-    # widened on the device, arithmetic unchanged) -- reported BESIDE e2e, not instead of it
-    e2e_f32 = None
-    try:
-        Kf = max(1, min(Ke, S - T - 8))
-        def host_slice_f32(a, b):
-            h = host_slice(a, b)
-            for k in estimator.BatchedEstimator.F32_KEYS:
-                h[k] = h[k].float().pin_memory()
-            return h
-        est.run_host_f32(T, 8, host_slice_f32(T, T + 8), vo_steps[T:T + 8], out=host_out(8), out_per_step=True)
-        T += 8
-        hf, hfo = host_slice_f32(T, T + Kf), host_out(Kf)
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        tw = time.perf_counter()
-        f0.record()
-        est.run_host_f32(T, Kf, hf, vo_steps[T:T + Kf], out=hfo, out_per_step=True)
-        chk_f = float(hfo["x"][:, 3, 0].sum())
-        f1.record()
-        barrier()
-        tw = time.perf_counter() - tw
-        ms_f = max_over_ranks(max(f0.elapsed_time(f1), tw * 1e3))
-        h2d_f = sum((sum(rows[k] for k in estimator.BatchedEstimator.F32_KEYS) * 4 + 8) * n
-                    + ((sum(rows[k] for k in keys[6:]) * 8 + 1) * n if vo_steps[T + j] else 0) for j in range(Kf))
-        T += Kf
-        e2e_f32 = {"value": n_total * Kf / (ms_f * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_f // Kf, "d2h_bytes_per_step": d2h,
-                   "steps": Kf, "ms_per_step": ms_f / Kf, "host_checksum": chk_f,
-                   "api": "dekf_run_host_f32 (gyro, accel, joint_pos, joint_vel, foot_force as float32 host streams; time stamps, "
-                          "VO messages and all arithmetic double)"}
-    except Exception as e:
-        e2e_f32 = {"unavailable": repr(e)[:200]}
+    e2e["single_tick_host_call_ms"] = (time.perf_counter() - t0) * 1e3 / max(Ks, 1)
+    est.close()
+    del stream
+    torch.cuda.empty_cache()
+
+    # ---- ragged VO arrival (per-instance camera phase: every tick carries messages for some instances), both solve modes
+    ragged = None
+    configs = None
+    if plain and not args.no_configs:
+        Kr = min(K, 60)
+        Sr = FILL + W + Kr
+        st_r, vo_r = gen_stream(robot, n, Sr, jitter=True)
+        ragged = {"vo": "30 Hz, 40 ms latency, per-instance camera phase (ragged arrival: every tick carries VO messages)", "steps": Kr}
+        for md in ("full", "incremental"):
+            _, r = device_pass(robot, n, N, args.precision, dict(window_solve=1 if md == "incremental" else 0), st_r, vo_r, Sr, FILL + W, Kr)
+            ragged[md] = {"value": n_total * Kr / (r["ms"] * 1e-3), "unit": UNIT, "ms_per_step": r["ms"] / Kr, "finite": r["finite"]}
+        del st_r
+        torch.cuda.empty_cache()
     clocks = sampler.stop()
+
+    # ---- BASELINE configs 3 / 4 / 5 as compact objects (the headline stays config 2)
+    peaks = estimator.measure_peaks(local_rank) if rank == 0 or True else None
+    if plain and not args.no_configs and robot == "go1":
+        configs = {}
+        cases = [("config3_cassie_fp64", "cassie", 65536, 20, "fp64", dict(window_solve=0), 40, False),
+                 ("config3_cassie_fp32", "cassie", 65536, 20, "fp32", dict(window_solve=0), 40, False),
+                 ("config4_pogox_box_16384", "pogox", 16384, 20, "fp64", dict(BOX), 12, False),
+                 ("config5_go1_N100_shard_125000", "go1", 125000, 100, "fp64", dict(window_solve=0), 12, True),
+                 ("go1_fp32", "go1", 65536, 20, "fp32", dict(window_solve=0), 40, False),
+                 ("go1_kf_alternative", "go1", 65536, 20, "fp64", dict(est_type=1), 40, False),
+                 ("go1_foot_states_16384", "go1", 16384, 20, "fp64", dict(leg_odom_type=1), 12, False)]
+        for name, rb, nn, NN, prec, over, kk, amp in cases:
+            try:
+                fl = fill_steps(NN)
+                SS = fl + 3 + kk
+                st_c, vo_c = gen_stream(rb, nn, SS, jitter=(rb == "pogox"), amp=amp)
+                _, r = device_pass(rb, nn, NN, prec, over, st_c, vo_c, SS, fl + 3, kk, profile_ticks=8 if "window_solve" in over else 0)
+                ent = {"robot": rb, "instances_per_gpu": nn, "N": NN, "precision": prec, "value": nn * world * kk / (r["ms"] * 1e-3), "unit": UNIT,
+                       "ms_per_step": r["ms"] / kk, "steps": kk, "finite": r["finite"], "device_bytes": r["bytes"]}
+                if "pms" in r and r["pcnt"].get("solve", 0):
+                    elt = 8 if prec == "fp64" else 4
+                    by, flp = algorithmic_work(NN, r["n_vo_mean"], elt)["solve"]
+                    dur = r["pms"]["solve"] / r["pcnt"]["solve"] * 1e-3
+                    pk = peaks["fp64_tflops"] if prec == "fp64" else peaks["fp32_tflops"]
+                    ent["roofline"] = {"kernel": "k_solve_tma", "kernel_ms": dur * 1e3, "bound": prec, "achieved": flp * nn / dur / 1e12,
+                                       "peak": pk, "unit": "TFLOP/s", "frac": flp * nn / dur / 1e12 / pk,
+                                       "flops_per_instance_step": flp, "bytes_per_instance_step": by}
+                for k_ in ("factorisations_mean", "active_bounds_mean"):
+                    if k_ in r:
+                        ent[k_] = r[k_]
+                if "factorisations_mean" in r:
+                    # k_box_team: ~60 kflop per block-tridiagonal factorisation of the window; latency-bound
+                    flp = 60e3 * r["factorisations_mean"]
+                    ent["roofline"] = {"kernel": "k_box_team", "bound": "latency (sequential stage recursion)", "achieved": flp * nn / (r["ms"] / kk * 1e-3) / 1e12,
+                                       "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": flp * nn / (r["ms"] / kk * 1e-3) / 1e12 / peaks["fp64_tflops"],
+                                       "flops_per_instance_step": flp, "note": "flops are an estimate (60 kflop per factorisation)"}
+                configs[name] = ent
+                del st_c
+                torch.cuda.empty_cache()
+            except Exception as e:  # a side object must not take the headline down
+                configs[name] = {"unavailable": repr(e)[:200]}
+
     # pinned-host copy bandwidth of this box (the roofline of the e2e path): one large H2D and D2H, both directions at once
     pcie = None
     try:
@@ -530,7 +692,7 @@ def main():
         s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         best = 0.0
         for _ in range(3):
-            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
             with torch.cuda.stream(s1):
                 db.copy_(hb, non_blocking=True)
@@ -539,19 +701,21 @@ def main():
             torch.cuda.synchronize()
             best = max(best, nb / (time.perf_counter() - t0) / 1e9)
         pcie = best
+        del hb, hb2, db, db2
     except Exception:
         pcie = None
+    e2e["pinned_copy_gbs_each_way_measured"] = pcie
+    e2e["host_binding"] = binding
 
     # ---- batch-1 step latency (BASELINE metric, second half): one instance, lock-step tick
     lat = lat_o = None
-    if rank == 0:
+    if rank == 0 and plain:
         lat = batch1_latency(estimator, synth, local_rank, args.precision, N, window_solve=1 if mode == "incremental" else 0)
         lat_o = batch1_latency(estimator, synth, local_rank, args.precision, N, window_solve=0 if mode == "incremental" else 1)
 
     line = None
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
-        peaks = estimator.measure_peaks(local_rank)
         elt = 8 if args.precision == "fp64" else 4
         fma_peak = peaks["fp64_tflops"] if args.precision == "fp64" else peaks["fp32_tflops"]
 
@@ -566,53 +730,47 @@ def main():
                 extra = {"tier": "A (full-window re-solve every step)", "vo_stages_in_window_mean": res["n_vo_mean"]}
             return kernel_report(md, work, res["pms"], res["pcnt"], n, hbm_peak, hbm_src, fma_peak, args.precision, extra)
 
-        roof = report(mode, main)
-        roof["measured_copy_gbs"] = peaks["copy_gbs"]
-        alt = {"window_solve": other_mode, "value": n_total * K / (other["ms"] * 1e-3), "unit": UNIT,
-               "ms_per_step": other["ms"] / K, "gpu_launches": other["launches"], "latency_batch1": lat_o,
-               "roofline": report(other_mode, other)}
+        cfg = shared_config(n, world, N, args.precision, robot, args.box, args.leg_odom_type, args.est_type, mode)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD if (n == 65536 and N == 20 and args.precision == "fp64") else
-                       f"go1_ekf_mhe_{n}x_N{N}_{args.precision}",
-                       "robot": "go1", "instances_per_gpu": n, "instances_total": n_total, "N": N, "rate_hz": 200,
-                       "vo": "30 Hz, 40 ms latency, lock-step arrival", "parallelism": f"instance-shard x{world}",
-                       "window_solve": mode + (" (library default = the reference's semantics: every update(T) re-solves the whole "
-                                               "window; the opt-in incremental solve, bit-identical outputs, is reported beside it "
-                                               "under `incremental`)" if mode == "full" else ""),
-                       "cache": "per-step working set (window ring + checkpoints + inputs, >400 MB at 65,536 instances) exceeds the "
-                                "126 MB L2; every step reads distinct input arrays",
-                       "fill_steps": FILL, "stream_gen_s": round(t_gen, 2)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // Ke, "d2h_bytes_per_step": d2h,
-                    "steps": Ke, "warmup_steps": Kw, "ms_per_step": ms_e2e / Ke,
-                    "h2d_gbs": (h2d / Ke) / (ms_e2e / Ke * 1e-3) / 1e9, "d2h_gbs": d2h / (ms_e2e / Ke * 1e-3) / 1e9,
-                    "pinned_copy_gbs_each_way_measured": pcie,
-                    "api": "dekf_run_host (pinned host streams; H2D | kernels | D2H pipelined over chunks of ticks, every "
-                           "tick's inputs copied in and results copied out)",
-                    "single_tick_host_call_ms": ms_step_host, "host_checksum": chk},
-            "e2e_f32_inputs": e2e_f32,
-            "latency_batch1": lat,
-            "ekf_only": {"value": n_total / (roof["all_kernels"]["ekf"]["ms"] * 1e-3) if "ekf" in roof.get("all_kernels", {}) else None,
-                         "unit": "EKF ticks/s", "note": "orien_ekf::timerCallback alone (k_ekf, event pairs, incl. the VO rewind/"
-                         "replay ticks): the reference runs this filter as its own 500 Hz process"},
+            "config": cfg,
+            "timed_region": {"api": "dekf_run, inputs resident in HBM", "outputs": "every tick writes quat, x, v_body, contact, status to "
+                             "per-tick device arrays (out_per_step)", "checksum_vx": main["checksum"], "finite": main["finite"],
+                             "fill_steps": FILL, "stream_gen_s": round(t_gen, 2), "vo_stream": "lock-step arrival (headline); the ragged "
+                             "stream is reported under `vo_ragged`"},
+            "e2e": e2e,
+            "e2e_f64_io": e2e64,
             "gpu_launches": launches,
             "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")},
-            "roofline": roof,
-            ("full_resweep" if other_mode == "full" else "incremental"): alt,
         }
+        if plain:
+            roof = report(mode, main)
+            roof["measured_copy_gbs"] = peaks["copy_gbs"]
+            line["roofline"] = roof
+            line["latency_batch1"] = lat
+            line["ekf_only"] = {"value": n_total / (roof["all_kernels"]["ekf"]["ms"] * 1e-3) if "ekf" in roof.get("all_kernels", {}) else None,
+                                "unit": "EKF ticks/s", "note": "orien_ekf::timerCallback alone (k_ekf, event pairs, incl. the VO rewind/"
+                                "replay ticks): the reference runs this filter as its own 500 Hz process"}
+            line["full_resweep" if other_mode == "full" else "incremental"] = {
+                "window_solve": other_mode, "value": n_total * K / (other["ms"] * 1e-3), "unit": UNIT, "ms_per_step": other["ms"] / K,
+                "gpu_launches": other["launches"], "latency_batch1": lat_o, "roofline": report(other_mode, other)}
+        else:
+            line["roofline"] = {"bound": "latency", "achieved": None, "peak": None, "unit": "TFLOP/s", "frac": None, "traffic": None,
+                                "note": "variant path (see DESIGN.md 8 / 9): no per-kernel tally"}
+        if ragged is not None:
+            line["vo_ragged"] = ragged
+        if configs is not None:
+            line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            # bounded sample sized for ~cpu-seconds of work at ~250 instance-steps/s/core
-            steps_cpu = 60
-            ipt = max(1, int(args.cpu_seconds * 250 / steps_cpu))
-            v, t, nn, SS = cpu_port_baseline(N, cores, steps_cpu, ipt, mode="admm")
-            vd, td, _, _ = cpu_port_baseline(N, cores, 200, 4, mode="direct")
+            # the same protocol as the reference arm (bench.py --impl reference), bounded to ~cpu-seconds of timed work
+            v, t, nn, ipt, cores = cpu_reference_run(N, 20, 3, min_seconds=min(args.cpu_seconds, 8.0), max_seconds=4 * args.cpu_seconds, mode="admm")
+            vd, td, _, _, _ = cpu_reference_run(N, 20, 3, min_seconds=2.0, max_seconds=20.0, mode="direct", ipt_min=8)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{nn} instances x {steps_cpu} steady-state ticks, one instance per thread; oracle port in "
-                          f"reference-faithful mode (OSQP-style ADMM, cold setup every tick, eps 1e-6, no time limit); {t:.1f} s",
+                "sample": f"{nn} instances ({ipt}/thread, {cores} pinned threads) x 20 steady-state ticks; oracle port in reference-faithful "
+                          f"mode (OSQP-style ADMM, cold setup every tick, eps_abs=eps_rel=1e-8, no time limit); timed {t:.1f} s",
                 "direct_solve_value": vd,
                 "direct_solve_note": "same port with the exact banded solve instead of ADMM (algorithmic CPU baseline)"}
     if world > 1:

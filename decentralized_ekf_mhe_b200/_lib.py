@@ -16,7 +16,7 @@ SYMBOLS = [
     "dekf_config_default_go1", "dekf_config_default_cassie", "dekf_config_default_pogox", "dekf_create",
     "dekf_destroy", "dekf_reset", "dekf_set_stream", "dekf_get_stream", "dekf_last_error", "dekf_num_joints", "dekf_state_dim",
     "dekf_ekf_step", "dekf_mhe_step", "dekf_step", "dekf_step_host", "dekf_mhe_step_host", "dekf_ekf_step_host",
-    "dekf_run", "dekf_run_host", "dekf_run_host_f32", "dekf_synchronize", "dekf_get_arrival_cost",
+    "dekf_run", "dekf_run_host", "dekf_run_host_f32", "dekf_run_host_f32io", "dekf_synchronize", "dekf_get_arrival_cost",
     "dekf_get_arrival_cov", "dekf_get_p_vo", "dekf_get_R_sb", "dekf_get_ekf_cov", "dekf_get_window_vo_count", "dekf_get_host", "dekf_debug_taps", "dekf_get_qp_info", "dekf_get_resweep_info",
     "dekf_launch_count", "dekf_device_bytes", "dekf_profile_enable", "dekf_profile_read", "dekf_measure_fma_peak",
     "dekf_measure_copy_bw",
@@ -73,6 +73,8 @@ def load():
     L.dekf_ekf_step.argtypes = [hp, C.POINTER(DekfInputs), C.POINTER(DekfOutputs)]
     L.dekf_ekf_step_host.argtypes = [hp, C.POINTER(DekfInputs), C.POINTER(DekfOutputs)]
     L.dekf_run_host_f32.argtypes = [hp, C.c_int32, C.c_int32, C.POINTER(DekfInputsF32), C.c_void_p, C.POINTER(DekfOutputs), C.c_int32]
+    # dekf_outputs_f32 has the layout of dekf_outputs (five pointers); quat / x / v_body point at float32 arrays
+    L.dekf_run_host_f32io.argtypes = [hp, C.c_int32, C.c_int32, C.POINTER(DekfInputsF32), C.c_void_p, C.POINTER(DekfOutputs), C.c_int32]
     for name in ("dekf_run", "dekf_run_host"):
         getattr(L, name).argtypes = [hp, C.c_int32, C.c_int32, C.POINTER(DekfInputs), C.c_void_p, C.POINTER(DekfOutputs),
                                      C.c_int32]

@@ -36,6 +36,7 @@ struct BoxConst {
   double qab[3];               // 1 / (dt^2 C_accel_bias)
   double qvo[3];               // 1 / vo_p_std^2
   double P0[9];
+  double lever[3];             // p_imu_2_opti (cfg), v_body = R_sb (v_s + omega x lever)
 };
 
 struct BoxBuffers {
@@ -498,7 +499,7 @@ DEKF_HD int mhe_solve_box(const MheConst<T> &c, const BoxConst &bc, const Dims &
   src.rot(0, Tk, RT);
   double om[3];
   for (int f = 0; f < 3; ++f) om[f] = in.gyro[(size_t)f * n + i];
-  const double lever[3] = {0.016041, 0.089061, 0.0579875};
+  const double *lever = bc.lever;
   const double u[3] = {xT[3] + (om[1] * lever[2] - om[2] * lever[1]), xT[4] + (om[2] * lever[0] - om[0] * lever[2]),
                        xT[5] + (om[0] * lever[1] - om[1] * lever[0])};
   double chk = 0.0;

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kTeamBlock, DEKF_MINB_BOXTEAM) k_box_team(cons
       if (out.v_body != nullptr && r < 3) {
         const T *rec = b.win + (size_t)(Tk % dm.NW) * REC_SIZE * dm.ns + i;
         const double om0 = in.gyro[(size_t)0 * n + i], om1 = in.gyro[(size_t)1 * n + i], om2 = in.gyro[(size_t)2 * n + i];
-        const double lever[3] = {0.016041, 0.089061, 0.0579875};
+        const double *lever = bc.lever;
         const double u0 = v0 + (om1 * lever[2] - om2 * lever[1]), u1 = v1 + (om2 * lever[0] - om0 * lever[2]),
                      u2 = v2 + (om0 * lever[1] - om1 * lever[0]);
         const double R0 = (double)rec[(size_t)(REC_R + r * 3 + 0) * dm.ns], R1 = (double)rec[(size_t)(REC_R + r * 3 + 1) * dm.ns],
@@ -228,9 +228,9 @@ __global__ void __launch_bounds__(kBlock) k_fused(const EkfConst<T> ec, const Mh
   if (mc.est_type == 1)
     st |= kf_update<T>(mc, dm, b, in, out, Tk, i);
   else if (Tk >= 1 && mc.window_solve == 1)
-    st |= mhe_solve_incr<T>(mc, dm, b, in, out, Tk, i);
+    st |= mhe_solve_incr<T>(mc, dm, b, in, out, Tk, i, true);  // true: prefetch the stage records (few warps, latency-bound)
   else if (Tk >= 1)
-    st |= mhe_solve<T>(mc, dm, b, in, out, Tk, i);
+    st |= mhe_solve<T>(mc, dm, b, in, out, Tk, i, true);
   tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
@@ -385,6 +385,8 @@ struct ChunkSet {
   int cap_f32 = 0;
   uint8_t *flag = nullptr;   // [cap][n]
   double *out = nullptr;     // quat [cap][4][n] | x [cap][9][n] | v_body [cap][3][n]
+  float *out_f32 = nullptr;  // dekf_run_host_f32io: the same three arrays rounded to float (allocated on first use)
+  int cap_out_f32 = 0;
   uint8_t *contact = nullptr;
   int32_t *status = nullptr;
 };
@@ -442,6 +444,18 @@ struct dekf_handle {
   CUtensorMap tmap;      // window ring as a 2-D tensor [NW*25][ns] (TMA box = one stage record of one tile)
   int fused_max = 4096;  // batches up to this size take the single fused launch (DEKF_FUSED_MAX_N at create)
   bool use_tma = true;   // window solve with TMA-staged stage tiles (DEKF_NO_TMA=1 at create: plain global loads)
+  // tuning knobs, read ONCE in dekf_create (environment), never on the step path
+  bool no_split = false;   // DEKF_NO_SPLIT=1: one k_solve_tma launch per tick in dekf_run
+  int split_tiles_env = 0; // DEKF_SPLIT_TILES=<k>: size of the first tile range (0: the last full wave)
+  int host_chunk = 8;      // DEKF_HOST_CHUNK=<B>: ticks per copy of dekf_run_host
+  // small batches through the *_host entry points: one pinned, device-mapped host block; the kernel reads the tick's inputs
+  // from it and writes the results into it over PCIe (no cudaMemcpy calls: the batch-1 tick is launch + kernel + sync)
+  char *hmap = nullptr;
+  size_t hmap_bytes = 0;
+  // scratch of the host getters (dekf_get_host): allocated once, on first use
+  double *get_scratch = nullptr;
+  size_t get_scratch_bytes = 0;
+  double *kf_Q = nullptr;  // [num_legs][6][n] per-leg Q_meas of the newest sample (cfg.kf_export_gain)
   // optional per-kernel timing: an event pair around every launch, no host synchronisation until the read
   bool prof = false;
   struct ProfRec {
@@ -565,7 +579,7 @@ Outputs to_outputs(const dekf_handle *h, const dekf_outputs *out) {
     r.contact = out->contact;
   }
   r.dbg_b_meas = h->tap_b_meas;
-  r.dbg_Q_meas = h->tap_Q_meas;
+  r.dbg_Q_meas = h->tap_Q_meas ? h->tap_Q_meas : h->kf_Q;  // kf_Q: cfg.kf_export_gain (K_KF_ getter)
   r.dbg_vo = h->tap_vo;
   r.dbg_ekf = h->tap_ekf;
   return r;
@@ -671,6 +685,7 @@ int dekf_config_default_cassie(dekf_config *cfg) {
   cfg->num_legs = 2;
   cfg->contact_effort_threshold = 150.0;
   cfg->p_ib[0] = cfg->p_ib[1] = cfg->p_ib[2] = 0.0;
+  cfg->p_imu_2_opti[0] = cfg->p_imu_2_opti[1] = cfg->p_imu_2_opti[2] = 0.0;  // the Go1 mocap marker offset means nothing here
   return DEKF_OK;
 }
 int dekf_config_default_pogox(dekf_config *cfg) {
@@ -680,6 +695,7 @@ int dekf_config_default_pogox(dekf_config *cfg) {
   cfg->num_legs = 1;
   cfg->contact_effort_threshold = 100.0;
   cfg->p_ib[0] = cfg->p_ib[1] = cfg->p_ib[2] = 0.0;
+  cfg->p_imu_2_opti[0] = cfg->p_imu_2_opti[1] = cfg->p_imu_2_opti[2] = 0.0;
   return DEKF_OK;
 }
 
@@ -722,6 +738,9 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
   }
   if (const char *e = std::getenv("DEKF_FUSED_MAX_N")) h->fused_max = std::atoi(e);
   if (const char *e = std::getenv("DEKF_NO_TMA")) h->use_tma = std::atoi(e) == 0;
+  if (const char *e = std::getenv("DEKF_NO_SPLIT")) h->no_split = std::atoi(e) != 0;
+  if (const char *e = std::getenv("DEKF_SPLIT_TILES")) h->split_tiles_env = std::atoi(e);
+  if (const char *e = std::getenv("DEKF_HOST_CHUNK")) h->host_chunk = std::atoi(e) > 0 ? std::atoi(e) : 8;
   ce = cudaFuncSetAttribute(k_solve_tma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_tma_smem_bytes<double>());
   if (ce == cudaSuccess)
     ce = cudaFuncSetAttribute(k_solve_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_tma_smem_bytes<float>());
@@ -838,6 +857,10 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     if ((ce = cudaMalloc((void **)&h->tap_ekf, (size_t)3 * n * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
     h->extra_bytes += (size_t)9 * h->nl * n * sizeof(double) + (size_t)11 * n * sizeof(int32_t);
   }
+  if (cfg->kf_export_gain && cfg->est_type == 1 && cfg->leg_odom_type == 0 && !cfg->debug_taps) {
+    if ((ce = cudaMalloc((void **)&h->kf_Q, (size_t)6 * h->nl * n * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+    h->extra_bytes += (size_t)6 * h->nl * n * sizeof(double);
+  }
   if ((ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(DEKF_ECUDA, "cudaStreamCreate", ce);
   h->own_stream = true;
   if ((ce = cudaDeviceSynchronize()) != cudaSuccess) return bail(DEKF_ECUDA, "sync", ce);
@@ -871,6 +894,9 @@ int dekf_destroy(dekf_handle *h) {
   free_stage_set(h->stage[1]);
   free_chunk_set(h->chunk[0]);
   free_chunk_set(h->chunk[1]);
+  cudaFree(h->get_scratch);
+  cudaFree(h->kf_Q);
+  if (h->hmap) cudaFreeHost(h->hmap);
   if (h->s_ekf) cudaStreamDestroy(h->s_ekf);
   if (h->s_mhe) cudaStreamDestroy(h->s_mhe);
   if (h->s_mhe_b) cudaStreamDestroy(h->s_mhe_b);
@@ -1135,6 +1161,7 @@ void free_chunk_set(ChunkSet &cs) {
   cudaFree(cs.out);
   cudaFree(cs.contact);
   cudaFree(cs.status);
+  cudaFree(cs.out_f32);
   cs = ChunkSet();
 }
 int alloc_chunk_set(dekf_handle *h, ChunkSet &cs, int cap) {
@@ -1240,9 +1267,76 @@ int device_call(dekf_handle *h, int kind, int32_t T_, const dekf_inputs *din, co
   }
 }
 
+// Small batches (n <= kZeroCopyMaxN): inputs are packed into a pinned, mapped host block the kernels read directly, results
+// are written by the kernels into the same block: no copy engine round trips on the single-robot latency path.
+constexpr int kZeroCopyMaxN = 256;
+int host_call_zero_copy(dekf_handle *h, int kind, int32_t T_, const dekf_inputs *in, const dekf_outputs *out) {
+  const size_t n = (size_t)h->dm.n, ds = (size_t)h->ds, nl = (size_t)h->nl;
+  size_t cnt[kNumIn], tot = 0;
+  in_counts(h, cnt);
+  for (int a = 0; a < kNumIn; ++a) tot += cnt[a];
+  const size_t out_d = (7 + ds) * n;
+  const size_t bytes = (tot + out_d) * sizeof(double) + n * sizeof(int32_t) + n /*flag*/ + nl * n /*contact*/;
+  if (h->hmap_bytes < bytes) {
+    if (h->hmap) cudaFreeHost(h->hmap);
+    h->hmap = nullptr;
+    h->hmap_bytes = 0;
+    CK(cudaHostAlloc((void **)&h->hmap, bytes, cudaHostAllocMapped));
+    h->hmap_bytes = bytes;
+  }
+  double *hin = (double *)h->hmap, *hout = hin + tot;
+  int32_t *hstatus = (int32_t *)(hout + out_d);
+  uint8_t *hflag = (uint8_t *)(hstatus + n), *hcontact = hflag + n;
+  const bool vo = in->vo_flag != nullptr;
+  const double *src[kNumIn] = {in->gyro, in->accel, in->imu_time, in->joint_pos, in->joint_vel, in->foot_force,
+                               vo ? in->vo_quat : nullptr, vo ? in->vo_time_pre : nullptr, vo ? in->vo_time_now : nullptr,
+                               vo ? in->vo_rel_p : nullptr, in->quat};
+  const double *dst[kNumIn];
+  size_t off = 0;
+  for (int a = 0; a < kNumIn; ++a) {
+    dst[a] = src[a] ? hin + off : nullptr;
+    if (src[a]) std::memcpy(hin + off, src[a], cnt[a] * sizeof(double));
+    off += cnt[a];
+  }
+  if (vo) std::memcpy(hflag, in->vo_flag, n);
+  dekf_inputs din;
+  std::memset(&din, 0, sizeof(din));
+  din.gyro = dst[0];
+  din.accel = dst[1];
+  din.imu_time = dst[2];
+  din.joint_pos = dst[3];
+  din.joint_vel = dst[4];
+  din.foot_force = dst[5];
+  din.vo_quat = dst[6];
+  din.vo_time_pre = dst[7];
+  din.vo_time_now = dst[8];
+  din.vo_rel_p = dst[9];
+  din.quat = dst[10];
+  din.vo_flag = vo ? hflag : nullptr;
+  dekf_outputs dout;
+  std::memset(&dout, 0, sizeof(dout));
+  dout.quat = hout;
+  dout.x = hout + 4 * n;
+  dout.v_body = hout + (4 + ds) * n;
+  dout.contact = (out && out->contact) ? hcontact : nullptr;
+  dout.status = (out && out->status) ? hstatus : nullptr;
+  int rc = device_call(h, kind, T_, &din, &dout);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  if (out) {
+    if (out->quat && kind != HK_MHE) std::memcpy(out->quat, hout, 4 * n * sizeof(double));
+    if (out->x && kind != HK_EKF) std::memcpy(out->x, hout + 4 * n, ds * n * sizeof(double));
+    if (out->v_body && kind != HK_EKF) std::memcpy(out->v_body, hout + (4 + ds) * n, 3 * n * sizeof(double));
+    if (out->contact && kind != HK_EKF) std::memcpy(out->contact, hcontact, nl * n);
+    if (out->status) std::memcpy(out->status, hstatus, n * sizeof(int32_t));
+  }
+  return DEKF_OK;
+}
+
 int host_call(dekf_handle *h, int kind, int32_t T_, const dekf_inputs *in, const dekf_outputs *out) {
   if (!h || !in) return fail(h, DEKF_EINVAL, "host entry point: null argument");
   CK(cudaSetDevice(h->cfg.device));
+  if (h->dm.n <= kZeroCopyMaxN && !h->cfg.debug_taps) return host_call_zero_copy(h, kind, T_, in, out);
   dekf_inputs din;
   dekf_outputs dout;
   int rc = alloc_stage_set(h, h->stage[0]);
@@ -1367,15 +1461,10 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
   // partial wave of tick s overlaps the full wave of tick s + 1 instead of leaving slots idle (DEKF_NO_SPLIT=1 disables).
   int split_tiles = 0;
   {
-    static const bool no_split = std::getenv("DEKF_NO_SPLIT") && std::atoi(std::getenv("DEKF_NO_SPLIT")) != 0;
     const int tiles = h->dm.ns / kTile, slots = h->solve_slots;
-    if (asm_ahead && !no_split && h->use_tma && h->mc64.window_solve == 0 && slots > 0 && tiles > slots && tiles % slots != 0)
+    if (asm_ahead && !h->no_split && h->use_tma && h->mc64.window_solve == 0 && slots > 0 && tiles > slots && tiles % slots != 0)
       split_tiles = tiles / slots * slots;
-    if (split_tiles > 0)
-      if (const char *e = std::getenv("DEKF_SPLIT_TILES")) {  // tuning: size of the first tile range
-        const int v = std::atoi(e);
-        if (v > 0 && v < tiles) split_tiles = v;
-      }
+    if (split_tiles > 0 && h->split_tiles_env > 0 && h->split_tiles_env < tiles) split_tiles = h->split_tiles_env;  // tuning
   }
   for (int32_t s = 0; s < S && rc == DEKF_OK; ++s) {
     const int slot = s % QA;
@@ -1456,14 +1545,19 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     if (ce != cudaSuccess) rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
   }
   h->stream = user;
-  cudaEventRecord(h->ev_join, h->s_mhe);
-  cudaStreamWaitEvent(user, h->ev_join, 0);
-  cudaEventRecord(h->ev_join, h->s_mhe_b);
-  cudaStreamWaitEvent(user, h->ev_join, 0);
-  cudaEventRecord(h->ev_join, h->s_asm);
-  cudaStreamWaitEvent(user, h->ev_join, 0);
-  cudaEventRecord(h->ev_join, h->s_ekf);
-  cudaStreamWaitEvent(user, h->ev_join, 0);
+  // join the internal streams back into the caller-visible one; if any of this fails (or the loop failed), drain them
+  // on the host so that nothing is in flight when the error is reported
+  cudaError_t je = cudaSuccess;
+  cudaStream_t internal[4] = {h->s_mhe, h->s_mhe_b, h->s_asm, h->s_ekf};
+  for (int k = 0; k < 4 && je == cudaSuccess; ++k) {
+    je = cudaEventRecord(h->ev_join, internal[k]);
+    if (je == cudaSuccess) je = cudaStreamWaitEvent(user, h->ev_join, 0);
+  }
+  if (je != cudaSuccess || rc != DEKF_OK) {
+    for (int k = 0; k < 4; ++k) cudaStreamSynchronize(internal[k]);
+    cudaStreamSynchronize(user);
+    if (rc == DEKF_OK) rc = fail(h, DEKF_ECUDA, "dekf_run: joining the internal streams", je);
+  }
   return rc;
 }
 
@@ -1472,17 +1566,36 @@ __global__ void __launch_bounds__(256) k_widen(const float *__restrict__ src, do
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (size_t)gridDim.x * blockDim.x) dst[k] = (double)src[k];
 }
 
-// in: all-double host streams; inf (non-null: dekf_run_host_f32): the five sensor arrays as float, the rest from inf too
+__global__ void __launch_bounds__(256) k_narrow(const double *__restrict__ src, float *__restrict__ dst, size_t count) {
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += (size_t)gridDim.x * blockDim.x) dst[k] = (float)src[k];
+}
+
+// in: all-double host streams; inf (non-null: dekf_run_host_f32): the five sensor arrays as float, the rest from inf too;
+// outf (non-null: dekf_run_host_f32io): quat / x / v_body leave the device as float, `out` then only carries contact / status
+static int run_host_body(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const dekf_inputs_f32 *inf, const uint8_t *vo_steps,
+                         const dekf_outputs *out, int32_t out_per_step, const dekf_outputs_f32 *outf);
 static int run_host_impl(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const dekf_inputs_f32 *inf, const uint8_t *vo_steps,
-                         const dekf_outputs *out, int32_t out_per_step) {
+                         const dekf_outputs *out, int32_t out_per_step, const dekf_outputs_f32 *outf = nullptr) {
+  const int rc = run_host_body(h, T0, S, in, inf, vo_steps, out, out_per_step, outf);
+  if (rc != DEKF_OK) {
+    // an error return must not leave copies into / out of caller-owned host buffers in flight
+    const std::string keep = h->err;
+    if (h->s_h2d) cudaStreamSynchronize(h->s_h2d);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->s_d2h) cudaStreamSynchronize(h->s_d2h);
+    h->err = keep;
+  }
+  return rc;
+}
+static int run_host_body(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const dekf_inputs_f32 *inf, const uint8_t *vo_steps,
+                         const dekf_outputs *out, int32_t out_per_step, const dekf_outputs_f32 *outf) {
   CK(cudaSetDevice(h->cfg.device));
   const size_t n = (size_t)h->dm.n;
   // Ticks move in chunks of B: every field of the host streams is [S][rows][n], so B consecutive ticks of one field are
   // ONE contiguous copy (6 input copies + the VO arrays of the ticks that carry a message per chunk, 5 result copies per
   // chunk) and the chunk runs through dekf_run (EKF ticks ahead of the MHE).  Chunks are software-pipelined over three
   // streams and two device staging sets: H2D of chunk c+1 | kernels of chunk c | D2H of chunk c-1.
-  int B = 8;
-  if (const char *e = std::getenv("DEKF_HOST_CHUNK")) B = std::atoi(e);
+  int B = h->host_chunk;
   {
     const size_t per_tick = (size_t)(16 + 2 * h->nq + h->nl + 7 + h->ds) * 8 * n;
     const size_t cap = (size_t)384 << 20;  // staging budget per set
@@ -1503,6 +1616,15 @@ static int run_host_impl(dekf_handle *h, int32_t T0, int32_t S, const dekf_input
         CK(cudaMalloc((void **)&h->chunk[k].in_f32, (size_t)h->chunk[k].cap * rows_f32 * n * sizeof(float)));
         h->chunk[k].cap_f32 = h->chunk[k].cap;
         h->extra_bytes += (size_t)h->chunk[k].cap * rows_f32 * n * sizeof(float);
+      }
+  if (outf)
+    for (int k = 0; k < 2; ++k)
+      if (h->chunk[k].cap_out_f32 < h->chunk[k].cap) {
+        cudaFree(h->chunk[k].out_f32);
+        h->chunk[k].out_f32 = nullptr;
+        CK(cudaMalloc((void **)&h->chunk[k].out_f32, (size_t)h->chunk[k].cap * (size_t)(7 + h->ds) * n * sizeof(float)));
+        h->chunk[k].cap_out_f32 = h->chunk[k].cap;
+        h->extra_bytes += (size_t)h->chunk[k].cap * (size_t)(7 + h->ds) * n * sizeof(float);
       }
   if (!h->s_h2d) {
     CK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
@@ -1595,13 +1717,34 @@ static int run_host_impl(dekf_handle *h, int32_t T0, int32_t S, const dekf_input
     // the chunk's own vo_steps mask (a tick whose VO arrays were not copied must not read them)
     rc = dekf_run(h, T0 + s0, Bc, &din, vo_steps ? vo_steps + s0 : nullptr, want_out ? &dout : nullptr, out_per_step ? 1 : 0);
     if (rc) return rc;
+    if (want_out && outf) {  // one rounding to float32 on the device, behind the chunk's kernels
+      const size_t cnt = (out_per_step ? (size_t)Bc : 1) * (size_t)(7 + h->ds) * n;
+      // quat | x | v_body are contiguous in the staging set only when the chunk is full: narrow the three ranges
+      const size_t k3[3] = {4, (size_t)h->ds, 3};
+      const double *s3[3] = {dout.quat, dout.x, dout.v_body};
+      size_t off = 0;
+      for (int a = 0; a < 3; ++a) {
+        const size_t c3 = (out_per_step ? (size_t)Bc : 1) * k3[a] * n;
+        k_narrow<<<148 * 2, 256, 0, h->stream>>>(s3[a], cs.out_f32 + off, c3);
+        h->launches++;
+        off += cap * k3[a] * n;
+      }
+      (void)cnt;
+    }
     CK(cudaEventRecord(h->ev_comp[b], h->stream));
     CK(cudaStreamWaitEvent(h->s_d2h, h->ev_comp[b], 0));
     if (want_out) {
       const size_t cnt = out_per_step ? (size_t)Bc : 1, so = out_per_step ? (size_t)s0 : 0;
-      if (out->quat) CK(cudaMemcpyAsync(out->quat + so * 4 * n, dout.quat, cnt * 4 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
-      if (out->x) CK(cudaMemcpyAsync(out->x + so * (size_t)h->ds * n, dout.x, cnt * (size_t)h->ds * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
-      if (out->v_body) CK(cudaMemcpyAsync(out->v_body + so * 3 * n, dout.v_body, cnt * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+      if (outf) {
+        const float *fq = cs.out_f32, *fx = fq + cap * 4 * n, *fv = fx + cap * (size_t)h->ds * n;
+        if (outf->quat) CK(cudaMemcpyAsync(outf->quat + so * 4 * n, fq, cnt * 4 * n * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+        if (outf->x) CK(cudaMemcpyAsync(outf->x + so * (size_t)h->ds * n, fx, cnt * (size_t)h->ds * n * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+        if (outf->v_body) CK(cudaMemcpyAsync(outf->v_body + so * 3 * n, fv, cnt * 3 * n * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+      } else {
+        if (out->quat) CK(cudaMemcpyAsync(out->quat + so * 4 * n, dout.quat, cnt * 4 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+        if (out->x) CK(cudaMemcpyAsync(out->x + so * (size_t)h->ds * n, dout.x, cnt * (size_t)h->ds * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+        if (out->v_body) CK(cudaMemcpyAsync(out->v_body + so * 3 * n, dout.v_body, cnt * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->s_d2h));
+      }
       if (out->contact) CK(cudaMemcpyAsync(out->contact + so * h->nl * n, cs.contact, cnt * h->nl * n, cudaMemcpyDeviceToHost, h->s_d2h));
       if (out->status) CK(cudaMemcpyAsync(out->status + so * n, cs.status, cnt * n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->s_d2h));
     }
@@ -1639,6 +1782,28 @@ int dekf_run_host_f32(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs_f
   in.vo_time_now = inf->vo_time_now;
   in.vo_rel_p = inf->vo_rel_p;
   return run_host_impl(h, T0, S, &in, inf, vo_steps, out, out_per_step);
+}
+
+int dekf_run_host_f32io(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs_f32 *inf, const uint8_t *vo_steps,
+                        const dekf_outputs_f32 *outf, int32_t out_per_step) {
+  if (!h || !inf || !outf || S < 0) return fail(h, DEKF_EINVAL, "dekf_run_host_f32io: bad argument");
+  if (!inf->gyro || !inf->accel || !inf->imu_time || !inf->joint_pos || !inf->joint_vel || !inf->foot_force)
+    return fail(h, DEKF_EINVAL, "dekf_run_host_f32io: null input");
+  if (inf->vo_flag && (!inf->vo_quat || !inf->vo_time_pre || !inf->vo_time_now || !inf->vo_rel_p))
+    return fail(h, DEKF_EINVAL, "dekf_run_host_f32io: vo_flag without the VO arrays");
+  dekf_inputs in;
+  std::memset(&in, 0, sizeof(in));
+  in.imu_time = inf->imu_time;
+  in.vo_flag = inf->vo_flag;
+  in.vo_quat = inf->vo_quat;
+  in.vo_time_pre = inf->vo_time_pre;
+  in.vo_time_now = inf->vo_time_now;
+  in.vo_rel_p = inf->vo_rel_p;
+  dekf_outputs out;  // contact / status keep their types; the three double arrays are replaced by outf's
+  std::memset(&out, 0, sizeof(out));
+  out.contact = outf->contact;
+  out.status = outf->status;
+  return run_host_impl(h, T0, S, &in, inf, vo_steps, &out, out_per_step, outf);
 }
 
 static int get_arrival(dekf_handle *h, double *P, double *x, int info) {
@@ -1717,9 +1882,42 @@ int dekf_get_host(dekf_handle *h, int32_t what, void *host_out) {
   const size_t n = (size_t)h->dm.n;
   const size_t dsz = (size_t)h->ds;
   const size_t rows[8] = {9, 3, dsz * dsz, dsz, 16, 1, dsz * dsz, dsz};
-  if (what < 0 || what > DEKF_GET_ARRIVAL_MEAN) return fail(h, DEKF_EINVAL, "dekf_get_host: unknown selector");
-  double *d = nullptr;
-  CK(cudaMalloc((void **)&d, (dsz * dsz + dsz) * n * sizeof(double)));
+  if (what < 0 || what > DEKF_GET_KF_GAIN) return fail(h, DEKF_EINVAL, "dekf_get_host: unknown selector");
+  // one scratch for the life of the handle (the 200 Hz node shells call this every tick)
+  const size_t need = (dsz * dsz + dsz + 6 * (size_t)h->nl) * n * sizeof(double);
+  if (h->get_scratch_bytes < need) {
+    cudaFree(h->get_scratch);
+    h->get_scratch = nullptr;
+    h->get_scratch_bytes = 0;
+    CK(cudaMalloc((void **)&h->get_scratch, need));
+    h->get_scratch_bytes = need;
+    h->extra_bytes += need;
+  }
+  double *d = h->get_scratch;
+  if (what == DEKF_GET_KF_GAIN) {
+    // K_KF_ = C_KF_ A_meas' C_meas^-1 (posterior form of DecentralEst.cpp:858): the 3 columns of leg i are C_KF_[:, v] Q_meas,i
+    const double *Qsrc = h->tap_Q_meas ? h->tap_Q_meas : h->kf_Q;
+    if (h->cfg.est_type != 1 || h->cfg.leg_odom_type != 0 || !Qsrc)
+      return fail(h, DEKF_EINVAL, "DEKF_GET_KF_GAIN needs est_type 1, leg_odom_type 0 and cfg.kf_export_gain");
+    int rc = dekf_get_arrival_cov(h, d, d + dsz * dsz * n);
+    if (rc) return rc;
+    const size_t L = (size_t)h->nl;
+    std::vector<double> C(81 * n), Q(6 * L * n);
+    CK(cudaMemcpyAsync(C.data(), d, 81 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(Q.data(), Qsrc, 6 * L * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    double *K = (double *)host_out;
+    const int sidx[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+    for (size_t i = 0; i < n; ++i)
+      for (size_t l = 0; l < L; ++l)
+        for (int r = 0; r < 9; ++r)
+          for (int c = 0; c < 3; ++c) {
+            double v = 0.0;
+            for (int k = 0; k < 3; ++k) v += C[(size_t)(r * 9 + 3 + k) * n + i] * Q[(l * 6 + sidx[k][c]) * n + i];
+            K[((size_t)r * 3 * L + 3 * l + c) * n + i] = v;
+          }
+    return DEKF_OK;
+  }
   int rc = DEKF_OK;
   const void *src = d;
   size_t bytes = rows[what] * n * sizeof(double);
@@ -1741,12 +1939,9 @@ int dekf_get_host(dekf_handle *h, int32_t what, void *host_out) {
       rc = dekf_get_window_vo_count(h, (int32_t *)d);
       bytes = n * sizeof(int32_t);
   }
-  cudaError_t ce = cudaSuccess;
-  if (rc == DEKF_OK) ce = cudaMemcpyAsync(host_out, src, bytes, cudaMemcpyDeviceToHost, h->stream);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
-  cudaFree(d);
   if (rc) return rc;
-  if (ce != cudaSuccess) return fail(h, DEKF_ECUDA, "dekf_get_host", ce);
+  CK(cudaMemcpyAsync(host_out, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
   return DEKF_OK;
 }
 

@@ -73,6 +73,7 @@ struct MheConst {
   T q_swing[3];
   T P0[9];   // prior covariance diag (p,v,b init std^2), prior mean 0
   T p_ib[3];
+  T lever[3];  // p_imu_2_opti: v_body = R_sb (v_s + omega x lever), DecentralEst.cpp:181-185
   double thr;  // contact threshold, compared in double on the raw input (bit-exact)
   double dt_d;
   int N;
@@ -1688,13 +1689,23 @@ struct GlobalStageSource {
   const Dims &dm;
   const Buffers<T> &b;
   int i;
-  DEKF_HD GlobalStageSource(const Dims &dm_, const Buffers<T> &b_, int i_) : dm(dm_), b(b_), i(i_) {}
+  // small batches (k_fused: a handful of warps on the whole device, nothing to hide a load behind): ask for the record of
+  // stage k + 2 while stage k is being processed, so that its loads hit L1 instead of paying an L2 round trip per stage
+  bool prefetch = false;
+  DEKF_HD GlobalStageSource(const Dims &dm_, const Buffers<T> &b_, int i_, bool pf = false) : dm(dm_), b(b_), i(i_), prefetch(pf) {}
   DEKF_HD void acquire(int /*ordinal*/) const {}
   DEKF_HD void release(int /*ordinal*/) const {}
   DEKF_HD const T *rec(int k) const { return b.win + (size_t)(k % dm.NW) * REC_SIZE * dm.ns + i; }
   DEKF_HD void meas(int, int k, S3<T> &Lam, V3<T> &eta) const {
     const T *r = rec(k);
     const size_t ns = (size_t)dm.ns;
+#if defined(__CUDA_ARCH__)
+    if (prefetch) {
+      const T *q = rec(k + 2);
+#pragma unroll
+      for (int f = 0; f < REC_SIZE; ++f) asm volatile("prefetch.global.L1 [%0];" ::"l"(q + f * ns));
+    }
+#endif
 #pragma unroll
     for (int f = 0; f < 6; ++f) Lam.a[f] = r[(REC_LAM + f) * ns];
 #pragma unroll
@@ -1841,7 +1852,7 @@ DEKF_HD int mhe_solve_sweep(const MheConst<T> &c, const Dims &dm, const Buffers<
 #pragma unroll
     for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
   }
-  const V3<T> lever = v3<T>(T(0.016041), T(0.089061), T(0.0579875));
+  const V3<T> lever = v3<T>(c.lever[0], c.lever[1], c.lever[2]);
   Vec9<T> xr;
 #pragma unroll
   for (int f = 0; f < 3; ++f) {
@@ -1879,8 +1890,8 @@ DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
 
 template <typename T>
 DEKF_HD int mhe_solve(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
-                      int Tk, int i) {
-  GlobalStageSource<T> src(dm, b, i);
+                      int Tk, int i, bool prefetch = false) {
+  GlobalStageSource<T> src(dm, b, i, prefetch);
   return mhe_solve<T>(c, dm, b, in, out, Tk, i, src);
 }
 
@@ -1970,7 +1981,7 @@ DEKF_HD int mhe_solve_incr(const MheConst<T> &c, const Dims &dm, const Buffers<T
   V3<T> om;
 #pragma unroll
   for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
-  const V3<T> lever = v3<T>(T(0.016041), T(0.089061), T(0.0579875));
+  const V3<T> lever = v3<T>(c.lever[0], c.lever[1], c.lever[2]);
   const V3<T> vb = mul(RT, add(x.v, cross(om, lever)));
   int status = 0;
   const T chk = x.p[0] + x.p[1] + x.p[2] + x.v[0] + x.v[1] + x.v[2] + x.b[0] + x.b[1] + x.b[2];
@@ -2003,8 +2014,8 @@ DEKF_HD int incr_restart_stage(const Dims &dm, const Buffers<T> &b, int Tk, int 
 
 template <typename T>
 DEKF_HD int mhe_solve_incr(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
-                           int Tk, int i) {
-  GlobalStageSource<T> src(dm, b, i);
+                           int Tk, int i, bool prefetch = false) {
+  GlobalStageSource<T> src(dm, b, i, prefetch);
   return mhe_solve_incr<T>(c, dm, b, in, out, Tk, i, src, incr_restart_stage(dm, b, Tk, i));
 }
 
@@ -2093,7 +2104,7 @@ DEKF_HD int kf_update(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b,
   V3<T> om;
 #pragma unroll
   for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
-  const V3<T> lever = v3<T>(T(0.016041), T(0.089061), T(0.0579875));
+  const V3<T> lever = v3<T>(c.lever[0], c.lever[1], c.lever[2]);
   const V3<T> vb = mul(R, add(x.v, cross(om, lever)));
   int status = 0;
   const T chk = x.p[0] + x.p[1] + x.p[2] + x.v[0] + x.v[1] + x.v[2] + x.b[0] + x.b[1] + x.b[2];

@@ -327,7 +327,7 @@ __device__ int foot_team_solve(const FootConst &fc, const Dims &dm, const Buffer
     if (out.x != nullptr) out.x[(size_t)lane * n + i] = xr;
     if (out.v_body != nullptr && lane < 3) {
       const double om0 = in.gyro[i], om1 = in.gyro[(size_t)n + i], om2 = in.gyro[(size_t)2 * n + i];
-      const double lever[3] = {0.016041, 0.089061, 0.0579875};
+      const double *lever = fc.bc.lever;
       const double u0 = v0 + (om1 * lever[2] - om2 * lever[1]), u1 = v1 + (om2 * lever[0] - om0 * lever[2]),
                    u2 = v2 + (om0 * lever[1] - om1 * lever[0]);
       out.v_body[(size_t)lane * n + i] = bt_sel3(lane, R[0], R[3], R[6]) * u0 + bt_sel3(lane, R[1], R[4], R[7]) * u1 +

@@ -263,7 +263,7 @@ DEKF_HD int foot_solve(const FootConst &fc, const Dims &dm, const Buffers<T> &b,
   f.solve(x);
   foot_common(dm, b, Tk, i, R, as, dlt, vo);
   const double om[3] = {in.gyro[i], in.gyro[(size_t)n + i], in.gyro[(size_t)2 * n + i]};
-  const double lever[3] = {0.016041, 0.089061, 0.0579875};
+  const double *lever = fc.bc.lever;
   const double u[3] = {x[3] + (om[1] * lever[2] - om[2] * lever[1]), x[4] + (om[2] * lever[0] - om[0] * lever[2]),
                        x[5] + (om[0] * lever[1] - om[1] * lever[0])};
   int status = 0;

@@ -73,6 +73,10 @@ inline void fill_go1_defaults(dekf_config *c) {
   }
   c->ekf_quaternion_init[0] = 1.0;
   c->ekf_rate = 500;
+  // Vector3d p_imu_2_opti(0.016041, 0.089061, 0.0579875), DecentralEst.cpp:181-185
+  c->p_imu_2_opti[0] = 0.016041;
+  c->p_imu_2_opti[1] = 0.089061;
+  c->p_imu_2_opti[2] = 0.0579875;
 }
 
 inline int robot_num_legs(int robot) { return robot == DEKF_ROBOT_CASSIE ? 2 : (robot == DEKF_ROBOT_POGOX ? 1 : 4); }
@@ -134,6 +138,7 @@ inline MheConst<T> make_mhe_const(const dekf_config &c) {
     m.P0[3 + i] = (T)std::pow(c.v_init_std[i], 2);
     m.P0[6 + i] = (T)std::pow(c.accel_bias_init_std[i], 2);
     m.p_ib[i] = (T)c.p_ib[i];
+    m.lever[i] = (T)c.p_imu_2_opti[i];
   }
   for (int i = 0; i < 3; ++i) {
     m.n1[i] = (i == 0) ? m.d1[0] : m.d1[i] - m.d1[0];
@@ -163,6 +168,7 @@ inline BoxConst make_box_const(const dekf_config &c) {
   for (int i = 0; i < 3; ++i) {
     b.lo[i] = c.v_box_lo[i];
     b.hi[i] = c.v_box_hi[i];
+    b.lever[i] = c.p_imu_2_opti[i];
     const double Cp = std::pow(c.p_process_std[i], 2), Ca = std::pow(c.accel_input_std[i], 2);
     const double d1 = dt * dt * Cp + 0.25 * dt * dt * dt * dt * Ca, d2 = 0.5 * dt * dt * dt * Ca, d3 = dt * dt * Ca;
     const double det = d1 * d3 - d2 * d2;  // (G C G')^-1 per axis, DecentralEst.cpp:409-418

@@ -243,6 +243,16 @@ class DecentralizedEstimation:
         return self.mhe_qp_.arrival_cov()[0]
 
     @property
+    def K_KF_(self):
+        """Kalman gain of the last correction, ``[9, 3 * num_legs, n]`` HOST numpy array (DecentralEst.hpp:290; needs
+        ``robot_params(est_type=1, kf_export_gain=1)``): dekf_get_host(DEKF_GET_KF_GAIN)."""
+        import numpy as np
+        h = self._hd
+        K = np.empty((9 * 3 * h.nl, h.n), dtype=np.float64)
+        h.check(h.L.dekf_get_host(h.h, 8, K.ctypes.data_as(C.c_void_p)), "dekf_get_host(DEKF_GET_KF_GAIN)")
+        return K.reshape(9, 3 * h.nl, h.n)
+
+    @property
     def contact_(self):
         return self._hd.contact
 
@@ -366,6 +376,8 @@ class BatchedEstimator:
         h.check(h.L.dekf_get_p_vo(h.h, _ptr(p)), "dekf_get_p_vo")
         return p
 
+    K_KF_ = DecentralizedEstimation.K_KF_
+
     def step(self, T, store):
         h = self._hd
         inp = h.inputs(store)
@@ -449,6 +461,15 @@ class BatchedEstimator:
         mask = None
         if vo_steps is not None:
             mask = (C.c_uint8 * S)(*[1 if v else 0 for v in vo_steps[:S]])
+        f32_out = out is not None and any(o.get(k) is not None and o[k].dtype == torch.float32 for k in ("quat", "x", "v_body"))
+        if f32_out:
+            # dekf_run_host_f32io: results rounded to float32 once on the device, 64 instead of 128 bytes per instance-tick
+            for k in ("quat", "x", "v_body"):
+                if o.get(k) is not None and o[k].dtype != torch.float32:
+                    raise DekfError("run_host_f32: quat / x / v_body must be all float32 or all float64")
+            h.check(h.L.dekf_run_host_f32io(h.h, int(T0), int(S), C.byref(inp), mask, C.byref(outs), int(bool(out_per_step))),
+                    "dekf_run_host_f32io")
+            return
         h.check(h.L.dekf_run_host_f32(h.h, int(T0), int(S), C.byref(inp), mask, C.byref(outs), int(bool(out_per_step))),
                 "dekf_run_host_f32")
 

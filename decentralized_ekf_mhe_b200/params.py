@@ -36,6 +36,7 @@ class DekfConfig(C.Structure):
         ("ekf_quaternion_init", C.c_double * 4), ("ekf_rate", C.c_int32), ("reserved2", C.c_int32),
         ("v_box_enable", C.c_int32), ("v_box_max_iter", C.c_int32),
         ("v_box_lo", C.c_double * 3), ("v_box_hi", C.c_double * 3),
+        ("p_imu_2_opti", C.c_double * 3), ("kf_export_gain", C.c_int32), ("reserved3", C.c_int32),
     ]
 
     def update(self, **over):

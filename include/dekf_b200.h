@@ -50,7 +50,7 @@
 extern "C" {
 #endif
 
-#define DEKF_ABI_VERSION 2
+#define DEKF_ABI_VERSION 3
 
 enum {
   DEKF_OK = 0,
@@ -117,6 +117,14 @@ typedef struct dekf_config {
    * v_box_lo <= v_s of x_k <= v_box_hi for every state of the window at solve time (est_type 0 only). */
   int32_t v_box_enable, v_box_max_iter; /* max_iter 0 = default (50 factorisations) */
   double v_box_lo[3], v_box_hi[3];
+
+  /* ---- lever arm from the IMU to the point whose body velocity is reported: v_MHE_b_ = R_sb (v_s + omega x p_imu_2_opti)
+   * (DecentralEst.cpp:181-185 hard-codes the Go1 mocap marker offset (0.016041, 0.089061, 0.0579875); the Go1 defaults
+   * carry that value, the builder-defined Cassie / PogoX defaults carry zero). */
+  double p_imu_2_opti[3];
+  /* est_type 1 only: keep the per-leg measurement information of the newest sample so that DEKF_GET_KF_GAIN can return
+   * K_KF_ (DecentralEst.hpp:290); costs 6 * num_legs doubles per instance of state and their write per tick. */
+  int32_t kf_export_gain, reserved3;
 } dekf_config;
 
 /* Per-tick sensor snapshot of all instances.  NULL vo_flag == no VO message for anybody. */
@@ -204,6 +212,20 @@ typedef struct dekf_inputs_f32 {
 } dekf_inputs_f32;
 int dekf_run_host_f32(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs_f32 *in, const uint8_t *vo_steps,
                       const dekf_outputs *out, int32_t out_per_step);
+/* The same with the RESULTS delivered in single precision as well (the ROS messages the reference publishes them in carry
+ * float64, but a fleet logger / controller consuming 65,536 robots' states rarely needs more than float32): quaternion,
+ * x_MHE_ and v_MHE_b_ are computed in double on the device exactly as in dekf_run_host, rounded to float32 once (round to
+ * nearest) by a device kernel and copied out as 64 instead of 128 bytes per instance-tick.  Contact flags and status words are
+ * unchanged.  Every value equals (float) of what dekf_run_host_f32 returns for the same call. */
+typedef struct dekf_outputs_f32 {
+  float *quat;      /* [4][n]  (per step: [S][4][n]) */
+  float *x;         /* [ds][n] */
+  float *v_body;    /* [3][n] */
+  uint8_t *contact; /* [num_legs][n] */
+  int32_t *status;  /* [n] */
+} dekf_outputs_f32;
+int dekf_run_host_f32io(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs_f32 *in, const uint8_t *vo_steps,
+                        const dekf_outputs_f32 *out, int32_t out_per_step);
 int dekf_synchronize(dekf_handle *h);
 
 /* Getters (device pointers, stream-ordered). */
@@ -225,7 +247,9 @@ enum {
   DEKF_GET_EKF_COV = 4,    /* [16][n] */
   DEKF_GET_VO_COUNT = 5,   /* [n] int32 */
   DEKF_GET_ARRIVAL_COV = 6,  /* [81][n] arrival covariance; est_type 1: C_KF_ (DecentralEst.hpp:288) */
-  DEKF_GET_ARRIVAL_MEAN = 7  /* [9][n]  arrival mean;       est_type 1: x_KF_ */
+  DEKF_GET_ARRIVAL_MEAN = 7, /* [9][n]  arrival mean;       est_type 1: x_KF_ */
+  DEKF_GET_KF_GAIN = 8       /* [9 * 3 * num_legs][n] K_KF_ (DecentralEst.hpp:290, DecentralEst.cpp:858), row-major 9 x 3L per
+                              * instance; est_type 1, leg_odom_type 0 and cfg.kf_export_gain only */
 };
 int dekf_get_host(dekf_handle *h, int32_t what, void *host_out);
 /* debug taps of the last step (only when cfg.debug_taps != 0): copied into caller DEVICE buffers, any may be NULL.

@@ -59,6 +59,9 @@ struct robot_params {
   // MheSrb.cpp:58-68, would add; never exercised by the reference)
   bool v_box_enable_ = false;
   std::vector<double> v_box_lo_{-1e30, -1e30, -1e30}, v_box_hi_{1e30, 1e30, 1e30};
+  // lever arm of v_MHE_b_ (DecentralEst.cpp:181-185 hard-codes this Go1 mocap marker offset)
+  std::vector<double> p_imu_2_opti_{0.016041, 0.089061, 0.0579875};
+  bool kf_export_gain_ = false;  // est_type_ 1: make K_KF_() available (DecentralEst.hpp:290)
 
   // go1_example/config/parameters_go1.yaml
   static robot_params go1() {
@@ -111,6 +114,8 @@ struct robot_params {
     p.ekf_rate_ = c.ekf_rate;
     p.robot_ = c.robot;
     p.ekf_hist_depth_ = c.ekf_hist_depth;
+    p.p_imu_2_opti_ = v(c.p_imu_2_opti, 3);
+    p.kf_export_gain_ = c.kf_export_gain != 0;
     p.v_box_enable_ = c.v_box_enable != 0;
     if (p.v_box_enable_) {
       p.v_box_lo_ = v(c.v_box_lo, 3);
@@ -155,6 +160,8 @@ struct robot_params {
     c.v_box_enable = v_box_enable_;
     put(c.v_box_lo, v_box_lo_, 3, "v_box_lo_");
     put(c.v_box_hi, v_box_hi_, 3, "v_box_hi_");
+    put(c.p_imu_2_opti, p_imu_2_opti_, 3, "p_imu_2_opti_");
+    c.kf_export_gain = kf_export_gain_;
     c.rho = rho_;
     c.alpha = alpha_;
     c.delta = delta_;

@@ -150,6 +150,10 @@ void orc_params_go1_defaults(orc_params *p) {
   p->time_limit = 0.0028;
   p->robot = ORC_ROBOT_GO1;
   p->solve_mode = 0;
+  /* DecentralEst.cpp:181: Vector3d p_imu_2_opti(0.016041, 0.089061, 0.0579875) */
+  p->p_imu_2_opti[0] = 0.016041;
+  p->p_imu_2_opti[1] = 0.089061;
+  p->p_imu_2_opti[2] = 0.0579875;
 }
 
 /* ------------------------------------------------------------------------- small helpers */
@@ -1230,7 +1234,7 @@ static void update_kf(orc_mhe *m) {
 /* ------------------------------------------------------------------------- public step */
 static void body_velocity(const orc_mhe *m, const double *x, double out[3]) {
   /* DecentralEst.cpp:183-185 / :192-194 */
-  const double p_imu_2_opti[3] = {0.016041, 0.089061, 0.0579875};
+  const double *p_imu_2_opti = m->P.p_imu_2_opti;
   const hist_t *bk = &m->stack[m->nstack - 1];
   double wxp[3], v[3];
   cross3(wxp, bk->angular_b, p_imu_2_opti);

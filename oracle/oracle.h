@@ -89,6 +89,8 @@ typedef struct {
    * active when v_box_enable != 0; rows lb<=v_s<=ub appended per state in the ADMM mode. */
   int v_box_enable;
   double v_box_lo[3], v_box_hi[3];
+  /* lever arm of the body-velocity read-out, DecentralEst.cpp:181-185 (the reference hard-codes the Go1 mocap marker) */
+  double p_imu_2_opti[3];
 } orc_params;
 
 void orc_params_go1_defaults(orc_params *p); /* parameters_go1.yaml */

@@ -39,6 +39,7 @@ class Params(C.Structure):
         ("dual_tol", C.c_double), ("time_limit", C.c_double),
         ("robot", C.c_int), ("solve_mode", C.c_int),
         ("v_box_enable", C.c_int), ("v_box_lo", C.c_double * 3), ("v_box_hi", C.c_double * 3),
+        ("p_imu_2_opti", C.c_double * 3),
     ]
 
 
@@ -335,6 +336,11 @@ class Mhe:
         v = np.zeros(3)
         lib().orc_mhe_get_kf(self.h, _p(x), _p(Cm), _p(v))
         return x, Cm.reshape(ds, ds), v
+
+
+def pin_threads(on=True):
+    """Pin worker thread t of run_batch to the t-th CPU of the process's affinity mask (bench.py's CPU baselines)."""
+    lib().orc_set_pin_threads(int(bool(on)))
 
 
 def run_batch(stream, prm=None, ep=None, *, i0=0, i1=None, nthreads=1, run_ekf=True, run_mhe=True,

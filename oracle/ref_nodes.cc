@@ -208,6 +208,12 @@ void ref_nodes_get_kf_cov(void *h, double *C) {
   DecentralizedEstimation &m = ((Nodes *)h)->est->mhe;
   for (int i = 0; i < m.C_KF_.rows(); ++i) for (int j = 0; j < m.C_KF_.cols(); ++j) C[i * m.C_KF_.cols() + j] = m.C_KF_(i, j);
 }
+// K_KF_ (DecentralEst.hpp:290, DecentralEst.cpp:858), row-major rows x cols; returns cols (0 before the first correction)
+int ref_nodes_get_kf_gain(void *h, double *K) {
+  DecentralizedEstimation &m = ((Nodes *)h)->est->mhe;
+  for (int i = 0; i < m.K_KF_.rows(); ++i) for (int j = 0; j < m.K_KF_.cols(); ++j) K[i * m.K_KF_.cols() + j] = m.K_KF_(i, j);
+  return m.K_KF_.cols();
+}
 // leg kinematics handed to the estimator by go1Sub::lo_callback: p_imu_2_foot_ (3*legs), J_imu_2_foot_ (3*legs x 3, row-major)
 void ref_nodes_get_kin(void *h, double *p, double *J) {
   Nodes *nd = (Nodes *)h;

@@ -4,8 +4,10 @@
  * (BASELINE.md section 2 protocol).  Call order per tick follows the reference's two timers run in
  * lock-step: orien_ekf::timerCallback (orien_ekf.cpp:77-89) then robotSub::timerCallback
  * (EstSub.cpp:58-75) consuming the freshly published quaternion. */
+#define _GNU_SOURCE
 #include "oracle.h"
 #include <pthread.h>
+#include <sched.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -40,8 +42,30 @@ typedef struct {
   orc_outputs *out;
   int i0, i1, run_ekf, run_mhe;
   int t_steady; /* first step counted in the timing */
+  int tid;
   double seconds;
 } job_t;
+
+/* bench.py's CPU baseline pins worker t to the t-th CPU of the process's affinity mask (stable timings on a busy box) */
+static int g_pin_threads = 0;
+void orc_set_pin_threads(int on) { g_pin_threads = on; }
+static void pin_to_allowed_cpu(int t) {
+  cpu_set_t allowed, one;
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return;
+  int cnt = CPU_COUNT(&allowed);
+  if (cnt <= 0) return;
+  int want = t % cnt, seen = 0;
+  for (int c = 0; c < CPU_SETSIZE; ++c)
+    if (CPU_ISSET(c, &allowed)) {
+      if (seen == want) {
+        CPU_ZERO(&one);
+        CPU_SET(c, &one);
+        pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+        return;
+      }
+      ++seen;
+    }
+}
 
 static double now_s(void) {
   struct timespec ts;
@@ -51,6 +75,7 @@ static double now_s(void) {
 
 static void *worker(void *arg) {
   job_t *jb = (job_t *)arg;
+  if (g_pin_threads) pin_to_allowed_cpu(jb->tid);
   const orc_stream *st = jb->st;
   int n = st->n, S = st->S, nq = st->nq, nl = st->nlegs;
   int ds, dm, dc, nV, nC;
@@ -188,6 +213,7 @@ double orc_run_batch(const orc_params *prm, const orc_ekf_params *eprm, const or
     jobs[t].run_ekf = run_ekf;
     jobs[t].run_mhe = run_mhe;
     jobs[t].t_steady = t_steady;
+    jobs[t].tid = t;
     pthread_create(&th[t], NULL, worker, &jobs[t]);
   }
   double busy = 0.0, bmax = 0.0;

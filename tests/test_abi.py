@@ -36,7 +36,7 @@ def test_config_struct_matches_header(lib):
     cfg = DekfConfig()
     assert lib.dekf_config_default_go1(C.byref(cfg)) == 0
     # parameters_go1.yaml values survive the round trip through the C struct layout
-    assert cfg.abi_version == 2 and cfg.N == 20 and cfg.rate == 200 and cfg.num_legs == 4
+    assert cfg.abi_version == 3 and cfg.N == 20 and cfg.rate == 200 and cfg.num_legs == 4
     assert list(cfg.accel_bias_std) == [0.07, 0.02, 0.03]
     assert cfg.contact_effort_threshold == 150.0 and cfg.timeLimit == 0.0028
     assert list(cfg.ekf_quaternion_init) == [1.0, 0.0, 0.0, 0.0] and cfg.ekf_rate == 500

@@ -316,6 +316,55 @@ def test_run_host_f32_equals_run_host_bit_for_bit(est_mod, oracle):
     assert torch.isfinite(res[1]["x"][1:]).all()
 
 
+def test_run_host_f32io_is_the_float32_rounding_of_run_host_f32(est_mod):
+    """dekf_run_host_f32io (results leave the device as float32: 64 instead of 128 bytes per instance-tick) returns exactly
+    float32(x) of what dekf_run_host_f32 returns; contact flags and status words are identical."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S = 5000, 45
+    st = synth.make_stream(n, S, vo_jitter=True)
+    host = {k: (st[k].float() if k in E.BatchedEstimator.F32_KEYS else st[k]).contiguous().pin_memory() for k in E.BatchedEstimator._IN_KEYS}
+    vo = [bool(st["vo_flag"][s].any()) for s in range(S)]
+    res = []
+    for dt in (torch.float64, torch.float32):
+        est = E.BatchedEstimator(E.robot_params("go1", ekf_rate=200), n)
+        out = {"quat": torch.empty(S, 4, n, dtype=dt).pin_memory(), "x": torch.empty(S, 9, n, dtype=dt).pin_memory(),
+               "v_body": torch.empty(S, 3, n, dtype=dt).pin_memory(), "contact": torch.empty(S, 4, n, dtype=torch.uint8).pin_memory(),
+               "status": torch.empty(S, n, dtype=torch.int32).pin_memory()}
+        est.run_host_f32(0, S, host, vo, out=out, out_per_step=True)
+        res.append({k: v.clone() for k, v in out.items()})
+        est.close()
+    assert torch.equal(res[0]["contact"], res[1]["contact"]) and torch.equal(res[0]["status"], res[1]["status"])
+    assert torch.equal(res[0]["quat"].float(), res[1]["quat"])
+    for k in ("x", "v_body"):
+        assert torch.equal(res[0][k][1:].float(), res[1][k][1:]), k
+
+
+def test_kf_gain_matches_the_reference_objects_K_KF(est_mod, oracle):
+    """K_KF_ (DecentralEst.hpp:290, DecentralEst.cpp:858) through dekf_get_host(DEKF_GET_KF_GAIN): against the reference's own
+    K_KF_ member read from the compiled reference sources (oracle/_ref/libref_nodes.so) when that library travelled, and in
+    any case against C_KF_ A' C_meas^-1 rebuilt from the C_KF_ getter and the Q_meas debug tap."""
+    from decentralized_ekf_mhe_b200 import synth
+    from oracle import pyref as pr
+    E = est_mod
+    n, S = 3, 40
+    st = pr.quantize_stream(synth.to_numpy(synth.make_stream(n, S, vo_jitter=True)))
+    d = _to_dev(st)
+    est = E.BatchedEstimator(E.robot_params("go1", ekf_rate=200, est_type=1, kf_export_gain=1), n)
+    for s in range(S):
+        est.step(s, E.robot_store.from_stream(d, s))
+    K = est.K_KF_
+    assert K.shape == (9, 12, n) and np.isfinite(K).all() and np.abs(K).max() > 0
+    if pr.available():
+        for i in range(n):
+            rn = pr.RefNodes(oracle.go1_params(est_type=1), oracle.ekf_params(rate=200))
+            for s in range(S):
+                rn.tick_from_stream(st, s, i)
+            Kr = rn.kf_gain()
+            assert np.abs(K[:, :, i] - Kr).max() < 1e-9 * max(1.0, np.abs(Kr).max())
+    est.close()
+
+
 def test_go1_matches_reference_at_the_deployment_rates(est_mod):
     """The reference's shipped rates -- orientation EKF at 500 Hz, estimator at 200 Hz, two timers over the same topics --
     replayed through the reference's class API of the CUDA path (E.orien_ekf.timerCallback, E.DecentralizedEstimation.
@@ -466,7 +515,7 @@ def _pogox_state_constrained_16384(est_mod, oracle, precision, tol):
     assert bind / (S - 1) > 0.2
     assert np.mean(iters) < 6
     sub = {k: np.ascontiguousarray(v[..., :m].cpu().numpy()) for k, v in st_t.items()}
-    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0))
+    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0), p_imu_2_opti=(0.0, 0.0, 0.0))
     ro, _, _ = oracle.run_batch(sub, oracle.go1_params(v_box_enable=1, v_box_lo=lo, v_box_hi=hi, **kw),
                                 oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1, want=("x",))
     assert np.abs(xs[1:, 3:6] - ro["x"][1:, 3:6]).max() < tol
@@ -656,7 +705,7 @@ def test_builder_models_vs_generalised_oracle(est_mod, oracle, robot, rid, nl, t
     st = synth.to_numpy(synth.make_stream(64, 200, robot=robot, vo_jitter=True))
     for precision, tol in (("fp64", TOL_V), ("fp32", TOL_V32)):
         est, r = _run_lockstep(est_mod, st, robot=robot, precision=precision)
-        prm = oracle.go1_params(robot=rid, num_legs=nl, contact_effort_threshold=thr, p_ib=(0.0, 0.0, 0.0))
+        prm = oracle.go1_params(robot=rid, num_legs=nl, contact_effort_threshold=thr, p_ib=(0.0, 0.0, 0.0), p_imu_2_opti=(0.0, 0.0, 0.0))
         ro, _, _ = oracle.run_batch(st, prm, oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1)
         assert np.abs(r["x"][1:, 3:6] - ro["x"][1:, 3:6]).max() < tol
         assert np.array_equal(r["contact"], ro["contact"])
@@ -769,7 +818,7 @@ def test_cassie_full_size_properties(est_mod, oracle, precision, tol):
     assert double_support > 0                                # the walk gait has double-support phases
     assert torch.isfinite(est.x_MHE_).all() and not (est.status_ & 32).any()
     sub = {k: np.ascontiguousarray(v[..., :m].cpu().numpy()) for k, v in stt.items()}
-    prm = oracle.go1_params(robot=1, num_legs=2, contact_effort_threshold=150.0, p_ib=(0.0, 0.0, 0.0))
+    prm = oracle.go1_params(robot=1, num_legs=2, contact_effort_threshold=150.0, p_ib=(0.0, 0.0, 0.0), p_imu_2_opti=(0.0, 0.0, 0.0))
     ro, _, _ = oracle.run_batch(sub, prm, oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1, want=("x",))
     assert np.abs(xs[1:, 3:6] - ro["x"][1:, 3:6]).max() < tol
     est.close()
