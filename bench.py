@@ -68,12 +68,13 @@ KERNEL_NAMES = {"full": {"solve": "k_solve_tma", "ekf": "k_ekf", "assemble": "k_
                 "incremental": {"solve": "k_solve_incr", "resweep": "k_solve_incr_tma", "ekf": "k_ekf", "assemble": "k_assemble"}}
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture
-    of this workload (profiles/r01_traffic.json), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def ncu_traffic(kernel, n=65536):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` over `n` instances, from the committed
+    ncu --set full capture of this workload (profiles/r02_traffic.json: bytes per instance of the captured launch), or None."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
-        return json.load(open(p)).get(kernel)
+        ent = json.load(open(p)).get(kernel)
+        return None if ent is None else ent["dram_bytes_per_instance"] * n
     except Exception:
         return None
 
@@ -103,7 +104,7 @@ def kernel_report(mode, work, pms, pcnt, n, hbm_peak, hbm_src, fma_peak, precisi
         "kernel": KERNEL_NAMES[mode][dom], "kernel_ms": kd["ms"], "kernel_share_of_step": kd["total_ms"] / tot,
         "kernel_ms_source": "CUDA event pair around every launch on the launching stream (dekf_profile_*), mean over a "
                             "separate tick-by-tick pass of the same workload, no host sync between launches",
-        "traffic": ncu_traffic(KERNEL_NAMES[mode][dom]),
+        "traffic": ncu_traffic(KERNEL_NAMES[mode][dom], n),
         "hbm": {"achieved": kd["gbs"], "peak": hbm_peak, "frac": kd["gbs"] / hbm_peak, "peak_source": hbm_src},
         "fma": {"achieved": kd["tflops"], "peak": fma_peak, "frac": kd["tflops"] / fma_peak if fma_peak else None,
                 "peak_source": "measured in this run (dekf_measure_fma_peak, non-tensor FMA)"},
@@ -221,7 +222,9 @@ def cpu_reference_run(N, K, W, min_seconds=5.0, max_seconds=150.0, mode="admm", 
     # calibration: 2 instances per thread x 6 timed ticks
     t_cal, n_cal = run(2, 6, 0)
     per_step = t_cal / (2 * 6)  # seconds per instance-step on the slowest thread
-    ipt = max(ipt_min, int(min_seconds / max(K * per_step, 1e-9)) + 1)
+    # the calibration ticks are the slowest ones (cold caches, frequency ramp): 1.6x margin so that the timed region really
+    # lasts min_seconds
+    ipt = max(ipt_min, int(1.6 * min_seconds / max(K * per_step, 1e-9)) + 1)
     total_est = ipt * (fill + W + K) * per_step
     if total_est > max_seconds:
         ipt = max(1, int(max_seconds / ((fill + W + K) * per_step)))

@@ -51,11 +51,12 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(SO_PATH):
+    so_path = os.environ.get("DEKF_B200_SO", SO_PATH)  # tuning variants of the library (tools/); the default is the product build
+    if not os.path.exists(so_path):
         raise RuntimeError(
             f"{SO_PATH} is missing: build it with `python -m decentralized_ekf_mhe_b200.build` "
             "(nvcc, sm_100a). There is no CPU or PyTorch fallback for the estimator hot path.")
-    L = C.CDLL(SO_PATH)
+    L = C.CDLL(so_path)
     hp = C.c_void_p
     cfgp = C.POINTER(DekfConfig)
     for name in ("dekf_config_default_go1", "dekf_config_default_cassie", "dekf_config_default_pogox"):

@@ -19,14 +19,17 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """`defines` / `out`: tuning variants of the library (tools/, never the product default)."""
+    target = out or SO
+    if not force and out is None and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [nvcc] + flags + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + [
+        os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd)
-    return SO
+    return target
 
 
 if __name__ == "__main__":

@@ -37,6 +37,10 @@ struct BoxConst {
   double qvo[3];               // 1 / vo_p_std^2
   double P0[9];
   double lever[3];             // p_imu_2_opti (cfg), v_body = R_sb (v_s + omega x lever)
+  // general per-component bounds (cfg.x_box_* merged with cfg.v_box_*): bit a of mask9 bounds component a of every window
+  // state (0..2 p_s, 3..5 v_s, 6..8 accel bias).  general != 0: a component outside v_s is bounded -> box_solve<T, true>.
+  int mask9, general;
+  double lo9[9], hi9[9];
 };
 
 struct BoxBuffers {
@@ -44,6 +48,28 @@ struct BoxBuffers {
   uint8_t *act;      // [NW][ns]  bits 0-2: lower bound active on v_x,v_y,v_z; bits 3-5: upper bound
   int32_t *iters;    // [ns] factorisations of the last solve
   int32_t *nactive;  // [ns] active bounds of the last solve
+  uint32_t *act32;   // [NW][ns]  general bounds only: bits 0-8 lower bound active on component a, bits 9-17 upper bound
+};
+
+// Active-set encodings.  GEN = false: the velocity box (uint8 masks, components 3..5 -- the layout k_box_team shares);
+// GEN = true: any of the 9 state components (uint32 masks).
+template <bool GEN>
+struct BoxSet {
+  static constexpr int NC = GEN ? 9 : 3;    // candidate components per state
+  static constexpr int OFF = GEN ? 0 : 3;   // state index of candidate 0
+  static constexpr int HB = GEN ? 512 : 8;  // bit of the upper bound of candidate 0
+  DEKF_HD static bool active(int mask, int c) { return (mask & ((1 << c) | (HB << c))) != 0; }
+  DEKF_HD static bool bounded(const BoxConst &bc, int c) { return GEN ? ((bc.mask9 >> c) & 1) != 0 : true; }
+  DEKF_HD static double lo(const BoxConst &bc, int c) { return GEN ? bc.lo9[c] : bc.lo[c]; }
+  DEKF_HD static double hi(const BoxConst &bc, int c) { return GEN ? bc.hi9[c] : bc.hi[c]; }
+  DEKF_HD static double bound(const BoxConst &bc, int mask, int c) { return (mask & (HB << c)) ? hi(bc, c) : lo(bc, c); }
+  DEKF_HD static int load(const BoxBuffers &bb, size_t at) { return GEN ? (int)bb.act32[at] : (int)bb.act[at]; }
+  DEKF_HD static void store(const BoxBuffers &bb, size_t at, int m) {
+    if (GEN)
+      bb.act32[at] = (uint32_t)m;
+    else
+      bb.act[at] = (uint8_t)m;
+  }
 };
 
 struct BoxStage {
@@ -198,9 +224,11 @@ DEKF_HD int box_prior_info(const double *Pa /*81*/, const double *xa /*9*/, doub
 
 // Constrained solve over the window states k0 .. Tk (K = Tk - k0 + 1 <= N) with the Gaussian prior
 // (Pa, xa) on x_k0.  Returns status bits; writes x_T to xT.
-template <typename T>
+template <typename T, bool GEN = false>
 DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, const BoxBuffers &bb, int k0, int Tk, int i,
                       const double *Pa /*81*/, const double *xa /*9*/, double *xT /*9*/) {
+  using BS = BoxSet<GEN>;
+  constexpr int NC = BS::NC, OFF = BS::OFF;
   const size_t ns = (size_t)dm.ns;
   const int K = Tk - k0 + 1;
   int status = 0;
@@ -208,7 +236,7 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
   double M[81], mv[9];
   status |= box_prior_info(Pa, xa, M, mv);
   // warm start: masks of the previous tick stay attached to their stage (ring slot), the new state starts free
-  bb.act[(size_t)(Tk % dm.NW) * ns + i] = 0;
+  BS::store(bb, (size_t)(Tk % dm.NW) * ns + i, 0);
   int iters = 0, nact = 0;
   bool converged = false;
   for (int it = 0; it < bc.max_iter && !converged; ++it) {
@@ -222,8 +250,8 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
       const int k = k0 + j;
       BoxStage s;
       box_load_stage(dm, b, k, i, s);
-      const int mask = bb.act[(size_t)(k % dm.NW) * ns + i];
-      const int mask_n = (j + 1 < K) ? bb.act[(size_t)((k + 1) % dm.NW) * ns + i] : 0;
+      const int mask = BS::load(bb, (size_t)(k % dm.NW) * ns + i);
+      const int mask_n = (j + 1 < K) ? BS::load(bb, (size_t)((k + 1) % dm.NW) * ns + i) : 0;
       double D[81], E[81], r[9], Dn[81], rn[9];
       for (int f = 0; f < 81; ++f) D[f] = Dc[f];
       for (int f = 0; f < 9; ++f) r[f] = rc[f];
@@ -238,34 +266,34 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
         for (int f = 0; f < 81; ++f) D[f] += AtQA[f];
         for (int f = 0; f < 9; ++f) r[f] += rj[f];
         // fixed components of state j+1: move column to the right-hand side of state j, zero it
-        for (int c = 0; c < 3; ++c)
-          if (box_is_active(mask_n, c)) {
-            const double beta = box_bound(bc, mask_n, c);
+        for (int c = 0; c < NC; ++c)
+          if (BS::active(mask_n, c)) {
+            const double beta = BS::bound(bc, mask_n, c);
             for (int rr = 0; rr < 9; ++rr) {
-              r[rr] -= E[rr * 9 + 3 + c] * beta;
-              E[rr * 9 + 3 + c] = 0.0;
+              r[rr] -= E[rr * 9 + OFF + c] * beta;
+              E[rr * 9 + OFF + c] = 0.0;
             }
           }
         // fixed components of state j: their row of E feeds the right-hand side of state j+1
-        for (int c = 0; c < 3; ++c)
-          if (box_is_active(mask, c)) {
-            const double beta = box_bound(bc, mask, c);
+        for (int c = 0; c < NC; ++c)
+          if (BS::active(mask, c)) {
+            const double beta = BS::bound(bc, mask, c);
             for (int cc = 0; cc < 9; ++cc) {
-              rn[cc] -= E[(3 + c) * 9 + cc] * beta;
-              E[(3 + c) * 9 + cc] = 0.0;
+              rn[cc] -= E[(OFF + c) * 9 + cc] * beta;
+              E[(OFF + c) * 9 + cc] = 0.0;
             }
           }
       }
-      for (int c = 0; c < 3; ++c)
-        if (box_is_active(mask, c)) {
-          const double beta = box_bound(bc, mask, c);
-          for (int rr = 0; rr < 9; ++rr) r[rr] -= D[rr * 9 + 3 + c] * beta;
+      for (int c = 0; c < NC; ++c)
+        if (BS::active(mask, c)) {
+          const double beta = BS::bound(bc, mask, c);
+          for (int rr = 0; rr < 9; ++rr) r[rr] -= D[rr * 9 + OFF + c] * beta;
         }
-      for (int c = 0; c < 3; ++c)
-        if (box_is_active(mask, c)) {
-          for (int rr = 0; rr < 9; ++rr) D[rr * 9 + 3 + c] = D[(3 + c) * 9 + rr] = 0.0;
-          D[(3 + c) * 9 + 3 + c] = 1.0;
-          r[3 + c] = box_bound(bc, mask, c);
+      for (int c = 0; c < NC; ++c)
+        if (BS::active(mask, c)) {
+          for (int rr = 0; rr < 9; ++rr) D[rr * 9 + OFF + c] = D[(OFF + c) * 9 + rr] = 0.0;
+          D[(OFF + c) * 9 + OFF + c] = 1.0;
+          r[OFF + c] = BS::bound(bc, mask, c);
         }
       // S_j = D_j - F_{j-1} F_{j-1}',  rhs_j = r_j - F_{j-1} y_{j-1}
       if (j > 0) {
@@ -337,74 +365,181 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
       if (j == K - 1)
         for (int f = 0; f < 9; ++f) xT[f] = xn[f];
     }
-    // ---- multipliers = gradient of the free cost w.r.t. v_j, active-set update
-    //   grad_v(j) = [M (x_0 - xa)]_v (j == 0) + Lam_j v_j - eta_j + [A'Q w_j]_v - [Q w_{j-1}]_v,
-    //   w_j = A x_j - x_{j+1} + c_j  (the VO rows only touch p)
     bool changed = false;
     nact = 0;
-    double Qw_prev[3] = {0.0, 0.0, 0.0};
-    for (int j = 0; j < K; ++j) {
-      const int k = k0 + j;
-      BoxStage s;
-      box_load_stage(dm, b, k, i, s);
-      double xj[9], x1[9];
-      const double *fj = bb.fac + ((size_t)j * BOX_FAC) * ns + i;
-      for (int f = 0; f < 9; ++f) xj[f] = fj[(size_t)(126 + f) * ns];
-      double g[3];
-      for (int a = 0; a < 3; ++a) {
-        double v = -s.eta[a];
-        for (int c = 0; c < 3; ++c) v += s.Lam[S3<double>::idx(a, c)] * xj[3 + c];
-        g[a] = v - Qw_prev[a];
-      }
-      if (j == 0) {
+    if constexpr (GEN) {
+      // ---- multipliers = gradient of the free cost w.r.t. every component of x_j: g_j = D_j x_j + E_{j-1}' x_{j-1} + E_j x_{j+1}
+      // - r_j with the UNMODIFIED blocks of the block-tridiagonal system (re-assembled here exactly as in the forward pass).
+      // Update rule: the plain primal-dual active set (add every violated bound, drop every bound whose multiplier has the
+      // wrong sign) for the first kSafeIt iterations; it can cycle when many bounds of different components interact, so
+      // afterwards bounds are only ADDED, and when nothing is violated the ONE bound with the most negative multiplier is
+      // dropped (single-exchange rule: finite on a strictly convex QP).
+      constexpr int kSafeIt = 8;
+      const bool safe = it >= kSafeIt;
+      int drop_j = -1, drop_c = -1, added = 0;
+      double drop_val = 0.0;
+      double Dc[81], rc[9], Ep[81], xp[9];
+      for (int f = 0; f < 81; ++f) Dc[f] = 0.5 * (M[f] + M[(f % 9) * 9 + f / 9]);
+      for (int f = 0; f < 9; ++f) rc[f] = mv[f];
+      for (int j = 0; j < K; ++j) {
+        const int k = k0 + j;
+        BoxStage s;
+        box_load_stage(dm, b, k, i, s);
+        double D[81], E[81], r[9], Dn[81], rn[9], xj[9], x1[9];
+        const double *fj = bb.fac + ((size_t)j * BOX_FAC) * ns + i;
+        for (int f = 0; f < 9; ++f) xj[f] = fj[(size_t)(126 + f) * ns];
+        for (int f = 0; f < 81; ++f) D[f] = Dc[f];
+        for (int f = 0; f < 9; ++f) r[f] = rc[f];
         for (int a = 0; a < 3; ++a) {
-          double v = -mv[3 + a];
-          for (int c = 0; c < 9; ++c) v += 0.5 * (M[(3 + a) * 9 + c] + M[c * 9 + 3 + a]) * xj[c];
-          g[a] += v;
+          for (int c = 0; c < 3; ++c) D[(3 + a) * 9 + 3 + c] += s.Lam[S3<double>::idx(a, c)];
+          r[3 + a] += s.eta[a];
         }
-      }
-      if (j + 1 < K) {
-        const double *f1 = bb.fac + ((size_t)(j + 1) * BOX_FAC) * ns + i;
-        for (int f = 0; f < 9; ++f) x1[f] = f1[(size_t)(126 + f) * ns];
-        const double dt = bc.dt, h = 0.5 * bc.dt * bc.dt;
-        double Rb[3], wp[3], wv[3];
-        for (int a = 0; a < 3; ++a) Rb[a] = s.R[a * 3 + 0] * xj[6] + s.R[a * 3 + 1] * xj[7] + s.R[a * 3 + 2] * xj[8];
-        for (int a = 0; a < 3; ++a) {
-          wp[a] = xj[a] + dt * xj[3 + a] - h * Rb[a] - x1[a] + h * s.as[a];
-          wv[a] = xj[3 + a] - dt * Rb[a] - x1[3 + a] + dt * s.as[a];
+        if (j + 1 < K) {
+          double AtQA[81], rj[9];
+          box_dyn_blocks(bc, s, AtQA, E, Dn, rj, rn);
+          for (int f = 0; f < 81; ++f) D[f] += AtQA[f];
+          for (int f = 0; f < 9; ++f) r[f] += rj[f];
+          const double *f1 = bb.fac + ((size_t)(j + 1) * BOX_FAC) * ns + i;
+          for (int f = 0; f < 9; ++f) x1[f] = f1[(size_t)(126 + f) * ns];
         }
-        double Ra[9], Rbm[9], Rc[9];
-        box_rdrt(s.R, bc.qa, Ra);
-        box_rdrt(s.R, bc.qb, Rbm);
-        box_rdrt(s.R, bc.qc, Rc);
-        for (int a = 0; a < 3; ++a) {
-          double qp = 0.0, qv = 0.0;
-          for (int c = 0; c < 3; ++c) {
-            qp += Ra[a * 3 + c] * wp[c] + Rbm[a * 3 + c] * wv[c];
-            qv += Rbm[a * 3 + c] * wp[c] + Rc[a * 3 + c] * wv[c];
+        const size_t at = (size_t)(k % dm.NW) * ns + i;
+        const int mask = BS::load(bb, at);
+        int nm = 0;
+        for (int c = 0; c < 9; ++c) {
+          if (!BS::bounded(bc, c)) continue;
+          // gs: magnitude of the terms that cancel in g.  A multiplier within round-off of zero (degenerate bound) keeps its
+          // constraint; the iterate is the same either way to within gtol / curvature.
+          double g = -r[c], gs = fabs(r[c]);
+          for (int cc = 0; cc < 9; ++cc) {
+            const double t = D[c * 9 + cc] * xj[cc];
+            g += t;
+            gs += fabs(t);
           }
-          g[a] += dt * qp + qv;  // [A'Q w]_v = dt (Qw)_p + (Qw)_v
-          Qw_prev[a] = qv;
+          if (j + 1 < K)
+            for (int cc = 0; cc < 9; ++cc) {
+              const double t = E[c * 9 + cc] * x1[cc];
+              g += t;
+              gs += fabs(t);
+            }
+          if (j > 0)
+            for (int rr = 0; rr < 9; ++rr) {
+              const double t = Ep[rr * 9 + c] * xp[rr];
+              g += t;
+              gs += fabs(t);
+            }
+          const double gtol = 1e-10 * gs;
+          const bool up = (mask & (BS::HB << c)) != 0, dn = (mask & (1 << c)) != 0;
+          if (up || dn) {
+            const double mult = up ? -g : g;  // multiplier of the active bound
+            bool keep = mult > -gtol;
+            if (!keep && safe) {              // candidate for the single drop, most negative (scaled) multiplier wins
+              const double v = mult / (gs > 0.0 ? gs : 1.0);
+              if (drop_j < 0 || v < drop_val) {
+                drop_val = v;
+                drop_j = j;
+                drop_c = c;
+              }
+              keep = true;
+            }
+            if (keep) nm |= up ? (BS::HB << c) : (1 << c);
+          } else if (xj[c] > BS::hi(bc, c)) {
+            nm |= (BS::HB << c);
+            added++;
+          } else if (xj[c] < BS::lo(bc, c)) {
+            nm |= (1 << c);
+            added++;
+          }
+          if (BS::active(nm, c)) nact++;
+        }
+        if (nm != mask) {
+          changed = true;
+          BS::store(bb, at, nm);
+        }
+        if (j + 1 < K) {
+          for (int f = 0; f < 81; ++f) {
+            Ep[f] = E[f];
+            Dc[f] = Dn[f];
+          }
+          for (int f = 0; f < 9; ++f) {
+            xp[f] = xj[f];
+            rc[f] = rn[f];
+          }
         }
       }
-      uint8_t *mp = bb.act + (size_t)(k % dm.NW) * ns + i;
-      const int mask = *mp;
-      int nm = 0;
-      for (int c = 0; c < 3; ++c) {
-        if (mask & (8 << c)) {
-          if (-g[c] > 0.0) nm |= (8 << c);  // multiplier of the upper bound stays positive
-        } else if (mask & (1 << c)) {
-          if (g[c] > 0.0) nm |= (1 << c);
-        } else if (xj[3 + c] > bc.hi[c]) {
-          nm |= (8 << c);
-        } else if (xj[3 + c] < bc.lo[c]) {
-          nm |= (1 << c);
-        }
-        if (nm & ((1 << c) | (8 << c))) nact++;
-      }
-      if (nm != mask) {
+      if (safe && added == 0 && drop_j >= 0) {
+        const size_t at = (size_t)((k0 + drop_j) % dm.NW) * ns + i;
+        BS::store(bb, at, BS::load(bb, at) & ~((1 << drop_c) | (BS::HB << drop_c)));
+        nact--;
         changed = true;
-        *mp = (uint8_t)nm;
+      }
+    } else {
+      // ---- multipliers = gradient of the free cost w.r.t. v_j, active-set update
+      //   grad_v(j) = [M (x_0 - xa)]_v (j == 0) + Lam_j v_j - eta_j + [A'Q w_j]_v - [Q w_{j-1}]_v,
+      //   w_j = A x_j - x_{j+1} + c_j  (the VO rows only touch p)
+      double Qw_prev[3] = {0.0, 0.0, 0.0};
+      for (int j = 0; j < K; ++j) {
+        const int k = k0 + j;
+        BoxStage s;
+        box_load_stage(dm, b, k, i, s);
+        double xj[9], x1[9];
+        const double *fj = bb.fac + ((size_t)j * BOX_FAC) * ns + i;
+        for (int f = 0; f < 9; ++f) xj[f] = fj[(size_t)(126 + f) * ns];
+        double g[3];
+        for (int a = 0; a < 3; ++a) {
+          double v = -s.eta[a];
+          for (int c = 0; c < 3; ++c) v += s.Lam[S3<double>::idx(a, c)] * xj[3 + c];
+          g[a] = v - Qw_prev[a];
+        }
+        if (j == 0) {
+          for (int a = 0; a < 3; ++a) {
+            double v = -mv[3 + a];
+            for (int c = 0; c < 9; ++c) v += 0.5 * (M[(3 + a) * 9 + c] + M[c * 9 + 3 + a]) * xj[c];
+            g[a] += v;
+          }
+        }
+        if (j + 1 < K) {
+          const double *f1 = bb.fac + ((size_t)(j + 1) * BOX_FAC) * ns + i;
+          for (int f = 0; f < 9; ++f) x1[f] = f1[(size_t)(126 + f) * ns];
+          const double dt = bc.dt, h = 0.5 * bc.dt * bc.dt;
+          double Rb[3], wp[3], wv[3];
+          for (int a = 0; a < 3; ++a) Rb[a] = s.R[a * 3 + 0] * xj[6] + s.R[a * 3 + 1] * xj[7] + s.R[a * 3 + 2] * xj[8];
+          for (int a = 0; a < 3; ++a) {
+            wp[a] = xj[a] + dt * xj[3 + a] - h * Rb[a] - x1[a] + h * s.as[a];
+            wv[a] = xj[3 + a] - dt * Rb[a] - x1[3 + a] + dt * s.as[a];
+          }
+          double Ra[9], Rbm[9], Rc[9];
+          box_rdrt(s.R, bc.qa, Ra);
+          box_rdrt(s.R, bc.qb, Rbm);
+          box_rdrt(s.R, bc.qc, Rc);
+          for (int a = 0; a < 3; ++a) {
+            double qp = 0.0, qv = 0.0;
+            for (int c = 0; c < 3; ++c) {
+              qp += Ra[a * 3 + c] * wp[c] + Rbm[a * 3 + c] * wv[c];
+              qv += Rbm[a * 3 + c] * wp[c] + Rc[a * 3 + c] * wv[c];
+            }
+            g[a] += dt * qp + qv;  // [A'Q w]_v = dt (Qw)_p + (Qw)_v
+            Qw_prev[a] = qv;
+          }
+        }
+        uint8_t *mp = bb.act + (size_t)(k % dm.NW) * ns + i;
+        const int mask = *mp;
+        int nm = 0;
+        for (int c = 0; c < 3; ++c) {
+          if (mask & (8 << c)) {
+            if (-g[c] > 0.0) nm |= (8 << c);  // multiplier of the upper bound stays positive
+          } else if (mask & (1 << c)) {
+            if (g[c] > 0.0) nm |= (1 << c);
+          } else if (xj[3 + c] > bc.hi[c]) {
+            nm |= (8 << c);
+          } else if (xj[3 + c] < bc.lo[c]) {
+            nm |= (1 << c);
+          }
+          if (nm & ((1 << c) | (8 << c))) nact++;
+        }
+        if (nm != mask) {
+          changed = true;
+          *mp = (uint8_t)nm;
+        }
       }
     }
     converged = !changed;
@@ -494,7 +629,7 @@ DEKF_HD int mhe_solve_box(const MheConst<T> &c, const BoxConst &bc, const Dims &
   int k0;
   box_prepare<T, Math>(c, dm, b, Tk, i, Pa, xa, k0);
   GlobalStageSource<T> src(dm, b, i);
-  int status = box_solve<T>(bc, dm, b, bb, k0, Tk, i, Pa, xa, xT);
+  int status = bc.general ? box_solve<T, true>(bc, dm, b, bb, k0, Tk, i, Pa, xa, xT) : box_solve<T, false>(bc, dm, b, bb, k0, Tk, i, Pa, xa, xT);
   M3<T> RT;
   src.rot(0, Tk, RT);
   double om[3];

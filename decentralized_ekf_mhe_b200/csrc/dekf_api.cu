@@ -44,15 +44,21 @@ __global__ void __launch_bounds__(kBlock, DEKF_MINB_EKF) k_ekf(const EkfConst<T>
   if (status_out != nullptr) status_out[i] = st;
 }
 
+// quat_copy (dekf_run only): the tick's quaternion also goes to the per-step output array from here -- it used to be a
+// device-to-device cudaMemcpyAsync per tick on the assembly stream, i.e. a copy-engine round trip in front of every solve
 template <typename T, typename Model>
 __global__ void __launch_bounds__(kBlock, DEKF_MINB_ASM) k_assemble(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
-                                                     const Outputs out, int Tk, const int32_t *prev_status) {
+                                                     const Outputs out, int Tk, const int32_t *prev_status, double *quat_copy) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dm.n) return;
   double q[4];
 #pragma unroll
   for (int f = 0; f < 4; ++f)
     q[f] = (in.quat != nullptr) ? in.quat[(size_t)f * dm.n + i] : (double)b.ekf_q[(size_t)f * dm.ns + i];
+  if (quat_copy != nullptr) {
+#pragma unroll
+    for (int f = 0; f < 4; ++f) quat_copy[(size_t)f * dm.n + i] = q[f];
+  }
   const int st = mhe_assemble<T, Model>(c, dm, b, in, out, Tk, i, q);
   tick_status(dm, b, Tk, i) = (prev_status != nullptr) ? (prev_status[i] | st) : st;  // prev_status: this tick's EKF status bits
 }
@@ -404,7 +410,7 @@ struct dekf_handle {
   Buffers<double> b64;
   Buffers<float> b32;
   BoxConst bc;
-  BoxBuffers bb = {nullptr, nullptr, nullptr, nullptr};
+  BoxBuffers bb = {nullptr, nullptr, nullptr, nullptr, nullptr};
   BoxTeamBuffers tb = {nullptr, nullptr};
   bool box_team = true;           // team form of the constrained solve (DEKF_BOX_SERIAL=1 selects one thread per instance)
   bool foot_team = true;          // one warp per instance for the foot-state model (DEKF_FOOT_SERIAL=1: one thread per instance)
@@ -456,6 +462,7 @@ struct dekf_handle {
   double *get_scratch = nullptr;
   size_t get_scratch_bytes = 0;
   double *kf_Q = nullptr;  // [num_legs][6][n] per-leg Q_meas of the newest sample (cfg.kf_export_gain)
+  double *asm_quat_copy = nullptr;  // dekf_run: where k_assemble also writes the tick's quaternion (per-step output)
   // optional per-kernel timing: an event pair around every launch, no host synchronisation until the read
   bool prof = false;
   struct ProfRec {
@@ -590,7 +597,7 @@ int launch_assemble(dekf_handle *h, const MheConst<T> &mc, const Buffers<T> &b, 
                     int T_, const int32_t *acc) {
   {
     ProfScope ps(h, 1);
-    k_assemble<T, Model><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(mc, h->dm, b, in, out, T_, acc);
+    k_assemble<T, Model><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(mc, h->dm, b, in, out, T_, acc, h->asm_quat_copy);
   }
   h->launches++;
   return 0;
@@ -662,6 +669,12 @@ int validate(const dekf_config *c, std::string &why) {
     if (c->est_type != 0) { why = "v_box_enable needs est_type 0 (the KF alternative has no constraints)"; return DEKF_EINVAL; }
     for (int i = 0; i < 3; ++i)
       if (!(c->v_box_lo[i] < c->v_box_hi[i])) { why = "v_box_lo must be < v_box_hi"; return DEKF_EINVAL; }
+  }
+  if (c->x_box_mask) {
+    if (c->x_box_mask & ~0x1ff) { why = "x_box_mask has 9 bits (p_s, v_s, accel bias)"; return DEKF_EINVAL; }
+    if (c->est_type != 0 || c->leg_odom_type != 0) { why = "x_box_mask needs est_type 0 and leg_odom_type 0"; return DEKF_EINVAL; }
+    for (int a = 0; a < 9; ++a)
+      if (((c->x_box_mask >> a) & 1) && !(c->x_box_lo[a] < c->x_box_hi[a])) { why = "x_box_lo must be < x_box_hi"; return DEKF_EINVAL; }
   }
   return DEKF_OK;
 }
@@ -787,7 +800,8 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     void *base = h->f32 ? (void *)h->b32.win : (void *)h->b64.win;
     const cuuint64_t gdim[2] = {(cuuint64_t)h->dm.ns, (cuuint64_t)h->dm.NW * REC_SIZE};
     const cuuint64_t gstride[1] = {(cuuint64_t)h->dm.ns * elt};
-    const cuuint32_t box[2] = {(cuuint32_t)kTile, (cuuint32_t)REC_SIZE};
+    // one TMA box = the stage record of one pipeline's instances: a warp (32) with per-warp pipelines, else the CTA's tile
+    const cuuint32_t box[2] = {(cuuint32_t)((h->f32 ? SolveCfg<float>::kPerWarp : SolveCfg<double>::kPerWarp) ? 32 : kTile), (cuuint32_t)REC_SIZE};
     const cuuint32_t estr[2] = {1, 1};
     CUresult cr = ((encode_fn)fn)(&h->tmap, h->f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim,
                                   gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -834,15 +848,20 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
     h->solve_slots = sms * per_sm;
   }
   if (const char *e = std::getenv("DEKF_FOOT_SERIAL")) h->foot_team = std::atoi(e) == 0;
-  if (cfg->v_box_enable) {
+  if (h->bc.enable) {
     const size_t ns = (size_t)h->dm.ns;
     const size_t fac = (size_t)h->dm.N * BOX_FAC * ns * sizeof(double), act = (size_t)h->dm.NW * ns;
+    if (h->bc.general) {  // bounds outside v_s: 18-bit masks, one thread per instance
+      if ((ce = cudaMalloc((void **)&h->bb.act32, act * sizeof(uint32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
+      h->extra_bytes += act * sizeof(uint32_t);
+      h->box_team = false;
+    }
     if ((ce = cudaMalloc((void **)&h->bb.fac, fac)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc(box factor scratch)", ce);
     if ((ce = cudaMalloc((void **)&h->bb.act, act)) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
     if ((ce = cudaMalloc((void **)&h->bb.iters, ns * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
     if ((ce = cudaMalloc((void **)&h->bb.nactive, ns * sizeof(int32_t))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
     h->extra_bytes += fac + act + 2 * ns * sizeof(int32_t);
-    if (const char *e = std::getenv("DEKF_BOX_SERIAL")) h->box_team = std::atoi(e) == 0;
+    if (const char *e = std::getenv("DEKF_BOX_SERIAL")) h->box_team = h->box_team && std::atoi(e) == 0;
     if (h->box_team) {
       const size_t tfac = (size_t)h->dm.N * BOX_TFAC * ns * sizeof(double);
       if ((ce = cudaMalloc((void **)&h->tb.prior, ns * BOX_PRIOR * sizeof(double))) != cudaSuccess) return bail(DEKF_ENOMEM, "cudaMalloc", ce);
@@ -888,6 +907,7 @@ int dekf_destroy(dekf_handle *h) {
   cudaFree(h->tb.prior);
   cudaFree(h->tb.fac);
   cudaFree(h->bb.act);
+  cudaFree(h->bb.act32);
   cudaFree(h->bb.iters);
   cudaFree(h->bb.nactive);
   free_stage_set(h->stage[0]);
@@ -946,6 +966,7 @@ int dekf_reset(dekf_handle *h) {
   }
   if (h->bb.act) {
     CK(cudaMemsetAsync(h->bb.act, 0, (size_t)h->dm.NW * h->dm.ns, h->stream));
+    if (h->bb.act32) CK(cudaMemsetAsync(h->bb.act32, 0, (size_t)h->dm.NW * h->dm.ns * sizeof(uint32_t), h->stream));
     CK(cudaMemsetAsync(h->bb.iters, 0, (size_t)h->dm.ns * sizeof(int32_t), h->stream));
     CK(cudaMemsetAsync(h->bb.nactive, 0, (size_t)h->dm.ns * sizeof(int32_t), h->stream));
   }
@@ -1501,13 +1522,14 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     }
     is.quat = qslot;
     h->stream = sa;
+    // the tick's quaternion leaves the ring slot BEFORE ev_mhe releases the slot to the EKF of tick s+QA (copying it on the
+    // solve stream raced with that EKF tick whenever the solves lagged behind the assembly): k_assemble writes it out
+    h->asm_quat_copy = os.quat;
     rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 1);
+    h->asm_quat_copy = nullptr;
     h->stream = user;
     if (rc) break;
-    // the tick's quaternion leaves the ring slot BEFORE ev_mhe releases the slot to the EKF of tick s+QA (copying it on the
-    // solve stream raced with that EKF tick whenever the solves lagged behind the assembly)
-    ce = os.quat ? cudaMemcpyAsync(os.quat, qslot, 4 * n * sizeof(double), cudaMemcpyDeviceToDevice, sa) : cudaSuccess;
-    if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_mhe[slot], sa);
+    ce = cudaEventRecord(h->ev_mhe[slot], sa);
     // ---- window solve of tick s
     if (ce == cudaSuccess && asm_ahead) ce = cudaStreamWaitEvent(h->s_mhe, h->ev_mhe[slot], 0);
     if (ce != cudaSuccess) {

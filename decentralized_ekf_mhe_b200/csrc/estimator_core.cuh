@@ -660,7 +660,14 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
   V3<T> beta_swing = v3<T>(T(0), T(0), T(0));  // sum over swing legs of beta_i
   int n_swing = 0;
   int contact_mask = 0;
+  // The leg loop stays ROLLED: one copy of the kinematics / covariance code in the instruction stream instead of NL
+  // (k_assemble<double, Go1>: 20.6 -> 18.8 us per launch, spill frame 104 -> 56 B; profiles/r02_tune_solve.md).
+  // -DDEKF_LEG_UNROLLED restores the unrolled form.
+#if defined(DEKF_LEG_UNROLLED)
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
   for (int leg = 0; leg < NL; ++leg) {
     const double force = in.foot_force[(size_t)leg * n + i];
     const bool contact = (force >= c.thr);  // go1Sub.cpp:74, exact

@@ -121,7 +121,7 @@ inline MheConst<T> make_mhe_const(const dekf_config &c) {
   m.dt_d = dt;
   m.N = c.N;
   m.est_type = c.est_type;
-  m.window_solve = (c.est_type == 0 && !c.v_box_enable) ? c.window_solve : 0;
+  m.window_solve = (c.est_type == 0 && !c.v_box_enable && !c.x_box_mask) ? c.window_solve : 0;
   m.thr = c.contact_effort_threshold;
   for (int i = 0; i < 3; ++i) {
     const double Cp = std::pow(c.p_process_std[i], 2), Ca = std::pow(c.accel_input_std[i], 2);
@@ -161,13 +161,20 @@ inline MheConst<T> make_mhe_const(const dekf_config &c) {
 inline BoxConst make_box_const(const dekf_config &c) {
   BoxConst b;
   std::memset(&b, 0, sizeof(b));
-  b.enable = c.v_box_enable != 0;
+  b.mask9 = (c.v_box_enable ? 0x38 : 0) | (c.x_box_mask & 0x1ff);
+  b.enable = b.mask9 != 0;
+  b.general = (b.mask9 & ~0x38) != 0;
+  for (int a = 0; a < 9; ++a) {
+    const bool gx = ((c.x_box_mask >> a) & 1) != 0, gv = c.v_box_enable && a >= 3 && a < 6;
+    b.lo9[a] = gx ? c.x_box_lo[a] : (gv ? c.v_box_lo[a - 3] : -1e300);
+    b.hi9[a] = gx ? c.x_box_hi[a] : (gv ? c.v_box_hi[a - 3] : 1e300);
+  }
   b.max_iter = c.v_box_max_iter > 0 ? c.v_box_max_iter : 50;
   const double dt = 1.0 / c.rate;
   b.dt = dt;
   for (int i = 0; i < 3; ++i) {
-    b.lo[i] = c.v_box_lo[i];
-    b.hi[i] = c.v_box_hi[i];
+    b.lo[i] = b.lo9[3 + i];  // the velocity box as the team kernel reads it
+    b.hi[i] = b.hi9[3 + i];
     b.lever[i] = c.p_imu_2_opti[i];
     const double Cp = std::pow(c.p_process_std[i], 2), Ca = std::pow(c.accel_input_std[i], 2);
     const double d1 = dt * dt * Cp + 0.25 * dt * dt * dt * dt * Ca, d2 = 0.5 * dt * dt * dt * Ca, d3 = dt * dt * Ca;

@@ -19,17 +19,20 @@ namespace dekf {
 // is signalled on a "full" mbarrier (expect_tx), consumers hand the buffer back through an "empty" mbarrier.
 // The stage record is read from shared memory at the point of use instead of being parked in registers.
 constexpr int kTile = 128;
-// Ring depth and CTAs per SM per element type (measured, profiles/r02_tune_solve.md).  fp64: the sweep needs ~250 registers,
-// i.e. 2 CTAs/SM; 4 stage tiles of 25.6 KB each per CTA.  fp32: 128 registers and 4 CTAs/SM without spills.
+// Ring depth, CTAs per SM and pipeline granularity per element type (measured, profiles/r02_tune_solve.md).  fp64: the sweep
+// needs ~250 registers, i.e. 2 CTAs/SM; 3 stage tiles of 25.6 KB each per CTA (2: 95 us, 3: 89 us, 4: 91 us per launch).
+// fp32: 128 registers and 4 CTAs/SM without spills.  One pipeline per CTA or one per warp makes no difference (89.2 / 89.6 us).
 template <typename T>
 struct SolveCfg {
   static constexpr int kStages = 3, kMinB = 1;
   static constexpr bool kXS = false;
+  static constexpr bool kPerWarp = false;
 };
 template <>
 struct SolveCfg<float> {
   static constexpr int kStages = 3, kMinB = 4;
   static constexpr bool kXS = false;
+  static constexpr bool kPerWarp = false;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,49 +124,59 @@ struct SmemStageSource {
 
 template <typename T, int TILE = kTile, int STAGES = SolveCfg<T>::kStages, bool XS = SolveCfg<T>::kXS>
 constexpr size_t solve_tma_smem_bytes() {
-  return (size_t)STAGES * REC_SIZE * TILE * sizeof(T) + 2 * STAGES * sizeof(uint64_t) + (XS ? (size_t)9 * TILE * sizeof(T) : 0);
+  // stage ring + full/empty barriers of up to TILE/32 pipelines (+ x when it lives in shared memory)
+  return (size_t)STAGES * REC_SIZE * TILE * sizeof(T) + (size_t)(TILE / 32) * 2 * STAGES * sizeof(uint64_t) + (XS ? (size_t)9 * TILE * sizeof(T) : 0);
 }
 
-// XS: keep the state mean x (9 scalars per instance) in shared memory instead of registers ([9][TILE] behind the ring)
+// XS: keep the state mean x (9 scalars per instance) in shared memory instead of registers ([9][TILE] behind the ring).
+// PW: one pipeline PER WARP (TMA box {32 instances, 25 rows}, the warp's own full / empty barriers, lane 0 refills): no warp
+// ever waits for another warp of its CTA -- with PW = false the whole CTA shares one pipeline fed by thread 0.
 template <typename T, int TILE = kTile, int STAGES = SolveCfg<T>::kStages, int MINB = SolveCfg<T>::kMinB, typename Math = DefaultMath<T>,
-          bool XS = SolveCfg<T>::kXS>
+          bool XS = SolveCfg<T>::kXS, bool PW = SolveCfg<T>::kPerWarp>
 __global__ void __launch_bounds__(TILE, MINB) k_solve_tma(const __grid_constant__ CUtensorMap tmap, const MheConst<T> c, const Dims dm,
                                                      const Buffers<T> b, const Inputs in, const Outputs out, int Tk,
                                                      int32_t *status_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemStageSource<T, TILE, STAGES> src;
-  src.tiles = reinterpret_cast<T *>(smem_raw);
-  src.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * REC_SIZE * TILE * sizeof(T));
+  constexpr int PT = PW ? 32 : TILE;           // instances per pipeline
+  constexpr int NP = TILE / PT;                // pipelines per CTA
+  const int pipe = PW ? (int)(threadIdx.x >> 5) : 0;
+  const int ptid = PW ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  SmemStageSource<T, PT, STAGES> src;
+  src.tiles = reinterpret_cast<T *>(smem_raw) + (size_t)pipe * STAGES * REC_SIZE * PT;
+  src.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * REC_SIZE * TILE * sizeof(T)) + (size_t)pipe * 2 * STAGES;
   src.empty = src.full + STAGES;
   src.map = &tmap;
   src.NW = dm.NW;
-  src.i0 = (blockIdx.x + dm.tile0) * TILE;
-  src.tid = threadIdx.x;
+  src.i0 = (blockIdx.x + dm.tile0) * TILE + pipe * PT;
+  src.tid = ptid;
   src.k0 = (Tk < dm.N) ? 0 : Tk - dm.N;
   src.nst = Tk - src.k0 + 1;
-  const int active = min(TILE, dm.n - src.i0);  // consumers in this CTA (thread 0 is always one of them)
+  const int active = min(PT, dm.n - src.i0);  // consumers of this pipeline (<= 0: the pipeline has no live instance)
   // the arrival-cost loads are in flight while the barriers are set up and the first tiles are requested
-  const int i = src.i0 + threadIdx.x;
+  const int i = src.i0 + ptid;
   Cov9<T> P;
   using XT = typename std::conditional<XS, MemVec9<T, TILE>, Vec9<T>>::type;
-  XT x = make_x<T, TILE, XS>(reinterpret_cast<T *>(smem_raw + (size_t)STAGES * REC_SIZE * TILE * sizeof(T) + 2 * STAGES * sizeof(uint64_t)) + threadIdx.x);
+  XT x = make_x<T, TILE, XS>(reinterpret_cast<T *>(smem_raw + (size_t)STAGES * REC_SIZE * TILE * sizeof(T) + (size_t)NP * 2 * STAGES * sizeof(uint64_t)) + threadIdx.x);
   if (i < dm.n) mhe_solve_start(c, dm, b, Tk, i, P, x);
-  if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  if (ptid == 0 && active > 0) {
+    if (threadIdx.x == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&src.full[s], 1);
       mbar_init(&src.empty[s], (uint32_t)active);
     }
     mbar_fence_init();
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  if constexpr (PW)
+    __syncwarp();
+  else
+    __syncthreads();
+  if (ptid == 0 && active > 0) {
     const int pre = src.nst < STAGES ? src.nst : STAGES;
     for (int j = 0; j < pre; ++j) src.issue(j);
   }
   if (i >= dm.n) return;
   int st = tick_status(dm, b, Tk, i);
-  st |= mhe_solve_sweep<T, SmemStageSource<T, TILE, STAGES>, Math, XT>(c, dm, b, in, out, Tk, i, src, P, x, src.k0);
+  st |= mhe_solve_sweep<T, SmemStageSource<T, PT, STAGES>, Math, XT>(c, dm, b, in, out, Tk, i, src, P, x, src.k0);
   tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }
@@ -171,44 +184,55 @@ __global__ void __launch_bounds__(TILE, MINB) k_solve_tma(const __grid_constant_
 // Incremental window solve on a tick that carries VO messages: the CTA agrees on the earliest restart stage of its 128
 // instances (re-sweeping from an earlier valid checkpoint gives the same bits) and streams the stage records
 // ks .. T through the same TMA ring as k_solve_tma.
-template <typename T, int TILE = kTile, int STAGES = SolveCfg<T>::kStages, typename Math = DefaultMath<T>>
+template <typename T, int TILE = kTile, int STAGES = SolveCfg<T>::kStages, typename Math = DefaultMath<T>, bool PW = SolveCfg<T>::kPerWarp>
 __global__ void __launch_bounds__(TILE, 1) k_solve_incr_tma(const __grid_constant__ CUtensorMap tmap, const MheConst<T> c,
                                                             const Dims dm, const Buffers<T> b, const Inputs in,
                                                             const Outputs out, int Tk, int32_t *status_out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ int s_ks;
-  SmemStageSource<T, TILE, STAGES> src;
-  src.tiles = reinterpret_cast<T *>(smem_raw);
-  src.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * REC_SIZE * TILE * sizeof(T));
+  constexpr int PT = PW ? 32 : TILE;
+  const int pipe = PW ? (int)(threadIdx.x >> 5) : 0;
+  const int ptid = PW ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+  SmemStageSource<T, PT, STAGES> src;
+  src.tiles = reinterpret_cast<T *>(smem_raw) + (size_t)pipe * STAGES * REC_SIZE * PT;
+  src.full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * REC_SIZE * TILE * sizeof(T)) + (size_t)pipe * 2 * STAGES;
   src.empty = src.full + STAGES;
   src.map = &tmap;
   src.NW = dm.NW;
-  src.i0 = blockIdx.x * TILE;
-  src.tid = threadIdx.x;
-  const int i = src.i0 + threadIdx.x;
-  const int active = min(TILE, dm.n - src.i0);
-  if (threadIdx.x == 0) {
-    s_ks = Tk - 1;
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+  src.i0 = blockIdx.x * TILE + pipe * PT;
+  src.tid = ptid;
+  const int i = src.i0 + ptid;
+  const int active = min(PT, dm.n - src.i0);
+  if (ptid == 0 && active > 0) {
+    if (threadIdx.x == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&src.full[s], 1);
       mbar_init(&src.empty[s], (uint32_t)active);
     }
     mbar_fence_init();
   }
-  __syncthreads();
-  if (i < dm.n) atomicMin(&s_ks, incr_restart_stage(dm, b, Tk, i));
-  __syncthreads();
-  const int ks = s_ks;
+  // the pipeline agrees on the earliest restart stage of its instances (re-sweeping from an earlier valid checkpoint gives
+  // the same bits): per warp with PW, per CTA otherwise
+  int ks;
+  if constexpr (PW) {
+    const int mine = (i < dm.n) ? incr_restart_stage(dm, b, Tk, i) : Tk - 1;
+    ks = __reduce_min_sync(0xffffffffu, mine);
+  } else {
+    if (threadIdx.x == 0) s_ks = Tk - 1;
+    __syncthreads();
+    if (i < dm.n) atomicMin(&s_ks, incr_restart_stage(dm, b, Tk, i));
+    __syncthreads();
+    ks = s_ks;
+  }
   src.k0 = ks;
   src.nst = Tk - ks + 1;
-  if (threadIdx.x == 0) {
+  if (ptid == 0 && active > 0) {
     const int pre = src.nst < STAGES ? src.nst : STAGES;
     for (int j = 0; j < pre; ++j) src.issue(j);
   }
   if (i >= dm.n) return;
   int st = tick_status(dm, b, Tk, i);
-  st |= mhe_solve_incr<T, SmemStageSource<T, TILE, STAGES>, Math>(c, dm, b, in, out, Tk, i, src, ks);
+  st |= mhe_solve_incr<T, SmemStageSource<T, PT, STAGES>, Math>(c, dm, b, in, out, Tk, i, src, ks);
   tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
 }

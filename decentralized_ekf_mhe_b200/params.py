@@ -37,6 +37,7 @@ class DekfConfig(C.Structure):
         ("v_box_enable", C.c_int32), ("v_box_max_iter", C.c_int32),
         ("v_box_lo", C.c_double * 3), ("v_box_hi", C.c_double * 3),
         ("p_imu_2_opti", C.c_double * 3), ("kf_export_gain", C.c_int32), ("reserved3", C.c_int32),
+        ("x_box_mask", C.c_int32), ("reserved4", C.c_int32), ("x_box_lo", C.c_double * 9), ("x_box_hi", C.c_double * 9),
     ]
 
     def update(self, **over):

@@ -125,6 +125,15 @@ typedef struct dekf_config {
   /* est_type 1 only: keep the per-leg measurement information of the newest sample so that DEKF_GET_KF_GAIN can return
    * K_KF_ (DecentralEst.hpp:290); costs 6 * num_legs doubles per instance of state and their write per tick. */
   int32_t kf_export_gain, reserved3;
+
+  /* ---- general per-component state bounds: what MHEproblem::addConstraints(name, lb, ub) with lb < ub plus a dependency on
+   * x_k through a selector row would add (MheSrb.cpp:58-68, :217-270; never exercised by the reference).  Bit a of x_box_mask
+   * (a = 0..8: p_s xyz, v_s xyz, accel bias xyz) adds the rows  x_box_lo[a] <= x_k[a] <= x_box_hi[a]  for every state of the
+   * window at solve time; combines with v_box_* (components 3..5; x_box_* wins where both bound a component).  est_type 0,
+   * leg_odom_type 0.  Bounds on p_s or bias components are solved by the one-thread-per-instance active-set kernel
+   * (k_solve_box), velocity-only bounds by the team kernel. */
+  int32_t x_box_mask, reserved4;
+  double x_box_lo[9], x_box_hi[9];
 } dekf_config;
 
 /* Per-tick sensor snapshot of all instances.  NULL vo_flag == no VO message for anybody. */

@@ -62,6 +62,9 @@ struct robot_params {
   // lever arm of v_MHE_b_ (DecentralEst.cpp:181-185 hard-codes this Go1 mocap marker offset)
   std::vector<double> p_imu_2_opti_{0.016041, 0.089061, 0.0579875};
   bool kf_export_gain_ = false;  // est_type_ 1: make K_KF_() available (DecentralEst.hpp:290)
+  // general rows lb <= x_k[a] <= ub on any state component a = 0..8 (MHEproblem::addConstraints with a selector row, MheSrb.cpp:58-68)
+  int x_box_mask_ = 0;
+  std::vector<double> x_box_lo_ = std::vector<double>(9, -1e30), x_box_hi_ = std::vector<double>(9, 1e30);
 
   // go1_example/config/parameters_go1.yaml
   static robot_params go1() {
@@ -116,6 +119,11 @@ struct robot_params {
     p.ekf_hist_depth_ = c.ekf_hist_depth;
     p.p_imu_2_opti_ = v(c.p_imu_2_opti, 3);
     p.kf_export_gain_ = c.kf_export_gain != 0;
+    p.x_box_mask_ = c.x_box_mask;
+    if (c.x_box_mask) {
+      p.x_box_lo_ = v(c.x_box_lo, 9);
+      p.x_box_hi_ = v(c.x_box_hi, 9);
+    }
     p.v_box_enable_ = c.v_box_enable != 0;
     if (p.v_box_enable_) {
       p.v_box_lo_ = v(c.v_box_lo, 3);
@@ -162,6 +170,12 @@ struct robot_params {
     put(c.v_box_hi, v_box_hi_, 3, "v_box_hi_");
     put(c.p_imu_2_opti, p_imu_2_opti_, 3, "p_imu_2_opti_");
     c.kf_export_gain = kf_export_gain_;
+    c.x_box_mask = x_box_mask_;
+    if (x_box_lo_.size() < 9 || x_box_hi_.size() < 9) throw std::runtime_error("robot_params.x_box_lo_/x_box_hi_ need 9 entries");
+    for (int a = 0; a < 9; ++a) {
+      c.x_box_lo[a] = x_box_lo_[(size_t)a];
+      c.x_box_hi[a] = x_box_hi_[(size_t)a];
+    }
     c.rho = rho_;
     c.alpha = alpha_;
     c.delta = delta_;

@@ -917,12 +917,20 @@ static int solve_exact(orc_mhe *m) {
     }
   }
   int rc;
-  if (m->P.v_box_enable) {
-    /* Builder extension (never exercised by the reference): rows lo <= v_s of x_j <= hi for every state of
-     * the window at solve time -- what MHEproblem::addConstraints(name, lb, ub) + a dependency on x_j with the
-     * selector [0 I 0] would add (MheSrb.cpp:58-68).  Exact optimum by a primal-dual active-set iteration on the
-     * normal equations in x: fix the active components at their bound, solve, read the multipliers off the
-     * residual of the free system, update the set; stops when the set repeats itself. */
+  if (m->P.v_box_enable || m->P.x_box_mask) {
+    /* Builder extension (never exercised by the reference): rows lo <= x_j[a] <= hi for the bounded components a of every
+     * state of the window at solve time -- what MHEproblem::addConstraints(name, lb, ub) + a dependency on x_j with a
+     * selector row would add (MheSrb.cpp:58-68).  v_box bounds v_s (a = 3..5), x_box_mask any of the 9 base components.
+     * Exact optimum by a primal-dual active-set iteration on the normal equations in x: fix the active components at their
+     * bound, solve, read the multipliers off the residual of the free system, update the set; stops when the set repeats. */
+    double blo[9], bhi[9];
+    int bmask = 0;
+    for (int a = 0; a < 9; ++a) {
+      int gx = (m->P.x_box_mask >> a) & 1, gv = m->P.v_box_enable && a >= 3 && a < 6;
+      blo[a] = gx ? m->P.x_box_lo[a] : (gv ? m->P.v_box_lo[a - 3] : -1e300);
+      bhi[a] = gx ? m->P.x_box_hi[a] : (gv ? m->P.v_box_hi[a - 3] : 1e300);
+      if (gx || gv) bmask |= 1 << a;
+    }
     double *N0 = dalloc(n * n), *r0 = dalloc(n), *xs = dalloc(n);
     int *act = (int *)calloc((size_t)n, sizeof(int)), *nact = (int *)calloc((size_t)n, sizeof(int));
     la_copy(N0, Nm, n * n);
@@ -934,12 +942,12 @@ static int solve_exact(orc_mhe *m) {
       la_copy(rhs, r0, n);
       for (int a = 0; a < n; ++a) {
         if (!act[a]) continue;
-        double beta = act[a] > 0 ? m->P.v_box_hi[(a % ds) - 3] : m->P.v_box_lo[(a % ds) - 3];
+        double beta = act[a] > 0 ? bhi[a % ds] : blo[a % ds];
         for (int i = 0; i < n; ++i) rhs[i] -= Nm[i * n + a] * beta;
       }
       for (int a = 0; a < n; ++a) {
         if (!act[a]) continue;
-        double beta = act[a] > 0 ? m->P.v_box_hi[(a % ds) - 3] : m->P.v_box_lo[(a % ds) - 3];
+        double beta = act[a] > 0 ? bhi[a % ds] : blo[a % ds];
         for (int i = 0; i < n; ++i) Nm[i * n + a] = Nm[a * n + i] = 0.0;
         Nm[a * n + a] = 1.0;
         rhs[a] = beta;
@@ -947,21 +955,47 @@ static int solve_exact(orc_mhe *m) {
       rc = la_chol_solve_banded(Nm, rhs, n, 2 * ds - 1);
       la_copy(xs, rhs, n);
       int changed = 0;
+      /* general bounds: after 8 plain primal-dual iterations bounds are only added, and when nothing is violated the single
+       * bound with the most negative (scaled) multiplier is dropped -- the plain rule can cycle when bounds of several
+       * components interact (the velocity box never did) */
+      int safe = m->P.x_box_mask && it >= 8, added = 0, drop_a = -1;
+      double drop_val = 0.0;
       for (int j = 0; j < K; ++j)
-        for (int c = 0; c < 3; ++c) {
-          int a = j * ds + 3 + c;
-          double grad = -r0[a];
-          for (int i = 0; i < n; ++i) grad += N0[a * n + i] * xs[i];
+        for (int c = 0; c < 9; ++c) {
+          if (!((bmask >> c) & 1)) continue;
+          int a = j * ds + c;
+          double grad = -r0[a], gs = fabs(r0[a]);
+          for (int i = 0; i < n; ++i) {
+            grad += N0[a * n + i] * xs[i];
+            gs += fabs(N0[a * n + i] * xs[i]);
+          }
+          /* a multiplier within round-off of zero keeps its bound (general bounds only); the velocity box keeps the exact
+           * sign test it was validated with */
+          double gtol = m->P.x_box_mask ? 1e-10 * gs : 0.0;
           int na;
-          if (act[a] > 0)
-            na = (-grad > 0.0) ? 1 : 0; /* multiplier of the upper bound */
-          else if (act[a] < 0)
-            na = (grad > 0.0) ? -1 : 0; /* multiplier of the lower bound */
-          else
-            na = (xs[a] > m->P.v_box_hi[c]) ? 1 : ((xs[a] < m->P.v_box_lo[c]) ? -1 : 0);
+          if (act[a] != 0) {
+            double mult = act[a] > 0 ? -grad : grad;
+            int keep = mult > -gtol;
+            if (!keep && safe) {
+              double v = mult / (gs > 0.0 ? gs : 1.0);
+              if (drop_a < 0 || v < drop_val) {
+                drop_val = v;
+                drop_a = a;
+              }
+              keep = 1;
+            }
+            na = keep ? act[a] : 0;
+          } else {
+            na = (xs[a] > bhi[c]) ? 1 : ((xs[a] < blo[c]) ? -1 : 0);
+            if (na) added++;
+          }
           nact[a] = na;
           if (na != act[a]) changed = 1;
         }
+      if (safe && added == 0 && drop_a >= 0) {
+        nact[drop_a] = 0;
+        changed = 1;
+      }
       if (!changed) break;
       memcpy(act, nact, sizeof(int) * (size_t)n);
     }

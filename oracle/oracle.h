@@ -91,6 +91,10 @@ typedef struct {
   double v_box_lo[3], v_box_hi[3];
   /* lever arm of the body-velocity read-out, DecentralEst.cpp:181-185 (the reference hard-codes the Go1 mocap marker) */
   double p_imu_2_opti[3];
+  /* general per-component bounds (builder extension like v_box): bit a of x_box_mask bounds component a (0..8) of every
+   * window state, x_box_lo[a] <= x_k[a] <= x_box_hi[a]; combines with v_box (x_box wins on components 3..5) */
+  int x_box_mask;
+  double x_box_lo[9], x_box_hi[9];
 } orc_params;
 
 void orc_params_go1_defaults(orc_params *p); /* parameters_go1.yaml */

@@ -39,6 +39,7 @@ struct Sim {
     bc = make_box_const(c);
     bb.fac = alloc<double>((size_t)dm.N * BOX_FAC * dm.ns);
     bb.act = alloc<uint8_t>((size_t)dm.NW * dm.ns);
+    bb.act32 = alloc<uint32_t>((size_t)dm.NW * dm.ns);
     bb.iters = alloc<int32_t>(dm.ns);
     bb.nactive = alloc<int32_t>(dm.ns);
     StateSizes s = state_sizes(dm);
@@ -127,15 +128,15 @@ void run(const dekf_config &cfg, int S, const double *gyro, const double *accel,
         if (cfg.est_type == 1 || s >= 1) st |= foot_solve<T, Model::NLEG>(sim.fc, sim.dm, sim.b, sim.fb, in, out, s, i);
       } else if (cfg.est_type == 1)
         st |= kf_update<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
-      else if (s >= 1 && cfg.v_box_enable)
+      else if (s >= 1 && sim.bc.enable)
         st |= mhe_solve_box<T>(sim.mc, sim.bc, sim.dm, sim.b, sim.bb, in, out, s, i);
       else if (s >= 1 && sim.mc.window_solve == 1)
         st |= mhe_solve_incr<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
       else if (s >= 1)
         st |= mhe_solve<T>(sim.mc, sim.dm, sim.b, in, out, s, i);
       if (qp_out) {
-        qp_out[((size_t)s * 2 + 0) * n + i] = cfg.v_box_enable && s >= 1 ? sim.bb.iters[i] : 0;
-        qp_out[((size_t)s * 2 + 1) * n + i] = cfg.v_box_enable && s >= 1 ? sim.bb.nactive[i] : 0;
+        qp_out[((size_t)s * 2 + 0) * n + i] = sim.bc.enable && s >= 1 ? sim.bb.iters[i] : 0;
+        qp_out[((size_t)s * 2 + 1) * n + i] = sim.bc.enable && s >= 1 ? sim.bb.nactive[i] : 0;
       }
       status_out[(size_t)s * n + i] = st;
       for (int f = 0; f < 3; ++f) pvo_out[((size_t)s * 3 + f) * n + i] = sim.b.p_vo[(size_t)f * sim.dm.ns + i];

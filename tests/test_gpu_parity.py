@@ -522,6 +522,39 @@ def _pogox_state_constrained_16384(est_mod, oracle, precision, tol):
     est.close()
 
 
+def test_general_component_bounds_vs_oracle(est_mod, oracle):
+    """cfg.x_box_mask: rows lb <= x_k[a] <= ub on any state component (here v_x, p_z and the three accel-bias components; what
+    MHEproblem::addConstraints(name, lb, ub) with selector rows would add, MheSrb.cpp:58-68) through the C ABI -- k_solve_box,
+    one thread per instance -- against the oracle's KKT-certified constrained optimum; no violation on any instance."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S, m = 512, 100, 8
+    st_t = synth.make_stream(n, S, robot="pogox", vo_jitter=True, device="cuda")
+    st = synth.to_numpy(st_t)
+    mask = (1 << 3) | (1 << 2) | (7 << 6)
+    lo9 = (0, 0, -2e-4, 0.47, 0, 0, -0.004, -0.004, -0.004)
+    hi9 = (0, 0, 2e-4, 0.52, 0, 0, 0.004, 0.004, 0.004)
+    est = E.BatchedEstimator(E.robot_params("pogox", ekf_rate=200, x_box_mask=mask, x_box_lo=lo9, x_box_hi=hi9), n)
+    d = {k: v.contiguous() for k, v in st_t.items()}
+    xs = np.full((S, 9, n), np.nan)
+    bad = 0
+    for s in range(S):
+        est.step(s, E.robot_store.from_stream(d, s))
+        xs[s] = est.x_MHE_.cpu().numpy()
+        bad += int((est.status_ & 64).sum().item())
+    est.close()
+    assert bad == 0                                                        # the active set converged everywhere
+    x = xs[1:]
+    for a in (2, 3, 6, 7, 8):
+        assert (x[:, a] <= hi9[a] + 1e-12).all() and (x[:, a] >= lo9[a] - 1e-12).all()   # no violation, any instance
+    assert (np.abs(x[:, 6:9]) == 0.004).mean() > 0.1 and (np.abs(x[:, 2]) == 2e-4).any()   # bias and position rows bind
+    sub = {k: np.ascontiguousarray(v[..., :m]) for k, v in st.items()}
+    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0), p_imu_2_opti=(0.0, 0.0, 0.0))
+    ro, _, _ = oracle.run_batch(sub, oracle.go1_params(x_box_mask=mask, x_box_lo=lo9, x_box_hi=hi9, **kw), oracle.ekf_params(rate=200),
+                                nthreads=os.cpu_count() or 1, want=("x",))
+    assert np.abs(xs[1:, :, :m] - ro["x"][1:]).max() < 1e-8
+
+
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 @pytest.mark.parametrize("n", [200, 4500])  # fused single-launch path / split kernels (dekf_run pipeline)
 def test_incremental_equals_full_resweep(est_mod, precision, n):

@@ -116,6 +116,34 @@ def test_state_constrained_solve_matches_oracle(oracle):
     assert r["qp"][1:, 0].mean() < 6                                     # warm start: few factorisations per tick
 
 
+def test_general_component_bounds_match_oracle(oracle):
+    """cfg.x_box_mask (bounds on any state component, here v_x + p_z + the accel bias): box_solve<T, true> (the kernel body of
+    k_solve_box, compiled for the host) against the oracle's exact constrained optimum; and the velocity box expressed through
+    x_box_* gives what v_box_* gives."""
+    import pyhostsim as hs
+    from decentralized_ekf_mhe_b200 import synth
+    st = synth.to_numpy(synth.make_stream(4, 120, robot="pogox", vo_jitter=True))
+    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0))
+    mask = (1 << 3) | (1 << 2) | (7 << 6)
+    lo9 = (0, 0, -2e-4, 0.47, 0, 0, -0.004, -0.004, -0.004)
+    hi9 = (0, 0, 2e-4, 0.52, 0, 0, 0.004, 0.004, 0.004)
+    r = hs.run(st, _cfg(x_box_mask=mask, x_box_lo=lo9, x_box_hi=hi9, **kw))
+    ro, _, _ = oracle.run_batch(st, oracle.go1_params(x_box_mask=mask, x_box_lo=lo9, x_box_hi=hi9, **kw), oracle.ekf_params(rate=200),
+                                nthreads=4, want=("x", "v_body"))
+    assert np.abs(r["x"][1:] - ro["x"][1:]).max() < 1e-8
+    x = r["x"][1:]
+    for a in (2, 3, 6, 7, 8):
+        assert (x[:, a] <= hi9[a] + 1e-12).all() and (x[:, a] >= lo9[a] - 1e-12).all()
+    assert (np.abs(x[:, 6:9]) == 0.004).any() and (np.abs(x[:, 2]) == 2e-4).any()   # bias and position rows bind
+    assert not (r["status"] & 64).any()
+    # the velocity box through the general interface == the velocity box through v_box_*
+    rv = hs.run(st, _cfg(v_box_enable=1, v_box_lo=BOX_LO, v_box_hi=BOX_HI, **kw))
+    lo_v = (0, 0, 0) + BOX_LO + (0, 0, 0)
+    hi_v = (0, 0, 0) + BOX_HI + (0, 0, 0)
+    rg = hs.run(st, _cfg(x_box_mask=0x38, x_box_lo=lo_v, x_box_hi=hi_v, **kw))
+    assert np.abs(rg["x"][1:] - rv["x"][1:]).max() < 1e-9
+
+
 def _dup_first(st):
     """Stream with sample 0 delivered twice: the KF alternative runs InitializeKF + UpdateKF on the same sample at
     T == 0 (DecentralEst.cpp:139-141), so x_KF_(T) is the MHE/filter estimate of this stream at T + 1."""

@@ -240,3 +240,50 @@ def test_foot_state_oracle_consistency(oracle):
             xT, xk = z[nV - ds - dm:nV - dm], sol[nV - ds - dm:nV - dm]
             assert np.abs(xT - m.x()).max() == 0.0
             assert np.abs(xT - xk).max() < 1e-7, (s, np.abs(xT - xk).max())
+
+
+def test_general_component_bounds_optimum_certificate(oracle):
+    """General rows  lb <= x_k[a] <= ub  on ANY state component (cfg.x_box_mask: here v_x, the z position and the three accel-bias
+    components at once -- what MHEproblem::addConstraints(name, lb, ub) with a selector row per component would add,
+    MheSrb.cpp:58-68): the oracle's constrained optimum carries a KKT certificate on the exported reference-ordered QP."""
+    from decentralized_ekf_mhe_b200 import synth
+    mask = (1 << 3) | (1 << 2) | (7 << 6)
+    lo9 = np.array([0, 0, -2e-4, 0.47, 0, 0, -0.004, -0.004, -0.004], float)
+    hi9 = np.array([0, 0, 2e-4, 0.52, 0, 0, 0.004, 0.004, 0.004], float)
+    st = synth.to_numpy(synth.make_stream(1, 60, robot="pogox", vo_jitter=True, truth=True))
+    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0), x_box_mask=mask,
+              x_box_lo=tuple(lo9), x_box_hi=tuple(hi9))
+    m = oracle.Mhe(oracle.go1_params(**kw))
+    comps = [a for a in range(9) if (mask >> a) & 1]
+    seen = {a: 0 for a in comps}
+    for s in range(60):
+        q = st["quat_true"][s, :, 0]
+        m.step(s, imu_time=st["imu_time"][s, 0], accel=st["accel"][s, :, 0], gyro=st["gyro"][s, :, 0], quat=q,
+               joint_pos=st["joint_pos"][s, :, 0], joint_vel=st["joint_vel"][s, :, 0], foot_force=st["foot_force"][s, :, 0],
+               vo=(st["vo_time_pre"][s, 0], st["vo_time_now"][s, 0], st["vo_rel_p"][s, :, 0]) if st["vo_flag"][s, 0] else None)
+        if s < 1:
+            continue
+        ds, dm, dc, nV, nC = m.dims()
+        H, g, A, l, u = m.export_qp()
+        z = m.solution()
+        K = (nV + ds + dc) // (2 * ds + dm + dc)
+        xi = [j * (2 * ds + dm + dc) for j in range(K)]
+        X = np.array([z[o:o + 9] for o in xi])
+        for a in comps:
+            assert (X[:, a] <= hi9[a] + 1e-12).all() and (X[:, a] >= lo9[a] - 1e-12).all()
+        eq = np.abs(u - l) < 1e-9
+        assert np.abs((A @ z - l)[eq]).max() < 1e-9 * max(1.0, np.abs(l[eq]).max())
+        act = [(j, a, +1 if X[j, a] >= hi9[a] else -1) for j in range(K) for a in comps if X[j, a] >= hi9[a] or X[j, a] <= lo9[a]]
+        for _, a, _ in act:
+            seen[a] += 1
+        B = np.zeros((len(act), nV))
+        for r, (j, a, sgn) in enumerate(act):
+            B[r, xi[j] + a] = 1.0
+        G = np.vstack([A[eq], B]).T
+        rhs = -(H @ z + g)
+        scale = np.abs(rhs).max() + 1.0
+        sol, *_ = np.linalg.lstsq(G, rhs, rcond=None)
+        assert np.abs(G @ sol - rhs).max() < 1e-7 * scale                      # stationarity
+        for (j, a, sgn), w in zip(act, sol[eq.sum():]):
+            assert sgn * w >= -1e-7 * scale                                     # multiplier signs
+    assert seen[2] > 5 and sum(seen[a] for a in (6, 7, 8)) > 20 and seen[3] > 0   # position, bias and velocity rows all bind

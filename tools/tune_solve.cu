@@ -93,16 +93,16 @@ struct Ctx {
   int reps;
 };
 
-template <typename T, int TILE, int STAGES, int MINB, typename Math = DefaultMath<T>, bool XS = false>
+template <typename T, int TILE, int STAGES, int MINB, typename Math = DefaultMath<T>, bool XS = false, bool PW = false>
 void run_variant(Ctx<T> &c, const char *name) {
-  auto kern = k_solve_tma<T, TILE, STAGES, MINB, Math, XS>;
+  auto kern = k_solve_tma<T, TILE, STAGES, MINB, Math, XS, PW>;
   const size_t smem = solve_tma_smem_bytes<T, TILE, STAGES, XS>();
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, kern));
   int occ = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE, smem));
-  CUtensorMap map = make_map<T>(c.dm, c.b.win, TILE);
+  CUtensorMap map = make_map<T>(c.dm, c.b.win, PW ? 32 : TILE);
   const int grid = c.dm.ns / TILE;
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
@@ -175,11 +175,13 @@ void run_all(int n, int N, int reps) {
     cudaEventElapsedTime(&ms, e0, e1);
     std::printf("%-28s %8.2f us/launch\n", "global-load kernel", 1e3 * ms / reps);
   }
-  run_variant<T, 128, SolveCfg<T>::kStages, SolveCfg<T>::kMinB>(c, "product config (meas4 prop5)");
-  run_variant<T, 128, 3, 1, MathSel<4, 4>>(c, "tma 128x3 minb1 meas4 prop4");
-  run_variant<T, 128, 3, 1, DefaultMath<T>, true>(c, "tma 128x3 minb1 x-in-smem");
-  run_variant<T, 128, 2, 3, DefaultMath<T>, true>(c, "tma 128x2 minb3 x-in-smem");
-  run_variant<T, 128, 2, 3, DefaultMath<T>, false>(c, "tma 128x2 minb3");
+  run_variant<T, 128, SolveCfg<T>::kStages, SolveCfg<T>::kMinB, DefaultMath<T>, false, SolveCfg<T>::kPerWarp>(c, "product config");
+  run_variant<T, 128, 3, SolveCfg<T>::kMinB, DefaultMath<T>, false, false>(c, "CTA pipeline x3");
+  run_variant<T, 128, 3, SolveCfg<T>::kMinB, DefaultMath<T>, false, true>(c, "warp pipelines x3");
+  run_variant<T, 128, 4, SolveCfg<T>::kMinB, DefaultMath<T>, false, true>(c, "warp pipelines x4");
+  run_variant<T, 128, 2, SolveCfg<T>::kMinB, DefaultMath<T>, false, true>(c, "warp pipelines x2");
+  run_variant<T, 64, 3, SolveCfg<T>::kMinB == 1 ? 1 : 8, DefaultMath<T>, false, true>(c, "warp pipelines x3, 64-thread CTAs");
+  run_variant<T, 32, 3, SolveCfg<T>::kMinB == 1 ? 1 : 16, DefaultMath<T>, false, true>(c, "warp pipelines x3, 32-thread CTAs");
   run_variant<T, 128, 3, 1, MathSel<2, 1>>(c, "tma 128x3 meas2 prop1 (r01)");
   cudaFree(c.b.arr_P);
   cudaFree(c.b.arr_x);
