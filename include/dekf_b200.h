@@ -82,7 +82,10 @@ typedef struct dekf_config {
   int32_t device;        /* CUDA device ordinal */
   int32_t precision;     /* DEKF_FP64 | DEKF_FP32 (arithmetic + state type; inputs/outputs stay double) */
   int32_t robot;         /* DEKF_ROBOT_* (kinematics compiled as __device__ functions) */
-  int32_t ekf_hist_depth;/* EKF replay ring depth in ticks (>= max VO latency in ticks + 2) */
+  int32_t ekf_hist_depth;/* EKF replay ring depth in ticks.  The reference keeps UNBOUNDED stacks (orien_ekf.cpp:158-163) and can rewind to
+                          * any past tick; here a VO pose older than ekf_hist_depth ticks is dropped with DEKF_ST_EKF_HIST_OVERFLOW set.
+                          * Needs >= (largest VO latency in seconds) * ekf_rate + 2; the default 64 covers 128 ms at the reference's
+                          * 500 Hz and 320 ms at the benchmark's 200 Hz (VO latency 40 ms); 216 bytes per instance and tick. */
   int32_t debug_taps;    /* allocate b_meas / Q_meas / index-logic taps (parity tests) */
   int32_t reserved0;
 

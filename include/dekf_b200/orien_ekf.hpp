@@ -19,6 +19,7 @@ class orien_ekf {
     const dekf_config cfg = params.to_config();
     detail::check(dekf_create(&cfg, &h_), nullptr, "dekf_create");
     n_ = cfg.n_instances;
+    hist_depth_ = cfg.ekf_hist_depth;
     quaternion_.assign(4 * (size_t)n_, 0.0);
     for (int i = 0; i < n_; ++i) quaternion_[i] = cfg.ekf_quaternion_init[0];
     Cov_q_.assign(16 * (size_t)n_, 0.0);
@@ -59,10 +60,13 @@ class orien_ekf {
   }
   std::vector<int32_t> status_;  // [n] DEKF_ST_EKF_* bits of the last tick
   int discrete_time_ = 0;
+  // depth of the device's history ring in ticks (the reference's stacks are unbounded, orien_ekf.cpp:158-163): a VO pose older
+  // than this is dropped with DEKF_ST_EKF_HIST_OVERFLOW in status_
+  int hist_depth() const { return hist_depth_; }
 
  private:
   dekf_handle *h_ = nullptr;
-  int n_ = 0;
+  int n_ = 0, hist_depth_ = 0;
   std::vector<double> Cov_q_;  // [16][n]
 };
 

@@ -70,6 +70,13 @@ class OrienSub : public rclcpp::Node {
     if (init_imu_) {
       ekf_->timerCallback(store_);
       store_.vo_new_[0] = 0;  // the reference clears its flag inside get_measurement (orien_ekf.cpp:169)
+      // the device keeps a ring of ekf_hist_depth ticks where the reference keeps unbounded stacks: a VO pose older than the
+      // ring cannot be rewound to and is dropped with this bit set -- make that visible (raise ekf_hist_depth)
+      if (ekf_->status_[0] & DEKF_ST_EKF_HIST_OVERFLOW) {
+        if (hist_overflows_++ % 500 == 0)
+          std::fprintf(stderr, "orien_sub: VO pose older than the EKF history ring (%d ticks); dropped (%ld so far)\n",
+                       ekf_->hist_depth(), hist_overflows_);
+      }
     }
     sensor_msgs::msg::Imu out;
     out.orientation.w = ekf_->quaternion_[0];
@@ -97,6 +104,7 @@ class OrienSub : public rclcpp::Node {
   rclcpp::TimerBase::SharedPtr timer_;
   double dt_ = 0.002, time_init_ = 0.0;
   bool init_imu_ = false;
+  long hist_overflows_ = 0;
 };
 
 }  // namespace dekf_ros
