@@ -426,16 +426,18 @@ struct dekf_handle {
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   // dekf_run: the EKF ticks run ahead of the MHE on their own stream through a small ring of quaternions / status words
   static constexpr int kAhead = 4;
-  cudaStream_t s_ekf = nullptr, s_asm = nullptr, s_mhe = nullptr;  // lowest / medium / highest stream priority
-  cudaStream_t s_mhe_b = nullptr;  // second solve stream: the tiles beyond the last full wave (dekf_run, full re-sweep)
-  cudaEvent_t ev_solb[kAhead] = {nullptr, nullptr, nullptr, nullptr};
+  static constexpr int kMaxWays = 8;
+  cudaStream_t s_ekf = nullptr, s_asm = nullptr;
+  // solve streams: s_sol[0] carries every undivided solve; the full re-sweep of a large batch is cut into tile ranges, range r
+  // runs on s_sol[r] (independent instances: range r of tick s+1 only waits for range r of tick s)
+  cudaStream_t s_sol[kMaxWays] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_solw[kMaxWays][kAhead] = {};
   int solve_tile0 = 0, solve_tiles = -1;  // tile range of the next k_solve_tma launch (-1: the whole batch)
   int solve_slots = 0;                    // CTAs of k_solve_tma resident on the whole device (occupancy x SM count)
   cudaEvent_t ev_join = nullptr;
   double *quat_ring = nullptr;      // [kAhead][4][n]
   int32_t *status_ring = nullptr;   // [kAhead][n]
   cudaEvent_t ev_ekf[kAhead] = {nullptr, nullptr, nullptr, nullptr}, ev_mhe[kAhead] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_sol[kAhead] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   // debug taps
@@ -453,7 +455,9 @@ struct dekf_handle {
   // tuning knobs, read ONCE in dekf_create (environment), never on the step path
   bool no_split = false;   // DEKF_NO_SPLIT=1: one k_solve_tma launch per tick in dekf_run
   int split_tiles_env = 0; // DEKF_SPLIT_TILES=<k>: size of the first tile range (0: the last full wave)
+  int split_ways_env = 0;  // DEKF_SPLIT_WAYS=<w>: w equal tile ranges on w streams instead of the two-range split
   int host_chunk = 8;      // DEKF_HOST_CHUNK=<B>: ticks per copy of dekf_run_host
+  int prio_mode = 0;       // DEKF_PRIO=<m>: stream priorities of dekf_run (0: all equal; 1: solve > assembly > EKF, round 1; 2: front kernels first)
   // small batches through the *_host entry points: one pinned, device-mapped host block; the kernel reads the tick's inputs
   // from it and writes the results into it over PCIe (no cudaMemcpy calls: the batch-1 tick is launch + kernel + sync)
   char *hmap = nullptr;
@@ -753,6 +757,8 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
   if (const char *e = std::getenv("DEKF_NO_TMA")) h->use_tma = std::atoi(e) == 0;
   if (const char *e = std::getenv("DEKF_NO_SPLIT")) h->no_split = std::atoi(e) != 0;
   if (const char *e = std::getenv("DEKF_SPLIT_TILES")) h->split_tiles_env = std::atoi(e);
+  if (const char *e = std::getenv("DEKF_SPLIT_WAYS")) h->split_ways_env = std::atoi(e);
+  if (const char *e = std::getenv("DEKF_PRIO")) h->prio_mode = std::atoi(e);
   if (const char *e = std::getenv("DEKF_HOST_CHUNK")) h->host_chunk = std::atoi(e) > 0 ? std::atoi(e) : 8;
   ce = cudaFuncSetAttribute(k_solve_tma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_tma_smem_bytes<double>());
   if (ce == cudaSuccess)
@@ -918,10 +924,11 @@ int dekf_destroy(dekf_handle *h) {
   cudaFree(h->kf_Q);
   if (h->hmap) cudaFreeHost(h->hmap);
   if (h->s_ekf) cudaStreamDestroy(h->s_ekf);
-  if (h->s_mhe) cudaStreamDestroy(h->s_mhe);
-  if (h->s_mhe_b) cudaStreamDestroy(h->s_mhe_b);
+  for (int r = 0; r < dekf_handle::kMaxWays; ++r)
+    if (h->s_sol[r]) cudaStreamDestroy(h->s_sol[r]);
   for (int k = 0; k < dekf_handle::kAhead; ++k)
-    if (h->ev_solb[k]) cudaEventDestroy(h->ev_solb[k]);
+    for (int r = 0; r < dekf_handle::kMaxWays; ++r)
+      if (h->ev_solw[r][k]) cudaEventDestroy(h->ev_solw[r][k]);
   if (h->s_asm) cudaStreamDestroy(h->s_asm);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->quat_ring);
@@ -929,7 +936,6 @@ int dekf_destroy(dekf_handle *h) {
   for (int k = 0; k < dekf_handle::kAhead; ++k) {
     if (h->ev_ekf[k]) cudaEventDestroy(h->ev_ekf[k]);
     if (h->ev_mhe[k]) cudaEventDestroy(h->ev_mhe[k]);
-    if (h->ev_sol[k]) cudaEventDestroy(h->ev_sol[k]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -1449,44 +1455,57 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     return fail(h, DEKF_EINVAL, "dekf_run: null input");
   if (in->vo_flag && (!in->vo_quat || !in->vo_time_pre || !in->vo_time_now || !in->vo_rel_p))
     return fail(h, DEKF_EINVAL, "dekf_run: vo_flag without the VO arrays");
+  constexpr int MW = dekf_handle::kMaxWays;
   if (!h->s_ekf) {
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = numerically largest = lowest priority
-    CK(cudaStreamCreateWithPriority(&h->s_ekf, cudaStreamNonBlocking, lo));
-    CK(cudaStreamCreateWithPriority(&h->s_asm, cudaStreamNonBlocking, (lo + hi) / 2));
-    CK(cudaStreamCreateWithPriority(&h->s_mhe, cudaStreamNonBlocking, hi));
-    CK(cudaStreamCreateWithPriority(&h->s_mhe_b, cudaStreamNonBlocking, hi));
+    // Stream priorities (DEKF_PRIO, measured in profiles/r02_pipeline.md).  Default: ALL EQUAL.  With the re-sweep cut into tile
+    // ranges the solve streams always hold CTAs that are ready to run; under "solve first" the assembly of the next tick only got
+    // SMs once the solves ran dry -- and the next solve then waited for that assembly: a bubble of one assembly per tick.
+    int p_ekf = lo, p_asm = lo, p_sol = lo;
+    if (h->prio_mode == 1) p_ekf = lo, p_asm = (lo + hi) / 2, p_sol = hi;  // round 1: solve first
+    if (h->prio_mode == 2) p_ekf = hi, p_asm = hi, p_sol = lo;             // front kernels first
+    CK(cudaStreamCreateWithPriority(&h->s_ekf, cudaStreamNonBlocking, p_ekf));
+    CK(cudaStreamCreateWithPriority(&h->s_asm, cudaStreamNonBlocking, p_asm));
+    for (int r = 0; r < MW; ++r) CK(cudaStreamCreateWithPriority(&h->s_sol[r], cudaStreamNonBlocking, p_sol));
     CK(cudaMalloc((void **)&h->quat_ring, (size_t)QA * 4 * n * sizeof(double)));
     CK(cudaMalloc((void **)&h->status_ring, (size_t)QA * n * sizeof(int32_t)));
     h->extra_bytes += (size_t)QA * n * (4 * sizeof(double) + sizeof(int32_t));
     for (int k = 0; k < QA; ++k) {
       CK(cudaEventCreateWithFlags(&h->ev_ekf[k], cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&h->ev_mhe[k], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&h->ev_sol[k], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&h->ev_solb[k], cudaEventDisableTiming));
+      for (int r = 0; r < MW; ++r) CK(cudaEventCreateWithFlags(&h->ev_solw[r][k], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   }
   // the assembly may only run ahead of the solve where the solve is the plain window sweep (full or incremental)
   const bool asm_ahead = h->cfg.est_type == 0 && !h->bc.enable && h->cfg.leg_odom_type == 0 && !h->prof;
+  // Full re-sweep with the TMA kernel: 65,536 instances are 512 tiles on 2 x 148 CTA slots = 1.73 waves.  The tick's solve is cut
+  // into `ways` tile ranges, one launch per range on its own stream; the ranges are independent instances, so range r of tick
+  // s + 1 starts as soon as range r of tick s is done and the partial wave of one tick overlaps the next tick instead of leaving
+  // slots idle (DEKF_NO_SPLIT=1 disables; DEKF_SPLIT_WAYS / DEKF_SPLIT_TILES tune).
+  int ways = 1, bound[MW + 1] = {0};
+  {
+    const int tiles = h->dm.ns / kTile, slots = h->solve_slots;
+    if (asm_ahead && !h->no_split && h->use_tma && h->mc64.window_solve == 0 && slots > 0 && tiles > slots) {
+      if (h->split_ways_env >= 2) {
+        ways = h->split_ways_env < MW ? h->split_ways_env : MW;
+        for (int r = 0; r < ways; ++r) bound[r] = (int)((int64_t)tiles * r / ways);
+      } else if (tiles % slots != 0) {
+        ways = 2;
+        bound[1] = tiles / slots * slots;  // the last full wave
+        if (h->split_tiles_env > 0 && h->split_tiles_env < tiles) bound[1] = h->split_tiles_env;
+      }
+    }
+    bound[ways] = tiles;
+  }
   // fork the internal streams off the caller-visible stream, join back at the end
   cudaStream_t user = h->stream;
   CK(cudaEventRecord(h->ev_fork, user));
   CK(cudaStreamWaitEvent(h->s_ekf, h->ev_fork, 0));
   CK(cudaStreamWaitEvent(h->s_asm, h->ev_fork, 0));
-  CK(cudaStreamWaitEvent(h->s_mhe, h->ev_fork, 0));
-  CK(cudaStreamWaitEvent(h->s_mhe_b, h->ev_fork, 0));
-  // Full re-sweep with the TMA kernel: 65,536 instances are 512 tiles on 2 x 148 CTA slots = 1.73 waves.  The tiles beyond
-  // the last full wave run as a second launch on their own stream; the two tile ranges are independent instances, so the
-  // partial wave of tick s overlaps the full wave of tick s + 1 instead of leaving slots idle (DEKF_NO_SPLIT=1 disables).
-  int split_tiles = 0;
-  {
-    const int tiles = h->dm.ns / kTile, slots = h->solve_slots;
-    if (asm_ahead && !h->no_split && h->use_tma && h->mc64.window_solve == 0 && slots > 0 && tiles > slots && tiles % slots != 0)
-      split_tiles = tiles / slots * slots;
-    if (split_tiles > 0 && h->split_tiles_env > 0 && h->split_tiles_env < tiles) split_tiles = h->split_tiles_env;  // tuning
-  }
+  for (int r = 0; r < ways; ++r) CK(cudaStreamWaitEvent(h->s_sol[r], h->ev_fork, 0));
   for (int32_t s = 0; s < S && rc == DEKF_OK; ++s) {
     const int slot = s % QA;
     dekf_inputs is;
@@ -1506,15 +1525,15 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     if (rc) break;
     if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_ekf[slot], h->s_ekf);
     // ---- stage assembly of tick s
-    cudaStream_t sa = asm_ahead ? h->s_asm : h->s_mhe;
+    cudaStream_t sa = asm_ahead ? h->s_asm : h->s_sol[0];
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sa, h->ev_ekf[slot], 0);
     if (asm_ahead) {
       // parity-buffered scratch + the spare ring slot allow ONE tick of lead: wait for the solve of tick s-2, and for the
       // solve of tick s-1 too when this tick rewrites VO rows inside the window that solve is reading
-      if (ce == cudaSuccess && s >= 2) ce = cudaStreamWaitEvent(sa, h->ev_sol[(s - 2) % QA], 0);
-      if (ce == cudaSuccess && s >= 2 && split_tiles) ce = cudaStreamWaitEvent(sa, h->ev_solb[(s - 2) % QA], 0);
-      if (ce == cudaSuccess && s >= 1 && vo_tick) ce = cudaStreamWaitEvent(sa, h->ev_sol[(s - 1) % QA], 0);
-      if (ce == cudaSuccess && s >= 1 && vo_tick && split_tiles) ce = cudaStreamWaitEvent(sa, h->ev_solb[(s - 1) % QA], 0);
+      for (int r = 0; r < ways && ce == cudaSuccess; ++r) {
+        if (s >= 2) ce = cudaStreamWaitEvent(sa, h->ev_solw[r][(s - 2) % QA], 0);
+        if (ce == cudaSuccess && s >= 1 && vo_tick) ce = cudaStreamWaitEvent(sa, h->ev_solw[r][(s - 1) % QA], 0);
+      }
     }
     if (ce != cudaSuccess) {
       rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
@@ -1530,53 +1549,46 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     h->stream = user;
     if (rc) break;
     ce = cudaEventRecord(h->ev_mhe[slot], sa);
-    // ---- window solve of tick s
-    if (ce == cudaSuccess && asm_ahead) ce = cudaStreamWaitEvent(h->s_mhe, h->ev_mhe[slot], 0);
-    if (ce != cudaSuccess) {
-      rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
-      break;
-    }
-    const bool split = split_tiles > 0 && T0 + s >= 1;  // tick 0 has no window solve (the non-TMA kernel handles it)
-    if (split) {
-      h->solve_tile0 = 0;
-      h->solve_tiles = split_tiles;
-    }
-    h->stream = h->s_mhe;
-    rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 2);
-    h->stream = user;
-    h->solve_tiles = -1;
-    if (rc) break;
-    ce = cudaEventRecord(h->ev_sol[slot], h->s_mhe);
-    if (ce == cudaSuccess && split_tiles) {
-      if (split) {
-        ce = cudaStreamWaitEvent(h->s_mhe_b, h->ev_mhe[slot], 0);
-        if (ce == cudaSuccess) {
-          h->solve_tile0 = split_tiles;
-          h->solve_tiles = h->dm.ns / kTile - split_tiles;
-          h->stream = h->s_mhe_b;
-          rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 2);
-          h->stream = user;
-          h->solve_tiles = -1;
-          if (rc) break;
+    // ---- window solve of tick s: one launch per tile range (tick 0 has no window sweep: one launch covers every instance)
+    const bool split = ways > 1 && T0 + s >= 1;
+    for (int r = 0; r < ways && ce == cudaSuccess && rc == DEKF_OK; ++r) {
+      if (r == 0 || split) {
+        if (asm_ahead) ce = cudaStreamWaitEvent(h->s_sol[r], h->ev_mhe[slot], 0);
+        if (ce != cudaSuccess) break;
+        if (split) {
+          h->solve_tile0 = bound[r];
+          h->solve_tiles = bound[r + 1] - bound[r];
         }
+        h->stream = h->s_sol[r];
+        rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 2);
+        h->stream = user;
+        h->solve_tiles = -1;
+        if (rc) break;
       } else {
-        ce = cudaStreamWaitEvent(h->s_mhe_b, h->ev_sol[slot], 0);  // tick 0: the one launch covered every instance
+        ce = cudaStreamWaitEvent(h->s_sol[r], h->ev_solw[0][slot], 0);  // undivided launch on s_sol[0]: keep the ranges ordered
       }
-      if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_solb[slot], h->s_mhe_b);
+      if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_solw[r][slot], h->s_sol[r]);
     }
+    if (rc) break;
     if (ce != cudaSuccess) rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
   }
   h->stream = user;
   // join the internal streams back into the caller-visible one; if any of this fails (or the loop failed), drain them
   // on the host so that nothing is in flight when the error is reported
   cudaError_t je = cudaSuccess;
-  cudaStream_t internal[4] = {h->s_mhe, h->s_mhe_b, h->s_asm, h->s_ekf};
-  for (int k = 0; k < 4 && je == cudaSuccess; ++k) {
+  cudaStream_t internal[MW + 2];
+  int ni = 0;
+  for (int r = 0; r < ways; ++r) internal[ni++] = h->s_sol[r];
+  internal[ni++] = h->s_asm;
+  internal[ni++] = h->s_ekf;
+  for (int k = 0; k < ni && je == cudaSuccess; ++k) {
     je = cudaEventRecord(h->ev_join, internal[k]);
     if (je == cudaSuccess) je = cudaStreamWaitEvent(user, h->ev_join, 0);
   }
   if (je != cudaSuccess || rc != DEKF_OK) {
-    for (int k = 0; k < 4; ++k) cudaStreamSynchronize(internal[k]);
+    for (int r = 0; r < MW; ++r) cudaStreamSynchronize(h->s_sol[r]);
+    cudaStreamSynchronize(h->s_asm);
+    cudaStreamSynchronize(h->s_ekf);
     cudaStreamSynchronize(user);
     if (rc == DEKF_OK) rc = fail(h, DEKF_ECUDA, "dekf_run: joining the internal streams", je);
   }
