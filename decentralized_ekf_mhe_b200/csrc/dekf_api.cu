@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kBlock, DEKF_MINB_EKF) k_ekf(const EkfConst<T>
 template <typename T, typename Model>
 __global__ void __launch_bounds__(kBlock, DEKF_MINB_ASM) k_assemble(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
                                                      const Outputs out, int Tk, const int32_t *prev_status, double *quat_copy) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x + dm.tile0) * blockDim.x + threadIdx.x;  // tile0: a launch may cover a tile range only (dekf_run, VO ticks)
   if (i >= dm.n) return;
   double q[4];
 #pragma unroll
@@ -434,10 +434,13 @@ struct dekf_handle {
   cudaEvent_t ev_solw[kMaxWays][kAhead] = {};
   int solve_tile0 = 0, solve_tiles = -1;  // tile range of the next k_solve_tma launch (-1: the whole batch)
   int solve_slots = 0;                    // CTAs of k_solve_tma resident on the whole device (occupancy x SM count)
+  int asm_tile0 = 0, asm_tiles = -1;      // tile range of the next k_assemble launch (-1: the whole batch)
+  cudaStream_t s_asmw[kMaxWays] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // s_asmw[0] == s_asm
+  cudaEvent_t ev_asmw[kMaxWays][kAhead] = {};  // assembly of tile range r of the tick in ring slot k is done
   cudaEvent_t ev_join = nullptr;
   double *quat_ring = nullptr;      // [kAhead][4][n]
   int32_t *status_ring = nullptr;   // [kAhead][n]
-  cudaEvent_t ev_ekf[kAhead] = {nullptr, nullptr, nullptr, nullptr}, ev_mhe[kAhead] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_ekf[kAhead] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
   // debug taps
@@ -454,6 +457,7 @@ struct dekf_handle {
   bool use_tma = true;   // window solve with TMA-staged stage tiles (DEKF_NO_TMA=1 at create: plain global loads)
   // tuning knobs, read ONCE in dekf_create (environment), never on the step path
   bool no_split = false;   // DEKF_NO_SPLIT=1: one k_solve_tma launch per tick in dekf_run
+  bool no_asm_split = false; // DEKF_NO_ASM_SPLIT=1: VO ticks assemble the whole batch in one launch behind the whole previous solve
   int split_tiles_env = 0; // DEKF_SPLIT_TILES=<k>: size of the first tile range (0: the last full wave)
   int split_ways_env = 0;  // DEKF_SPLIT_WAYS=<w>: w equal tile ranges on w streams instead of the two-range split
   int host_chunk = 8;      // DEKF_HOST_CHUNK=<B>: ticks per copy of dekf_run_host
@@ -601,7 +605,10 @@ int launch_assemble(dekf_handle *h, const MheConst<T> &mc, const Buffers<T> &b, 
                     int T_, const int32_t *acc) {
   {
     ProfScope ps(h, 1);
-    k_assemble<T, Model><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(mc, h->dm, b, in, out, T_, acc, h->asm_quat_copy);
+    Dims adm = h->dm;
+    adm.tile0 = h->asm_tiles >= 0 ? h->asm_tile0 : 0;
+    const int grid = h->asm_tiles >= 0 ? h->asm_tiles : grid_for(h->dm.n);
+    k_assemble<T, Model><<<grid, kBlock, 0, h->stream>>>(mc, adm, b, in, out, T_, acc, h->asm_quat_copy);
   }
   h->launches++;
   return 0;
@@ -757,6 +764,7 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
   if (const char *e = std::getenv("DEKF_NO_TMA")) h->use_tma = std::atoi(e) == 0;
   if (const char *e = std::getenv("DEKF_NO_SPLIT")) h->no_split = std::atoi(e) != 0;
   if (const char *e = std::getenv("DEKF_SPLIT_TILES")) h->split_tiles_env = std::atoi(e);
+  if (const char *e = std::getenv("DEKF_NO_ASM_SPLIT")) h->no_asm_split = std::atoi(e) != 0;
   if (const char *e = std::getenv("DEKF_SPLIT_WAYS")) h->split_ways_env = std::atoi(e);
   if (const char *e = std::getenv("DEKF_PRIO")) h->prio_mode = std::atoi(e);
   if (const char *e = std::getenv("DEKF_HOST_CHUNK")) h->host_chunk = std::atoi(e) > 0 ? std::atoi(e) : 8;
@@ -930,12 +938,16 @@ int dekf_destroy(dekf_handle *h) {
     for (int r = 0; r < dekf_handle::kMaxWays; ++r)
       if (h->ev_solw[r][k]) cudaEventDestroy(h->ev_solw[r][k]);
   if (h->s_asm) cudaStreamDestroy(h->s_asm);
+  for (int r = 1; r < dekf_handle::kMaxWays; ++r)
+    if (h->s_asmw[r]) cudaStreamDestroy(h->s_asmw[r]);
+  for (int k = 0; k < dekf_handle::kAhead; ++k)
+    for (int r = 0; r < dekf_handle::kMaxWays; ++r)
+      if (h->ev_asmw[r][k]) cudaEventDestroy(h->ev_asmw[r][k]);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->quat_ring);
   cudaFree(h->status_ring);
   for (int k = 0; k < dekf_handle::kAhead; ++k) {
     if (h->ev_ekf[k]) cudaEventDestroy(h->ev_ekf[k]);
-    if (h->ev_mhe[k]) cudaEventDestroy(h->ev_mhe[k]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
@@ -1468,13 +1480,15 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     CK(cudaStreamCreateWithPriority(&h->s_ekf, cudaStreamNonBlocking, p_ekf));
     CK(cudaStreamCreateWithPriority(&h->s_asm, cudaStreamNonBlocking, p_asm));
     for (int r = 0; r < MW; ++r) CK(cudaStreamCreateWithPriority(&h->s_sol[r], cudaStreamNonBlocking, p_sol));
+    h->s_asmw[0] = h->s_asm;
+    for (int r = 1; r < MW; ++r) CK(cudaStreamCreateWithPriority(&h->s_asmw[r], cudaStreamNonBlocking, p_asm));
     CK(cudaMalloc((void **)&h->quat_ring, (size_t)QA * 4 * n * sizeof(double)));
     CK(cudaMalloc((void **)&h->status_ring, (size_t)QA * n * sizeof(int32_t)));
     h->extra_bytes += (size_t)QA * n * (4 * sizeof(double) + sizeof(int32_t));
     for (int k = 0; k < QA; ++k) {
       CK(cudaEventCreateWithFlags(&h->ev_ekf[k], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&h->ev_mhe[k], cudaEventDisableTiming));
       for (int r = 0; r < MW; ++r) CK(cudaEventCreateWithFlags(&h->ev_solw[r][k], cudaEventDisableTiming));
+      for (int r = 0; r < MW; ++r) CK(cudaEventCreateWithFlags(&h->ev_asmw[r][k], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -1506,6 +1520,7 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
   CK(cudaStreamWaitEvent(h->s_ekf, h->ev_fork, 0));
   CK(cudaStreamWaitEvent(h->s_asm, h->ev_fork, 0));
   for (int r = 0; r < ways; ++r) CK(cudaStreamWaitEvent(h->s_sol[r], h->ev_fork, 0));
+  for (int r = 1; r < ways; ++r) CK(cudaStreamWaitEvent(h->s_asmw[r], h->ev_fork, 0));
   for (int32_t s = 0; s < S && rc == DEKF_OK; ++s) {
     const int slot = s % QA;
     dekf_inputs is;
@@ -1517,43 +1532,62 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     double *qslot = h->quat_ring + (size_t)slot * 4 * n;
     int32_t *sslot = h->status_ring + (size_t)slot * n;
     cudaError_t ce = cudaSuccess;
-    if (s >= QA) ce = cudaStreamWaitEvent(h->s_ekf, h->ev_mhe[slot], 0);  // k_assemble of tick s-QA has consumed the slot
+    if (s >= QA) {  // k_assemble of tick s-QA (every tile range of it) has consumed the slot
+      for (int r = 0; r < ways && ce == cudaSuccess; ++r) ce = cudaStreamWaitEvent(h->s_ekf, h->ev_asmw[r][slot], 0);
+    }
     dekf_outputs oe;
     std::memset(&oe, 0, sizeof(oe));
     oe.quat = qslot;
     if (ce == cudaSuccess) rc = ekf_launch(h, &is, &oe, sslot, h->s_ekf);
     if (rc) break;
     if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_ekf[slot], h->s_ekf);
-    // ---- stage assembly of tick s
-    cudaStream_t sa = asm_ahead ? h->s_asm : h->s_sol[0];
-    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(sa, h->ev_ekf[slot], 0);
-    if (asm_ahead) {
-      // parity-buffered scratch + the spare ring slot allow ONE tick of lead: wait for the solve of tick s-2, and for the
-      // solve of tick s-1 too when this tick rewrites VO rows inside the window that solve is reading
-      for (int r = 0; r < ways && ce == cudaSuccess; ++r) {
-        if (s >= 2) ce = cudaStreamWaitEvent(sa, h->ev_solw[r][(s - 2) % QA], 0);
-        if (ce == cudaSuccess && s >= 1 && vo_tick) ce = cudaStreamWaitEvent(sa, h->ev_solw[r][(s - 1) % QA], 0);
+    // ---- stage assembly of tick s.  Parity-buffered scratch + the spare ring slot allow ONE tick of lead: it waits for the solve
+    // of tick s-2, and for the solve of tick s-1 too when this tick rewrites VO rows inside the window that solve is reading.
+    // On such a tick the assembly is cut into the solve's tile ranges: range r only waits for range r of the previous solve and
+    // releases range r of this tick's solve, so the other ranges keep the SMs busy meanwhile.
+    is.quat = qslot;
+    const bool asm_split = asm_ahead && ways > 1 && vo_tick && s >= 1 && T0 + s >= 2 && !h->no_asm_split;
+    const int aways = asm_split ? ways : 1;
+    for (int ra = 0; ra < aways && ce == cudaSuccess && rc == DEKF_OK; ++ra) {
+      cudaStream_t sa = asm_ahead ? h->s_asmw[ra] : h->s_sol[0];
+      ce = cudaStreamWaitEvent(sa, h->ev_ekf[slot], 0);
+      if (asm_ahead) {
+        for (int r = (asm_split ? ra : 0); r < (asm_split ? ra + 1 : ways) && ce == cudaSuccess; ++r) {
+          if (s >= 1) ce = cudaStreamWaitEvent(sa, h->ev_asmw[r][(s - 1) % QA], 0);  // assembly of the previous tick (any stream)
+          if (ce == cudaSuccess && s >= 2) ce = cudaStreamWaitEvent(sa, h->ev_solw[r][(s - 2) % QA], 0);
+          if (ce == cudaSuccess && s >= 1 && vo_tick) ce = cudaStreamWaitEvent(sa, h->ev_solw[r][(s - 1) % QA], 0);
+        }
       }
+      if (ce != cudaSuccess) break;
+      h->stream = sa;
+      if (asm_split) {
+        h->asm_tile0 = bound[ra];
+        h->asm_tiles = bound[ra + 1] - bound[ra];
+      }
+      // the tick's quaternion leaves the ring slot BEFORE the slot is released to the EKF of tick s+QA (copying it on the
+      // solve stream raced with that EKF tick whenever the solves lagged behind the assembly): k_assemble writes it out
+      h->asm_quat_copy = os.quat;
+      rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 1);
+      h->asm_quat_copy = nullptr;
+      h->asm_tiles = -1;
+      h->stream = user;
+      if (rc) break;
+      for (int r = (asm_split ? ra : 0); r < (asm_split ? ra + 1 : ways) && ce == cudaSuccess; ++r)
+        ce = cudaEventRecord(h->ev_asmw[r][slot], sa);
     }
+    if (rc) break;
     if (ce != cudaSuccess) {
       rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);
       break;
     }
-    is.quat = qslot;
-    h->stream = sa;
-    // the tick's quaternion leaves the ring slot BEFORE ev_mhe releases the slot to the EKF of tick s+QA (copying it on the
-    // solve stream raced with that EKF tick whenever the solves lagged behind the assembly): k_assemble writes it out
-    h->asm_quat_copy = os.quat;
-    rc = mhe_step_impl(h, T0 + s, &is, &os, sslot, 1);
-    h->asm_quat_copy = nullptr;
-    h->stream = user;
-    if (rc) break;
-    ce = cudaEventRecord(h->ev_mhe[slot], sa);
     // ---- window solve of tick s: one launch per tile range (tick 0 has no window sweep: one launch covers every instance)
     const bool split = ways > 1 && T0 + s >= 1;
     for (int r = 0; r < ways && ce == cudaSuccess && rc == DEKF_OK; ++r) {
       if (r == 0 || split) {
-        if (asm_ahead) ce = cudaStreamWaitEvent(h->s_sol[r], h->ev_mhe[slot], 0);
+        if (asm_ahead) {
+          for (int q = (split ? r : 0); q < (split ? r + 1 : ways) && ce == cudaSuccess; ++q)
+            ce = cudaStreamWaitEvent(h->s_sol[r], h->ev_asmw[q][slot], 0);
+        }
         if (ce != cudaSuccess) break;
         if (split) {
           h->solve_tile0 = bound[r];
@@ -1576,10 +1610,10 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
   // join the internal streams back into the caller-visible one; if any of this fails (or the loop failed), drain them
   // on the host so that nothing is in flight when the error is reported
   cudaError_t je = cudaSuccess;
-  cudaStream_t internal[MW + 2];
+  cudaStream_t internal[2 * MW + 2];
   int ni = 0;
   for (int r = 0; r < ways; ++r) internal[ni++] = h->s_sol[r];
-  internal[ni++] = h->s_asm;
+  for (int r = 0; r < ways; ++r) internal[ni++] = h->s_asmw[r];
   internal[ni++] = h->s_ekf;
   for (int k = 0; k < ni && je == cudaSuccess; ++k) {
     je = cudaEventRecord(h->ev_join, internal[k]);
@@ -1587,7 +1621,7 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
   }
   if (je != cudaSuccess || rc != DEKF_OK) {
     for (int r = 0; r < MW; ++r) cudaStreamSynchronize(h->s_sol[r]);
-    cudaStreamSynchronize(h->s_asm);
+    for (int r = 0; r < MW; ++r) cudaStreamSynchronize(h->s_asmw[r]);
     cudaStreamSynchronize(h->s_ekf);
     cudaStreamSynchronize(user);
     if (rc == DEKF_OK) rc = fail(h, DEKF_ECUDA, "dekf_run: joining the internal streams", je);
