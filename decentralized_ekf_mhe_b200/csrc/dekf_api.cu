@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kBlock, DEKF_MINB_ASM) k_assemble(const MheCon
                                                      const Outputs out, int Tk, const int32_t *prev_status, double *quat_copy) {
   const int i = (blockIdx.x + dm.tile0) * blockDim.x + threadIdx.x;  // tile0: a launch may cover a tile range only (dekf_run, VO ticks)
   if (i >= dm.n) return;
+  const int prev = (prev_status != nullptr) ? prev_status[i] : 0;  // this tick's EKF status bits (asked for first: not a stall at the end)
   double q[4];
 #pragma unroll
   for (int f = 0; f < 4; ++f)
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(kBlock, DEKF_MINB_ASM) k_assemble(const MheCon
     for (int f = 0; f < 4; ++f) quat_copy[(size_t)f * dm.n + i] = q[f];
   }
   const int st = mhe_assemble<T, Model>(c, dm, b, in, out, Tk, i, q);
-  tick_status(dm, b, Tk, i) = (prev_status != nullptr) ? (prev_status[i] | st) : st;  // prev_status: this tick's EKF status bits
+  tick_status(dm, b, Tk, i) = prev | st;
 }
 
 template <typename T>

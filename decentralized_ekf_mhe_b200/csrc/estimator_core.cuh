@@ -502,6 +502,22 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
   int status = 0;
   if (b.resweep != nullptr) tick_resweep(dm, b, Tk, i) = 0x7fffffff;
 
+  // ---- contact detection (go1Sub.cpp:74, exact) and the first leg's joint sample: requested up front so that the loads are in
+  // flight during the VO synchronisation instead of stalling every pass of the (rolled) leg loop below
+  int contact_mask = 0;
+#pragma unroll
+  for (int leg = 0; leg < NL; ++leg) {
+    const bool contact = (in.foot_force[(size_t)leg * n + i] >= c.thr);
+    if (out.contact != nullptr) out.contact[(size_t)leg * n + i] = contact ? 1 : 0;
+    contact_mask |= (contact ? 1 : 0) << leg;
+  }
+  T q_next[NJ], dq_next[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    q_next[j] = (T)in.joint_pos[(size_t)j * n + i];
+    dq_next[j] = (T)in.joint_vel[(size_t)j * n + i];
+  }
+
   // ---- VO synchronisation against the history BEFORE this sample is pushed (:883-945)
   int vo_new = (in.vo_flag != nullptr) ? (int)in.vo_flag[i] : 0;
   double t_pre = 0.0, t_now = 0.0, relp[3] = {0.0, 0.0, 0.0};
@@ -659,7 +675,6 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
   V3<T> Qbeta_sum = v3<T>(T(0), T(0), T(0));  // sum over stance legs of (G C G')^-1 beta_i
   V3<T> beta_swing = v3<T>(T(0), T(0), T(0));  // sum over swing legs of beta_i
   int n_swing = 0;
-  int contact_mask = 0;
   // The leg loop stays ROLLED: one copy of the kinematics / covariance code in the instruction stream instead of NL
   // (k_assemble<double, Go1>: 20.6 -> 18.8 us per launch, spill frame 104 -> 56 B; profiles/r02_tune_solve.md).
   // -DDEKF_LEG_UNROLLED restores the unrolled form.
@@ -669,15 +684,19 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
 #pragma unroll 1
 #endif
   for (int leg = 0; leg < NL; ++leg) {
-    const double force = in.foot_force[(size_t)leg * n + i];
-    const bool contact = (force >= c.thr);  // go1Sub.cpp:74, exact
-    if (out.contact != nullptr) out.contact[(size_t)leg * n + i] = contact ? 1 : 0;
-    contact_mask |= (contact ? 1 : 0) << leg;
+    const bool contact = ((contact_mask >> leg) & 1) != 0;
     T q[NJ], dq[NJ];
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
-      q[j] = (T)in.joint_pos[(size_t)(leg * NJ + j) * n + i];
-      dq[j] = (T)in.joint_vel[(size_t)(leg * NJ + j) * n + i];
+      q[j] = q_next[j];
+      dq[j] = dq_next[j];
+    }
+    if (leg + 1 < NL) {  // the next leg's joint sample travels while this leg is computed
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        q_next[j] = (T)in.joint_pos[(size_t)((leg + 1) * NJ + j) * n + i];
+        dq_next[j] = (T)in.joint_vel[(size_t)((leg + 1) * NJ + j) * n + i];
+      }
     }
     V3<T> p;
     T J[3 * NJ];
