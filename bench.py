@@ -585,9 +585,13 @@ def main():
     def e2e_pass(f32_in, f32_out, T, kk):
         fn = est.run_host_f32 if f32_in else est.run_host
         odt = torch.float32 if f32_out else torch.float64
-        fn(T, Kw, host_slice(T, T + Kw, f32_in), vo_steps[T:T + Kw], out=host_out(Kw, odt), out_per_step=True)
+        # every host buffer (warm-up and timed) is filled and pinned FIRST: staging ~1 GB on the host takes seconds, and a GPU /
+        # PCIe link that idled that long spends the first 3-4 ms of the next call waking up (measured: tools/e2e_f32_probe.py,
+        # 274 vs 244 us per tick over 100 ticks) -- the untimed warm-up call must run right before the timed one
+        hst_w, hout_w = host_slice(T, T + Kw, f32_in), host_out(Kw, odt)
+        hst, hout = host_slice(T + Kw, T + Kw + kk, f32_in), host_out(kk, odt)
+        fn(T, Kw, hst_w, vo_steps[T:T + Kw], out=hout_w, out_per_step=True)
         T += Kw
-        hst, hout = host_slice(T, T + kk, f32_in), host_out(kk, odt)
         in_b = sum(rows[k] * (4 if (f32_in and k in F32) else 8) for k in keys[:6])
         h2d = sum(in_b * n + ((sum(rows[k] for k in keys[6:]) * 8 + 1) * n if vo_steps[T + j] else 0) for j in range(kk))
         d2h = (7 + ds_rows) * (4 if f32_out else 8) * n + nl * n + 4 * n

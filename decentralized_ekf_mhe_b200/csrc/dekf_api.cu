@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kBlock) k_fused(const EkfConst<T> ec, const Mh
   double q[4];
 #pragma unroll
   for (int f = 0; f < 4; ++f) q[f] = (double)b.ekf_q[(size_t)f * dm.ns + i];
-  st |= mhe_assemble<T, Model>(mc, dm, b, in, out, Tk, i, q);
+  st |= mhe_assemble<T, Model, false>(mc, dm, b, in, out, Tk, i, q);
   if (mc.est_type == 1)
     st |= kf_update<T>(mc, dm, b, in, out, Tk, i);
   else if (Tk >= 1 && mc.window_solve == 1)
@@ -240,6 +240,140 @@ __global__ void __launch_bounds__(kBlock) k_fused(const EkfConst<T> ec, const Mh
     st |= mhe_solve<T>(mc, dm, b, in, out, Tk, i, true);
   tick_status(dm, b, Tk, i) = st;
   if (status_out != nullptr) status_out[i] = st;
+}
+
+// Whole tick in one launch, ROLE form (small batches, est_type 0, leg_odom_type 0): one CTA = 32 instances (lane = instance), one
+// warp per ROLE, so that the pieces of a tick that do not depend on each other run side by side instead of one after the other in
+// a single thread (k_fused: 53 us per batch-1 tick, two thirds of it in straight-line code that is fetched once per launch):
+//   warp 0            front:  VO synchronisation (mhe_vo_sync) -> orientation EKF tick -> leg sums -> stage record of tick T
+//   warps 1 .. NL     legs:   contact, kinematics and the leg-odometry statistic of ONE leg each (leg_statistic)
+//   warp NL + 1       sweep:  window sweep over the stages T-N .. T-1 (they do not depend on this tick's sample), then the stage of
+//                             tick T once the front warp has written its record, read-out of x_T
+// The warps meet at three named barriers (non-aligned barrier.sync / barrier.arrive, one count per thread):
+//   1: VO rows of the window are final (front -> sweep)   2: leg statistics are in shared memory (legs -> front)
+//   3: the record of stage T is written (front -> sweep)
+// Every operand and every operation is the one k_fused / the large-batch kernels use (same device functions, leg sums added in
+// leg order), so the results are bit-identical (tests/test_gpu_parity.py::test_role_kernel_equals_fused_kernel).
+__device__ __forceinline__ void role_bar_sync(int id, int cnt) { asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(cnt) : "memory"); }
+__device__ __forceinline__ void role_bar_arrive(int id, int cnt) { asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(cnt) : "memory"); }
+
+template <typename T>
+struct RoleStageSource : GlobalStageSource<T> {
+  int jlast;  // ordinal of stage T in this sweep
+  __device__ RoleStageSource(const Dims &dm_, const Buffers<T> &b_, int i_, int jl) : GlobalStageSource<T>(dm_, b_, i_, true), jlast(jl) {}
+  __device__ __forceinline__ void acquire(int j) const {
+    if (j == jlast) role_bar_sync(3, 64);
+  }
+};
+
+template <typename T, typename Model>
+__global__ void __launch_bounds__((Model::NLEG + 2) * 32, 1) k_fused_roles(const EkfConst<T> ec, const MheConst<T> mc, const Dims dm,
+                                                                          const Buffers<T> b, const Inputs in, const Outputs out, int k,
+                                                                          int Tk, int32_t *status_out) {
+  constexpr int NL = Model::NLEG, NJ = Model::NJ;
+  __shared__ T s_leg[NL][12][32];  // per leg: Qb (6), Qb beta (3), beta (3)
+  __shared__ int s_contact[NL][32];
+  __shared__ int s_status[32];
+  const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const int n = dm.n;
+  const bool valid = i < n;
+  if (role == 0) {
+    int st = 0;
+    if (valid) st = mhe_vo_sync<T>(mc, dm, b, in, out, Tk, i, nullptr);
+    __threadfence_block();
+    role_bar_arrive(1, 64);
+    double q[4] = {1.0, 0.0, 0.0, 0.0};
+    M3<T> R;
+    V3<T> as = v3<T>(T(0), T(0), T(0));
+    if (valid) {
+      st |= ekf_tick<T>(ec, dm, b, in, out, k, i);
+#pragma unroll
+      for (int f = 0; f < 4; ++f) q[f] = (double)b.ekf_q[(size_t)f * dm.ns + i];
+      // current sample (DecentralEst.cpp:867-879)
+      R = quat_to_rot<T>((T)q[0], (T)q[1], (T)q[2], (T)q[3]);
+      V3<T> ab;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) ab[f] = (T)in.accel[(size_t)f * n + i];
+      as = mul(R, ab);
+      as[2] += T(-9.81);
+    }
+    role_bar_sync(2, (NL + 1) * 32);
+    if (valid) {
+      S3<T> Qb_sum;
+#pragma unroll
+      for (int f = 0; f < 6; ++f) Qb_sum.a[f] = T(0);
+      V3<T> Qbeta_sum = v3<T>(T(0), T(0), T(0)), beta_swing = v3<T>(T(0), T(0), T(0));
+      int n_swing = 0, contact_mask = 0;
+#pragma unroll
+      for (int leg = 0; leg < NL; ++leg) {  // leg order: the same sums as the serial loop of mhe_assemble
+        const bool contact = s_contact[leg][lane] != 0;
+        contact_mask |= (contact ? 1 : 0) << leg;
+        if (contact) {
+#pragma unroll
+          for (int f = 0; f < 6; ++f) Qb_sum.a[f] += s_leg[leg][f][lane];
+          Qbeta_sum = add(Qbeta_sum, v3<T>(s_leg[leg][6][lane], s_leg[leg][7][lane], s_leg[leg][8][lane]));
+        } else {
+          beta_swing = add(beta_swing, v3<T>(s_leg[leg][9][lane], s_leg[leg][10][lane], s_leg[leg][11][lane]));
+          n_swing++;
+        }
+      }
+      mhe_push_sample<T>(mc, dm, b, in, Tk, i, q, R, as, Qb_sum, Qbeta_sum, beta_swing, n_swing, contact_mask, NL);
+    }
+    s_status[lane] = st;
+    __threadfence_block();
+    role_bar_arrive(3, 64);
+  } else if (role <= NL) {
+    const int leg = role - 1;
+    if (valid) {
+      const bool contact = (in.foot_force[(size_t)leg * n + i] >= mc.thr);  // go1Sub.cpp:74, exact
+      if (out.contact != nullptr) out.contact[(size_t)leg * n + i] = contact ? 1 : 0;
+      T q[NJ], dq[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        q[j] = (T)in.joint_pos[(size_t)(leg * NJ + j) * n + i];
+        dq[j] = (T)in.joint_vel[(size_t)(leg * NJ + j) * n + i];
+      }
+      V3<T> om;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) om[f] = (T)in.gyro[(size_t)f * n + i];
+      V3<T> p, beta, Qbeta;
+      T J[3 * NJ];
+      S3<T> Qb;
+      leg_statistic<T, Model>(mc, leg, q, dq, om, p, J, beta, Qb, Qbeta);
+      s_contact[leg][lane] = contact ? 1 : 0;
+#pragma unroll
+      for (int f = 0; f < 6; ++f) s_leg[leg][f][lane] = Qb.a[f];
+#pragma unroll
+      for (int f = 0; f < 3; ++f) {
+        s_leg[leg][6 + f][lane] = Qbeta[f];
+        s_leg[leg][9 + f][lane] = beta[f];
+      }
+    }
+    __threadfence_block();
+    role_bar_arrive(2, (NL + 1) * 32);
+  } else {
+    role_bar_sync(1, 64);
+    int st = 0;
+    if (valid && Tk >= 1) {
+      if (mc.window_solve == 1) {
+        const int ks = incr_restart_stage(dm, b, Tk, i);
+        RoleStageSource<T> src(dm, b, i, Tk - ks);
+        st = mhe_solve_incr<T, RoleStageSource<T>>(mc, dm, b, in, out, Tk, i, src, ks);
+      } else {
+        const int k0 = (Tk < dm.N) ? 0 : Tk - dm.N;
+        RoleStageSource<T> src(dm, b, i, Tk - k0);
+        st = mhe_solve<T, RoleStageSource<T>>(mc, dm, b, in, out, Tk, i, src);
+      }
+    } else {
+      role_bar_sync(3, 64);
+    }
+    if (valid) {
+      st |= s_status[lane];
+      tick_status(dm, b, Tk, i) = st;
+      if (status_out != nullptr) status_out[i] = st;
+    }
+  }
 }
 
 template <typename T>
@@ -462,6 +596,8 @@ struct dekf_handle {
   int split_tiles_env = 0; // DEKF_SPLIT_TILES=<k>: size of the first tile range (0: the last full wave)
   int split_ways_env = 0;  // DEKF_SPLIT_WAYS=<w>: w equal tile ranges on w streams instead of the two-range split
   int host_chunk = 8;      // DEKF_HOST_CHUNK=<B>: ticks per copy of dekf_run_host
+  bool host_ramp = true;   // DEKF_HOST_RAMP=0: every chunk of dekf_run_host is B ticks (no ramp at the ends of a call)
+  int roles_max = 4096;    // DEKF_ROLES_MAX_N=<n>: batches up to n take the role form of the fused tick (0: always the serial form)
   int prio_mode = 0;       // DEKF_PRIO=<m>: stream priorities of dekf_run (0: all equal; 1: solve > assembly > EKF, round 1; 2: front kernels first)
   // small batches through the *_host entry points: one pinned, device-mapped host block; the kernel reads the tick's inputs
   // from it and writes the results into it over PCIe (no cudaMemcpy calls: the batch-1 tick is launch + kernel + sync)
@@ -631,7 +767,11 @@ int launch_fused(dekf_handle *h, const EkfConst<T> &ec, const MheConst<T> &mc, c
                  const Outputs &out, int k, int T_, int32_t *status) {
   {
     ProfScope ps(h, 2);
-    k_fused<T, Model><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(ec, mc, h->dm, b, in, out, k, T_, status);
+    // role form (one warp per piece of the tick) for the plain MHE; the KF alternative and tapped handles keep the serial form
+    if (h->dm.n <= h->roles_max && h->cfg.est_type == 0 && !h->cfg.debug_taps)
+      k_fused_roles<T, Model><<<(h->dm.n + 31) / 32, (Model::NLEG + 2) * 32, 0, h->stream>>>(ec, mc, h->dm, b, in, out, k, T_, status);
+    else
+      k_fused<T, Model><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(ec, mc, h->dm, b, in, out, k, T_, status);
   }
   h->launches++;
   return 0;
@@ -765,9 +905,11 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
   if (const char *e = std::getenv("DEKF_NO_TMA")) h->use_tma = std::atoi(e) == 0;
   if (const char *e = std::getenv("DEKF_NO_SPLIT")) h->no_split = std::atoi(e) != 0;
   if (const char *e = std::getenv("DEKF_SPLIT_TILES")) h->split_tiles_env = std::atoi(e);
+  if (const char *e = std::getenv("DEKF_ROLES_MAX_N")) h->roles_max = std::atoi(e);
   if (const char *e = std::getenv("DEKF_NO_ASM_SPLIT")) h->no_asm_split = std::atoi(e) != 0;
   if (const char *e = std::getenv("DEKF_SPLIT_WAYS")) h->split_ways_env = std::atoi(e);
   if (const char *e = std::getenv("DEKF_PRIO")) h->prio_mode = std::atoi(e);
+  if (const char *e = std::getenv("DEKF_HOST_RAMP")) h->host_ramp = std::atoi(e) != 0;
   if (const char *e = std::getenv("DEKF_HOST_CHUNK")) h->host_chunk = std::atoi(e) > 0 ? std::atoi(e) : 8;
   ce = cudaFuncSetAttribute(k_solve_tma<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_tma_smem_bytes<double>());
   if (ce == cudaSuccess)
@@ -1713,10 +1855,16 @@ static int run_host_body(dekf_handle *h, int32_t T0, int32_t S, const dekf_input
                              inf ? inf->joint_vel : nullptr, inf ? inf->foot_force : nullptr};
   const size_t rows_vo[4] = {4, 1, 1, 3};
   const double *src_vo[4] = {in->vo_quat, in->vo_time_pre, in->vo_time_now, in->vo_rel_p};
-  int c = 0;
-  for (int32_t s0 = 0; s0 < S; s0 += B, ++c) {
+  // Chunk sizes ramp up (1, 2, 4, ... B) and down again at the end of the call: the first copy that nothing can overlap and the
+  // last kernels + result copy that nothing overlaps either are ONE tick each instead of B ticks (DEKF_HOST_RAMP=0: all B).
+  int c = 0, ramp = h->host_ramp ? 1 : B;
+  for (int32_t s0 = 0, Bc = 0; s0 < S; s0 += Bc, ++c) {
     const int b = c & 1;
-    const int Bc = (S - s0 < B) ? (S - s0) : B;
+    Bc = ramp < B ? ramp : B;
+    if (h->host_ramp && Bc > (S - s0 + 1) / 2) Bc = (S - s0 + 1) / 2;
+    if (Bc > S - s0) Bc = S - s0;
+    if (Bc < 1) Bc = 1;
+    ramp = ramp * 2 < B ? ramp * 2 : B;
     ChunkSet &cs = h->chunk[b];
     const size_t cap = (size_t)cs.cap;
     if (c >= 2) CK(cudaStreamWaitEvent(h->s_h2d, h->ev_comp[b], 0));  // kernels of chunk c-2 are done with staging set b

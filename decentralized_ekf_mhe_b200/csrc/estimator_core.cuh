@@ -494,29 +494,16 @@ DEKF_HD void foot_leg_record(const T *cenc_p, const M3<T> &R, const V3<T> &p, co
 // 374-424, 474-478, 496-572, 864-985) + UpdateVOConstraints (:987-1009) for instance i.
 // q_ext: orientation to use ([w,x,y,z]); written to the history ring un-normalised like the reference
 // stores R of the normalised quaternion.
-template <typename T, typename Model>
-DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in,
-                         const Outputs &out, int Tk, int i, const double qd[4]) {
-  constexpr int NL = Model::NLEG, NJ = Model::NJ;
+// GetMeasurement(T), VO half (DecentralEst.cpp:883-945) + UpdateVOConstraints (:987-1009) for instance i: time synchronisation of
+// the VO message against the history BEFORE this tick's sample is pushed, p_vo_accmulate_, the Bezier way points and the VO rows of
+// the window stages the message bounds.  Touches nothing the orientation EKF or the leg kinematics of this tick produce -- except
+// in the KF alternative at T == 0, which sees this tick's own sample (qd; may be null when est_type == 0).
+template <typename T>
+DEKF_HD int mhe_vo_sync(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out, int Tk, int i,
+                        const double *qd) {
   const int n = dm.n, ns = dm.ns, N = dm.N, NW = dm.NW, HR = dm.HR;
   int status = 0;
   if (b.resweep != nullptr) tick_resweep(dm, b, Tk, i) = 0x7fffffff;
-
-  // ---- contact detection (go1Sub.cpp:74, exact) and the first leg's joint sample: requested up front so that the loads are in
-  // flight during the VO synchronisation instead of stalling every pass of the (rolled) leg loop below
-  int contact_mask = 0;
-#pragma unroll
-  for (int leg = 0; leg < NL; ++leg) {
-    const bool contact = (in.foot_force[(size_t)leg * n + i] >= c.thr);
-    if (out.contact != nullptr) out.contact[(size_t)leg * n + i] = contact ? 1 : 0;
-    contact_mask |= (contact ? 1 : 0) << leg;
-  }
-  T q_next[NJ], dq_next[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) {
-    q_next[j] = (T)in.joint_pos[(size_t)j * n + i];
-    dq_next[j] = (T)in.joint_vel[(size_t)j * n + i];
-  }
 
   // ---- VO synchronisation against the history BEFORE this sample is pushed (:883-945)
   int vo_new = (in.vo_flag != nullptr) ? (int)in.vo_flag[i] : 0;
@@ -657,116 +644,62 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
     for (int f = 0; f < 8; ++f) out.dbg_vo[(size_t)f * n + i] = dbg[f];
   }
 
-  // ---- current sample (:867-879)
-  const M3<T> R = quat_to_rot<T>((T)qd[0], (T)qd[1], (T)qd[2], (T)qd[3]);
-  V3<T> ab, om;
-#pragma unroll
-  for (int f = 0; f < 3; ++f) {
-    ab[f] = (T)in.accel[(size_t)f * n + i];
-    om[f] = (T)in.gyro[(size_t)f * n + i];
-  }
-  V3<T> as = mul(R, ab);
-  as[2] += T(-9.81);
+  return status;
+}
 
-  // ---- legs: contact, kinematics, leg-odometry statistic (go1Sub.cpp:64-125, DecentralEst.cpp:509-546)
-  S3<T> Qb_sum;  // sum over stance legs of (G C G')^-1, body frame
+// Per-leg statistic of the leg-odometry rows (go1Sub.cpp:64-125 kinematics, DecentralEst.cpp:509-546): foot position p in the IMU
+// frame, Jacobian J, beta = -(J dq + omega x p) (b_meas = R beta), Qb = (G C G')^-1 in the body frame and Qb beta.
+template <typename T, typename Model>
+DEKF_HD void leg_statistic(const MheConst<T> &c, int leg, const T *q, const T *dq, const V3<T> &om, V3<T> &p, T *J /*3 x NJ*/,
+                           V3<T> &beta, S3<T> &Qb, V3<T> &Qbeta) {
+  constexpr int NJ = Model::NJ;
+  Model::leg_fk(leg, q, p, J);
+  p[0] += c.p_ib[0];
+  p[1] += c.p_ib[1];
+  p[2] += c.p_ib[2];
+  // beta = -(J dq + omega x p)   (b_meas = R beta, :515-516)
+  V3<T> Jdq = v3<T>(T(0), T(0), T(0));
 #pragma unroll
-  for (int f = 0; f < 6; ++f) Qb_sum.a[f] = T(0);
-  V3<T> Qbeta_sum = v3<T>(T(0), T(0), T(0));  // sum over stance legs of (G C G')^-1 beta_i
-  V3<T> beta_swing = v3<T>(T(0), T(0), T(0));  // sum over swing legs of beta_i
-  int n_swing = 0;
-  // The leg loop stays ROLLED: one copy of the kinematics / covariance code in the instruction stream instead of NL
-  // (k_assemble<double, Go1>: 20.6 -> 18.8 us per launch, spill frame 104 -> 56 B; profiles/r02_tune_solve.md).
-  // -DDEKF_LEG_UNROLLED restores the unrolled form.
-#if defined(DEKF_LEG_UNROLLED)
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-  for (int leg = 0; leg < NL; ++leg) {
-    const bool contact = ((contact_mask >> leg) & 1) != 0;
-    T q[NJ], dq[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      q[j] = q_next[j];
-      dq[j] = dq_next[j];
-    }
-    if (leg + 1 < NL) {  // the next leg's joint sample travels while this leg is computed
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        q_next[j] = (T)in.joint_pos[(size_t)((leg + 1) * NJ + j) * n + i];
-        dq_next[j] = (T)in.joint_vel[(size_t)((leg + 1) * NJ + j) * n + i];
-      }
-    }
-    V3<T> p;
-    T J[3 * NJ];
-    Model::leg_fk(leg, q, p, J);
-    p[0] += c.p_ib[0];
-    p[1] += c.p_ib[1];
-    p[2] += c.p_ib[2];
-    if (b.foot_leg != nullptr)  // leg_odom_type 1: b_meas = R p, C_meas = R J C_enc_pos J' R' (:550-564)
-      foot_leg_record<T, NJ>(c.cenc_p, R, p, J, b.foot_leg + (size_t)(Tk % NW) * (9 * NL + 1) * ns + i, (size_t)ns, leg);
-    // beta = -(J dq + omega x p)   (b_meas = R beta, :515-516)
-    V3<T> Jdq = v3<T>(T(0), T(0), T(0));
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      Jdq[0] += J[0 * NJ + j] * dq[j];
-      Jdq[1] += J[1 * NJ + j] * dq[j];
-      Jdq[2] += J[2 * NJ + j] * dq[j];
-    }
-    const V3<T> wxp = cross(om, p);
-    const V3<T> beta = v3<T>(-(Jdq[0] + wxp[0]), -(Jdq[1] + wxp[1]), -(Jdq[2] + wxp[2]));
-    // C_b = G C G', G = [-J, -omega^x J, p^x], C = blkdiag(C_enc_vel, C_enc_pos, C_gyro) (:523-543)
-    S3<T> Cb;
-#pragma unroll
-    for (int f = 0; f < 6; ++f) Cb.a[f] = T(0);
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-      const V3<T> col = v3<T>(J[0 * NJ + j], J[1 * NJ + j], J[2 * NJ + j]);
-      const V3<T> wc = cross(om, col);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = r; cc < 3; ++cc)
-          Cb.a[S3<T>::idx(r, cc)] += c.cenc_v[j] * col[r] * col[cc] + c.cenc_p[j] * wc[r] * wc[cc];
-    }
-    {
-      const M3<T> ps = skew(p);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int cc = r; cc < 3; ++cc)
-          Cb.a[S3<T>::idx(r, cc)] += c.cgy[0] * ps(r, 0) * ps(cc, 0) + c.cgy[1] * ps(r, 1) * ps(cc, 1) + c.cgy[2] * ps(r, 2) * ps(cc, 2);
-    }
-    const S3<T> Qb = inverse(Cb);
-    const V3<T> Qbeta = mul(Qb, beta);
-    if (contact) {
-#pragma unroll
-      for (int f = 0; f < 6; ++f) Qb_sum.a[f] += Qb.a[f];
-      Qbeta_sum = add(Qbeta_sum, Qbeta);
-    } else {
-      beta_swing = add(beta_swing, beta);
-      n_swing++;
-    }
-    if (out.dbg_b_meas != nullptr) {
-      const V3<T> bm = mul(R, beta);
-#pragma unroll
-      for (int f = 0; f < 3; ++f) out.dbg_b_meas[(size_t)(leg * 3 + f) * n + i] = (double)bm[f];
-    }
-    if (out.dbg_Q_meas != nullptr) {
-      S3<T> Qw = rsrt(R, Qb);
-      if (!contact) {
-        Qw.a[0] = c.q_swing[0];
-        Qw.a[1] = T(0);
-        Qw.a[2] = T(0);
-        Qw.a[3] = c.q_swing[1];
-        Qw.a[4] = T(0);
-        Qw.a[5] = c.q_swing[2];
-      }
-#pragma unroll
-      for (int f = 0; f < 6; ++f) out.dbg_Q_meas[(size_t)(leg * 6 + f) * n + i] = (double)Qw.a[f];
-    }
+  for (int j = 0; j < NJ; ++j) {
+    Jdq[0] += J[0 * NJ + j] * dq[j];
+    Jdq[1] += J[1 * NJ + j] * dq[j];
+    Jdq[2] += J[2 * NJ + j] * dq[j];
   }
+  const V3<T> wxp = cross(om, p);
+  beta = v3<T>(-(Jdq[0] + wxp[0]), -(Jdq[1] + wxp[1]), -(Jdq[2] + wxp[2]));
+  // C_b = G C G', G = [-J, -omega^x J, p^x], C = blkdiag(C_enc_vel, C_enc_pos, C_gyro) (:523-543)
+  S3<T> Cb;
+#pragma unroll
+  for (int f = 0; f < 6; ++f) Cb.a[f] = T(0);
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const V3<T> col = v3<T>(J[0 * NJ + j], J[1 * NJ + j], J[2 * NJ + j]);
+    const V3<T> wc = cross(om, col);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = r; cc < 3; ++cc)
+        Cb.a[S3<T>::idx(r, cc)] += c.cenc_v[j] * col[r] * col[cc] + c.cenc_p[j] * wc[r] * wc[cc];
+  }
+  {
+    const M3<T> ps = skew(p);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = r; cc < 3; ++cc)
+        Cb.a[S3<T>::idx(r, cc)] += c.cgy[0] * ps(r, 0) * ps(cc, 0) + c.cgy[1] * ps(r, 1) * ps(cc, 1) + c.cgy[2] * ps(r, 2) * ps(cc, 2);
+  }
+  Qb = inverse(Cb);
+  Qbeta = mul(Qb, beta);
+}
+
+// Tail of GetMeasurement(T) + the Measurement_T / Dynamic_T data of UpdateMHE (DecentralEst.cpp:374-424, 474-478, 949-975): the
+// leg sums become (Lambda, eta), the sample is pushed to the history ring and the stage record of discrete time Tk is written.
+template <typename T>
+DEKF_HD void mhe_push_sample(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, int Tk, int i, const double qd[4],
+                             const M3<T> &R, const V3<T> &as, const S3<T> &Qb_sum, const V3<T> &Qbeta_sum, const V3<T> &beta_swing,
+                             int n_swing, int contact_mask, int NL) {
+  const int ns = dm.ns, NW = dm.NW, HR = dm.HR;
   // Lambda = R Qb_sum R' + n_swing diag(q_swing);  eta = R Qbeta_sum + diag(q_swing) R beta_swing
   S3<T> Lam = rsrt(R, Qb_sum);
   Lam.a[0] += (T)n_swing * c.q_swing[0];
@@ -799,6 +732,124 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
     for (int f = 0; f < 3; ++f) rec[(size_t)(REC_DLT + f) * ns] = T(0);
     rec[(size_t)REC_FLAG * ns] = T(0);  // VO row of stage Tk starts as a free placeholder (:474-481)
   }
+}
+
+// HOIST: contact detection and the legs' joint samples are requested ahead of their use (k_assemble, large batches: 99.4 -> 98.6 us
+// per tick at 65,536 instances); the single-warp fused tick is faster without it (53.1 vs 56.7 us), so k_fused passes false.
+template <typename T, typename Model, bool HOIST = true>
+DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in,
+                         const Outputs &out, int Tk, int i, const double qd[4]) {
+  constexpr int NL = Model::NLEG, NJ = Model::NJ;
+  const int n = dm.n, ns = dm.ns, NW = dm.NW;
+  int status = 0;
+
+  // ---- contact detection (go1Sub.cpp:74, exact) and the first leg's joint sample: requested up front so that the loads are in
+  // flight during the VO synchronisation instead of stalling every pass of the (rolled) leg loop below
+  int contact_mask = 0;
+  T q_next[NJ], dq_next[NJ];
+  if constexpr (HOIST) {
+#pragma unroll
+    for (int leg = 0; leg < NL; ++leg) {
+      const bool contact = (in.foot_force[(size_t)leg * n + i] >= c.thr);
+      if (out.contact != nullptr) out.contact[(size_t)leg * n + i] = contact ? 1 : 0;
+      contact_mask |= (contact ? 1 : 0) << leg;
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      q_next[j] = (T)in.joint_pos[(size_t)j * n + i];
+      dq_next[j] = (T)in.joint_vel[(size_t)j * n + i];
+    }
+  }
+
+  status |= mhe_vo_sync<T>(c, dm, b, in, out, Tk, i, qd);
+
+  // ---- current sample (:867-879)
+  const M3<T> R = quat_to_rot<T>((T)qd[0], (T)qd[1], (T)qd[2], (T)qd[3]);
+  V3<T> ab, om;
+#pragma unroll
+  for (int f = 0; f < 3; ++f) {
+    ab[f] = (T)in.accel[(size_t)f * n + i];
+    om[f] = (T)in.gyro[(size_t)f * n + i];
+  }
+  V3<T> as = mul(R, ab);
+  as[2] += T(-9.81);
+
+  // ---- legs: contact, kinematics, leg-odometry statistic (go1Sub.cpp:64-125, DecentralEst.cpp:509-546)
+  S3<T> Qb_sum;  // sum over stance legs of (G C G')^-1, body frame
+#pragma unroll
+  for (int f = 0; f < 6; ++f) Qb_sum.a[f] = T(0);
+  V3<T> Qbeta_sum = v3<T>(T(0), T(0), T(0));  // sum over stance legs of (G C G')^-1 beta_i
+  V3<T> beta_swing = v3<T>(T(0), T(0), T(0));  // sum over swing legs of beta_i
+  int n_swing = 0;
+  // The leg loop stays ROLLED: one copy of the kinematics / covariance code in the instruction stream instead of NL
+  // (k_assemble<double, Go1>: 20.6 -> 18.8 us per launch, spill frame 104 -> 56 B; profiles/r02_tune_solve.md).
+  // -DDEKF_LEG_UNROLLED restores the unrolled form.
+#if defined(DEKF_LEG_UNROLLED)
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+  for (int leg = 0; leg < NL; ++leg) {
+    bool contact;
+    T q[NJ], dq[NJ];
+    if constexpr (HOIST) {
+      contact = ((contact_mask >> leg) & 1) != 0;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        q[j] = q_next[j];
+        dq[j] = dq_next[j];
+      }
+      if (leg + 1 < NL) {  // the next leg's joint sample travels while this leg is computed
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          q_next[j] = (T)in.joint_pos[(size_t)((leg + 1) * NJ + j) * n + i];
+          dq_next[j] = (T)in.joint_vel[(size_t)((leg + 1) * NJ + j) * n + i];
+        }
+      }
+    } else {
+      contact = (in.foot_force[(size_t)leg * n + i] >= c.thr);  // go1Sub.cpp:74, exact
+      if (out.contact != nullptr) out.contact[(size_t)leg * n + i] = contact ? 1 : 0;
+      contact_mask |= (contact ? 1 : 0) << leg;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        q[j] = (T)in.joint_pos[(size_t)(leg * NJ + j) * n + i];
+        dq[j] = (T)in.joint_vel[(size_t)(leg * NJ + j) * n + i];
+      }
+    }
+    V3<T> p, beta, Qbeta;
+    T J[3 * NJ];
+    S3<T> Qb;
+    leg_statistic<T, Model>(c, leg, q, dq, om, p, J, beta, Qb, Qbeta);
+    if (b.foot_leg != nullptr)  // leg_odom_type 1: b_meas = R p, C_meas = R J C_enc_pos J' R' (:550-564)
+      foot_leg_record<T, NJ>(c.cenc_p, R, p, J, b.foot_leg + (size_t)(Tk % NW) * (9 * NL + 1) * ns + i, (size_t)ns, leg);
+    if (contact) {
+#pragma unroll
+      for (int f = 0; f < 6; ++f) Qb_sum.a[f] += Qb.a[f];
+      Qbeta_sum = add(Qbeta_sum, Qbeta);
+    } else {
+      beta_swing = add(beta_swing, beta);
+      n_swing++;
+    }
+    if (out.dbg_b_meas != nullptr) {
+      const V3<T> bm = mul(R, beta);
+#pragma unroll
+      for (int f = 0; f < 3; ++f) out.dbg_b_meas[(size_t)(leg * 3 + f) * n + i] = (double)bm[f];
+    }
+    if (out.dbg_Q_meas != nullptr) {
+      S3<T> Qw = rsrt(R, Qb);
+      if (!contact) {
+        Qw.a[0] = c.q_swing[0];
+        Qw.a[1] = T(0);
+        Qw.a[2] = T(0);
+        Qw.a[3] = c.q_swing[1];
+        Qw.a[4] = T(0);
+        Qw.a[5] = c.q_swing[2];
+      }
+#pragma unroll
+      for (int f = 0; f < 6; ++f) out.dbg_Q_meas[(size_t)(leg * 6 + f) * n + i] = (double)Qw.a[f];
+    }
+  }
+  mhe_push_sample<T>(c, dm, b, in, Tk, i, qd, R, as, Qb_sum, Qbeta_sum, beta_swing, n_swing, contact_mask, NL);
   return status;
 }
 

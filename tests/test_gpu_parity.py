@@ -587,6 +587,42 @@ def test_incremental_equals_full_resweep(est_mod, precision, n):
     assert (a["status"] & 16).any()  # VO bounds were inserted (re-sweeps happened)
 
 
+@pytest.mark.parametrize("robot", ["go1", "cassie", "pogox"])
+@pytest.mark.parametrize("precision,window_solve,n", [("fp64", 0, 1), ("fp64", 1, 37), ("fp32", 0, 200), ("fp64", 0, 1000)])
+def test_role_kernel_equals_fused_kernel(est_mod, monkeypatch, robot, precision, window_solve, n):
+    """k_fused_roles (small batches: one warp per piece of the tick -- VO sync + EKF + record / one leg each / window sweep --
+    meeting at named barriers) runs the same device functions on the same operands as the one-thread-per-instance k_fused:
+    every output, the status words and the arrival cost must be BIT-identical, through the window fill and with ragged VO
+    arrival, for every robot model, both solve modes and both precisions."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    S = 90
+    st = synth.make_stream(n, S, robot=robot, vo_jitter=True, device="cuda")
+    d = {k: v.contiguous() for k, v in st.items()}
+    nl = st["foot_force"].shape[1]
+    outs = []
+    for roles in ("4096", "0"):
+        monkeypatch.setenv("DEKF_ROLES_MAX_N", roles)
+        est = E.BatchedEstimator(E.robot_params(robot, ekf_rate=200, window_solve=window_solve), n, precision=precision)
+        o = dict(x=torch.zeros(S, 9, n, dtype=torch.float64, device="cuda"), v_body=torch.zeros(S, 3, n, dtype=torch.float64, device="cuda"),
+                 quat=torch.zeros(S, 4, n, dtype=torch.float64, device="cuda"), status=torch.zeros(S, n, dtype=torch.int32, device="cuda"),
+                 contact=torch.zeros(S, nl, n, dtype=torch.uint8, device="cuda"))
+        for s in range(S):
+            est.step(s, E.robot_store.from_stream(d, s))
+            o["x"][s], o["v_body"][s], o["status"][s] = est.x_MHE_, est.v_MHE_b_, est.status_
+            o["quat"][s], o["contact"][s] = est.quaternion_, est.contact_
+        M, nn = est.mhe_qp_.arrival_cov()
+        outs.append((o, M.clone(), nn.clone(), est.p_vo_accmulate_.clone()))
+        est.close()
+    (a, aM, an, ap), (b, bM, bn, bp) = outs
+    for key in ("quat", "contact", "status"):
+        assert torch.equal(a[key], b[key]), key
+    assert torch.equal(a["x"][1:], b["x"][1:]) and torch.equal(a["v_body"][1:], b["v_body"][1:])
+    assert torch.equal(aM, bM) and torch.equal(an, bn) and torch.equal(ap, bp)
+    assert torch.isfinite(a["x"][1:]).all()
+    assert (a["status"] & 16).any()  # VO bounds were inserted
+
+
 def test_foot_state_model_vs_oracle(est_mod, oracle):
     """leg_odom_type 1: 21-state model, information-form sweep (csrc/footstate.cuh).
     Exact reference = the oracle solving the whole history in one banded system (no marginalisation); the literal
