@@ -12,7 +12,9 @@
 //   :163-165           T_world_to_body = T_world_to_body_init^-1 * T_world_to_camera * T_body_to_camera^-1, its rotation
 //                      as a quaternion -> topic orb/pos (:168-179) -> dekf_inputs.vo_quat ([w,x,y,z])
 // Plain C++17, no Eigen (not available in this image); Eigen's Quaterniond(Matrix3d) branch structure is kept so that
-// the quaternion sign convention matches.
+// the quaternion sign convention matches.  Pinned to the reference node itself: stereo-pub-node.cpp compiles unmodified against
+// stand-in headers into oracle/_ref/vo_pin, and every field of the orb/vo and orb/pos messages it publishes for scripted tracked
+// poses is reproduced (tests/test_vo_frontend.py, tests/golden/vo_frontend_golden.npz).
 #pragma once
 #include <array>
 #include <cmath>

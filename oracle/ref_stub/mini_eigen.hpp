@@ -432,6 +432,31 @@ class Quaterniond {
  public:
   Quaterniond() : w_(0), x_(0), y_(0), z_(0) {}  // Eigen leaves it uninitialised
   Quaterniond(double w, double x, double y, double z) : w_(w), x_(x), y_(y), z_(z) {}
+  // Quaterniond(const Matrix3d &): Eigen's quaternionbase_assign_impl<Other, 3, 3> (Shepperd's method, same branches and order)
+  explicit Quaterniond(const Mat &m) {
+    double t = m(0, 0) + m(1, 1) + m(2, 2);
+    if (t > 0.0) {
+      t = std::sqrt(t + 1.0);
+      w_ = 0.5 * t;
+      t = 0.5 / t;
+      x_ = (m(2, 1) - m(1, 2)) * t;
+      y_ = (m(0, 2) - m(2, 0)) * t;
+      z_ = (m(1, 0) - m(0, 1)) * t;
+    } else {
+      int i = 0;
+      if (m(1, 1) > m(0, 0)) i = 1;
+      if (m(2, 2) > m(i, i)) i = 2;
+      const int j = (i + 1) % 3, k = (j + 1) % 3;
+      t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+      double v[3];
+      v[i] = 0.5 * t;
+      t = 0.5 / t;
+      w_ = (m(k, j) - m(j, k)) * t;
+      v[j] = (m(j, i) + m(i, j)) * t;
+      v[k] = (m(k, i) + m(i, k)) * t;
+      x_ = v[0]; y_ = v[1]; z_ = v[2];
+    }
+  }
   double &w() { return w_; }
   double &x() { return x_; }
   double &y() { return y_; }
@@ -462,6 +487,7 @@ class Quaterniond {
     R(2, 0) = txz - twy; R(2, 1) = tyz + twx; R(2, 2) = 1.0 - (txx + tyy);
     return R;
   }
+  Matrix3d matrix() const { return toRotationMatrix(); }
  private:
   double w_, x_, y_, z_;
 };

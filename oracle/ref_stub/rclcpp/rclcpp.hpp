@@ -10,6 +10,7 @@
 //     default given by the node -- the role of the YAML file in the reference's launch file.
 #pragma once
 #include <chrono>
+#include <cstdio>
 #include <cstdint>
 #include <functional>
 #include <iostream>
@@ -17,6 +18,12 @@
 #include <memory>
 #include <string>
 #include <vector>
+
+#include "std_msgs/msg/header.hpp"
+
+#ifndef RCLCPP_ERROR
+#define RCLCPP_ERROR(logger, ...) do { (void)(logger); std::fprintf(stderr, __VA_ARGS__); std::fputc('\n', stderr); } while (0)
+#endif
 
 namespace refstub {
 struct ParamValue {
@@ -53,6 +60,12 @@ class Time {
   explicit Time(int64_t ns) : ns_(ns) {}
   int64_t nanoseconds() const { return ns_; }
   double seconds() const { return (double)ns_ / 1e9; }
+  operator builtin_interfaces::msg::Time() const {  // header.stamp = node->now()
+    builtin_interfaces::msg::Time t;
+    t.sec = (int32_t)(ns_ / 1000000000LL);
+    t.nanosec = (uint32_t)(ns_ % 1000000000LL);
+    return t;
+  }
  private:
   int64_t ns_;
 };
