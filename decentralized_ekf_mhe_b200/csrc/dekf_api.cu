@@ -34,21 +34,62 @@ constexpr int kBlock = 128;
 #define DEKF_MINB_INCR 2  // the sweep stage needs the full register file: 128 registers spill 944 B and lose (33 vs 26 us)
 #endif
 
-template <typename T>
-__global__ void __launch_bounds__(kBlock, DEKF_MINB_EKF) k_ekf(const EkfConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
-                                                const Outputs out, int k, int32_t *status_state, int32_t *status_out) {
+__global__ void k_zero_i32(int32_t *p) { *p = 0; }
+
+// Indices of the instances whose vo_flag is set, in arbitrary order (warp-aggregated append; *count must be 0 at launch).
+__global__ void __launch_bounds__(256) k_vo_compact(const uint8_t *__restrict__ flag, int n, int32_t *__restrict__ list,
+                                                    int32_t *__restrict__ count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= dm.n) return;
-  const int st = ekf_tick<T>(c, dm, b, in, out, k, i);
+  const bool f = i < n && flag[i] != 0;
+  const unsigned m = __ballot_sync(0xffffffffu, f);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == __ffs(m) - 1) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (f) list[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
+// PART (see ekf_tick): EKF_ALL = one launch does the whole tick; with a VO-carrying tick of a large batch the tick is two launches,
+// EKF_REPLAY over the compacted list of the instances that received a pose (thread t handles list[t], t < *count) and EKF_UPDATE
+// over all instances.
+template <typename T, int PART = EKF_ALL>
+__global__ void __launch_bounds__(kBlock, DEKF_MINB_EKF) k_ekf(const EkfConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
+                                                const Outputs out, int k, int32_t *status_state, int32_t *status_out,
+                                                const int32_t *__restrict__ list, const int32_t *__restrict__ count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (PART == EKF_REPLAY) {
+    if (i >= *count) return;
+    i = list[i];
+  } else if (i >= dm.n) {
+    return;
+  }
+  const int st = ekf_tick<T, PART>(c, dm, b, in, out, k, i);
+  if (PART == EKF_UPDATE && in.vo_flag != nullptr && in.vo_flag[i]) return;  // the replay launch wrote this instance's status bits
   status_state[i] = st;  // b.status, or a ring slot when the EKF runs ahead of the MHE (dekf_run)
   if (status_out != nullptr) status_out[i] = st;
 }
 
 // quat_copy (dekf_run only): the tick's quaternion also goes to the per-step output array from here -- it used to be a
 // device-to-device cudaMemcpyAsync per tick on the assembly stream, i.e. a copy-engine round trip in front of every solve
-template <typename T, typename Model>
+// VO synchronisation of the instances that carry a VO message, over the compacted list of those instances (thread t handles
+// list[t], t < *count; a launch may be restricted to the instances of a tile range, like k_assemble).  Runs BEFORE k_assemble
+// pushes the tick's sample; leaves its status bits in vo_stat for k_assemble<..., VOSPLIT = true> to pick up.
+template <typename T>
+__global__ void __launch_bounds__(kBlock) k_vo_sync(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
+                                                    const Outputs out, int Tk, const int32_t *__restrict__ list,
+                                                    const int32_t *__restrict__ count, int i_lo, int i_hi, int32_t *__restrict__ vo_stat) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= *count) return;
+  const int i = list[t];
+  if (i < i_lo || i >= i_hi) return;
+  vo_stat[i] = mhe_vo_sync<T>(c, dm, b, in, out, Tk, i, nullptr);
+}
+
+template <typename T, typename Model, bool VOSPLIT = false>
 __global__ void __launch_bounds__(kBlock, DEKF_MINB_ASM) k_assemble(const MheConst<T> c, const Dims dm, const Buffers<T> b, const Inputs in,
-                                                     const Outputs out, int Tk, const int32_t *prev_status, double *quat_copy) {
+                                                     const Outputs out, int Tk, const int32_t *prev_status, double *quat_copy,
+                                                     const int32_t *vo_stat) {
   const int i = (blockIdx.x + dm.tile0) * blockDim.x + threadIdx.x;  // tile0: a launch may cover a tile range only (dekf_run, VO ticks)
   if (i >= dm.n) return;
   const int prev = (prev_status != nullptr) ? prev_status[i] : 0;  // this tick's EKF status bits (asked for first: not a stall at the end)
@@ -60,7 +101,7 @@ __global__ void __launch_bounds__(kBlock, DEKF_MINB_ASM) k_assemble(const MheCon
 #pragma unroll
     for (int f = 0; f < 4; ++f) quat_copy[(size_t)f * dm.n + i] = q[f];
   }
-  const int st = mhe_assemble<T, Model>(c, dm, b, in, out, Tk, i, q);
+  const int st = mhe_assemble<T, Model, true, VOSPLIT>(c, dm, b, in, out, Tk, i, q, vo_stat);
   tick_status(dm, b, Tk, i) = prev | st;
 }
 
@@ -597,6 +638,14 @@ struct dekf_handle {
   int split_ways_env = 0;  // DEKF_SPLIT_WAYS=<w>: w equal tile ranges on w streams instead of the two-range split
   int host_chunk = 8;      // DEKF_HOST_CHUNK=<B>: ticks per copy of dekf_run_host
   bool host_ramp = true;   // DEKF_HOST_RAMP=0: every chunk of dekf_run_host is B ticks (no ramp at the ends of a call)
+  bool ekf_serial = false;  // DEKF_EKF_SERIAL=1: no EKF launch of dekf_run overlaps a window solve (diagnosis)
+  // DEKF_VO_COMPACT=1 (opt-in): VO-carrying ticks of large batches compact the flagged instances and run the EKF replay and the
+  // VO synchronisation over that list (ragged arrival: +17 % throughput); off by default, see DESIGN.md section 10
+  bool vo_compact = false;
+  int32_t *vo_stat = nullptr;  // [kAhead][n] status bits of k_vo_sync, picked up by k_assemble<..., VOSPLIT>
+  int32_t *vo_list = nullptr, *vo_count = nullptr;  // [kAhead][n] / [kAhead]: instances flagged with a VO message, per ring slot
+  int vo_slot = 0;             // ring slot of the tick being queued (dekf_run: s % kAhead; single ticks: 0)
+  bool vo_list_valid = false;  // the list of vo_slot was built for the tick being queued (by its EKF launch)
   int roles_max = 4096;    // DEKF_ROLES_MAX_N=<n>: batches up to n take the role form of the fused tick (0: always the serial form)
   int prio_mode = 0;       // DEKF_PRIO=<m>: stream priorities of dekf_run (0: all equal; 1: solve > assembly > EKF, round 1; 2: front kernels first)
   // small batches through the *_host entry points: one pinned, device-mapped host block; the kernel reads the tick's inputs
@@ -741,11 +790,41 @@ template <typename T, typename Model>
 int launch_assemble(dekf_handle *h, const MheConst<T> &mc, const Buffers<T> &b, const Inputs &in, const Outputs &out,
                     int T_, const int32_t *acc) {
   {
-    ProfScope ps(h, 1);
     Dims adm = h->dm;
     adm.tile0 = h->asm_tiles >= 0 ? h->asm_tile0 : 0;
     const int grid = h->asm_tiles >= 0 ? h->asm_tiles : grid_for(h->dm.n);
-    k_assemble<T, Model><<<grid, kBlock, 0, h->stream>>>(mc, adm, b, in, out, T_, acc, h->asm_quat_copy);
+    // large batches from T = 2 on (the VO latch of T = 0 / 1 is over): the VO synchronisation leaves k_assemble -- ticks
+    // without a message skip it altogether, ticks with messages run it over the compacted list of the flagged instances
+    const bool lean = T_ >= 2 && !h->cfg.debug_taps && h->dm.n > h->fused_max;  // k_assemble without the VO code is legal
+    if (lean && h->vo_compact && in.vo_flag != nullptr) {
+      int32_t *list = h->vo_list ? h->vo_list + (size_t)h->vo_slot * h->dm.n : nullptr, *count = h->vo_count ? h->vo_count + h->vo_slot : nullptr;
+      if (!h->vo_list_valid || !list) {  // no EKF launch built the list for this tick (dekf_mhe_step on its own)
+        if (!h->vo_list) {
+          if (cudaMalloc((void **)&h->vo_list, (size_t)dekf_handle::kAhead * h->dm.n * sizeof(int32_t)) != cudaSuccess) return DEKF_ENOMEM;
+          if (cudaMalloc((void **)&h->vo_stat, (size_t)dekf_handle::kAhead * h->dm.n * sizeof(int32_t)) != cudaSuccess) return DEKF_ENOMEM;
+          if (cudaMalloc((void **)&h->vo_count, dekf_handle::kAhead * sizeof(int32_t)) != cudaSuccess) return DEKF_ENOMEM;
+          h->extra_bytes += (size_t)dekf_handle::kAhead * (2 * h->dm.n + 1) * sizeof(int32_t);
+        }
+        list = h->vo_list + (size_t)h->vo_slot * h->dm.n;
+        count = h->vo_count + h->vo_slot;
+        k_zero_i32<<<1, 1, 0, h->stream>>>(count);
+        k_vo_compact<<<(h->dm.n + 255) / 256, 256, 0, h->stream>>>(in.vo_flag, h->dm.n, list, count);
+        h->vo_list_valid = true;
+      }
+      ProfScope ps(h, 1);
+      const int i_lo = adm.tile0 * kBlock, i_hi = h->asm_tiles >= 0 ? (adm.tile0 + h->asm_tiles) * kBlock : h->dm.n;
+      int32_t *vstat = h->vo_stat + (size_t)h->vo_slot * h->dm.n;
+      k_vo_sync<T><<<grid_for(h->dm.n), kBlock, 0, h->stream>>>(mc, h->dm, b, in, out, T_, list, count, i_lo, i_hi, vstat);
+      k_assemble<T, Model, true><<<grid, kBlock, 0, h->stream>>>(mc, adm, b, in, out, T_, acc, h->asm_quat_copy, vstat);
+      h->launches++;
+    } else if (lean && in.vo_flag == nullptr) {
+      // a tick without any VO message: the VO synchronisation is a no-op for every instance -- the kernel without that code
+      ProfScope ps(h, 1);
+      k_assemble<T, Model, true><<<grid, kBlock, 0, h->stream>>>(mc, adm, b, in, out, T_, acc, h->asm_quat_copy, nullptr);
+    } else {
+      ProfScope ps(h, 1);
+      k_assemble<T, Model><<<grid, kBlock, 0, h->stream>>>(mc, adm, b, in, out, T_, acc, h->asm_quat_copy, nullptr);
+    }
   }
   h->launches++;
   return 0;
@@ -905,6 +984,8 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
   if (const char *e = std::getenv("DEKF_NO_TMA")) h->use_tma = std::atoi(e) == 0;
   if (const char *e = std::getenv("DEKF_NO_SPLIT")) h->no_split = std::atoi(e) != 0;
   if (const char *e = std::getenv("DEKF_SPLIT_TILES")) h->split_tiles_env = std::atoi(e);
+  if (const char *e = std::getenv("DEKF_VO_COMPACT")) h->vo_compact = std::atoi(e) != 0;
+  if (std::getenv("DEKF_EKF_SERIAL")) h->ekf_serial = true;
   if (const char *e = std::getenv("DEKF_ROLES_MAX_N")) h->roles_max = std::atoi(e);
   if (const char *e = std::getenv("DEKF_NO_ASM_SPLIT")) h->no_asm_split = std::atoi(e) != 0;
   if (const char *e = std::getenv("DEKF_SPLIT_WAYS")) h->split_ways_env = std::atoi(e);
@@ -1089,6 +1170,9 @@ int dekf_destroy(dekf_handle *h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   cudaFree(h->quat_ring);
   cudaFree(h->status_ring);
+  cudaFree(h->vo_list);
+  cudaFree(h->vo_stat);
+  cudaFree(h->vo_count);
   for (int k = 0; k < dekf_handle::kAhead; ++k) {
     if (h->ev_ekf[k]) cudaEventDestroy(h->ev_ekf[k]);
   }
@@ -1163,14 +1247,46 @@ static int ekf_launch(dekf_handle *h, const dekf_inputs *in, const dekf_outputs 
   const Inputs di = to_inputs(in);
   const Outputs dout = to_outputs(h, out);
   int32_t *st = out ? out->status : nullptr;
-  {
+  const int g = grid_for(h->dm.n);
+  int32_t *ss = status_state ? status_state : (h->f32 ? h->b32.status : h->b64.status);
+  // A tick of a large batch that carries VO poses: compact the flagged instances, replay them densely, then the ordinary
+  // update of everybody (ragged arrival: ~15 % of the instances are flagged on EVERY tick; one launch made every warp walk the
+  // replay loop).  Lock-step arrival flags all instances: the replay launch then simply covers them all.
+  const bool split = h->vo_compact && di.vo_flag != nullptr && !h->cfg.debug_taps && h->dm.n > h->fused_max;
+  h->vo_list_valid = false;
+  if (split) {
+    if (!h->vo_list) {
+      CK(cudaMalloc((void **)&h->vo_list, (size_t)dekf_handle::kAhead * h->dm.n * sizeof(int32_t)));
+      CK(cudaMalloc((void **)&h->vo_stat, (size_t)dekf_handle::kAhead * h->dm.n * sizeof(int32_t)));
+      CK(cudaMalloc((void **)&h->vo_count, dekf_handle::kAhead * sizeof(int32_t)));
+      h->extra_bytes += (size_t)dekf_handle::kAhead * (2 * h->dm.n + 1) * sizeof(int32_t);
+    }
+    int32_t *list = h->vo_list + (size_t)h->vo_slot * h->dm.n, *count = h->vo_count + h->vo_slot;
+    k_zero_i32<<<1, 1, 0, stream>>>(count);
+    k_vo_compact<<<(h->dm.n + 255) / 256, 256, 0, stream>>>(di.vo_flag, h->dm.n, list, count);
+    ProfScope ps(h, 0, stream);
+    if (h->f32) {
+      k_ekf<float, EKF_REPLAY><<<g, kBlock, 0, stream>>>(h->ec32, h->dm, h->b32, di, dout, h->ekf_k, ss, st, list, count);
+      k_ekf<float, EKF_UPDATE><<<g, kBlock, 0, stream>>>(h->ec32, h->dm, h->b32, di, dout, h->ekf_k, ss, st, list, count);
+    } else {
+      k_ekf<double, EKF_REPLAY><<<g, kBlock, 0, stream>>>(h->ec64, h->dm, h->b64, di, dout, h->ekf_k, ss, st, list, count);
+      k_ekf<double, EKF_UPDATE><<<g, kBlock, 0, stream>>>(h->ec64, h->dm, h->b64, di, dout, h->ekf_k, ss, st, list, count);
+    }
+    h->launches += 2;
+    h->vo_list_valid = true;
+  } else if (di.vo_flag == nullptr && !h->cfg.debug_taps) {
+    // no VO pose on this tick: the update half alone IS the whole tick (no replay code in the kernel: no spill frame)
     ProfScope ps(h, 0, stream);
     if (h->f32)
-      k_ekf<float><<<grid_for(h->dm.n), kBlock, 0, stream>>>(h->ec32, h->dm, h->b32, di, dout, h->ekf_k,
-                                                             status_state ? status_state : h->b32.status, st);
+      k_ekf<float, EKF_UPDATE><<<g, kBlock, 0, stream>>>(h->ec32, h->dm, h->b32, di, dout, h->ekf_k, ss, st, nullptr, nullptr);
     else
-      k_ekf<double><<<grid_for(h->dm.n), kBlock, 0, stream>>>(h->ec64, h->dm, h->b64, di, dout, h->ekf_k,
-                                                              status_state ? status_state : h->b64.status, st);
+      k_ekf<double, EKF_UPDATE><<<g, kBlock, 0, stream>>>(h->ec64, h->dm, h->b64, di, dout, h->ekf_k, ss, st, nullptr, nullptr);
+  } else {
+    ProfScope ps(h, 0, stream);
+    if (h->f32)
+      k_ekf<float><<<g, kBlock, 0, stream>>>(h->ec32, h->dm, h->b32, di, dout, h->ekf_k, ss, st, nullptr, nullptr);
+    else
+      k_ekf<double><<<g, kBlock, 0, stream>>>(h->ec64, h->dm, h->b64, di, dout, h->ekf_k, ss, st, nullptr, nullptr);
   }
   h->launches++;
   CK(cudaGetLastError());
@@ -1182,7 +1298,10 @@ int dekf_ekf_step(dekf_handle *h, const dekf_inputs *in, const dekf_outputs *out
   if (!h || !in || !in->gyro || !in->accel || !in->imu_time) return fail(h, DEKF_EINVAL, "dekf_ekf_step: null input");
   if (in->vo_flag && (!in->vo_quat || !in->vo_time_now)) return fail(h, DEKF_EINVAL, "dekf_ekf_step: vo_flag without vo_quat/vo_time_now");
   CK(cudaSetDevice(h->cfg.device));
-  return ekf_launch(h, in, out, nullptr, h->stream);
+  h->vo_slot = 0;
+  const int rc = ekf_launch(h, in, out, nullptr, h->stream);
+  h->vo_list_valid = false;  // the list belonged to this EKF tick only
+  return rc;
 }
 
 // phases: 1 = stage assembly, 2 = window solve, 3 = both (on h->stream)
@@ -1266,6 +1385,8 @@ int dekf_mhe_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_
   int rc = check_T(h, T_);
   if (rc) return rc;
   CK(cudaSetDevice(h->cfg.device));
+  h->vo_slot = 0;
+  h->vo_list_valid = false;  // stepped on its own: the assembly compacts this call's vo_flag itself
   return mhe_step_impl(h, T_, in, out, nullptr);
 }
 
@@ -1298,9 +1419,12 @@ int dekf_step(dekf_handle *h, int32_t T_, const dekf_inputs *in, const dekf_outp
   std::memset(&o_ekf, 0, sizeof(o_ekf));
   if (out) o_ekf.quat = out->quat;
   int32_t *slot = (h->f32 ? h->b32.status : h->b64.status) + (size_t)(T_ & 1) * h->dm.ns;  // tick_status(T_)
+  h->vo_slot = 0;
   rc = ekf_launch(h, &in2, &o_ekf, slot, h->stream);
   if (rc) return rc;
-  return mhe_step_impl(h, T_, &in2, out, slot);
+  rc = mhe_step_impl(h, T_, &in2, out, slot);  // same vo_flag, same stream: the assembly reuses the EKF launch's list
+  h->vo_list_valid = false;
+  return rc;
 }
 
 int dekf_synchronize(dekf_handle *h) {
@@ -1681,6 +1805,9 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     dekf_outputs oe;
     std::memset(&oe, 0, sizeof(oe));
     oe.quat = qslot;
+    h->vo_slot = slot;
+    if (h->ekf_serial && s >= 1)  // diagnosis: no EKF launch overlaps a window solve
+      for (int r = 0; r < ways && ce == cudaSuccess; ++r) ce = cudaStreamWaitEvent(h->s_ekf, h->ev_solw[r][(s - 1) % QA], 0);
     if (ce == cudaSuccess) rc = ekf_launch(h, &is, &oe, sslot, h->s_ekf);
     if (rc) break;
     if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_ekf[slot], h->s_ekf);
@@ -1718,6 +1845,7 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
       for (int r = (asm_split ? ra : 0); r < (asm_split ? ra + 1 : ways) && ce == cudaSuccess; ++r)
         ce = cudaEventRecord(h->ev_asmw[r][slot], sa);
     }
+    h->vo_list_valid = false;
     if (rc) break;
     if (ce != cudaSuccess) {
       rc = fail(h, DEKF_ECUDA, "dekf_run pipeline", ce);

@@ -359,7 +359,16 @@ DEKF_HD int ring_upper_bound(const double *times, int n, int i, int first, int s
 
 // One EKF timer tick for instance i at discrete time k (orien_ekf.cpp:77-89 + get_measurement
 // :156-212).  Returns status bits.
-template <typename T>
+// PART selects which half of the tick runs:
+//   EKF_ALL     the whole tick
+//   EKF_REPLAY  instance i HAS a VO pose: history push, rewind, VO correction, replay; the state goes back to ekf_q / ekf_P
+//   EKF_UPDATE  history push unless the instance has a VO pose (EKF_REPLAY pushed it), then this tick's predict / correct.
+//               On a tick without any VO pose (in.vo_flag == nullptr) this IS the whole tick, compiled without the replay code
+//               (no spill frame): what dekf_run launches for large batches on such ticks.
+// REPLAY + UPDATE perform the operations of EKF_ALL on the same operands (the state makes one round trip through memory); they
+// serve the opt-in compaction of ragged VO arrival (DEKF_VO_COMPACT=1).
+enum { EKF_ALL = 0, EKF_REPLAY = 1, EKF_UPDATE = 2 };
+template <typename T, int PART = EKF_ALL>
 DEKF_HD int ekf_tick(const EkfConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in, const Outputs &out,
                      int k, int i) {
   const int n = dm.n, ns = dm.ns, D = dm.D;
@@ -376,8 +385,9 @@ DEKF_HD int ekf_tick(const EkfConst<T> &c, const Dims &dm, const Buffers<T> &b, 
     a[f] = (T)in.accel[(size_t)f * n + i];
   }
   const double t_imu = in.imu_time[i];
+  const bool has_vo = in.vo_flag != nullptr && in.vo_flag[i];
   // push (state BEFORE this tick's update), :158-163
-  {
+  if (PART != EKF_UPDATE || !has_vo) {
     T *h = b.ekf_hist + (size_t)(k % D) * EKF_HIST_FIELDS * ns + i;
 #pragma unroll
     for (int f = 0; f < 3; ++f) {
@@ -391,7 +401,7 @@ DEKF_HD int ekf_tick(const EkfConst<T> &c, const Dims &dm, const Buffers<T> &b, 
     b.ekf_hist_time[(size_t)(k % D) * ns + i] = t_imu;
   }
   int dbg_cur = -2, dbg_idx = -2, dbg_nr = -2;
-  if (in.vo_flag != nullptr && in.vo_flag[i]) {
+  if (PART != EKF_UPDATE && has_vo) {
     const double vt = in.vo_time_now[i];
     T qv[4];
 #pragma unroll
@@ -431,13 +441,15 @@ DEKF_HD int ekf_tick(const EkfConst<T> &c, const Dims &dm, const Buffers<T> &b, 
       }
     }
   }
-  ekf_predict(c, s, w);  // :82
-  ekf_correct(c, s, a);  // :83
+  if (PART != EKF_REPLAY) {
+    ekf_predict(c, s, w);  // :82
+    ekf_correct(c, s, a);  // :83
+  }
 #pragma unroll
   for (int f = 0; f < 4; ++f) b.ekf_q[(size_t)f * ns + i] = s.q[f];
 #pragma unroll
   for (int f = 0; f < 16; ++f) b.ekf_P[(size_t)f * ns + i] = s.P[f];
-  if (out.quat != nullptr) {
+  if (PART != EKF_REPLAY && out.quat != nullptr) {
 #pragma unroll
     for (int f = 0; f < 4; ++f) out.quat[(size_t)f * n + i] = (double)s.q[f];
   }
@@ -736,9 +748,12 @@ DEKF_HD void mhe_push_sample(const MheConst<T> &c, const Dims &dm, const Buffers
 
 // HOIST: contact detection and the legs' joint samples are requested ahead of their use (k_assemble, large batches: 99.4 -> 98.6 us
 // per tick at 65,536 instances); the single-warp fused tick is faster without it (53.1 vs 56.7 us), so k_fused passes false.
-template <typename T, typename Model, bool HOIST = true>
+// VOSPLIT: the VO synchronisation of the instances that carry a message ran as its own launch over the compacted list of those
+// instances (k_vo_sync; it left its status bits in the vo_stat scratch): here a flagged instance only picks those bits up, an
+// unflagged one marks "no re-sweep" -- exactly what mhe_vo_sync does for it at T >= 2.
+template <typename T, typename Model, bool HOIST = true, bool VOSPLIT = false>
 DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> &b, const Inputs &in,
-                         const Outputs &out, int Tk, int i, const double qd[4]) {
+                         const Outputs &out, int Tk, int i, const double qd[4], const int32_t *vo_stat = nullptr) {
   constexpr int NL = Model::NLEG, NJ = Model::NJ;
   const int n = dm.n, ns = dm.ns, NW = dm.NW;
   int status = 0;
@@ -761,7 +776,14 @@ DEKF_HD int mhe_assemble(const MheConst<T> &c, const Dims &dm, const Buffers<T> 
     }
   }
 
-  status |= mhe_vo_sync<T>(c, dm, b, in, out, Tk, i, qd);
+  if constexpr (VOSPLIT) {
+    if (in.vo_flag != nullptr && in.vo_flag[i])
+      status |= vo_stat[i];
+    else if (b.resweep != nullptr)
+      tick_resweep(dm, b, Tk, i) = 0x7fffffff;
+  } else {
+    status |= mhe_vo_sync<T>(c, dm, b, in, out, Tk, i, qd);
+  }
 
   // ---- current sample (:867-879)
   const M3<T> R = quat_to_rot<T>((T)qd[0], (T)qd[1], (T)qd[2], (T)qd[3]);

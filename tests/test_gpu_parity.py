@@ -623,6 +623,36 @@ def test_role_kernel_equals_fused_kernel(est_mod, monkeypatch, robot, precision,
     assert (a["status"] & 16).any()  # VO bounds were inserted
 
 
+@pytest.mark.parametrize("ragged,window_solve,compact", [(False, 0, "0"), (True, 0, "0"), (True, 1, "0"), (True, 0, "1")])
+def test_dekf_run_is_repeatable_at_the_benchmark_size(est_mod, monkeypatch, ragged, window_solve, compact):
+    """Stress: the multi-stream pipeline of dekf_run (EKF ticks ahead, assembly ahead, split window solve) must give the same bits
+    on every run -- 65,536 instances x 100 ticks, four runs, lock-step and ragged VO arrival, both solve modes, and the opt-in
+    compaction of the VO-carrying instances (DEKF_VO_COMPACT=1) against the default path.  Any ordering hole between the streams
+    shows up here as a run that differs (DESIGN.md section 10 has the one we chased)."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S, F = 65536, 100, 30
+    st = synth.make_stream(n, S, device="cuda", device_rng=True, vo_jitter=ragged)
+    vo = [bool(st["vo_flag"][s].any()) for s in range(S)]
+    cut = {k: v for k, v in st.items() if torch.is_tensor(v) and v.shape[0] == S}
+    ref = None
+    for rep in range(4):
+        monkeypatch.setenv("DEKF_VO_COMPACT", compact if rep else "0")
+        est = E.BatchedEstimator(E.robot_params("go1", ekf_rate=200, window_solve=window_solve), n)
+        o = dict(x=torch.empty(S, 9, n, dtype=torch.float64, device="cuda"), quat=torch.empty(S, 4, n, dtype=torch.float64, device="cuda"),
+                 status=torch.empty(S, n, dtype=torch.int32, device="cuda"))
+        est.run(0, F, {k: v[:F] for k, v in cut.items()}, vo[:F], out={k: v[:F] for k, v in o.items()}, out_per_step=True)
+        est.run(F, S - F, {k: v[F:] for k, v in cut.items()}, vo[F:], out={k: v[F:] for k, v in o.items()}, out_per_step=True)
+        torch.cuda.synchronize()
+        est.close()
+        if ref is None:
+            ref = o
+            continue
+        for key in ("quat", "x", "status"):
+            bad = (o[key][1:] != ref[key][1:]).flatten(1).any(dim=1).nonzero().flatten().tolist()
+            assert not bad, f"run {rep}: {key} differs from run 0 at ticks {[b + 1 for b in bad][:8]}"
+
+
 def test_foot_state_model_vs_oracle(est_mod, oracle):
     """leg_odom_type 1: 21-state model, information-form sweep (csrc/footstate.cuh).
     Exact reference = the oracle solving the whole history in one banded system (no marginalisation); the literal

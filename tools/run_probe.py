@@ -1,5 +1,5 @@
 """ms per tick of dekf_run at the benchmark size (65,536 Go1 instances, N=20, per-tick outputs), for tuning the tick pipeline.
-Environment knobs (DEKF_PRIO, DEKF_NO_SPLIT, ...) are read by dekf_create.  usage: run_probe.py [window_solve] [K] [n]"""
+Environment knobs (DEKF_PRIO, DEKF_NO_SPLIT, ...) are read by dekf_create.  usage: run_probe.py [window_solve] [K] [n] [ragged]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,10 +8,11 @@ build.build()
 ws = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 n = int(sys.argv[3]) if len(sys.argv) > 3 else 65536
+ragged = len(sys.argv) > 4 and sys.argv[4] == "ragged"  # per-instance camera phase: every tick carries VO messages
 N, FILL = 20, 34
 S = FILL + K
 dev = torch.device("cuda", 0)
-st = synth.make_stream(n, S, device=dev, device_rng=True)
+st = synth.make_stream(n, S, device=dev, device_rng=True, vo_jitter=ragged)
 vo = [bool(st["vo_flag"][s].any()) for s in range(S)]
 cut = {k: v for k, v in st.items() if torch.is_tensor(v) and v.shape[0] == S}
 best = None
@@ -33,4 +34,4 @@ for rep in range(3):
     est.close()
     del outs
 knobs = {k: v for k, v in os.environ.items() if k.startswith("DEKF_")}
-print(f"run_probe ws={ws} n={n} K={K} knobs={knobs}: {best*1e3:.1f} us/tick  {n/best/1e3:.4g} instance-steps/s  checksum {chk:.6f}")
+print(f"run_probe ws={ws} n={n} K={K} {'ragged ' if ragged else ''}knobs={knobs}: {best*1e3:.1f} us/tick  {n/best/1e3:.4g} instance-steps/s  checksum {chk:.6f}")
