@@ -755,6 +755,20 @@ def main():
         if plain:
             roof = report(mode, main)
             roof["measured_copy_gbs"] = peaks["copy_gbs"]
+            # the whole step against its roofline (BASELINE north_star: "the slower of bytes-per-step over HBM bandwidth and
+            # flops-per-step over FP64/FP32 peak"): algorithmic bytes / flops of ALL kernels of a tick over the timed ms_per_step
+            # of the pipelined region -- in dekf_run the launches of consecutive ticks overlap, so this, not the duration of one
+            # launch timed alone (`kernel_ms` above: 1.73 waves at 65,536 instances), is what the timed region achieves
+            ak = roof.get("all_kernels", {})
+            sb = sum(v["bytes_per_instance"] * v["launches"] for v in ak.values()) / max(1, max(v["launches"] for v in ak.values())) if ak else 0.0
+            sf = sum(v["flops_per_instance"] * v["launches"] for v in ak.values()) / max(1, max(v["launches"] for v in ak.values())) if ak else 0.0
+            step_s = ms_value / K * 1e-3
+            t_h, t_f = sb * n / (hbm_peak * 1e9), (sf * n / (fma_peak * 1e12) if fma_peak else 0.0)
+            roof["step"] = {"bytes_per_instance_step": sb, "flops_per_instance_step": sf, "ms_per_step": ms_value / K,
+                            "bound": "hbm" if t_h >= t_f else ("fp64" if args.precision == "fp64" else "fp32"),
+                            "hbm_gbs": sb * n / step_s / 1e9, "hbm_frac": sb * n / step_s / 1e9 / hbm_peak,
+                            "tflops": sf * n / step_s / 1e12, "fma_frac": (sf * n / step_s / 1e12 / fma_peak) if fma_peak else None,
+                            "frac": max(t_h, t_f) / step_s}
             line["roofline"] = roof
             line["latency_batch1"] = lat
             line["ekf_only"] = {"value": n_total / (roof["all_kernels"]["ekf"]["ms"] * 1e-3) if "ekf" in roof.get("all_kernels", {}) else None,
@@ -772,7 +786,9 @@ def main():
             line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
             # the same protocol as the reference arm (bench.py --impl reference), bounded to ~cpu-seconds of timed work
-            v, t, nn, ipt, cores = cpu_reference_run(N, 20, 3, min_seconds=min(args.cpu_seconds, 8.0), max_seconds=4 * args.cpu_seconds, mode="admm")
+            # (same sample size and duration as `--impl reference --steps 20 --warmup 3`: 16 pinned threads run at a higher clock in a
+            # 6 s region than in a 13 s one -- 7.6e3 vs 5.4e3 measured on one box -- so the two legs must not differ in length)
+            v, t, nn, ipt, cores = cpu_reference_run(N, 20, 3, min_seconds=5.0, mode="admm", ipt_min=args.ref_instances_per_thread)
             vd, td, _, _, _ = cpu_reference_run(N, 20, 3, min_seconds=2.0, max_seconds=20.0, mode="direct", ipt_min=8)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": cores, "kind": "port",
