@@ -444,7 +444,16 @@ def main():
     torch.cuda.set_device(local_rank)
     binding = bind_rank_to_host(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL (the contract's backend) carries only the barrier and the max-over-ranks of the device time; DEKF_BENCH_BACKEND=gloo
+        # exists to tell a slow rank from an effect of the communicator itself (profiles/r02b_multigpu.md)
+        # NVLS (NVLink SHARP multicast, which NCCL sets up from 4 GPUs on) is switched off for this communicator: with it three of
+        # four ranks ran the SAME kernels 10 % slower (0.1075 vs 0.0978 ms per tick; 0.098 with gloo; independent processes 0.0975),
+        # and an 8-byte all-reduce gains nothing from in-switch reduction.  NCCL_NVLS_ENABLE in the environment overrides.
+        os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
+        if os.environ.get("DEKF_BENCH_BACKEND", "nccl") == "gloo":
+            dist.init_process_group("gloo")
+        else:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W, K = max(args.warmup, 3), args.steps
     Ke = max(1, min(args.e2e_steps, K))
     n = args.instances  # per GPU (weak scaling)
@@ -495,8 +504,13 @@ def main():
         est.run(t0, kk, timed, vo[t0:t0 + kk], out=outs, out_per_step=True)
         ev1.record()
         barrier()
-        ms = max_over_ranks(ev0.elapsed_time(ev1))
-        res = dict(ms=ms, launches=est.launch_count() - l0, checksum=float(outs["x"][:, 3].double().sum().item()),
+        ms_rank = ev0.elapsed_time(ev1)
+        ms = max_over_ranks(ms_rank)
+        per_rank = [ms_rank]
+        if world > 1:
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, ms_rank)
+        res = dict(ms=ms, ms_per_rank=per_rank, launches=est.launch_count() - l0, checksum=float(outs["x"][:, 3].double().sum().item()),
                    finite=bool(torch.isfinite(outs["x"]).all().item()), bytes=est.device_bytes())
         if over.get("v_box_enable"):
             it, na = est.qp_info()
@@ -740,7 +754,8 @@ def main():
         cfg = shared_config(n, world, N, args.precision, robot, args.box, args.leg_odom_type, args.est_type, mode)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_value / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_value / K, "ms_per_step_per_rank": [m / K for m in main["ms_per_rank"]], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
             "dtype": "f64" if args.precision == "fp64" else "f32", "data": "synthetic",
             "config": cfg,
             "timed_region": {"api": "dekf_run, inputs resident in HBM", "outputs": "every tick writes quat, x, v_body, contact, status to "

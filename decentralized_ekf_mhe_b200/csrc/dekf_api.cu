@@ -1746,9 +1746,12 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     if (h->prio_mode == 2) p_ekf = hi, p_asm = hi, p_sol = lo;             // front kernels first
     CK(cudaStreamCreateWithPriority(&h->s_ekf, cudaStreamNonBlocking, p_ekf));
     CK(cudaStreamCreateWithPriority(&h->s_asm, cudaStreamNonBlocking, p_asm));
-    for (int r = 0; r < MW; ++r) CK(cudaStreamCreateWithPriority(&h->s_sol[r], cudaStreamNonBlocking, p_sol));
+    // only the streams the tile ranges need (a process has a handful of hardware queues: streams beyond them share one and
+    // serialise behind each other)
+    const int nsol = h->split_ways_env >= 2 ? (h->split_ways_env < MW ? h->split_ways_env : MW) : 2;
+    for (int r = 0; r < nsol; ++r) CK(cudaStreamCreateWithPriority(&h->s_sol[r], cudaStreamNonBlocking, p_sol));
     h->s_asmw[0] = h->s_asm;
-    for (int r = 1; r < MW; ++r) CK(cudaStreamCreateWithPriority(&h->s_asmw[r], cudaStreamNonBlocking, p_asm));
+    for (int r = 1; r < nsol; ++r) CK(cudaStreamCreateWithPriority(&h->s_asmw[r], cudaStreamNonBlocking, p_asm));
     CK(cudaMalloc((void **)&h->quat_ring, (size_t)QA * 4 * n * sizeof(double)));
     CK(cudaMalloc((void **)&h->status_ring, (size_t)QA * n * sizeof(int32_t)));
     h->extra_bytes += (size_t)QA * n * (4 * sizeof(double) + sizeof(int32_t));
@@ -1891,8 +1894,10 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     if (je == cudaSuccess) je = cudaStreamWaitEvent(user, h->ev_join, 0);
   }
   if (je != cudaSuccess || rc != DEKF_OK) {
-    for (int r = 0; r < MW; ++r) cudaStreamSynchronize(h->s_sol[r]);
-    for (int r = 0; r < MW; ++r) cudaStreamSynchronize(h->s_asmw[r]);
+    for (int r = 0; r < MW; ++r)
+      if (h->s_sol[r]) cudaStreamSynchronize(h->s_sol[r]);
+    for (int r = 0; r < MW; ++r)
+      if (h->s_asmw[r]) cudaStreamSynchronize(h->s_asmw[r]);
     cudaStreamSynchronize(h->s_ekf);
     cudaStreamSynchronize(user);
     if (rc == DEKF_OK) rc = fail(h, DEKF_ECUDA, "dekf_run: joining the internal streams", je);

@@ -24,8 +24,11 @@ for rep in range(3):
             "status": torch.empty(K, n, dtype=torch.int32, device=dev)}
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    import time
     e0.record()
+    th = time.perf_counter()
     est.run(FILL, K, {k: v[FILL:] for k, v in cut.items()}, vo[FILL:], out=outs, out_per_step=True)
+    th = time.perf_counter() - th  # host time to QUEUE the K ticks (the call returns before the GPU is done)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / K
@@ -34,4 +37,5 @@ for rep in range(3):
     est.close()
     del outs
 knobs = {k: v for k, v in os.environ.items() if k.startswith("DEKF_")}
+print(f"host enqueue {1e6 * th / K:.1f} us/tick; ", end="")
 print(f"run_probe ws={ws} n={n} K={K} {'ragged ' if ragged else ''}knobs={knobs}: {best*1e3:.1f} us/tick  {n/best/1e3:.4g} instance-steps/s  checksum {chk:.6f}")
