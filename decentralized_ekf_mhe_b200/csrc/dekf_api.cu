@@ -877,6 +877,25 @@ int do_fused(dekf_handle *h, const EkfConst<T> &ec, const MheConst<T> &mc, const
   return DEKF_EINVAL;
 }
 
+// DIAGNOSIS ONLY (DEKF_DBG_CARVEOUT=1): every kernel of the large-batch tick asks for the maximum shared-memory
+// carve-out, i.e. the smallest L1 -- the setting under which the transient deviation of section 10 shows up within a few ticks.
+template <typename K>
+static void prefer_max_shared(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+}
+template <typename T>
+static void prefer_max_shared_all() {
+  prefer_max_shared(k_ekf<T, EKF_ALL>);
+  prefer_max_shared(k_ekf<T, EKF_REPLAY>);
+  prefer_max_shared(k_ekf<T, EKF_UPDATE>);
+  prefer_max_shared(k_vo_sync<T>);
+  prefer_max_shared(k_assemble<T, Go1Model<T>, false>);
+  prefer_max_shared(k_assemble<T, Go1Model<T>, true>);
+  prefer_max_shared(k_solve_tma<T>);
+  prefer_max_shared(k_solve_incr_tma<T>);
+  prefer_max_shared(k_solve_incr<T>);
+  prefer_max_shared(k_solve<T>);
+}
 int check_T(dekf_handle *h, int32_t T_) {
   if (T_ != h->next_T) return fail(h, DEKF_ESTATE, "T must advance by one per call starting at 0 (initialize) -- call dekf_reset to restart");
   return DEKF_OK;
@@ -986,6 +1005,12 @@ int dekf_create(const dekf_config *cfg, dekf_handle **out) {
   if (const char *e = std::getenv("DEKF_SPLIT_TILES")) h->split_tiles_env = std::atoi(e);
   if (const char *e = std::getenv("DEKF_VO_COMPACT")) h->vo_compact = std::atoi(e) != 0;
   if (std::getenv("DEKF_EKF_SERIAL")) h->ekf_serial = true;
+  if (std::getenv("DEKF_DBG_CARVEOUT")) {
+    prefer_max_shared_all<double>();
+    prefer_max_shared_all<float>();
+    prefer_max_shared(k_vo_compact);
+    prefer_max_shared(k_zero_i32);
+  }
   if (const char *e = std::getenv("DEKF_ROLES_MAX_N")) h->roles_max = std::atoi(e);
   if (const char *e = std::getenv("DEKF_NO_ASM_SPLIT")) h->no_asm_split = std::atoi(e) != 0;
   if (const char *e = std::getenv("DEKF_SPLIT_WAYS")) h->split_ways_env = std::atoi(e);
