@@ -22,11 +22,18 @@ constexpr int kTile = 128;
 // Ring depth, CTAs per SM and pipeline granularity per element type (measured, profiles/r02_tune_solve.md).  fp64: the sweep
 // needs ~250 registers, i.e. 2 CTAs/SM; 3 stage tiles of 25.6 KB each per CTA (2: 95 us, 3: 89 us, 4: 91 us per launch).
 // fp32: 128 registers and 4 CTAs/SM without spills.  One pipeline per CTA or one per warp makes no difference (89.2 / 89.6 us).
+// (the DEKF_SOLVE_* macros exist for the diagnosis builds of DESIGN.md section 10.1; the product build defines none of them)
+#ifndef DEKF_SOLVE_STAGES
+#define DEKF_SOLVE_STAGES 3
+#endif
+#ifndef DEKF_SOLVE_PW
+#define DEKF_SOLVE_PW false
+#endif
 template <typename T>
 struct SolveCfg {
-  static constexpr int kStages = 3, kMinB = 1;
+  static constexpr int kStages = DEKF_SOLVE_STAGES, kMinB = 1;
   static constexpr bool kXS = false;
-  static constexpr bool kPerWarp = false;
+  static constexpr bool kPerWarp = DEKF_SOLVE_PW;
 };
 template <>
 struct SolveCfg<float> {
@@ -91,6 +98,16 @@ struct SmemStageSource {
   }
   __device__ __forceinline__ void acquire(int j) const { mbar_wait(&full[j % STAGES], (uint32_t)((j / STAGES) & 1)); }
   __device__ __forceinline__ void release(int j) const {
+#if defined(DEKF_SOLVE_SYNC_EVERY_STAGE)
+    __syncthreads();  // diagnosis: every thread of the CTA has finished reading the stage before anybody goes on
+#endif
+#if !defined(DEKF_SOLVE_NO_PROXY_FENCE)
+    // This thread's LDS of the stage record (generic proxy) must be performed before the refill of the buffer -- a TMA write, i.e. the
+    // ASYNC proxy, issued by ANOTHER warp once all arrivals are in.  mbarrier.arrive alone does not order the two proxies: with the
+    // load / store queues of the SM backed up by a co-resident kernel, a warp's loads were still pending when the refill landed
+    // (a transient wrong stage record for one warp, only under ragged VO arrival).
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#endif
     mbar_arrive(&empty[j % STAGES]);
     // the elected thread refills the buffer of the PREVIOUS stage (everybody has long released it) with the
     // stage STAGES-1 ahead of the current one

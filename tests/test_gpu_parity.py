@@ -623,12 +623,13 @@ def test_role_kernel_equals_fused_kernel(est_mod, monkeypatch, robot, precision,
     assert (a["status"] & 16).any()  # VO bounds were inserted
 
 
-@pytest.mark.parametrize("ragged,window_solve,compact", [(False, 0, "0"), (True, 0, "0"), (True, 1, "0"), (True, 0, "1")])
+@pytest.mark.parametrize("ragged,window_solve,compact", [(False, 0, "1"), (True, 0, "1"), (True, 1, "1"), (True, 1, "0")])
 def test_dekf_run_is_repeatable_at_the_benchmark_size(est_mod, monkeypatch, ragged, window_solve, compact):
     """Stress: the multi-stream pipeline of dekf_run (EKF ticks ahead, assembly ahead, split window solve) must give the same bits
-    on every run -- 65,536 instances x 100 ticks, four runs, lock-step and ragged VO arrival, both solve modes, and the opt-in
-    compaction of the VO-carrying instances (DEKF_VO_COMPACT=1) against the default path.  Any ordering hole between the streams
-    shows up here as a run that differs (DESIGN.md section 10 has the one we chased)."""
+    on every run -- 65,536 instances x 100 ticks, four runs, lock-step and ragged VO arrival, both solve modes; run 0 is the
+    one-launch form of the EKF / VO synchronisation (DEKF_VO_COMPACT=0), runs 1-3 the compacted form (or the one-launch form again).
+    Any ordering hole between the streams or inside the TMA ring shows up here as a run that differs: DESIGN.md section 10.1 has
+    the one this test was written for (a missing proxy fence; it needed ragged arrival and a busy SM to show)."""
     from decentralized_ekf_mhe_b200 import synth
     E = est_mod
     n, S, F = 65536, 100, 30
