@@ -253,6 +253,39 @@ def test_dekf_run_pipeline_equals_tick_by_tick(est_mod, precision, window_solve,
         assert torch.equal(a[k][1:], b[k][1:]), k
 
 
+@pytest.mark.parametrize("env", [{"DEKF_NO_SPLIT": "1"}, {"DEKF_SPLIT_TILES": "201"}, {"DEKF_SPLIT_WAYS": "3"}, {"DEKF_PRIO": "1"},
+                                 {"DEKF_VO_COMPACT": "0", "DEKF_NO_ASM_SPLIT": "1"}, {"DEKF_PRIO": "2", "DEKF_SPLIT_WAYS": "4"}],
+                         ids=["no-split", "odd-split-point", "three-ranges", "solve-first-priorities", "one-launch-vo-ticks", "four-ranges-front-first"])
+def test_dekf_run_pipeline_knobs_do_not_change_a_bit(est_mod, monkeypatch, env):
+    """Every way dekf_run can cut and order a tick (tile ranges of the re-sweep, split point, stream priorities, per-range assembly
+    on VO ticks, compaction of the VO-carrying instances) must give the bits of the default configuration: 65,536 instances,
+    ragged VO arrival, full re-sweep, calls of 31 ticks (a split that spans several dekf_run calls)."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S, CH = 65536, 62, 31
+    st = {k: v.contiguous() for k, v in synth.make_stream(n, S, vo_jitter=True, device="cuda", device_rng=True).items()}
+    vo = [bool(st["vo_flag"][s].any()) for s in range(S)]
+    res = []
+    for knobs in ({}, env):
+        for k in ("DEKF_NO_SPLIT", "DEKF_SPLIT_TILES", "DEKF_SPLIT_WAYS", "DEKF_PRIO", "DEKF_VO_COMPACT", "DEKF_NO_ASM_SPLIT"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in knobs.items():
+            monkeypatch.setenv(k, v)
+        est = E.BatchedEstimator(E.robot_params("go1", ekf_rate=200, window_solve=0), n)
+        o = {"quat": torch.zeros(S, 4, n, dtype=torch.float64, device="cuda"), "x": torch.zeros(S, 9, n, dtype=torch.float64, device="cuda"),
+             "v_body": torch.zeros(S, 3, n, dtype=torch.float64, device="cuda"), "status": torch.zeros(S, n, dtype=torch.int32, device="cuda")}
+        for s0 in range(0, S, CH):
+            est.run(s0, CH, {k: v[s0:s0 + CH] for k, v in st.items()}, vo[s0:s0 + CH], out={k: v[s0:s0 + CH] for k, v in o.items()},
+                    out_per_step=True)
+        torch.cuda.synchronize()
+        est.close()
+        res.append(o)
+    for k in ("quat", "status"):
+        assert torch.equal(res[0][k], res[1][k]), k
+    for k in ("x", "v_body"):
+        assert torch.equal(res[0][k][1:], res[1][k][1:]), k
+
+
 def test_run_host_equals_device_run_at_benchmark_size(est_mod):
     """dekf_run_host (H2D of chunk c+1 | kernels of chunk c | D2H of chunk c-1 over two staging sets) against dekf_run on
     device-resident streams at the benchmark size: every per-tick result identical bit for bit (staging-set reuse hazards)."""
