@@ -1752,13 +1752,12 @@ int dekf_run(dekf_handle *h, int32_t T0, int32_t S, const dekf_inputs *in, const
     }
     return DEKF_OK;
   }
-  // Large batches: three streams.  The orientation EKF does not depend on the MHE, so its ticks run ahead (up to kAhead
-  // ticks) on a LOW-priority stream and hand each tick's quaternion / status word over through a ring.  The stage assembly
-  // of tick s+1 does not depend on the window solve of tick s either (per-tick scratch words are double-buffered by tick
-  // parity, the stage ring has one slot more than the window), unless tick s+1 inserts VO bounds into stages the solve
-  // of tick s is reading: it runs one tick ahead on a MEDIUM-priority stream and is serialised behind the solve only on
-  // ticks that carry VO messages.  The window solves run on a HIGH-priority stream: the block scheduler dispatches
-  // EKF / assembly CTAs into the SMs the solve kernel leaves idle (1.73 waves at 65,536 instances).
+  // Large batches: several streams.  The orientation EKF does not depend on the MHE, so its ticks run ahead (up to kAhead
+  // ticks) on their own stream and hand each tick's quaternion / status word over through a ring.  The stage assembly of tick
+  // s+1 does not depend on the window solve of tick s either (per-tick scratch words are double-buffered by tick parity, the
+  // stage ring has one slot more than the window), unless tick s+1 inserts VO bounds into stages the solve of tick s is
+  // reading: it runs one tick ahead on a second stream and is serialised behind the solve only on ticks that carry VO
+  // messages.  The window solves run on one stream per tile range.  All streams have the SAME priority.
   constexpr int QA = dekf_handle::kAhead;
   int rc = check_T(h, T0);
   if (rc) return rc;
