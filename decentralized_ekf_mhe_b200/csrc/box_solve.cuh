@@ -24,7 +24,7 @@
 
 namespace dekf {
 
-enum { BOX_FAC = 135 };  // per stage: L (45, packed lower) + F (81) + y/x (9)
+enum { BOX_FAC = 144 };  // per stage: L (45, packed lower) + F (81) + y/x (9) + the feasible iterate of the finite method (9)
 
 struct BoxConst {
   int enable;
@@ -41,6 +41,9 @@ struct BoxConst {
   // state (0..2 p_s, 3..5 v_s, 6..8 accel bias).  general != 0: a component outside v_s is bounded -> box_solve<T, true>.
   int mask9, general;
   double lo9[9], hi9[9];
+  // general linear rows (dekf_add_state_rows): the solve runs in y = W x, where rows 0 .. nrows-1 are the components mask9 bounds;
+  // BoxBuffers::V holds W^-1.  0: none.
+  int nrows;
 };
 
 struct BoxBuffers {
@@ -49,6 +52,7 @@ struct BoxBuffers {
   int32_t *iters;    // [ns] factorisations of the last solve
   int32_t *nactive;  // [ns] active bounds of the last solve
   uint32_t *act32;   // [NW][ns]  general bounds only: bits 0-8 lower bound active on component a, bits 9-17 upper bound
+  const double *V;   // [81] W^-1 of the row basis (general linear rows only, else nullptr)
 };
 
 // Active-set encodings.  GEN = false: the velocity box (uint8 masks, components 3..5 -- the layout k_box_team shares);
@@ -222,6 +226,53 @@ DEKF_HD int box_prior_info(const double *Pa /*81*/, const double *xa /*9*/, doub
   return status;
 }
 
+// Change of basis x = V y of the block system: A <- V' A V (9x9 row-major, in place), r <- V' r.
+DEKF_HD void box_congruence(const double *V, double *A) {
+  double t[81];
+  for (int a = 0; a < 9; ++a)
+    for (int b = 0; b < 9; ++b) {
+      double v = 0.0;
+      for (int k = 0; k < 9; ++k) v += V[k * 9 + a] * A[k * 9 + b];
+      t[a * 9 + b] = v;
+    }
+  for (int a = 0; a < 9; ++a)
+    for (int b = 0; b < 9; ++b) {
+      double v = 0.0;
+      for (int k = 0; k < 9; ++k) v += t[a * 9 + k] * V[k * 9 + b];
+      A[a * 9 + b] = v;
+    }
+}
+DEKF_HD void box_tvec(const double *V, double *r) {
+  double t[9];
+  for (int a = 0; a < 9; ++a) {
+    double v = 0.0;
+    for (int k = 0; k < 9; ++k) v += V[k * 9 + a] * r[k];
+    t[a] = v;
+  }
+  for (int a = 0; a < 9; ++a) r[a] = t[a];
+}
+// One window state's contribution to the block system in the row basis (general linear rows): Ds = V' (Lam on the v block + A'QA) V,
+// rs = V' (eta on v + r_j), and E, Dn, rn transformed alike.  `more`: there is a state j+1.
+DEKF_HD void box_stage_rows(const BoxConst &bc, const BoxStage &s, const double *V, bool more, double *Ds, double *rs, double *E,
+                            double *Dn, double *rn) {
+  for (int f = 0; f < 81; ++f) Ds[f] = 0.0;
+  for (int f = 0; f < 9; ++f) rs[f] = 0.0;
+  if (more) {
+    double rj[9];
+    box_dyn_blocks(bc, s, Ds, E, Dn, rj, rn);
+    for (int f = 0; f < 9; ++f) rs[f] = rj[f];
+    box_congruence(V, E);
+    box_congruence(V, Dn);
+    box_tvec(V, rn);
+  }
+  for (int a = 0; a < 3; ++a) {
+    for (int c = 0; c < 3; ++c) Ds[(3 + a) * 9 + 3 + c] += s.Lam[S3<double>::idx(a, c)];
+    rs[3 + a] += s.eta[a];
+  }
+  box_congruence(V, Ds);
+  box_tvec(V, rs);
+}
+
 // Constrained solve over the window states k0 .. Tk (K = Tk - k0 + 1 <= N) with the Gaussian prior
 // (Pa, xa) on x_k0.  Returns status bits; writes x_T to xT.
 template <typename T, bool GEN = false>
@@ -235,10 +286,25 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
   // prior in information form: M = Pa^-1, m = M xa
   double M[81], mv[9];
   status |= box_prior_info(Pa, xa, M, mv);
+  const bool rows = GEN && bc.nrows > 0;  // general linear rows: everything below happens in y = W x
+  double Vm[81];
+  if (rows) {
+    for (int f = 0; f < 81; ++f) Vm[f] = bb.V[f];
+    double Ms[81];
+    for (int f = 0; f < 81; ++f) Ms[f] = 0.5 * (M[f] + M[(f % 9) * 9 + f / 9]);
+    box_congruence(Vm, Ms);
+    for (int f = 0; f < 81; ++f) M[f] = Ms[f];
+    box_tvec(Vm, mv);
+  }
   // warm start: masks of the previous tick stay attached to their stage (ring slot), the new state starts free
   BS::store(bb, (size_t)(Tk % dm.NW) * ns + i, 0);
   int iters = 0, nact = 0;
   bool converged = false;
+  // general bounds: 0 = plain primal-dual rule; after kSafeIt iterations the finite primal active-set method takes over:
+  // 1 = bounds are only added until the iterate is feasible, 2 = at a feasible equality-constrained minimiser: drop the bound with
+  // the most negative multiplier (or stop), 3 = move from the feasible iterate xc towards the new minimiser, stopping at (and
+  // adding) the first bound the segment crosses.  Monotone in the cost, finite on a strictly convex QP.
+  int phase = 0;
   for (int it = 0; it < bc.max_iter && !converged; ++it) {
     iters = it + 1;
     // ---- forward: assemble, apply the active set, block Cholesky
@@ -255,16 +321,25 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
       double D[81], E[81], r[9], Dn[81], rn[9];
       for (int f = 0; f < 81; ++f) D[f] = Dc[f];
       for (int f = 0; f < 9; ++f) r[f] = rc[f];
-      // leg odometry rows: 1/2 v' Lam v - eta' v
-      for (int a = 0; a < 3; ++a) {
-        for (int c = 0; c < 3; ++c) D[(3 + a) * 9 + 3 + c] += s.Lam[S3<double>::idx(a, c)];
-        r[3 + a] += s.eta[a];
+      if (rows) {
+        double Ds[81], rs[9];
+        box_stage_rows(bc, s, Vm, j + 1 < K, Ds, rs, E, Dn, rn);
+        for (int f = 0; f < 81; ++f) D[f] += Ds[f];
+        for (int f = 0; f < 9; ++f) r[f] += rs[f];
+      } else {
+        // leg odometry rows: 1/2 v' Lam v - eta' v
+        for (int a = 0; a < 3; ++a) {
+          for (int c = 0; c < 3; ++c) D[(3 + a) * 9 + 3 + c] += s.Lam[S3<double>::idx(a, c)];
+          r[3 + a] += s.eta[a];
+        }
       }
       if (j + 1 < K) {
-        double AtQA[81], rj[9];
-        box_dyn_blocks(bc, s, AtQA, E, Dn, rj, rn);
-        for (int f = 0; f < 81; ++f) D[f] += AtQA[f];
-        for (int f = 0; f < 9; ++f) r[f] += rj[f];
+        if (!rows) {
+          double AtQA[81], rj[9];
+          box_dyn_blocks(bc, s, AtQA, E, Dn, rj, rn);
+          for (int f = 0; f < 81; ++f) D[f] += AtQA[f];
+          for (int f = 0; f < 9; ++f) r[f] += rj[f];
+        }
         // fixed components of state j+1: move column to the right-hand side of state j, zero it
         for (int c = 0; c < NC; ++c)
           if (BS::active(mask_n, c)) {
@@ -368,14 +443,54 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
     bool changed = false;
     nact = 0;
     if constexpr (GEN) {
+      constexpr int kSafeIt = 8;
+      if (phase == 0 && it >= kSafeIt) phase = 1;
+      if (phase == 3) {
+        // ---- line search of the finite method: xc (feasible) -> the minimiser just computed (x in the scratch)
+        double alpha = 1.0;
+        int bj = -1, bcmp = -1, bside = 0;
+        for (int j = 0; j < K; ++j) {
+          const double *fj = bb.fac + ((size_t)j * BOX_FAC) * ns + i;
+          const int mask = BS::load(bb, (size_t)((k0 + j) % dm.NW) * ns + i);
+          for (int c = 0; c < 9; ++c) {
+            if (!BS::bounded(bc, c) || BS::active(mask, c)) continue;
+            const double xn_ = fj[(size_t)(126 + c) * ns], xc_ = fj[(size_t)(135 + c) * ns], d = xn_ - xc_;
+            if (d > 0.0 && xn_ > BS::hi(bc, c)) {
+              double t = (BS::hi(bc, c) - xc_) / d;
+              t = t < 0.0 ? 0.0 : t;
+              if (t < alpha) { alpha = t; bj = j; bcmp = c; bside = 1; }
+            } else if (d < 0.0 && xn_ < BS::lo(bc, c)) {
+              double t = (BS::lo(bc, c) - xc_) / d;
+              t = t < 0.0 ? 0.0 : t;
+              if (t < alpha) { alpha = t; bj = j; bcmp = c; bside = -1; }
+            }
+          }
+        }
+        for (int j = 0; j < K; ++j) {
+          double *fj = bb.fac + ((size_t)j * BOX_FAC) * ns + i;
+          for (int c = 0; c < 9; ++c) {
+            const double xn_ = fj[(size_t)(126 + c) * ns], xc_ = fj[(size_t)(135 + c) * ns];
+            fj[(size_t)(135 + c) * ns] = bj < 0 ? xn_ : xc_ + alpha * (xn_ - xc_);
+          }
+        }
+        if (bj >= 0) {  // blocked: the bound joins the set, the equality-constrained problem is solved again
+          const size_t at = (size_t)((k0 + bj) % dm.NW) * ns + i;
+          BS::store(bb, at, BS::load(bb, at) | (bside > 0 ? (BS::HB << bcmp) : (1 << bcmp)));
+          if (K > 0) {  // x_T reported if the cap is hit here: the feasible iterate
+            const double *fl = bb.fac + ((size_t)(K - 1) * BOX_FAC) * ns + i;
+            for (int f = 0; f < 9; ++f) xT[f] = fl[(size_t)(135 + f) * ns];
+          }
+          continue;
+        }
+        phase = 2;
+      }
       // ---- multipliers = gradient of the free cost w.r.t. every component of x_j: g_j = D_j x_j + E_{j-1}' x_{j-1} + E_j x_{j+1}
       // - r_j with the UNMODIFIED blocks of the block-tridiagonal system (re-assembled here exactly as in the forward pass).
       // Update rule: the plain primal-dual active set (add every violated bound, drop every bound whose multiplier has the
       // wrong sign) for the first kSafeIt iterations; it can cycle when many bounds of different components interact, so
-      // afterwards bounds are only ADDED, and when nothing is violated the ONE bound with the most negative multiplier is
-      // dropped (single-exchange rule: finite on a strictly convex QP).
-      constexpr int kSafeIt = 8;
-      const bool safe = it >= kSafeIt;
+      // afterwards the finite method above takes over: bounds are only ADDED until the iterate is feasible, then the ONE bound
+      // with the most negative multiplier is dropped and the iterate moves by a line search (phase 3).
+      const bool safe = phase >= 1;
       int drop_j = -1, drop_c = -1, added = 0;
       double drop_val = 0.0;
       double Dc[81], rc[9], Ep[81], xp[9];
@@ -390,15 +505,24 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
         for (int f = 0; f < 9; ++f) xj[f] = fj[(size_t)(126 + f) * ns];
         for (int f = 0; f < 81; ++f) D[f] = Dc[f];
         for (int f = 0; f < 9; ++f) r[f] = rc[f];
-        for (int a = 0; a < 3; ++a) {
-          for (int c = 0; c < 3; ++c) D[(3 + a) * 9 + 3 + c] += s.Lam[S3<double>::idx(a, c)];
-          r[3 + a] += s.eta[a];
+        if (rows) {
+          double Ds[81], rs[9];
+          box_stage_rows(bc, s, Vm, j + 1 < K, Ds, rs, E, Dn, rn);
+          for (int f = 0; f < 81; ++f) D[f] += Ds[f];
+          for (int f = 0; f < 9; ++f) r[f] += rs[f];
+        } else {
+          for (int a = 0; a < 3; ++a) {
+            for (int c = 0; c < 3; ++c) D[(3 + a) * 9 + 3 + c] += s.Lam[S3<double>::idx(a, c)];
+            r[3 + a] += s.eta[a];
+          }
         }
         if (j + 1 < K) {
-          double AtQA[81], rj[9];
-          box_dyn_blocks(bc, s, AtQA, E, Dn, rj, rn);
-          for (int f = 0; f < 81; ++f) D[f] += AtQA[f];
-          for (int f = 0; f < 9; ++f) r[f] += rj[f];
+          if (!rows) {
+            double AtQA[81], rj[9];
+            box_dyn_blocks(bc, s, AtQA, E, Dn, rj, rn);
+            for (int f = 0; f < 81; ++f) D[f] += AtQA[f];
+            for (int f = 0; f < 9; ++f) r[f] += rj[f];
+          }
           const double *f1 = bb.fac + ((size_t)(j + 1) * BOX_FAC) * ns + i;
           for (int f = 0; f < 9; ++f) x1[f] = f1[(size_t)(126 + f) * ns];
         }
@@ -466,11 +590,21 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
           }
         }
       }
-      if (safe && added == 0 && drop_j >= 0) {
-        const size_t at = (size_t)((k0 + drop_j) % dm.NW) * ns + i;
-        BS::store(bb, at, BS::load(bb, at) & ~((1 << drop_c) | (BS::HB << drop_c)));
-        nact--;
-        changed = true;
+      if (safe && added == 0) {
+        // feasible equality-constrained minimiser: it becomes the iterate xc of the finite method
+        for (int j = 0; j < K; ++j) {
+          double *fj = bb.fac + ((size_t)j * BOX_FAC) * ns + i;
+          for (int c = 0; c < 9; ++c) fj[(size_t)(135 + c) * ns] = fj[(size_t)(126 + c) * ns];
+        }
+        if (drop_j >= 0) {
+          const size_t at = (size_t)((k0 + drop_j) % dm.NW) * ns + i;
+          BS::store(bb, at, BS::load(bb, at) & ~((1 << drop_c) | (BS::HB << drop_c)));
+          nact--;
+          changed = true;
+          phase = 3;
+        }
+      } else if (safe) {
+        phase = 1;  // something was violated (added): back to the feasibility phase
       }
     } else {
       // ---- multipliers = gradient of the free cost w.r.t. v_j, active-set update
@@ -545,6 +679,15 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
     converged = !changed;
   }
   if (!converged) status |= ST_QP_MAXITER;
+  if (rows) {  // x_T = V y_T
+    double xv[9];
+    for (int a = 0; a < 9; ++a) {
+      double v = 0.0;
+      for (int k = 0; k < 9; ++k) v += Vm[a * 9 + k] * xT[k];
+      xv[a] = v;
+    }
+    for (int a = 0; a < 9; ++a) xT[a] = xv[a];
+  }
   bb.iters[i] = iters;
   bb.nactive[i] = nact;
   return status;

@@ -586,7 +586,8 @@ struct dekf_handle {
   Buffers<double> b64;
   Buffers<float> b32;
   BoxConst bc;
-  BoxBuffers bb = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  BoxBuffers bb = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double *row_V = nullptr;  // device copy of W^-1 (dekf_add_state_rows)
   BoxTeamBuffers tb = {nullptr, nullptr};
   bool box_team = true;           // team form of the constrained solve (DEKF_BOX_SERIAL=1 selects one thread per instance)
   bool foot_team = true;          // one warp per instance for the foot-state model (DEKF_FOOT_SERIAL=1: one thread per instance)
@@ -1175,6 +1176,7 @@ int dekf_destroy(dekf_handle *h) {
   cudaFree(h->bb.act32);
   cudaFree(h->bb.iters);
   cudaFree(h->bb.nactive);
+  cudaFree(h->row_V);
   free_stage_set(h->stage[0]);
   free_stage_set(h->stage[1]);
   free_chunk_set(h->chunk[0]);
@@ -2323,6 +2325,51 @@ int dekf_get_host(dekf_handle *h, int32_t what, void *host_out) {
   if (rc) return rc;
   CK(cudaMemcpyAsync(host_out, src, bytes, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  return DEKF_OK;
+}
+
+int dekf_add_state_rows(dekf_handle *h, int32_t count, const double *a, const double *lb, const double *ub) {
+  if (!h || count < 1 || count > 9 || !a || !lb || !ub) return fail(h, DEKF_EINVAL, "dekf_add_state_rows: bad argument");
+  if (h->cfg.est_type != 0 || h->cfg.leg_odom_type != 0)
+    return fail(h, DEKF_EINVAL, "dekf_add_state_rows: needs est_type 0 and leg_odom_type 0");
+  if (h->next_T != 0 || h->ekf_k != 0) return fail(h, DEKF_ESTATE, "dekf_add_state_rows: call before the first step (or after dekf_reset)");
+  CK(cudaSetDevice(h->cfg.device));
+  double W[81], V[81], lo[9], hi[9];
+  const int m = make_row_basis(h->cfg, count, a, lb, ub, W, V, lo, hi);
+  if (m < 1) return fail(h, DEKF_EINVAL, "dekf_add_state_rows: rows (with the component bounds of the config) must be <= 9, linearly independent, lb < ub");
+  const size_t ns = (size_t)h->dm.ns;
+  const size_t fac = (size_t)h->dm.N * BOX_FAC * ns * sizeof(double), act = (size_t)h->dm.NW * ns;
+  if (!h->bb.fac) {  // the handle was created without constraints: scratch of the one-thread-per-instance solve
+    CK(cudaMalloc((void **)&h->bb.fac, fac));
+    CK(cudaMalloc((void **)&h->bb.act, act));
+    CK(cudaMalloc((void **)&h->bb.iters, ns * sizeof(int32_t)));
+    CK(cudaMalloc((void **)&h->bb.nactive, ns * sizeof(int32_t)));
+    h->extra_bytes += fac + act + 2 * ns * sizeof(int32_t);
+  }
+  if (!h->bb.act32) {
+    CK(cudaMalloc((void **)&h->bb.act32, act * sizeof(uint32_t)));
+    h->extra_bytes += act * sizeof(uint32_t);
+  }
+  if (!h->row_V) CK(cudaMalloc((void **)&h->row_V, 81 * sizeof(double)));
+  CK(cudaMemcpyAsync(h->row_V, V, sizeof(V), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->bb.act, 0, act, h->stream));
+  CK(cudaMemsetAsync(h->bb.act32, 0, act * sizeof(uint32_t), h->stream));
+  CK(cudaMemsetAsync(h->bb.iters, 0, ns * sizeof(int32_t), h->stream));
+  CK(cudaMemsetAsync(h->bb.nactive, 0, ns * sizeof(int32_t), h->stream));
+  CK(cudaStreamSynchronize(h->stream));  // V is a stack array
+  h->bb.V = h->row_V;
+  if (!h->bc.enable) h->bc = make_box_const(h->cfg);  // model constants of the information form (dt, noise weights, lever arm)
+  h->bc.enable = 1;
+  h->bc.general = 1;
+  h->bc.nrows = m;
+  h->bc.mask9 = (1 << m) - 1;
+  for (int r = 0; r < 9; ++r) {
+    h->bc.lo9[r] = r < m ? lo[r] : -1e300;
+    h->bc.hi9[r] = r < m ? hi[r] : 1e300;
+  }
+  // the finite method (box_solve.cuh, phases 1-3) moves one bound per factorisation: give it room unless the config set a cap
+  h->bc.max_iter = h->cfg.v_box_max_iter > 0 ? h->cfg.v_box_max_iter : 400;
+  h->box_team = false;  // the team kernel knows the velocity box only
   return DEKF_OK;
 }
 

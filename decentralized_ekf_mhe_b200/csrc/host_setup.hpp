@@ -2,6 +2,8 @@
 // constant blocks the kernels take by value.  Plain C++ (no CUDA) so the CPU math-debug harness in
 // tests/hostsim can share it.
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cmath>
 #include <cstring>
 
@@ -186,6 +188,93 @@ inline BoxConst make_box_const(const dekf_config &c) {
     b.qvo[i] = 1.0 / std::pow(c.vo_p_std[i], 2);                    // Q_vo, :477
   }
   return b;
+}
+
+// Row basis of the general linear rows (dekf_add_state_rows): W = [the count rows of `a`; the component bounds of the config as unit
+// rows; unit vectors completing them to a basis (greedy: the unit vector farthest from the span so far)], V = W^-1 by Gauss-Jordan
+// with partial pivoting; lo / hi in row order.  Returns the number of bounded rows m, or -1 (dependent rows, more than 9, lb >= ub).
+inline int make_row_basis(const dekf_config &c, int count, const double *a, const double *lb, const double *ub, double *W, double *V,
+                          double *lo, double *hi) {
+  double Q[81];
+  int nq = 0, m = 0;
+  auto push = [&](const double *row, double l, double u) -> bool {
+    if (m >= 9 || !(l < u)) return false;
+    double r[9], na = 0.0, nr = 0.0;
+    for (int k = 0; k < 9; ++k) {
+      r[k] = row[k];
+      na += row[k] * row[k];
+    }
+    for (int q = 0; q < nq; ++q) {
+      double d = 0.0;
+      for (int k = 0; k < 9; ++k) d += Q[q * 9 + k] * r[k];
+      for (int k = 0; k < 9; ++k) r[k] -= d * Q[q * 9 + k];
+    }
+    for (int k = 0; k < 9; ++k) nr += r[k] * r[k];
+    if (na == 0.0 || !(nr > 1e-16 * na)) return false;
+    for (int k = 0; k < 9; ++k) Q[nq * 9 + k] = r[k] / std::sqrt(nr);
+    ++nq;
+    for (int k = 0; k < 9; ++k) W[m * 9 + k] = row[k];
+    lo[m] = l;
+    hi[m] = u;
+    ++m;
+    return true;
+  };
+  for (int i = 0; i < count; ++i)
+    if (!push(a + (size_t)i * 9, lb[i], ub[i])) return -1;
+  for (int i = 0; i < 9; ++i) {
+    const bool gx = ((c.x_box_mask >> i) & 1) != 0, gv = c.v_box_enable && i >= 3 && i < 6;
+    if (!gx && !gv) continue;
+    double e[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    e[i] = 1.0;
+    if (!push(e, gx ? c.x_box_lo[i] : c.v_box_lo[i - 3], gx ? c.x_box_hi[i] : c.v_box_hi[i - 3])) return -1;
+  }
+  const int rows = m;
+  while (nq < 9) {
+    int best = -1;
+    double bestn = -1.0, br[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = 0; k < 9; ++k) {
+      double r[9], nr = 0.0;
+      for (int cc = 0; cc < 9; ++cc) r[cc] = cc == k ? 1.0 : 0.0;
+      for (int q = 0; q < nq; ++q) {
+        const double d = Q[q * 9 + k];
+        for (int cc = 0; cc < 9; ++cc) r[cc] -= d * Q[q * 9 + cc];
+      }
+      for (int cc = 0; cc < 9; ++cc) nr += r[cc] * r[cc];
+      if (nr > bestn) {
+        bestn = nr;
+        best = k;
+        for (int cc = 0; cc < 9; ++cc) br[cc] = r[cc];
+      }
+    }
+    for (int cc = 0; cc < 9; ++cc) Q[nq * 9 + cc] = br[cc] / std::sqrt(bestn);
+    for (int cc = 0; cc < 9; ++cc) W[nq * 9 + cc] = cc == best ? 1.0 : 0.0;
+    ++nq;
+  }
+  double A[9][18];
+  for (int r = 0; r < 9; ++r)
+    for (int cc = 0; cc < 9; ++cc) {
+      A[r][cc] = W[r * 9 + cc];
+      A[r][9 + cc] = r == cc ? 1.0 : 0.0;
+    }
+  for (int cc = 0; cc < 9; ++cc) {
+    int pv = cc;
+    for (int r = cc + 1; r < 9; ++r)
+      if (std::fabs(A[r][cc]) > std::fabs(A[pv][cc])) pv = r;
+    if (A[pv][cc] == 0.0) return -1;
+    if (pv != cc)
+      for (int k = 0; k < 18; ++k) std::swap(A[cc][k], A[pv][k]);
+    const double d = 1.0 / A[cc][cc];
+    for (int k = 0; k < 18; ++k) A[cc][k] *= d;
+    for (int r = 0; r < 9; ++r) {
+      if (r == cc) continue;
+      const double f = A[r][cc];
+      if (f != 0.0)
+        for (int k = 0; k < 18; ++k) A[r][k] -= f * A[cc][k];
+    }
+  }
+  for (int r = 0; r < 9; ++r)
+    for (int cc = 0; cc < 9; ++cc) V[r * 9 + cc] = A[r][9 + cc];
+  return rows;
 }
 
 // constants of the foot-state model (leg_odom_type 1; always double)

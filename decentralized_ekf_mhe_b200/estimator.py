@@ -486,6 +486,20 @@ class BatchedEstimator:
         h.check(h.L.dekf_get_window_vo_count(h.h, _ptr(c)), "dekf_get_window_vo_count")
         return c
 
+    def add_state_rows(self, a, lb, ub):
+        """General inequality rows  lb[i] <= a[i] . x_k <= ub[i]  on every window state (MHEproblem::addConstraints(name, lb, ub) with
+        a dependency row on x_k, MheSrb.cpp:58-68, :217-270); `a` [count][9] over (p_s, v_s, accel bias).  Before the first step."""
+        import ctypes as C
+        import numpy as np
+        h = self._hd
+        a = np.ascontiguousarray(np.asarray(a, dtype=np.float64).reshape(-1, 9))
+        lb = np.ascontiguousarray(np.asarray(lb, dtype=np.float64).reshape(-1))
+        ub = np.ascontiguousarray(np.asarray(ub, dtype=np.float64).reshape(-1))
+        assert lb.size == a.shape[0] == ub.size
+        dp = C.POINTER(C.c_double)
+        h.check(h.L.dekf_add_state_rows(h.h, a.shape[0], a.ctypes.data_as(dp), lb.ctypes.data_as(dp), ub.ctypes.data_as(dp)),
+                "dekf_add_state_rows")
+
     def qp_info(self):
         """(factorisations, active bounds) [n] int32 of the last state-constrained solve (params.v_box_enable)."""
         h = self._hd

@@ -286,6 +286,17 @@ int dekf_get_resweep_info(dekf_handle *h, int32_t *depth /*[n]*/, int32_t *n_vo 
 int dekf_measure_fma_peak(int32_t device, int32_t precision, double *tflops);
 int dekf_measure_copy_bw(int32_t device, double *gbs);
 
+/* General inequality rows on the window states: lb[i] <= a[i] . x_k <= ub[i] for EVERY state x_k of the window, i < count.
+ * Replaces MHEproblem::addConstraints(name, lb, ub) + a dependency row on x_k
+ * (/root/reference/src/decentral_legged_est/src/MheSrb.cpp:58-68, :217-270 -- the mechanism the reference offers for state
+ * constraints and never exercises).  `a` is [count][9] row-major over (p_s, v_s, accel bias), count <= 9 together with the component
+ * bounds of dekf_config (v_box / x_box, which count as unit rows); all rows must be linearly independent, lb < ub.  Call after
+ * dekf_create and before the first step (DEKF_ESTATE afterwards); est_type 0, leg_odom_type 0.  The window QP is then solved
+ * exactly by the active-set iteration of the state-constrained solve in the basis y = W x whose first coordinates are the rows
+ * (host arrays).  Repeated calls replace the rows. */
+int dekf_add_state_rows(dekf_handle *h, int32_t count, const double *a /*[count][9]*/, const double *lb /*[count]*/,
+                        const double *ub /*[count]*/);
+
 /* State-constrained solve bookkeeping of the last step (device pointers, any may be NULL): factorisations used and
  * number of active bounds in the window, per instance.  DEKF_EINVAL unless the handle has v_box_enable. */
 int dekf_get_qp_info(dekf_handle *h, int32_t *iters /*[n]*/, int32_t *n_active /*[n]*/);

@@ -265,6 +265,9 @@ class DecentralizedEstimation {
     }
     const dekf_config cfg = params_ptr_->to_config();
     detail::check(dekf_create(&cfg, &h_), nullptr, "dekf_create");
+    if (!rows_lb_.empty())
+      detail::check(dekf_add_state_rows(h_, (int32_t)rows_lb_.size(), rows_a_.data(), rows_lb_.data(), rows_ub_.data()), h_,
+                    "dekf_add_state_rows");
     n_ = cfg.n_instances;
     nl_ = cfg.num_legs;
     nq_ = dekf_num_joints(h_);
@@ -278,6 +281,15 @@ class DecentralizedEstimation {
     p_vo_accmulate_.assign(3 * (size_t)n_, 0.0);
     status_.assign(n_, 0);
     step(0);
+  }
+  // General inequality rows  lb[i] <= a[i] . x_k <= ub[i]  on every window state -- what MHEproblem::addConstraints(name, lb, ub)
+  // with a dependency row on x_k adds in the reference (MheSrb.cpp:58-68, :217-270; never exercised there).  `a` is [count][9]
+  // row-major over (p_s, v_s, accel bias).  Call BEFORE initialize(): the rows are handed to the handle when it is created.
+  void addStateRows(const std::vector<double> &a, const std::vector<double> &lb, const std::vector<double> &ub) {
+    if (lb.size() != ub.size() || a.size() != 9 * lb.size()) throw std::runtime_error("addStateRows: a must be [count][9]");
+    rows_a_ = a;
+    rows_lb_ = lb;
+    rows_ub_ = ub;
   }
   // DecentralEst.hpp:102, DecentralEst.cpp:152-198
   void update(int T) {
@@ -355,6 +367,7 @@ class DecentralizedEstimation {
 
   std::shared_ptr<robot_store> robot_sub_ptr_;
   std::shared_ptr<robot_params> params_ptr_;
+  std::vector<double> rows_a_, rows_lb_, rows_ub_;  // addStateRows()
   dekf_handle *h_ = nullptr;
   int n_ = 0, nl_ = 0, nq_ = 0;
   bool kf_ = false;

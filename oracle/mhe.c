@@ -859,6 +859,180 @@ void orc_mhe_export_qp(const orc_mhe *m, double *H, double *g, double *A, double
 /* Exact optimum of the assembled QP (stand-in for OSQP converged to eps->0): every row carries its
  * own slack with coefficient -I, so v = A_meas x - l etc.; free rows ([-1e30,1e30]) leave their
  * slack at 0.  Normal equations in x are block tridiagonal -> banded Cholesky. */
+/* Equality-constrained solve of the window normal equations with the components flagged in act[] (+1: at its upper bound, -1: at its
+ * lower bound) fixed: xs = argmin 1/2 x'N0 x - r0'x  s.t.  x[a] = bound(a).  Nm / rhs are scratch. */
+static int active_solve(const double *N0, const double *r0, int n, int ds, const int *act, const double *blo, const double *bhi,
+                        double *Nm, double *rhs, double *xs) {
+  la_copy(Nm, N0, n * n);
+  la_copy(rhs, r0, n);
+  for (int a = 0; a < n; ++a) {
+    if (!act[a]) continue;
+    double beta = act[a] > 0 ? bhi[a % ds] : blo[a % ds];
+    for (int i = 0; i < n; ++i) rhs[i] -= Nm[i * n + a] * beta;
+  }
+  for (int a = 0; a < n; ++a) {
+    if (!act[a]) continue;
+    double beta = act[a] > 0 ? bhi[a % ds] : blo[a % ds];
+    for (int i = 0; i < n; ++i) Nm[i * n + a] = Nm[a * n + i] = 0.0;
+    Nm[a * n + a] = 1.0;
+    rhs[a] = beta;
+  }
+  int rc = la_chol_solve_banded(Nm, rhs, n, 2 * ds - 1);
+  la_copy(xs, rhs, n);
+  return rc;
+}
+
+/* Textbook PRIMAL active-set method on the same problem (finite and monotone on a strictly convex QP), used when the fast
+ * primal-dual iteration has not settled: (1) bounds are only added until the iterate is feasible; (2) while some active bound has
+ * a multiplier of the wrong sign, the worst one is dropped and the iterate moves towards the new equality-constrained minimiser,
+ * stopping at (and adding) the first bound it would cross.  bmask: bounded components of every state.  Returns iterations used. */
+static int primal_active_set(const double *N0, const double *r0, int n, int ds, int K, int bmask, const double *blo,
+                             const double *bhi, int *act, double *Nm, double *rhs, double *xs) {
+  double *xc = dalloc(n), *xn = dalloc(n);
+  int iters = 0;
+  for (;;) { /* phase 1: feasibility */
+    active_solve(N0, r0, n, ds, act, blo, bhi, Nm, rhs, xs);
+    iters++;
+    int added = 0;
+    for (int j = 0; j < K; ++j)
+      for (int c = 0; c < ds && c < 9; ++c) {
+        if (!((bmask >> c) & 1)) continue;
+        int a = j * ds + c;
+        if (act[a]) continue;
+        if (xs[a] > bhi[c]) { act[a] = 1; added++; }
+        else if (xs[a] < blo[c]) { act[a] = -1; added++; }
+      }
+    if (!added || iters > 10 * n) break;
+  }
+  la_copy(xc, xs, n);
+  for (int outer = 0; outer < 50 * n; ++outer) { /* phase 2 */
+    int drop = -1;
+    double worst = 0.0;
+    for (int a = 0; a < n; ++a) {
+      if (!act[a]) continue;
+      double grad = -r0[a], gs = fabs(r0[a]);
+      for (int i = 0; i < n; ++i) {
+        grad += N0[a * n + i] * xc[i];
+        gs += fabs(N0[a * n + i] * xc[i]);
+      }
+      double mult = act[a] > 0 ? -grad : grad;
+      double v = mult / (gs > 0.0 ? gs : 1.0);
+      if (v < -1e-10 && (drop < 0 || v < worst)) { worst = v; drop = a; }
+    }
+    if (drop < 0) break;
+    act[drop] = 0;
+    for (int inner = 0; inner < 10 * n; ++inner) {
+      active_solve(N0, r0, n, ds, act, blo, bhi, Nm, rhs, xn);
+      iters++;
+      double alpha = 1.0;
+      int block = -1, side = 0;
+      for (int j = 0; j < K; ++j)
+        for (int c = 0; c < ds && c < 9; ++c) {
+          if (!((bmask >> c) & 1)) continue;
+          int a = j * ds + c;
+          if (act[a]) continue;
+          double d = xn[a] - xc[a];
+          if (d > 0.0 && xn[a] > bhi[c]) {
+            double t = (bhi[c] - xc[a]) / d;
+            if (t < alpha) { alpha = t < 0.0 ? 0.0 : t; block = a; side = 1; }
+          } else if (d < 0.0 && xn[a] < blo[c]) {
+            double t = (blo[c] - xc[a]) / d;
+            if (t < alpha) { alpha = t < 0.0 ? 0.0 : t; block = a; side = -1; }
+          }
+        }
+      for (int i = 0; i < n; ++i) xc[i] += alpha * (xn[i] - xc[i]);
+      if (block < 0) break;
+      act[block] = side;
+    }
+  }
+  la_copy(xs, xc, n);
+  free(xc);
+  free(xn);
+  return iters;
+}
+
+/* General rows lo <= a_i . x_k <= hi (orc_params.x_row_*), together with the component bounds of v_box / x_box as unit rows:
+ * a change of basis y = W x whose first m coordinates ARE the rows turns them into component bounds on y.  W = [rows; unit vectors
+ * that complete them to a basis (greedy: the unit vector farthest from the span so far)], V = W^-1 by Gauss-Jordan.  Returns m, or
+ * -1 if the rows are linearly dependent / too many. */
+static int rows_basis(const orc_params *P, double *W /*81*/, double *V /*81*/, double *lo /*9*/, double *hi /*9*/) {
+  int m = 0;
+  double Q[81]; /* orthonormal basis of the span so far, row-major */
+  int nq = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    int cnt = pass == 0 ? P->x_row_count : 9;
+    for (int i = 0; i < cnt; ++i) {
+      double a[9];
+      double l, u;
+      if (pass == 0) {
+        for (int c = 0; c < 9; ++c) a[c] = P->x_row_a[i * 9 + c];
+        l = P->x_row_lo[i];
+        u = P->x_row_hi[i];
+      } else {
+        int gx = (P->x_box_mask >> i) & 1, gv = P->v_box_enable && i >= 3 && i < 6;
+        if (!gx && !gv) continue;
+        for (int c = 0; c < 9; ++c) a[c] = (c == i) ? 1.0 : 0.0;
+        l = gx ? P->x_box_lo[i] : P->v_box_lo[i - 3];
+        u = gx ? P->x_box_hi[i] : P->v_box_hi[i - 3];
+      }
+      if (m >= 9) return -1;
+      double r[9], na = 0.0, nr = 0.0;
+      for (int c = 0; c < 9; ++c) { r[c] = a[c]; na += a[c] * a[c]; }
+      for (int q = 0; q < nq; ++q) {
+        double d = 0.0;
+        for (int c = 0; c < 9; ++c) d += Q[q * 9 + c] * r[c];
+        for (int c = 0; c < 9; ++c) r[c] -= d * Q[q * 9 + c];
+      }
+      for (int c = 0; c < 9; ++c) nr += r[c] * r[c];
+      if (!(nr > 1e-16 * na) || na == 0.0) return -1;
+      for (int c = 0; c < 9; ++c) Q[nq * 9 + c] = r[c] / sqrt(nr);
+      nq++;
+      for (int c = 0; c < 9; ++c) W[m * 9 + c] = a[c];
+      lo[m] = l;
+      hi[m] = u;
+      m++;
+    }
+  }
+  int rows = m;
+  while (nq < 9) { /* completion */
+    int best = -1;
+    double bestn = -1.0, br[9];
+    for (int k = 0; k < 9; ++k) {
+      double r[9], nr = 0.0;
+      for (int c = 0; c < 9; ++c) r[c] = (c == k) ? 1.0 : 0.0;
+      for (int q = 0; q < nq; ++q) {
+        double d = Q[q * 9 + k];
+        for (int c = 0; c < 9; ++c) r[c] -= d * Q[q * 9 + c];
+      }
+      for (int c = 0; c < 9; ++c) nr += r[c] * r[c];
+      if (nr > bestn) { bestn = nr; best = k; for (int c = 0; c < 9; ++c) br[c] = r[c]; }
+    }
+    for (int c = 0; c < 9; ++c) Q[nq * 9 + c] = br[c] / sqrt(bestn);
+    for (int c = 0; c < 9; ++c) W[nq * 9 + c] = (c == best) ? 1.0 : 0.0;
+    nq++;
+  }
+  /* V = W^-1 */
+  double A[9][18];
+  for (int r = 0; r < 9; ++r)
+    for (int c = 0; c < 9; ++c) { A[r][c] = W[r * 9 + c]; A[r][9 + c] = (r == c) ? 1.0 : 0.0; }
+  for (int c = 0; c < 9; ++c) {
+    int pv = c;
+    for (int r = c + 1; r < 9; ++r) if (fabs(A[r][c]) > fabs(A[pv][c])) pv = r;
+    if (A[pv][c] == 0.0) return -1;
+    if (pv != c) for (int k = 0; k < 18; ++k) { double t = A[c][k]; A[c][k] = A[pv][k]; A[pv][k] = t; }
+    double d = 1.0 / A[c][c];
+    for (int k = 0; k < 18; ++k) A[c][k] *= d;
+    for (int r = 0; r < 9; ++r) {
+      if (r == c) continue;
+      double f = A[r][c];
+      if (f != 0.0) for (int k = 0; k < 18; ++k) A[r][k] -= f * A[c][k];
+    }
+  }
+  for (int r = 0; r < 9; ++r)
+    for (int c = 0; c < 9; ++c) V[r * 9 + c] = A[r][9 + c];
+  return rows;
+}
+
 static int solve_exact(orc_mhe *m) {
   int ds = m->ds, dm = m->dm, K = m->nwin, n = K * ds;
   double *Nm = dalloc(n * n), *rhs = dalloc(n);
@@ -917,7 +1091,49 @@ static int solve_exact(orc_mhe *m) {
     }
   }
   int rc;
-  if (m->P.v_box_enable || m->P.x_box_mask) {
+  /* general rows: solve in y = W x (block-diagonal congruence of the normal equations), where the rows are component bounds */
+  double Wm[81], Vm[81], rlo[9], rhi[9];
+  int nrows = 0;
+  if (m->P.x_row_count > 0 && ds == 9) {
+    nrows = rows_basis(&m->P, Wm, Vm, rlo, rhi);
+    if (nrows > 0) {
+      double *blk = dalloc(81), *tmpb = dalloc(81);
+      for (int j = 0; j < K; ++j) {
+        for (int j2 = (j > 0 ? j - 1 : 0); j2 <= (j + 1 < K ? j + 1 : j); ++j2) {
+          for (int a = 0; a < 9; ++a)
+            for (int b = 0; b < 9; ++b) blk[a * 9 + b] = Nm[(j * 9 + a) * n + j2 * 9 + b];
+          for (int a = 0; a < 9; ++a) /* tmp = V' blk */
+            for (int b = 0; b < 9; ++b) {
+              double v = 0.0;
+              for (int k = 0; k < 9; ++k) v += Vm[k * 9 + a] * blk[k * 9 + b];
+              tmpb[a * 9 + b] = v;
+            }
+          for (int a = 0; a < 9; ++a) /* N' = tmp V */
+            for (int b = 0; b < 9; ++b) {
+              double v = 0.0;
+              for (int k = 0; k < 9; ++k) v += tmpb[a * 9 + k] * Vm[k * 9 + b];
+              Nm[(j * 9 + a) * n + j2 * 9 + b] = v;
+            }
+        }
+        double rv[9];
+        for (int a = 0; a < 9; ++a) {
+          double v = 0.0;
+          for (int k = 0; k < 9; ++k) v += Vm[k * 9 + a] * rhs[j * 9 + k];
+          rv[a] = v;
+        }
+        for (int a = 0; a < 9; ++a) rhs[j * 9 + a] = rv[a];
+      }
+      /* symmetrise what round-off left */
+      for (int a = 0; a < n; ++a)
+        for (int b = a + 1; b < n; ++b) {
+          double v = 0.5 * (Nm[a * n + b] + Nm[b * n + a]);
+          Nm[a * n + b] = Nm[b * n + a] = v;
+        }
+      free(blk);
+      free(tmpb);
+    }
+  }
+  if (m->P.v_box_enable || m->P.x_box_mask || nrows > 0) {
     /* Builder extension (never exercised by the reference): rows lo <= x_j[a] <= hi for the bounded components a of every
      * state of the window at solve time -- what MHEproblem::addConstraints(name, lb, ub) + a dependency on x_j with a
      * selector row would add (MheSrb.cpp:58-68).  v_box bounds v_s (a = 3..5), x_box_mask any of the 9 base components.
@@ -931,13 +1147,22 @@ static int solve_exact(orc_mhe *m) {
       bhi[a] = gx ? m->P.x_box_hi[a] : (gv ? m->P.v_box_hi[a - 3] : 1e300);
       if (gx || gv) bmask |= 1 << a;
     }
+    if (nrows > 0) { /* in y coordinates the first nrows components carry every bound (component bounds became unit rows) */
+      bmask = (1 << nrows) - 1;
+      for (int a = 0; a < 9; ++a) {
+        blo[a] = a < nrows ? rlo[a] : -1e300;
+        bhi[a] = a < nrows ? rhi[a] : 1e300;
+      }
+    }
+    const int general = m->P.x_box_mask || nrows > 0;
     double *N0 = dalloc(n * n), *r0 = dalloc(n), *xs = dalloc(n);
     int *act = (int *)calloc((size_t)n, sizeof(int)), *nact = (int *)calloc((size_t)n, sizeof(int));
     la_copy(N0, Nm, n * n);
     la_copy(r0, rhs, n);
     rc = 0;
     int it = 0;
-    for (it = 0; it < 200; ++it) {
+    int settled = 0;
+    for (it = 0; it < (general ? 40 : 200); ++it) {
       la_copy(Nm, N0, n * n);
       la_copy(rhs, r0, n);
       for (int a = 0; a < n; ++a) {
@@ -958,7 +1183,7 @@ static int solve_exact(orc_mhe *m) {
       /* general bounds: after 8 plain primal-dual iterations bounds are only added, and when nothing is violated the single
        * bound with the most negative (scaled) multiplier is dropped -- the plain rule can cycle when bounds of several
        * components interact (the velocity box never did) */
-      int safe = m->P.x_box_mask && it >= 8, added = 0, drop_a = -1;
+      int safe = general && it >= 8, added = 0, drop_a = -1;
       double drop_val = 0.0;
       for (int j = 0; j < K; ++j)
         for (int c = 0; c < 9; ++c) {
@@ -971,7 +1196,7 @@ static int solve_exact(orc_mhe *m) {
           }
           /* a multiplier within round-off of zero keeps its bound (general bounds only); the velocity box keeps the exact
            * sign test it was validated with */
-          double gtol = m->P.x_box_mask ? 1e-10 * gs : 0.0;
+          double gtol = general ? 1e-10 * gs : 0.0;
           int na;
           if (act[a] != 0) {
             double mult = act[a] > 0 ? -grad : grad;
@@ -996,11 +1221,26 @@ static int solve_exact(orc_mhe *m) {
         nact[drop_a] = 0;
         changed = 1;
       }
-      if (!changed) break;
+      if (!changed) {
+        settled = 1;
+        break;
+      }
       memcpy(act, nact, sizeof(int) * (size_t)n);
     }
+    if (general && !settled) /* the fast iteration cycled: the finite method, warm-started from its last set */
+      it += primal_active_set(N0, r0, n, ds, K, bmask, blo, bhi, act, Nm, rhs, xs);
     m->admm_iters = it + 1;
     la_copy(rhs, xs, n);
+    if (nrows > 0) /* back to x = V y */
+      for (int j = 0; j < K; ++j) {
+        double xv[9];
+        for (int a = 0; a < 9; ++a) {
+          double v = 0.0;
+          for (int k = 0; k < 9; ++k) v += Vm[a * 9 + k] * xs[j * 9 + k];
+          xv[a] = v;
+        }
+        for (int a = 0; a < 9; ++a) rhs[j * 9 + a] = xv[a];
+      }
     free(N0);
     free(r0);
     free(xs);

@@ -95,6 +95,11 @@ typedef struct {
    * window state, x_box_lo[a] <= x_k[a] <= x_box_hi[a]; combines with v_box (x_box wins on components 3..5) */
   int x_box_mask;
   double x_box_lo[9], x_box_hi[9];
+  /* general linear rows (builder extension): x_row_lo[i] <= x_row_a[i] . x_k <= x_row_hi[i] for every window state, i <
+   * x_row_count <= 9, rows linearly independent -- MHEproblem::addConstraints(name, lb, ub) with an arbitrary dependency row on
+   * x_k (MheSrb.cpp:58-68, :217-270).  Component bounds (v_box / x_box) given at the same time count as unit rows. */
+  int x_row_count;
+  double x_row_a[81], x_row_lo[9], x_row_hi[9];
 } orc_params;
 
 void orc_params_go1_defaults(orc_params *p); /* parameters_go1.yaml */

@@ -41,6 +41,7 @@ class Params(C.Structure):
         ("v_box_enable", C.c_int), ("v_box_lo", C.c_double * 3), ("v_box_hi", C.c_double * 3),
         ("p_imu_2_opti", C.c_double * 3),
         ("x_box_mask", C.c_int), ("x_box_lo", C.c_double * 9), ("x_box_hi", C.c_double * 9),
+        ("x_row_count", C.c_int), ("x_row_a", C.c_double * 81), ("x_row_lo", C.c_double * 9), ("x_row_hi", C.c_double * 9),
     ]
 
 

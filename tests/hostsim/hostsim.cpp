@@ -14,8 +14,13 @@
 using namespace dekf;
 
 namespace {
+// general linear rows for the NEXT hostsim_run (hostsim_set_rows): what dekf_add_state_rows does on a handle
+int g_rows = 0;
+double g_row_a[81], g_row_lb[9], g_row_ub[9];
+
 template <typename T>
 struct Sim {
+  double Vrow[81];
   dekf_config cfg;
   Dims dm;
   EkfConst<T> ec;
@@ -42,6 +47,23 @@ struct Sim {
     bb.act32 = alloc<uint32_t>((size_t)dm.NW * dm.ns);
     bb.iters = alloc<int32_t>(dm.ns);
     bb.nactive = alloc<int32_t>(dm.ns);
+    bb.V = nullptr;
+    if (g_rows > 0) {
+      double W[81], lo[9], hi[9];
+      const int m = make_row_basis(c, g_rows, g_row_a, g_row_lb, g_row_ub, W, Vrow, lo, hi);
+      if (m > 0) {
+        bb.V = Vrow;
+        bc.enable = 1;
+        bc.general = 1;
+        bc.nrows = m;
+        bc.max_iter = c.v_box_max_iter > 0 ? c.v_box_max_iter : 400;
+        bc.mask9 = (1 << m) - 1;
+        for (int r = 0; r < 9; ++r) {
+          bc.lo9[r] = r < m ? lo[r] : -1e300;
+          bc.hi9[r] = r < m ? hi[r] : 1e300;
+        }
+      }
+    }
     StateSizes s = state_sizes(dm);
     b.ekf_q = alloc<T>(s.ekf_q);
     b.ekf_P = alloc<T>(s.ekf_P);
@@ -153,6 +175,14 @@ void run(const dekf_config &cfg, int S, const double *gyro, const double *accel,
 
 extern "C" {
 void hostsim_default_go1(dekf_config *c) { fill_go1_defaults(c); }
+void hostsim_set_rows(int count, const double *a, const double *lb, const double *ub) {
+  g_rows = count > 9 ? 9 : (count < 0 ? 0 : count);
+  for (int i = 0; i < g_rows; ++i) {
+    for (int k = 0; k < 9; ++k) g_row_a[i * 9 + k] = a[i * 9 + k];
+    g_row_lb[i] = lb[i];
+    g_row_ub[i] = ub[i];
+  }
+}
 int hostsim_run(const dekf_config *cfg, int S, const double *gyro, const double *accel, const double *imu_time,
                 const double *joint_pos, const double *joint_vel, const double *foot_force, const uint8_t *vo_flag,
                 const double *vo_quat, const double *vo_time_pre, const double *vo_time_now, const double *vo_rel_p,

@@ -30,8 +30,15 @@ def build():
     return so
 
 
-def run(stream, cfg, quat_in=None):
+def run(stream, cfg, quat_in=None, rows=None):
+    """rows = (a [count][9], lb, ub): general linear rows on every window state (what dekf_add_state_rows sets on a handle)."""
     lib = C.CDLL(build())
+    if rows is not None:
+        ra, rl, ru = (np.ascontiguousarray(np.asarray(v, dtype=np.float64)) for v in rows)
+        lib.hostsim_set_rows(int(rl.size), ra.ctypes.data_as(C.POINTER(C.c_double)), rl.ctypes.data_as(C.POINTER(C.c_double)),
+                             ru.ctypes.data_as(C.POINTER(C.c_double)))
+    else:
+        lib.hostsim_set_rows(0, None, None, None)
     S, _, n = stream["gyro"].shape
     nl = stream["foot_force"].shape[1]
     cfg.n_instances = n

@@ -687,6 +687,52 @@ def test_dekf_run_is_repeatable_at_the_benchmark_size(est_mod, monkeypatch, ragg
             assert not bad, f"run {rep}: {key} differs from run 0 at ticks {[b + 1 for b in bad][:8]}"
 
 
+def test_general_linear_rows_vs_oracle(est_mod, oracle):
+    """dekf_add_state_rows: arbitrary rows  lb <= a . x_k <= ub  on every window state (MHEproblem::addConstraints with a
+    non-selector dependency row, MheSrb.cpp:58-68, :217-270) -- three rows mixing velocity, bias and position components plus a
+    component bound from the config (x_box on v_y) -- against the oracle, whose optimum carries the KKT certificate of
+    tests/test_oracle_mhe.py::test_general_linear_rows_optimum_certificate: x within 1e-8, no row violated, the rows bind."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n, S = 256, 90
+    A3 = np.zeros((3, 9))
+    A3[0, 3], A3[0, 5] = 1.0, 0.5
+    A3[1, 6], A3[1, 7] = 1.0, -1.0
+    A3[2, 2], A3[2, 8] = 1.0, 0.02
+    lo3, hi3 = np.array([0.47, -0.003, -2e-4]), np.array([0.52, 0.003, 2e-4])
+    xlo, xhi = [0.0] * 9, [0.0] * 9
+    xlo[4], xhi[4] = -0.02, 0.02
+    st_t = synth.make_stream(n, S, robot="pogox", vo_jitter=True)
+    st = synth.to_numpy(st_t)
+    dev = {k: v.cuda().contiguous() for k, v in st_t.items()}
+    prm = E.robot_params("pogox", ekf_rate=200, x_box_mask=1 << 4, x_box_lo=tuple(xlo), x_box_hi=tuple(xhi))
+    est = E.BatchedEstimator(prm, n)
+    est.add_state_rows(A3, lo3, hi3)
+    xs = np.full((S, 9, n), np.nan)
+    for s in range(S):
+        est.step(s, E.robot_store.from_stream(dev, s))
+        xs[s] = est.x_MHE_.cpu().numpy()
+    it, na = est.qp_info()
+    assert int(it.max()) < 50 and not (est.status_.cpu().numpy() & 64).any()
+    # a handle that has stepped refuses new rows
+    with pytest.raises(Exception):
+        est.add_state_rows(A3, lo3, hi3)
+    est.close()
+    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0), x_row_count=3,
+              x_row_a=tuple(A3.reshape(-1)) + (0.0,) * 54, x_row_lo=tuple(lo3) + (0.0,) * 6, x_row_hi=tuple(hi3) + (0.0,) * 6,
+              x_box_mask=1 << 4, x_box_lo=tuple(xlo), x_box_hi=tuple(xhi))
+    m = 48
+    sub = {k: np.ascontiguousarray(v[..., :m]) for k, v in st.items()}
+    ref, _, _ = oracle.run_batch(sub, oracle.go1_params(**kw), oracle.ekf_params(rate=200), nthreads=os.cpu_count() or 1, want=("x",))
+    assert np.abs(xs[1:, :, :m] - ref["x"][1:]).max() < 1e-8
+    rows = np.vstack([A3, np.eye(9)[4:5]])
+    lo, hi = np.concatenate([lo3, [-0.02]]), np.concatenate([hi3, [0.02]])
+    val = np.einsum("rc,scn->srn", rows, xs[1:])
+    assert (val <= hi[None, :, None] + 1e-10).all() and (val >= lo[None, :, None] - 1e-10).all()   # no row violated, 256 instances
+    bind = ((val >= hi[None, :, None] - 1e-10) | (val <= lo[None, :, None] + 1e-10)).sum(axis=(0, 2))
+    assert (bind[:3] > 0).all(), bind
+
+
 def test_foot_state_model_vs_oracle(est_mod, oracle):
     """leg_odom_type 1: 21-state model, information-form sweep (csrc/footstate.cuh).
     Exact reference = the oracle solving the whole history in one banded system (no marginalisation); the literal

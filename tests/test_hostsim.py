@@ -144,6 +144,36 @@ def test_general_component_bounds_match_oracle(oracle):
     assert np.abs(rg["x"][1:] - rv["x"][1:]).max() < 1e-9
 
 
+def test_general_linear_rows_match_oracle(oracle):
+    """General rows  lb <= a . x_k <= ub  (dekf_add_state_rows; three rows mixing velocity / bias / position components, plus a
+    component bound from the config): box_solve<T, true> in the row basis y = W x (the kernel body of k_solve_box, compiled for
+    the host) against the oracle's exact constrained optimum (KKT-certified in tests/test_oracle_mhe.py)."""
+    import pyhostsim as hs
+    from decentralized_ekf_mhe_b200 import synth
+    st = synth.to_numpy(synth.make_stream(4, 120, robot="pogox", vo_jitter=True))
+    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0))
+    A3 = np.zeros((3, 9))
+    A3[0, 3], A3[0, 5] = 1.0, 0.5
+    A3[1, 6], A3[1, 7] = 1.0, -1.0
+    A3[2, 2], A3[2, 8] = 1.0, 0.02
+    lo3, hi3 = np.array([0.47, -0.003, -2e-4]), np.array([0.52, 0.003, 2e-4])
+    xlo, xhi = [0.0] * 9, [0.0] * 9
+    xlo[4], xhi[4] = -0.02, 0.02
+    r = hs.run(st, _cfg(x_box_mask=1 << 4, x_box_lo=tuple(xlo), x_box_hi=tuple(xhi), **kw), rows=(A3, lo3, hi3))
+    ro, _, _ = oracle.run_batch(st, oracle.go1_params(x_row_count=3, x_row_a=tuple(A3.reshape(-1)) + (0.0,) * 54,
+                                                      x_row_lo=tuple(lo3) + (0.0,) * 6, x_row_hi=tuple(hi3) + (0.0,) * 6,
+                                                      x_box_mask=1 << 4, x_box_lo=tuple(xlo), x_box_hi=tuple(xhi), **kw),
+                                oracle.ekf_params(rate=200), nthreads=4, want=("x", "v_body"))
+    assert np.abs(r["x"][1:] - ro["x"][1:]).max() < 1e-8
+    rows = np.vstack([A3, np.eye(9)[4:5]])
+    lo, hi = np.concatenate([lo3, [-0.02]]), np.concatenate([hi3, [0.02]])
+    val = np.einsum("rc,scn->srn", rows, r["x"][1:])
+    assert (val <= hi[None, :, None] + 1e-10).all() and (val >= lo[None, :, None] - 1e-10).all()
+    bind = ((val >= hi[None, :, None] - 1e-10) | (val <= lo[None, :, None] + 1e-10)).sum(axis=(0, 2))
+    assert (bind[:3] > 0).all(), bind
+    assert not (r["status"] & 64).any()
+
+
 def _dup_first(st):
     """Stream with sample 0 delivered twice: the KF alternative runs InitializeKF + UpdateKF on the same sample at
     T == 0 (DecentralEst.cpp:139-141), so x_KF_(T) is the MHE/filter estimate of this stream at T + 1."""

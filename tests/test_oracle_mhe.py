@@ -287,3 +287,68 @@ def test_general_component_bounds_optimum_certificate(oracle):
         for (j, a, sgn), w in zip(act, sol[eq.sum():]):
             assert sgn * w >= -1e-7 * scale                                     # multiplier signs
     assert seen[2] > 5 and sum(seen[a] for a in (6, 7, 8)) > 20 and seen[3] > 0   # position, bias and velocity rows all bind
+
+
+def _general_rows():
+    """Three non-selector rows on the PogoX state: a velocity combination, a bias difference, position against bias."""
+    A = np.zeros((3, 9))
+    A[0, 3], A[0, 5] = 1.0, 0.5          # v_x + 0.5 v_z
+    A[1, 6], A[1, 7] = 1.0, -1.0         # b_x - b_y
+    A[2, 2], A[2, 8] = 1.0, 0.02         # p_z + 0.02 b_z
+    lo = np.array([0.47, -0.003, -2e-4])
+    hi = np.array([0.52, 0.003, 2e-4])
+    return A, lo, hi
+
+
+def test_general_linear_rows_optimum_certificate(oracle):
+    """Arbitrary rows  lb <= a . x_k <= ub  on every window state (orc_params.x_row_*: what MHEproblem::addConstraints(name, lb, ub)
+    with a non-selector dependency row on x_k would add, MheSrb.cpp:58-68, :217-270), here three rows that mix velocity, bias and
+    position components, TOGETHER with a component bound (x_box on v_y): the oracle solves in the basis y = W x in which the rows are
+    coordinates; its optimum carries a KKT certificate on the exported reference-ordered QP with the rows themselves as the
+    active constraint normals."""
+    from decentralized_ekf_mhe_b200 import synth
+    A3, lo3, hi3 = _general_rows()
+    rows = np.vstack([A3, np.eye(9)[4:5]])                 # + the component bound on v_y as a unit row, for the certificate
+    lo = np.concatenate([lo3, [-0.02]])
+    hi = np.concatenate([hi3, [0.02]])
+    st = synth.to_numpy(synth.make_stream(1, 60, robot="pogox", vo_jitter=True, truth=True))
+    xlo, xhi = [0.0] * 9, [0.0] * 9
+    xlo[4], xhi[4] = -0.02, 0.02
+    kw = dict(robot=2, num_legs=1, contact_effort_threshold=100.0, p_ib=(0.0, 0.0, 0.0), x_row_count=3,
+              x_row_a=tuple(A3.reshape(-1)) + (0.0,) * 54, x_row_lo=tuple(lo3) + (0.0,) * 6, x_row_hi=tuple(hi3) + (0.0,) * 6,
+              x_box_mask=1 << 4, x_box_lo=tuple(xlo), x_box_hi=tuple(xhi))
+    m = oracle.Mhe(oracle.go1_params(**kw))
+    seen = np.zeros(len(rows), int)
+    for s in range(60):
+        q = st["quat_true"][s, :, 0]
+        m.step(s, imu_time=st["imu_time"][s, 0], accel=st["accel"][s, :, 0], gyro=st["gyro"][s, :, 0], quat=q,
+               joint_pos=st["joint_pos"][s, :, 0], joint_vel=st["joint_vel"][s, :, 0], foot_force=st["foot_force"][s, :, 0],
+               vo=(st["vo_time_pre"][s, 0], st["vo_time_now"][s, 0], st["vo_rel_p"][s, :, 0]) if st["vo_flag"][s, 0] else None)
+        if s < 1:
+            continue
+        ds, dm, dc, nV, nC = m.dims()
+        H, g, A, l, u = m.export_qp()
+        z = m.solution()
+        K = (nV + ds + dc) // (2 * ds + dm + dc)
+        xi = [j * (2 * ds + dm + dc) for j in range(K)]
+        X = np.array([z[o:o + 9] for o in xi])
+        val = X @ rows.T                                                      # [K, rows]
+        tol = 1e-9
+        assert (val <= hi + tol).all() and (val >= lo - tol).all()            # feasibility of every row at every state
+        eq = np.abs(u - l) < 1e-9
+        assert np.abs((A @ z - l)[eq]).max() < 1e-9 * max(1.0, np.abs(l[eq]).max())
+        act = [(j, r, +1 if val[j, r] >= hi[r] - tol else -1) for j in range(K) for r in range(len(rows))
+               if val[j, r] >= hi[r] - tol or val[j, r] <= lo[r] + tol]
+        for _, r, _ in act:
+            seen[r] += 1
+        B = np.zeros((len(act), nV))
+        for k, (j, r, sgn) in enumerate(act):
+            B[k, xi[j]:xi[j] + 9] = rows[r]
+        G = np.vstack([A[eq], B]).T
+        rhs = -(H @ z + g)
+        scale = np.abs(rhs).max() + 1.0
+        sol, *_ = np.linalg.lstsq(G, rhs, rcond=None)
+        assert np.abs(G @ sol - rhs).max() < 1e-7 * scale                      # stationarity
+        for (j, r, sgn), w in zip(act, sol[eq.sum():]):
+            assert sgn * w >= -1e-7 * scale                                     # multiplier signs
+    assert (seen[:3] > 0).all(), seen                                           # every general row binds somewhere
