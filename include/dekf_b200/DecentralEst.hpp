@@ -255,15 +255,36 @@ class DecentralizedEstimation {
     if (h_) dekf_destroy(h_);
   }
 
+  // Optional: create the device handle (allocations, first CUDA context use) ahead of time, e.g. in a node constructor, so that
+  // the first timer tick is not the one that pays for it; initialize() with the same parameter object then only steps T = 0.
+  void prepare(std::shared_ptr<robot_params> params_ptr) {
+    create_handle(*params_ptr);
+    prepared_for_ = params_ptr.get();
+  }
   // DecentralEst.hpp:101, DecentralEst.cpp:9-150 (T == 0: prior, first measurement; no solve)
   void initialize(std::shared_ptr<robot_store> sub_ptr, std::shared_ptr<robot_params> params_ptr) {
     robot_sub_ptr_ = std::move(sub_ptr);
     params_ptr_ = std::move(params_ptr);
+    if (h_ && prepared_for_ == params_ptr_.get()) {
+      prepared_for_ = nullptr;  // a later initialize() starts from a fresh handle like the reference's re-initialisation
+    } else {
+      create_handle(*params_ptr_);
+    }
+    step(0);
+  }
+  // DecentralEst.hpp:102, DecentralEst.cpp:152-198
+  void update(int T) {
+    if (!h_) throw std::runtime_error("DecentralizedEstimation::update before initialize");
+    step(T);
+  }
+
+ private:
+  void create_handle(const robot_params &prm) {
     if (h_) {
       dekf_destroy(h_);
       h_ = nullptr;
     }
-    const dekf_config cfg = params_ptr_->to_config();
+    const dekf_config cfg = prm.to_config();
     detail::check(dekf_create(&cfg, &h_), nullptr, "dekf_create");
     if (!rows_lb_.empty())
       detail::check(dekf_add_state_rows(h_, (int32_t)rows_lb_.size(), rows_a_.data(), rows_lb_.data(), rows_ub_.data()), h_,
@@ -280,8 +301,9 @@ class DecentralizedEstimation {
     R_sb_.assign(9 * (size_t)n_, 0.0);
     p_vo_accmulate_.assign(3 * (size_t)n_, 0.0);
     status_.assign(n_, 0);
-    step(0);
   }
+
+ public:
   // General inequality rows  lb[i] <= a[i] . x_k <= ub[i]  on every window state -- what MHEproblem::addConstraints(name, lb, ub)
   // with a dependency row on x_k adds in the reference (MheSrb.cpp:58-68, :217-270; never exercised there).  `a` is [count][9]
   // row-major over (p_s, v_s, accel bias).  Call BEFORE initialize(): the rows are handed to the handle when it is created.
@@ -290,11 +312,6 @@ class DecentralizedEstimation {
     rows_a_ = a;
     rows_lb_ = lb;
     rows_ub_ = ub;
-  }
-  // DecentralEst.hpp:102, DecentralEst.cpp:152-198
-  void update(int T) {
-    if (!h_) throw std::runtime_error("DecentralizedEstimation::update before initialize");
-    step(T);
   }
   // DecentralEst.hpp:103
   void reset() {
@@ -367,6 +384,7 @@ class DecentralizedEstimation {
 
   std::shared_ptr<robot_store> robot_sub_ptr_;
   std::shared_ptr<robot_params> params_ptr_;
+  const robot_params *prepared_for_ = nullptr;  // prepare()
   std::vector<double> rows_a_, rows_lb_, rows_ub_;  // addStateRows()
   dekf_handle *h_ = nullptr;
   int n_ = 0, nl_ = 0, nq_ = 0;

@@ -43,6 +43,7 @@ class EstSub : public rclcpp::Node {
     robot_params_ = std::make_shared<dekf::robot_params>(dekf::robot_params::go1());
     load_parameters();
     robot_store_->resize(1, 3 * robot_params_->num_legs_, robot_params_->num_legs_);
+    mhe.prepare(robot_params_);  // the device handle exists before the first timer tick (the reference allocates in initialize())
     using std::placeholders::_1;
     imu_sub_ = create_subscription<sensor_msgs::msg::Imu>("/unitree/imu", 10, std::bind(&EstSub::imu_callback, this, _1));
     joint_sub_ = create_subscription<sensor_msgs::msg::JointState>("/unitree/joint_state", 10, std::bind(&EstSub::lo_callback, this, _1));
