@@ -733,6 +733,40 @@ def test_general_linear_rows_vs_oracle(est_mod, oracle):
     assert (bind[:3] > 0).all(), bind
 
 
+def test_add_state_rows_rejects_what_it_cannot_solve(est_mod):
+    """dekf_add_state_rows error behaviour: dependent rows, rows dependent on a component bound of the config, lb >= ub, more than 9
+    rows in total, the KF alternative and the foot-state model are refused with DEKF_EINVAL (the handle stays usable); unit rows are
+    the component bounds (same result as cfg.x_box_*)."""
+    from decentralized_ekf_mhe_b200 import synth
+    E = est_mod
+    n = 64
+    e = np.eye(9)
+    est = E.BatchedEstimator(E.robot_params("pogox", ekf_rate=200, v_box_enable=1, v_box_lo=(-0.45, -0.03, -0.015), v_box_hi=(0.55, 0.03, 0.015)), n)
+    for a, lb, ub in ((np.vstack([e[0] + e[1], 2 * e[0] + 2 * e[1]]), [-1, -1], [1, 1]),      # dependent rows
+                      (e[3:4], [-1], [1]),                                                      # v_x is already bounded by v_box
+                      (e[0:1], [1.0], [1.0]),                                                   # lb == ub
+                      (e[[0, 1, 2, 6, 7, 8, 0]], [-1] * 7, [1] * 7)):                           # 7 rows + 3 of v_box > 9
+        with pytest.raises(Exception):
+            est.add_state_rows(a, lb, ub)
+    est.add_state_rows(e[0:1] + 0.5 * e[6:7], [-5.0], [5.0])                                   # a legal row (never binding)
+    st = synth.make_stream(n, 12, robot="pogox", vo_jitter=True)
+    dev = {k: v.cuda().contiguous() for k, v in st.items()}
+    for s in range(12):
+        est.step(s, E.robot_store.from_stream(dev, s))
+    x_rows = est.x_MHE_.clone()
+    est.close()
+    ref = E.BatchedEstimator(E.robot_params("pogox", ekf_rate=200, v_box_enable=1, v_box_lo=(-0.45, -0.03, -0.015), v_box_hi=(0.55, 0.03, 0.015)), n)
+    for s in range(12):
+        ref.step(s, E.robot_store.from_stream(dev, s))
+    assert (x_rows - ref.x_MHE_).abs().max() < 1e-9      # a row that never binds changes nothing: the velocity box through the row basis
+    ref.close()
+    for kw in (dict(est_type=1), dict(leg_odom_type=1)):
+        h = E.BatchedEstimator(E.robot_params("go1", ekf_rate=200, **kw), 8)
+        with pytest.raises(Exception):
+            h.add_state_rows(e[0:1], [-1], [1])
+        h.close()
+
+
 def test_foot_state_model_vs_oracle(est_mod, oracle):
     """leg_odom_type 1: 21-state model, information-form sweep (csrc/footstate.cuh).
     Exact reference = the oracle solving the whole history in one banded system (no marginalisation); the literal
