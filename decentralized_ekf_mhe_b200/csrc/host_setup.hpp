@@ -190,8 +190,8 @@ inline BoxConst make_box_const(const dekf_config &c) {
   return b;
 }
 
-// Row basis of the general linear rows (dekf_add_state_rows): W = [the count rows of `a`; the component bounds of the config as unit
-// rows; unit vectors completing them to a basis (greedy: the unit vector farthest from the span so far)], V = W^-1 by Gauss-Jordan
+// Row basis of the general linear rows (dekf_add_state_rows): W = [the count rows of `a`, normalised; the component bounds of the config
+// as unit rows; an orthonormal completion (Gram-Schmidt residuals of the unit vectors farthest from the span so far)], V = W^-1 by Gauss-Jordan
 // with partial pivoting; lo / hi in row order.  Returns the number of bounded rows m, or -1 (dependent rows, more than 9, lb >= ub).
 inline int make_row_basis(const dekf_config &c, int count, const double *a, const double *lb, const double *ub, double *W, double *V,
                           double *lo, double *hi) {
@@ -213,9 +213,10 @@ inline int make_row_basis(const dekf_config &c, int count, const double *a, cons
     if (na == 0.0 || !(nr > 1e-16 * na)) return false;
     for (int k = 0; k < 9; ++k) Q[nq * 9 + k] = r[k] / std::sqrt(nr);
     ++nq;
-    for (int k = 0; k < 9; ++k) W[m * 9 + k] = row[k];
-    lo[m] = l;
-    hi[m] = u;
+    const double inv = 1.0 / std::sqrt(na);  // rows enter the basis with unit length (conditioning of W): bounds scale along
+    for (int k = 0; k < 9; ++k) W[m * 9 + k] = row[k] * inv;
+    lo[m] = l * inv;
+    hi[m] = u * inv;
     ++m;
     return true;
   };
@@ -246,8 +247,9 @@ inline int make_row_basis(const dekf_config &c, int count, const double *a, cons
         for (int cc = 0; cc < 9; ++cc) br[cc] = r[cc];
       }
     }
+    (void)best;
     for (int cc = 0; cc < 9; ++cc) Q[nq * 9 + cc] = br[cc] / std::sqrt(bestn);
-    for (int cc = 0; cc < 9; ++cc) W[nq * 9 + cc] = cc == best ? 1.0 : 0.0;
+    for (int cc = 0; cc < 9; ++cc) W[nq * 9 + cc] = Q[nq * 9 + cc];  // orthonormal to everything so far: cond(W) = cond(rows)
     ++nq;
   }
   double A[9][18];

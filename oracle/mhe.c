@@ -987,9 +987,9 @@ static int rows_basis(const orc_params *P, double *W /*81*/, double *V /*81*/, d
       if (!(nr > 1e-16 * na) || na == 0.0) return -1;
       for (int c = 0; c < 9; ++c) Q[nq * 9 + c] = r[c] / sqrt(nr);
       nq++;
-      for (int c = 0; c < 9; ++c) W[m * 9 + c] = a[c];
-      lo[m] = l;
-      hi[m] = u;
+      for (int c = 0; c < 9; ++c) W[m * 9 + c] = a[c] / sqrt(na); /* unit-length rows: bounds scale along */
+      lo[m] = l / sqrt(na);
+      hi[m] = u / sqrt(na);
       m++;
     }
   }
@@ -1007,8 +1007,9 @@ static int rows_basis(const orc_params *P, double *W /*81*/, double *V /*81*/, d
       for (int c = 0; c < 9; ++c) nr += r[c] * r[c];
       if (nr > bestn) { bestn = nr; best = k; for (int c = 0; c < 9; ++c) br[c] = r[c]; }
     }
+    (void)best;
     for (int c = 0; c < 9; ++c) Q[nq * 9 + c] = br[c] / sqrt(bestn);
-    for (int c = 0; c < 9; ++c) W[nq * 9 + c] = (c == best) ? 1.0 : 0.0;
+    for (int c = 0; c < 9; ++c) W[nq * 9 + c] = Q[nq * 9 + c]; /* orthonormal completion: cond(W) = cond(rows) */
     nq++;
   }
   /* V = W^-1 */
