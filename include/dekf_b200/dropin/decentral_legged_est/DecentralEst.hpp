@@ -163,6 +163,8 @@ class DecentralizedEstimation {
     c.n_instances = 1;
     c.kf_export_gain = p.est_type_ == 1 && p.leg_odom_type_ == 0;
     check(dekf_create(&c, &h_), "dekf_create");
+    if (!rows_lb_.empty())
+      check(dekf_add_state_rows(h_, (int32_t)rows_lb_.size(), rows_a_.data(), rows_lb_.data(), rows_ub_.data()), "dekf_add_state_rows");
     nq_ = dekf_num_joints(h_);
     nl_ = c.num_legs;
     ds_ = dekf_state_dim(h_);
@@ -171,6 +173,20 @@ class DecentralizedEstimation {
     x_KF_ = VectorXd::Zero(ds_);
     R_sb_ = Matrix3d::Zero();
     step(0);
+  }
+  // General inequality rows  lb(i) <= A.row(i) . x_k <= ub(i)  on every window state: MHEproblem::addConstraints(name, lb, ub) with a
+  // dependency row on x_k (MheSrb.cpp:58-68, :217-270; the reference never calls it with lb < ub).  A is count x 9 over
+  // (p_s, v_s, accel bias).  Call before initialize().
+  void addStateRows(const MatrixXd &A, const VectorXd &lb, const VectorXd &ub) {
+    if (A.cols() != 9 || A.rows() != lb.size() || lb.size() != ub.size()) throw std::runtime_error("addStateRows: A must be count x 9");
+    rows_a_.assign((size_t)A.rows() * 9, 0.0);
+    rows_lb_.assign((size_t)A.rows(), 0.0);
+    rows_ub_.assign((size_t)A.rows(), 0.0);
+    for (int i = 0; i < (int)A.rows(); ++i) {
+      for (int k = 0; k < 9; ++k) rows_a_[(size_t)i * 9 + k] = A(i, k);
+      rows_lb_[i] = lb(i);
+      rows_ub_[i] = ub(i);
+    }
   }
   // DecentralEst.hpp:102, DecentralEst.cpp:152-198
   void update(int T) {
@@ -293,6 +309,7 @@ class DecentralizedEstimation {
 
   std::shared_ptr<robot_store> robot_sub_ptr_;
   std::shared_ptr<robot_params> params_ptr_;
+  std::vector<double> rows_a_, rows_lb_, rows_ub_;  // addStateRows()
   dekf_handle *h_ = nullptr;
   int nq_ = 12, nl_ = 4, ds_ = 9;
   bool kf_ = false;
