@@ -305,6 +305,7 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
   // the most negative multiplier (or stop), 3 = move from the feasible iterate xc towards the new minimiser, stopping at (and
   // adding) the first bound the segment crosses.  Monotone in the cost, finite on a strictly convex QP.
   int phase = 0;
+  bool have_xc = false;  // the scratch holds a FEASIBLE iterate of the finite method (reported if the iteration cap is hit)
   for (int it = 0; it < bc.max_iter && !converged; ++it) {
     iters = it + 1;
     // ---- forward: assemble, apply the active set, block Cholesky
@@ -476,10 +477,6 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
         if (bj >= 0) {  // blocked: the bound joins the set, the equality-constrained problem is solved again
           const size_t at = (size_t)((k0 + bj) % dm.NW) * ns + i;
           BS::store(bb, at, BS::load(bb, at) | (bside > 0 ? (BS::HB << bcmp) : (1 << bcmp)));
-          if (K > 0) {  // x_T reported if the cap is hit here: the feasible iterate
-            const double *fl = bb.fac + ((size_t)(K - 1) * BOX_FAC) * ns + i;
-            for (int f = 0; f < 9; ++f) xT[f] = fl[(size_t)(135 + f) * ns];
-          }
           continue;
         }
         phase = 2;
@@ -592,6 +589,7 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
       }
       if (safe && added == 0) {
         // feasible equality-constrained minimiser: it becomes the iterate xc of the finite method
+        have_xc = true;
         for (int j = 0; j < K; ++j) {
           double *fj = bb.fac + ((size_t)j * BOX_FAC) * ns + i;
           for (int c = 0; c < 9; ++c) fj[(size_t)(135 + c) * ns] = fj[(size_t)(126 + c) * ns];
@@ -679,6 +677,12 @@ DEKF_HD int box_solve(const BoxConst &bc, const Dims &dm, const Buffers<T> &b, c
     converged = !changed;
   }
   if (!converged) status |= ST_QP_MAXITER;
+  if constexpr (GEN) {
+    if (!converged && have_xc) {  // cap hit inside the finite method: report its feasible (not yet optimal) iterate, never a violated bound
+      const double *fl = bb.fac + ((size_t)(K - 1) * BOX_FAC) * ns + i;
+      for (int f = 0; f < 9; ++f) xT[f] = fl[(size_t)(135 + f) * ns];
+    }
+  }
   if (rows) {  // x_T = V y_T
     double xv[9];
     for (int a = 0; a < 9; ++a) {
